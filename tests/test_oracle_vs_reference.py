@@ -1,0 +1,53 @@
+"""Live diff of the oracle against the reference's unmodified code (cogent3 shimmed).
+Runs only where /root/reference exists (the build container); the recorded form of the
+same check is tests/golden/ref_graph_fuzz.json."""
+import os
+import random
+import sys
+
+import pytest
+
+REF = "/root/reference/src"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
+
+
+def test_live_reference_fuzz():
+    here = os.path.dirname(os.path.abspath(__file__))
+    shim = os.path.join(os.path.dirname(here), "oracle", "cogent3_shim")
+    saved = list(sys.path)
+    sys.path[:0] = [shim, REF]
+    try:
+        from dbga.debruijn_pairwise import DeBruijnPairwise
+        from oracle import dbga_oracle as O
+        rng = random.Random(99)
+        n_ok = n_cyc = 0
+        for _ in range(300):
+            n = rng.choice([10, 30, 90, 200])
+            k = rng.choice([2, 3, 5, 7])
+            s0 = "".join(rng.choice("ACGT") for _ in range(n))
+            s1 = "".join(c if rng.random() > 0.08 else rng.choice("ACGT") for c in s0)
+            if rng.random() < 0.5:
+                cut = rng.randrange(len(s1))
+                s1 = s1[:cut] + s1[cut + rng.randint(1, 5):]
+            if len(s1) < k:
+                continue
+            r = O.align_pair(s0, s1, k)
+            try:
+                db = DeBruijnPairwise([s0, s1], k, "dna")
+            except ValueError:
+                assert r.status == O.CYCLE
+                n_cyc += 1
+                continue
+            assert r.status == O.OK
+            assert db.seq_node_idx == r.graph.seq_node_idx
+            assert db.merge_node_idx == r.graph.merge_node_idx
+            assert db.id_count == r.graph.id_count
+            aln = db.alignment()
+            d = aln if isinstance(aln, dict) else aln.to_dict()
+            assert (d[0], d[1]) == (r.aln0, r.aln1)
+            n_ok += 1
+        assert n_ok > 100
+    finally:
+        sys.path[:] = saved
+        for m in [m for m in sys.modules if m == "dbga" or m.startswith("dbga.") or m.startswith("cogent3") or m == "graphviz"]:
+            del sys.modules[m]
