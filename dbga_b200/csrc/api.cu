@@ -1,0 +1,647 @@
+// C-ABI host side: plan (sizing, classing, metadata upload), run (kernel pipeline on one
+// stream, no host round trips), fetch (device -> pinned host).  See include/dbga_b200.h.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace dbga;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct SmallClass {
+    uint32_t cap;
+    int words, maxq;
+    int begin, count;   // range in the small pair list
+};
+struct LargeWave {
+    int begin, count;   // range in the large list / LargeDesc array
+    int max_n;
+    size_t table_bytes;
+};
+
+}  // namespace
+
+struct dbga_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int num_sms = 148;
+    char err[512] = {0};
+    int64_t scratch_limit = 8LL << 30;
+    cudaEvent_t ev[8] = {};
+
+    // ---- plan
+    bool planned = false, ran = false;
+    int64_t P = 0, total_bytes = 0, sumN0 = 0, sumN1 = 0;
+    int max_n0 = 0, max_n1 = 0;
+    dbga_params prm{};
+    bool no_anchors = false;
+    DpParams dp{};
+    int max_abs_score = 0;
+    std::vector<PairDesc> h_pairs;
+    std::vector<int32_t> h_list;          // small classes first, then large
+    std::vector<SmallClass> classes;
+    std::vector<LargeDesc> h_large;
+    std::vector<LargeWave> waves;
+    int large_begin = 0;
+    int stage2_threads = 128;
+    int64_t runs_cap = 0, slots_cap = 0, tb_cap = 0;
+    int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
+    int grid_warp = 0, grid_cta = 0;
+    int launches = 0;
+    const uint8_t *d_seqs_run = nullptr;
+
+    // ---- device buffers (grow only)
+    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_slots, d_lt, d_lw,
+        d_lc, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_len, d_aln_off, d_run_cnt,
+        d_run_off, d_scan_tmp, d_aln0, d_aln1, d_runs_out, d_score, d_cells, d_nseg, d_nanch, d_status_out,
+        d_sink;
+    // ---- pinned host result buffers
+    HostBuf h_status, h_score, h_cells, h_nseg, h_nanch, h_aln_off, h_run_off, h_aln0, h_aln1, h_runs, h_nd0,
+        h_nd1, h_poff, h_qoff, h_ctr;
+};
+
+namespace {
+
+int fail(dbga_ctx *ctx, int code, const char *msg) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
+    return code;
+}
+
+int dev_reserve(dbga_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return DBGA_SUCCESS;
+    if (b.p) { DBGA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); DBGA_CUDA_CHECK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = std::max<size_t>(bytes, 256);
+    want = (want + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        b.p = nullptr;
+        return DBGA_ERR_NOMEM;
+    }
+    b.cap = want;
+    return DBGA_SUCCESS;
+}
+int host_reserve(dbga_ctx *ctx, HostBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return DBGA_SUCCESS;
+    if (b.p) { DBGA_CUDA_CHECK(cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = std::max<size_t>(bytes + bytes / 8, 4096);
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaHostAlloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+        b.p = nullptr;
+        return DBGA_ERR_NOMEM;
+    }
+    b.cap = want;
+    return DBGA_SUCCESS;
+}
+#define RESERVE(buf, bytes)                                         \
+    do {                                                            \
+        int _r = dev_reserve(ctx, ctx->buf, (size_t)(bytes));       \
+        if (_r != DBGA_SUCCESS) return _r;                          \
+    } while (0)
+#define HRESERVE(buf, bytes)                                        \
+    do {                                                            \
+        int _r = host_reserve(ctx, ctx->buf, (size_t)(bytes));      \
+        if (_r != DBGA_SUCCESS) return _r;                          \
+    } while (0)
+
+uint32_t pow2_at_least(uint64_t v, uint32_t lo) {
+    uint64_t c = lo;
+    while (c < v) c <<= 1;
+    return (uint32_t)c;
+}
+
+const int ORDER_PRIO[6][3] = {
+    // priority (2 = wins ties) of {M, X, Y} for XMY, XYM, MXY, MYX, YXM, YMX
+    {1, 2, 0}, {0, 2, 1}, {2, 1, 0}, {2, 0, 1}, {0, 1, 2}, {1, 0, 2}};
+
+int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
+    if (p.pred_order < 0 || p.pred_order > 5 || p.end_order < 0 || p.end_order > 5)
+        return fail(ctx, DBGA_ERR_ARG, "pred_order / end_order must be in 0..5");
+    if (p.gap_open < 0 || p.gap_extend < 0 || p.gap_open > 100000 || p.gap_extend > 100000)
+        return fail(ctx, DBGA_ERR_ARG, "gap costs must be in 0..100000");
+    DpParams &d = ctx->dp;
+    d.go_raw = p.gap_len_mode ? p.gap_open + p.gap_extend : p.gap_open;
+    d.ge_raw = p.gap_extend;
+    d.go = SCALE * d.go_raw;
+    d.ge = SCALE * d.ge_raw;
+    d.tagM = TAGMUL * ORDER_PRIO[p.pred_order][0];
+    d.tagX = TAGMUL * ORDER_PRIO[p.pred_order][1];
+    d.tagY = TAGMUL * ORDER_PRIO[p.pred_order][2];
+    d.endM = ORDER_PRIO[p.end_order][0];
+    d.endX = ORDER_PRIO[p.end_order][1];
+    d.endY = ORDER_PRIO[p.end_order][2];
+    d.xy = p.xy_allowed ? 1 : 0;
+    int mx = 0;
+    for (int a = 0; a < 4; ++a) {
+        uint32_t v[4];
+        for (int c = 0; c < 4; ++c) {
+            const int s = p.score[a * 4 + c];
+            mx = std::max(mx, std::abs(s));
+            if (std::abs(s) > 500) return fail(ctx, DBGA_ERR_ARG, "|substitution score| must be <= 500");
+            v[c] = (uint32_t)(uint16_t)(int16_t)(SCALE * s + d.tagM);
+        }
+        d.lut_lo[a] = v[0] | (v[1] << 16);
+        d.lut_hi[a] = v[2] | (v[3] << 16);
+    }
+    ctx->max_abs_score = mx;
+    return DBGA_SUCCESS;
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+constexpr size_t L2_TABLE_BUDGET = 64u << 20;
+
+int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params *params, bool no_anchors) {
+    ctx->planned = false; ctx->ran = false;
+    if (!offsets || !params || P < 0) return fail(ctx, DBGA_ERR_ARG, "null argument");
+    if (P > 0x7fffff00LL) return fail(ctx, DBGA_ERR_ARG, "too many pairs in one batch");
+    if (!no_anchors && (params->k < 1 || params->k > 31)) return fail(ctx, DBGA_ERR_ARG, "k must be in 1..31");
+    if (params->stages != 2 && params->stages != 3) return fail(ctx, DBGA_ERR_ARG, "stages must be 2 or 3");
+    ctx->prm = *params;
+    ctx->no_anchors = no_anchors;
+    int rc = make_dp_params(ctx, *params);
+    if (rc != DBGA_SUCCESS) return rc;
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int k = no_anchors ? 1 : params->k;
+    const bool full = params->want_graph != 0 && !no_anchors;
+    ctx->P = P;
+    ctx->h_pairs.resize((size_t)P);
+    ctx->total_bytes = P > 0 ? offsets[2 * P] : 0;
+    int64_t qb = 0, pb = 0;
+    int mx0 = 0, mx1 = 0;
+    for (int64_t i = 0; i < P; ++i) {
+        const int64_t o0 = offsets[2 * i], o1 = offsets[2 * i + 1], o2 = offsets[2 * i + 2];
+        if (o0 < 0 || o1 < o0 || o2 < o1) return fail(ctx, DBGA_ERR_ARG, "offsets must be non-decreasing");
+        if (o1 - o0 > 0x7ffffff0LL || o2 - o1 > 0x7ffffff0LL) return fail(ctx, DBGA_ERR_ARG, "sequence longer than 2^31");
+        PairDesc &pd = ctx->h_pairs[(size_t)i];
+        pd.off0 = o0; pd.off1 = o1; pd.n0 = (int32_t)(o1 - o0); pd.n1 = (int32_t)(o2 - o1);
+        pd.q_base = qb; pd.p_base = pb;
+        qb += std::max(0, pd.n1 - k + 1);
+        pb += std::max(0, pd.n0 - k + 1);
+        mx0 = std::max(mx0, pd.n0); mx1 = std::max(mx1, pd.n1);
+    }
+    ctx->sumN1 = qb; ctx->sumN0 = pb; ctx->max_n0 = mx0; ctx->max_n1 = mx1;
+
+    // ---- stage-1 classing
+    ctx->classes.clear(); ctx->h_list.clear(); ctx->h_large.clear(); ctx->waves.clear();
+    if (!no_anchors) {
+        const int key_bytes = k <= 15 ? 4 : 8;
+        std::vector<std::vector<int32_t>> by_cap(32);
+        std::vector<int32_t> large;
+        for (int64_t i = 0; i < P; ++i) {
+            const PairDesc &pd = ctx->h_pairs[(size_t)i];
+            const int64_t N0 = std::max(0, pd.n0 - k + 1), N1 = std::max(0, pd.n1 - k + 1);
+            const uint64_t keys = full ? (uint64_t)(N0 + N1) : (uint64_t)N0;
+            const uint32_t cap = pow2_at_least(keys + keys / 2 + 1, 256);
+            const int nmax = std::max(pd.n0, pd.n1);
+            const int words = (((nmax + 15) / 16 + 3) + 1) & ~1;
+            const bool fits = cap <= 32768 && stage1_small_smem(key_bytes, cap, words, (int)N1) <= SMEM_LIMIT;
+            if (fits) {
+                int lg = 0;
+                while ((1u << lg) < cap) ++lg;
+                by_cap[lg].push_back((int32_t)i);
+            } else {
+                large.push_back((int32_t)i);
+            }
+        }
+        for (int lg = 0; lg < 32; ++lg) {
+            if (by_cap[lg].empty()) continue;
+            SmallClass c;
+            c.cap = 1u << lg; c.begin = (int)ctx->h_list.size(); c.count = (int)by_cap[lg].size();
+            int nmax = 0, qmax = 0;
+            for (int32_t i : by_cap[lg]) {
+                const PairDesc &pd = ctx->h_pairs[(size_t)i];
+                nmax = std::max(nmax, std::max(pd.n0, pd.n1));
+                qmax = std::max(qmax, std::max(0, pd.n1 - k + 1));
+                ctx->h_list.push_back(i);
+            }
+            c.words = (((nmax + 15) / 16 + 3) + 1) & ~1;
+            c.maxq = qmax;
+            if (stage1_small_smem(key_bytes, c.cap, c.words, c.maxq) > SMEM_LIMIT) {
+                // mixed extremes inside one class: fall back to the large path for this class
+                ctx->h_list.resize((size_t)c.begin);
+                for (int32_t i : by_cap[lg]) large.push_back(i);
+                continue;
+            }
+            ctx->classes.push_back(c);
+        }
+        ctx->large_begin = (int)ctx->h_list.size();
+        // waves of large pairs whose tables stay L2 resident together
+        size_t wave_tbl = 0, wave_pk = 0;
+        LargeWave w{(int)ctx->h_large.size(), 0, 0, 0};
+        auto flush = [&]() {
+            if (w.count) { w.table_bytes = wave_tbl * 16; ctx->waves.push_back(w); }
+            w = LargeWave{(int)ctx->h_large.size(), 0, 0, 0};
+            wave_tbl = 0; wave_pk = 0;
+        };
+        for (int32_t i : large) {
+            const PairDesc &pd = ctx->h_pairs[(size_t)i];
+            const int64_t N0 = std::max(0, pd.n0 - k + 1), N1 = std::max(0, pd.n1 - k + 1);
+            const uint64_t keys = full ? (uint64_t)(N0 + N1) : (uint64_t)N0;
+            const uint64_t cap = pow2_at_least(keys + keys / 2 + 1, 1024);
+            if (cap > (1ull << 31)) return fail(ctx, DBGA_ERR_ARG, "sequence too long for the k-mer table");
+            if (w.count && ((wave_tbl + cap) * 16 > L2_TABLE_BUDGET || w.count >= 32768)) flush();
+            LargeDesc ld;
+            ld.tbl = (int64_t)wave_tbl; ld.mask = (uint32_t)(cap - 1); ld.pad = 0;
+            ld.pk0 = (int64_t)wave_pk; wave_pk += (size_t)(pd.n0 + 15) / 16 + 4;
+            ld.pk1 = (int64_t)wave_pk; wave_pk += (size_t)(pd.n1 + 15) / 16 + 4;
+            wave_tbl += cap;
+            ctx->h_large.push_back(ld);
+            ctx->h_list.push_back(i);
+            w.count++;
+            w.max_n = std::max(w.max_n, std::max(pd.n0, pd.n1));
+        }
+        flush();
+    }
+
+    // ---- device metadata
+    RESERVE(d_pairs, sizeof(PairDesc) * std::max<int64_t>(P, 1));
+    RESERVE(d_list, sizeof(int32_t) * std::max<size_t>(ctx->h_list.size(), 1));
+    RESERVE(d_large, sizeof(LargeDesc) * std::max<size_t>(ctx->h_large.size(), 1));
+    if (P) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * P, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->h_list.empty()) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_list.p, ctx->h_list.data(), sizeof(int32_t) * ctx->h_list.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->h_large.empty()) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_large.p, ctx->h_large.data(), sizeof(LargeDesc) * ctx->h_large.size(), cudaMemcpyHostToDevice, ctx->stream));
+    size_t max_tbl = 0, max_pk = 0;
+    for (size_t wi = 0; wi < ctx->waves.size(); ++wi) {
+        const LargeWave &w = ctx->waves[wi];
+        max_tbl = std::max(max_tbl, w.table_bytes);
+        const LargeDesc &last = ctx->h_large[(size_t)(w.begin + w.count - 1)];
+        const PairDesc &pd = ctx->h_pairs[(size_t)ctx->h_list[(size_t)(ctx->large_begin + w.begin + w.count - 1)]];
+        max_pk = std::max(max_pk, (size_t)last.pk1 + (size_t)(pd.n1 + 15) / 16 + 4);
+    }
+    RESERVE(d_table, max_tbl);
+    RESERVE(d_packed, max_pk * 4);
+
+    // ---- workspaces
+    RESERVE(d_status, 4 * std::max<int64_t>(P, 1));
+    RESERVE(d_status_out, 4 * std::max<int64_t>(P, 1));
+    RESERVE(d_aof, 4 * std::max<int64_t>(ctx->sumN1, 1));
+    if (full) { RESERVE(d_nd0, std::max<int64_t>(ctx->sumN0, 1)); RESERVE(d_nd1, std::max<int64_t>(ctx->sumN1, 1)); }
+    RESERVE(d_pout, sizeof(PairOut) * std::max<int64_t>(P, 1));
+    RESERVE(d_ctr, sizeof(Counters));
+    const int64_t worst_runs = ctx->sumN1 + 1;
+    ctx->runs_cap = std::max<int64_t>(ctx->runs_cap, std::min<int64_t>(worst_runs, ctx->sumN1 / 16 + 4 * P + 1024));
+    ctx->slots_cap = std::max<int64_t>(ctx->slots_cap, ctx->runs_cap + P + 16);
+    ctx->tb_cap = std::max<int64_t>(ctx->tb_cap, std::min<int64_t>(ctx->scratch_limit, 64LL << 20));
+    ctx->stage2_threads = mx1 <= 4096 ? 128 : (mx1 <= 65536 ? 256 : 1024);
+    // boundary rows for multi-pass wavefronts
+    ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, WARP_CLASS_MAX_CELLS / (WF_ROWS_PER_WARP + 1) + 2);
+    ctx->bnd_stride_cta = (int64_t)mx1 + 1;
+    ctx->grid_warp = ctx->num_sms * 16;
+    {
+        const int64_t per = 2 * ctx->bnd_stride_cta * 16;
+        int64_t g = (1LL << 30) / std::max<int64_t>(per, 1);
+        ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, g));
+    }
+    const bool any_non_tiny = (mx0 > TINY_MAX_M) || (mx1 > TINY_MAX_N);
+    const bool any_cta = (int64_t)mx0 * mx1 > WARP_CLASS_MAX_CELLS;
+    if (!any_non_tiny) ctx->grid_warp = 0;
+    if (!any_cta) ctx->grid_cta = 0;
+    if (params->stages == 3) {
+        RESERVE(d_str, 2 * std::max<int64_t>(ctx->total_bytes, 1));
+        if (ctx->grid_warp) RESERVE(d_bnd_w, (size_t)ctx->grid_warp * 2 * ctx->bnd_stride_warp * 16);
+        if (ctx->grid_cta) RESERVE(d_bnd_c, (size_t)ctx->grid_cta * 2 * ctx->bnd_stride_cta * 16);
+        RESERVE(d_aln0, std::max<int64_t>(ctx->total_bytes, 1));
+        RESERVE(d_aln1, std::max<int64_t>(ctx->total_bytes, 1));
+    }
+    RESERVE(d_aln_len, 8 * (P + 1)); RESERVE(d_aln_off, 8 * (P + 2));
+    RESERVE(d_run_cnt, 8 * (P + 1)); RESERVE(d_run_off, 8 * (P + 2));
+    RESERVE(d_scan_tmp, 8 * (P / 2048 + 2));
+    RESERVE(d_score, 8 * (P + 1)); RESERVE(d_cells, 8 * (P + 1)); RESERVE(d_nseg, 4 * (P + 1));
+    RESERVE(d_nanch, 8 * (P + 1));
+    ctx->planned = true;
+    return DBGA_SUCCESS;
+}
+
+int reserve_pools(dbga_ctx *ctx) {
+    RESERVE(d_runs, 12 * ctx->runs_cap);
+    RESERVE(d_runs_out, 12 * ctx->runs_cap);
+    if (ctx->prm.stages == 3) {
+        RESERVE(d_slots, sizeof(Slot) * ctx->slots_cap);
+        RESERVE(d_lt, 4 * ctx->slots_cap); RESERVE(d_lw, 4 * ctx->slots_cap); RESERVE(d_lc, 4 * ctx->slots_cap);
+        if (ctx->grid_warp || ctx->grid_cta) RESERVE(d_tb, ctx->tb_cap);
+    }
+    return DBGA_SUCCESS;
+}
+
+// stages 2..assemble; may be re-run after growing pools
+int run_from_stage2(dbga_ctx *ctx) {
+    cudaStream_t st = ctx->stream;
+    const int64_t P = ctx->P;
+    const bool seg = ctx->prm.stages == 3;
+    int rc = reserve_pools(ctx);
+    if (rc != DBGA_SUCCESS) return rc;
+    DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(Counters), st));
+    Pools pools;
+    pools.runs = (int32_t *)ctx->d_runs.p; pools.runs_cap = ctx->runs_cap;
+    pools.slots = (Slot *)ctx->d_slots.p; pools.slots_cap = ctx->slots_cap;
+    pools.tb_cap = (ctx->grid_warp || ctx->grid_cta) ? ctx->tb_cap : 0;
+    pools.list_tiny = (int32_t *)ctx->d_lt.p; pools.list_warp = (int32_t *)ctx->d_lw.p; pools.list_cta = (int32_t *)ctx->d_lc.p;
+    pools.list_cap = ctx->slots_cap;
+    Counters *ctr = (Counters *)ctx->d_ctr.p;
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[2], st));
+    DBGA_CUDA_CHECK(launch_stage2((PairDesc *)ctx->d_pairs.p, P, ctx->no_anchors ? 1 : ctx->prm.k, ctx->no_anchors, seg,
+                                  (int32_t *)ctx->d_aof.p, (int32_t *)ctx->d_status.p, (PairOut *)ctx->d_pout.p, pools, ctr,
+                                  ctx->stage2_threads, ctx->num_sms, ctx->max_abs_score, ctx->dp.go_raw, ctx->dp.ge_raw, st));
+    ctx->launches += 1;
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));
+    if (seg) {
+        const uint8_t *seqs = ctx->d_seqs_run;
+        DBGA_CUDA_CHECK(launch_dp_tiny(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.list_tiny, &ctr->n_tiny,
+                                       ctx->slots_cap, ctx->dp, (uint8_t *)ctx->d_str.p, ctx->num_sms, st));
+        ctx->launches += 1;
+        if (ctx->grid_warp) {
+            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.list_warp, &ctr->n_warp,
+                                                ctx->grid_warp, false, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
+                                                (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
+            ctx->launches += 1;
+        }
+        if (ctx->grid_cta) {
+            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.list_cta, &ctr->n_cta,
+                                                ctx->grid_cta, true, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
+                                                (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
+            ctx->launches += 1;
+        }
+    }
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[4], st));
+    DBGA_CUDA_CHECK(launch_assemble(ctx->d_seqs_run, (PairDesc *)ctx->d_pairs.p, P, (PairOut *)ctx->d_pout.p,
+                                    (int32_t *)ctx->d_status_out.p, (int32_t *)ctx->d_runs.p, (Slot *)ctx->d_slots.p,
+                                    (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p, (int64_t *)ctx->d_aln_off.p,
+                                    (int64_t *)ctx->d_run_cnt.p, (int64_t *)ctx->d_run_off.p, (int64_t *)ctx->d_scan_tmp.p,
+                                    (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p, (int32_t *)ctx->d_runs_out.p,
+                                    (int64_t *)ctx->d_score.p, (int64_t *)ctx->d_cells.p, (int32_t *)ctx->d_nseg.p,
+                                    (int64_t *)ctx->d_nanch.p, ctr, ctx->num_sms, st, &ctx->launches));
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
+    return DBGA_SUCCESS;
+}
+
+int do_run(dbga_ctx *ctx, const uint8_t *d_seqs) {
+    if (!ctx->planned) return fail(ctx, DBGA_ERR_ARG, "dbga_plan_run without a plan");
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    ctx->d_seqs_run = d_seqs;
+    ctx->launches = 0;
+    const bool full = ctx->prm.want_graph != 0 && !ctx->no_anchors;
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], st));
+    DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_status.p, 0, 4 * std::max<int64_t>(ctx->P, 1), st));
+    if (!ctx->no_anchors) {
+        for (const SmallClass &c : ctx->classes) {
+            DBGA_CUDA_CHECK(launch_stage1_small(d_seqs, (PairDesc *)ctx->d_pairs.p, (int32_t *)ctx->d_list.p + c.begin, c.count,
+                                                ctx->prm.k, c.cap, c.words, c.maxq, full, (int32_t *)ctx->d_status.p,
+                                                (int32_t *)ctx->d_aof.p, (uint8_t *)ctx->d_nd0.p, (uint8_t *)ctx->d_nd1.p,
+                                                ctx->num_sms, st));
+            ctx->launches += 1;
+        }
+        for (const LargeWave &w : ctx->waves) {
+            DBGA_CUDA_CHECK(launch_stage1_large(d_seqs, (PairDesc *)ctx->d_pairs.p, (LargeDesc *)ctx->d_large.p + w.begin,
+                                                (int32_t *)ctx->d_list.p + ctx->large_begin + w.begin, w.count, w.max_n,
+                                                ctx->prm.k, full, (uint32_t *)ctx->d_packed.p, ctx->d_table.p, w.table_bytes,
+                                                (int32_t *)ctx->d_status.p, (int32_t *)ctx->d_aof.p, (uint8_t *)ctx->d_nd0.p,
+                                                (uint8_t *)ctx->d_nd1.p, st, &ctx->launches));
+        }
+    }
+    int rc = run_from_stage2(ctx);
+    if (rc != DBGA_SUCCESS) return rc;
+    ctx->ran = true;
+    return DBGA_SUCCESS;
+}
+
+int do_fetch(dbga_ctx *ctx, dbga_result *out) {
+    if (!ctx->ran) return fail(ctx, DBGA_ERR_ARG, "dbga_plan_fetch before dbga_plan_run");
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t P = ctx->P;
+    HRESERVE(h_ctr, sizeof(Counters));
+    Counters *hc = (Counters *)ctx->h_ctr.p;
+    // pool overflow: grow to the measured need and re-run stages 2.. (stage 1 output is kept)
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+        bool grow = false;
+        if ((int64_t)hc->runs_used > ctx->runs_cap) { ctx->runs_cap = (int64_t)hc->runs_used + 1024; grow = true; }
+        if ((int64_t)hc->slots_used > ctx->slots_cap) { ctx->slots_cap = (int64_t)hc->slots_used + 1024; grow = true; }
+        ctx->slots_cap = std::max(ctx->slots_cap, ctx->runs_cap + P + 16);
+        if ((int64_t)hc->tb_used > ctx->tb_cap && ctx->tb_cap < ctx->scratch_limit) {
+            ctx->tb_cap = std::min<int64_t>(ctx->scratch_limit, (int64_t)hc->tb_used + (1 << 20));
+            grow = true;
+        }
+        if (!grow) break;
+        int rc = run_from_stage2(ctx);
+        if (rc != DBGA_SUCCESS) return rc;
+    }
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[6], st));
+    const bool seg = ctx->prm.stages == 3;
+    const bool full = ctx->prm.want_graph != 0 && !ctx->no_anchors;
+    HRESERVE(h_status, 4 * (P + 1)); HRESERVE(h_score, 8 * (P + 1)); HRESERVE(h_cells, 8 * (P + 1));
+    HRESERVE(h_nseg, 4 * (P + 1)); HRESERVE(h_nanch, 8 * (P + 1)); HRESERVE(h_aln_off, 8 * (P + 2));
+    HRESERVE(h_run_off, 8 * (P + 2));
+    const int64_t total_aln = seg ? (int64_t)hc->total_aln : 0, total_runs = (int64_t)hc->total_runs;
+    HRESERVE(h_aln0, std::max<int64_t>(total_aln, 1)); HRESERVE(h_aln1, std::max<int64_t>(total_aln, 1));
+    HRESERVE(h_runs, 12 * std::max<int64_t>(total_runs, 1));
+    if (P) {
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status_out.p, 4 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_score.p, ctx->d_score.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cells.p, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nseg.p, ctx->d_nseg.p, 4 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nanch.p, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_aln_off.p, ctx->d_aln_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_run_off.p, ctx->d_run_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+        if (total_aln) {
+            DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_aln0.p, ctx->d_aln0.p, total_aln, cudaMemcpyDeviceToHost, st));
+            DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_aln1.p, ctx->d_aln1.p, total_aln, cudaMemcpyDeviceToHost, st));
+        }
+        if (total_runs) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs_out.p, 12 * total_runs, cudaMemcpyDeviceToHost, st));
+    } else {
+        ((int64_t *)ctx->h_aln_off.p)[0] = 0; ((int64_t *)ctx->h_run_off.p)[0] = 0;
+    }
+    if (full) {
+        HRESERVE(h_nd0, std::max<int64_t>(ctx->sumN0, 1)); HRESERVE(h_nd1, std::max<int64_t>(ctx->sumN1, 1));
+        HRESERVE(h_poff, 8 * (P + 1)); HRESERVE(h_qoff, 8 * (P + 1));
+        if (ctx->sumN0) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nd0.p, ctx->d_nd0.p, ctx->sumN0, cudaMemcpyDeviceToHost, st));
+        if (ctx->sumN1) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nd1.p, ctx->d_nd1.p, ctx->sumN1, cudaMemcpyDeviceToHost, st));
+        int64_t *po = (int64_t *)ctx->h_poff.p, *qo = (int64_t *)ctx->h_qoff.p;
+        for (int64_t i = 0; i < P; ++i) { po[i] = ctx->h_pairs[(size_t)i].p_base; qo[i] = ctx->h_pairs[(size_t)i].q_base; }
+        po[P] = ctx->sumN0; qo[P] = ctx->sumN1;
+    }
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[7], st));
+    DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+    memset(out, 0, sizeof(*out));
+    out->num_pairs = P;
+    out->status = (int32_t *)ctx->h_status.p; out->score = (int64_t *)ctx->h_score.p;
+    out->dp_cells = (int64_t *)ctx->h_cells.p; out->dp_segments = (int32_t *)ctx->h_nseg.p;
+    out->n_anchors = (int64_t *)ctx->h_nanch.p; out->run_off = (int64_t *)ctx->h_run_off.p;
+    out->runs = (int32_t *)ctx->h_runs.p; out->aln_off = (int64_t *)ctx->h_aln_off.p;
+    out->aln0 = (uint8_t *)ctx->h_aln0.p; out->aln1 = (uint8_t *)ctx->h_aln1.p;
+    if (!seg && P) { for (int64_t i = 0; i <= P; ++i) ((int64_t *)ctx->h_aln_off.p)[i] = 0; }
+    if (full) {
+        out->p_off = (int64_t *)ctx->h_poff.p; out->nondup0 = (uint8_t *)ctx->h_nd0.p;
+        out->q_off = (int64_t *)ctx->h_qoff.p; out->nondup1 = (uint8_t *)ctx->h_nd1.p;
+    }
+    cudaEventElapsedTime(&out->ms_stage1, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&out->ms_stage2, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&out->ms_stage3, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&out->ms_assemble, ctx->ev[4], ctx->ev[5]);
+    cudaEventElapsedTime(&out->ms_d2h, ctx->ev[6], ctx->ev[7]);
+    cudaEventElapsedTime(&out->ms_total, ctx->ev[1], ctx->ev[7]);
+    out->dp_cells_total = (int64_t)hc->cells;
+    out->dp_segments_total = (int64_t)hc->nseg;
+    out->kernel_launches = ctx->launches;
+    return DBGA_SUCCESS;
+}
+
+int align_common(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P, const dbga_params *params,
+                 dbga_result *out, bool no_anchors) {
+    if (!ctx || !out || (!seqs && P > 0)) return DBGA_ERR_ARG;
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    int rc = do_plan(ctx, offsets, P, params, no_anchors);
+    if (rc != DBGA_SUCCESS) return rc;
+    RESERVE(d_seqs, std::max<int64_t>(ctx->total_bytes, 16) + 16);
+    if (ctx->total_bytes)
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_seqs.p, seqs, (size_t)ctx->total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = do_run(ctx, (const uint8_t *)ctx->d_seqs.p);
+    if (rc != DBGA_SUCCESS) return rc;
+    rc = do_fetch(ctx, out);
+    if (rc != DBGA_SUCCESS) return rc;
+    cudaEventElapsedTime(&out->ms_h2d, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&out->ms_total, ctx->ev[0], ctx->ev[7]);
+    return DBGA_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dbga_version(void) { return 100; }
+
+int dbga_create(int device, dbga_ctx **out) {
+    if (!out) return DBGA_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DBGA_ERR_CUDA;
+    dbga_ctx *ctx = new dbga_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
+    for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
+    *out = ctx;
+    return DBGA_SUCCESS;
+}
+
+void dbga_destroy(dbga_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf *dbs[] = {&ctx->d_seqs, &ctx->d_pairs, &ctx->d_list, &ctx->d_large, &ctx->d_status, &ctx->d_aof, &ctx->d_nd0,
+                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_slots, &ctx->d_lt, &ctx->d_lw, &ctx->d_lc, &ctx->d_ctr,
+                     &ctx->d_tb, &ctx->d_bnd_w, &ctx->d_bnd_c, &ctx->d_str, &ctx->d_packed, &ctx->d_table, &ctx->d_aln_len,
+                     &ctx->d_aln_off, &ctx->d_run_cnt, &ctx->d_run_off, &ctx->d_scan_tmp, &ctx->d_aln0, &ctx->d_aln1,
+                     &ctx->d_runs_out, &ctx->d_score, &ctx->d_cells, &ctx->d_nseg, &ctx->d_nanch, &ctx->d_status_out,
+                     &ctx->d_sink};
+    for (DevBuf *b : dbs) if (b->p) cudaFree(b->p);
+    HostBuf *hbs[] = {&ctx->h_status, &ctx->h_score, &ctx->h_cells, &ctx->h_nseg, &ctx->h_nanch, &ctx->h_aln_off,
+                      &ctx->h_run_off, &ctx->h_aln0, &ctx->h_aln1, &ctx->h_runs, &ctx->h_nd0, &ctx->h_nd1, &ctx->h_poff,
+                      &ctx->h_qoff, &ctx->h_ctr};
+    for (HostBuf *b : hbs) if (b->p) cudaFreeHost(b->p);
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *dbga_last_error(dbga_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int dbga_set_stream(dbga_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return DBGA_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return DBGA_SUCCESS;
+}
+
+int dbga_set_scratch_limit(dbga_ctx *ctx, int64_t bytes) {
+    if (!ctx || bytes < (1 << 20)) return DBGA_ERR_ARG;
+    ctx->scratch_limit = bytes;
+    return DBGA_SUCCESS;
+}
+
+void *dbga_host_alloc(int64_t bytes) {
+    void *p = nullptr;
+    if (bytes <= 0) bytes = 1;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void dbga_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int dbga_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t num_pairs,
+                     const dbga_params *params, dbga_result *out) {
+    return align_common(ctx, seqs, offsets, num_pairs, params, out, false);
+}
+
+int dbga_global_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t num_pairs,
+                            const dbga_params *params, dbga_result *out) {
+    if (!params) return DBGA_ERR_ARG;
+    dbga_params p = *params;
+    p.stages = 3; p.want_graph = 0;
+    return align_common(ctx, seqs, offsets, num_pairs, &p, out, true);
+}
+
+int dbga_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t num_pairs, const dbga_params *params) {
+    if (!ctx) return DBGA_ERR_ARG;
+    return do_plan(ctx, offsets, num_pairs, params, false);
+}
+int dbga_plan_global(dbga_ctx *ctx, const int64_t *offsets, int64_t num_pairs, const dbga_params *params) {
+    if (!ctx || !params) return DBGA_ERR_ARG;
+    dbga_params p = *params;
+    p.stages = 3; p.want_graph = 0;
+    return do_plan(ctx, offsets, num_pairs, &p, true);
+}
+int dbga_plan_run(dbga_ctx *ctx, const uint8_t *device_seqs) {
+    if (!ctx) return DBGA_ERR_ARG;
+    return do_run(ctx, device_seqs);
+}
+int dbga_plan_fetch(dbga_ctx *ctx, dbga_result *out) {
+    if (!ctx || !out) return DBGA_ERR_ARG;
+    return do_fetch(ctx, out);
+}
+
+int dbga_measure_int_peak(dbga_ctx *ctx, double out[3]) {
+    if (!ctx || !out) return DBGA_ERR_ARG;
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    RESERVE(d_sink, 256);
+    const int iters = 4096;
+    for (int which = 0; which < 3; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
+            DBGA_CUDA_CHECK(launch_int_peak(which, iters, (int *)ctx->d_sink.p, ctx->num_sms, ctx->stream));
+            DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], ctx->stream));
+            DBGA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        const double ops = (double)ctx->num_sms * 8 * 256 * (double)iters * 16 * 9;
+        out[which] = ops / (best * 1e-3);
+    }
+    return DBGA_SUCCESS;
+}
+
+}  // extern "C"

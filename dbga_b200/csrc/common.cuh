@@ -1,0 +1,111 @@
+// Shared device/host definitions for the dbga_b200 kernels (sm_100a).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/dbga_b200.h"
+
+namespace dbga {
+
+// ------------------------------------------------------------------ data layout in HBM
+// One record per pair, built on the host from `offsets` (plan time).
+struct PairDesc {
+    int64_t off0, off1;   // byte offsets of seq1 / seq2 in the concatenated buffer
+    int32_t n0, n1;       // lengths
+    int64_t q_base;       // prefix of (n1-k+1) over pairs: base of this pair in aof[]
+    int64_t p_base;       // prefix of (n0-k+1): base in nondup0 flags / large-path memo
+};
+
+// Per-pair outcome of stages 1-2 (device), consumed by stage 3 and the assembler.
+struct PairOut {
+    int32_t status;
+    int32_t n_runs;       // maximal runs of consecutive anchors (a+u, b+u)
+    int64_t run_base;     // first run in runs pool (int32 triples)
+    int64_t slot_base;    // first segment slot; slots: [first, mid_1..mid_{R-1}, tail]
+    int32_t n_slots;
+    int32_t pad;
+    int64_t n_anchors;
+    int64_t aln_len;      // filled by the assembler's length pass
+};
+
+// One alignment segment (what the reference hands to dna_global_aln, utils.py:157-192).
+struct Slot {
+    int32_t x0, m;        // seq1[x0 : x0+m]
+    int32_t y0, n;        // seq2[y0 : y0+n]
+    int32_t score;        // DP score (0 when one side is empty)
+    int32_t len;          // aligned columns produced (before any first-column drop)
+    int64_t str_off;      // scratch: reversed rows; row x at [str_off, +m+n), row y after
+    int64_t tb_off;       // scratch: traceback bytes (warp / cta classes)
+    int32_t pair;
+    int32_t cls;          // DP class: -1 none, 0 tiny, 1 warp, 2 cta
+};
+
+enum : int32_t { CLS_NONE = -1, CLS_TINY = 0, CLS_WARP = 1, CLS_CTA = 2 };
+
+// DP geometry (shared by host sizing and kernels)
+constexpr int TINY_G = 8;        // lanes per tiny segment
+constexpr int TINY_R = 4;        // rows per lane  -> m <= 32
+constexpr int TINY_MAX_M = TINY_G * TINY_R;
+constexpr int TINY_MAX_N = 32;
+constexpr int WF_R = 8;          // rows per lane in the wavefront kernels
+constexpr int WF_ROWS_PER_WARP = 32 * WF_R;   // 256
+constexpr int WF_CTA_WARPS = 8;  // warps per CTA in the long-segment kernel
+constexpr int WF_D = 64;         // step delay between consecutive warps
+constexpr int WF_C = 32;         // steps per barrier
+constexpr int WF_RING = 128;     // ring entries (columns) per warp boundary
+constexpr int64_t WARP_CLASS_MAX_CELLS = 1 << 18;   // above this a segment gets a CTA
+
+// Scores are kept as 64*V + 21*tag(state): the three 2-bit tag fields make every max()
+// break ties in the configured state order and leave the winner's identity in the low
+// bits (bits 0-1 used for the M state, 2-3 for X, 4-5 for Y).
+constexpr int SCALE = 64;
+constexpr int TAGMUL = 21;
+constexpr int32_t NEG_V = -(1 << 24);          // "minus infinity" in score units
+constexpr int64_t MAX_ABS_SCORE = (1 << 24) - (1 << 20);
+
+struct DpParams {
+    int32_t go, ge;           // SCALE * gap open (first gap char), SCALE * extend
+    int32_t tagM, tagX, tagY; // TAGMUL * priority (0..2); higher priority wins ties
+    int32_t endM, endX, endY; // priorities at the terminal cell
+    int32_t xy;               // allow X<->Y
+    uint32_t lut_lo[4];       // per seq1 base: int16 (SCALE*S + tagM) for seq2 base A,C
+    uint32_t lut_hi[4];       //                                             ...  G,T
+    int32_t go_raw, ge_raw;
+};
+
+__host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int warps) {
+    const int64_t rows_per_pass = (int64_t)warps * WF_ROWS_PER_WARP;
+    const int64_t passes = (m + rows_per_pass - 1) / rows_per_pass;
+    return passes * warps * (n + 32) * WF_ROWS_PER_WARP;
+}
+
+// ------------------------------------------------------------------ small device utils
+__device__ __forceinline__ int base_code(uint8_t c) {
+    // A=0 C=1 G=2 T=3 for upper-case ACGT; callers validate separately
+    return ((c >> 1) ^ (c >> 2)) & 3;
+}
+__device__ __forceinline__ bool is_acgt(uint8_t c) {
+    return c == 'A' || c == 'C' || c == 'G' || c == 'T';
+}
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ uint32_t hash64(uint64_t z) {
+    z ^= z >> 33; z *= 0xff51afd7ed558ccdULL; z ^= z >> 33;
+    z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33;
+    return (uint32_t)z;
+}
+
+#define DBGA_CUDA_CHECK(expr)                                                        \
+    do {                                                                             \
+        cudaError_t _e = (expr);                                                     \
+        if (_e != cudaSuccess) {                                                     \
+            snprintf(ctx->err, sizeof(ctx->err), "%s:%d: %s: %s", __FILE__, __LINE__, \
+                     #expr, cudaGetErrorString(_e));                                 \
+            return DBGA_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+}  // namespace dbga

@@ -1,0 +1,72 @@
+// Launchers of every kernel of the library (one translation unit per stage).
+#pragma once
+#include "common.cuh"
+
+namespace dbga {
+
+// per-pair placement for the global-memory (large) stage-1 path, one entry per list item
+struct LargeDesc {
+    int64_t tbl;     // first slot of this pair's table
+    int64_t pk0, pk1; // word offsets of the packed sequences
+    uint32_t mask;   // capacity - 1
+    uint32_t pad;
+};
+
+// device-side bump allocators and work-list counters (one struct per context)
+struct Counters {
+    unsigned long long runs_used;      // in runs
+    unsigned long long slots_used;     // in slots
+    unsigned long long tb_used;        // bytes of traceback scratch
+    unsigned int n_tiny, n_warp, n_cta;
+    unsigned int overflow;             // a pool was exhausted (host grows and re-runs)
+    unsigned long long cells;          // sum of DP cells
+    unsigned long long nseg;           // DP segments
+    unsigned long long total_runs;
+    unsigned long long total_aln;
+};
+
+struct Pools {
+    int32_t *runs;   int64_t runs_cap;     // (a, b, len) triples
+    Slot *slots;     int64_t slots_cap;
+    int64_t tb_cap;                        // bytes
+    int32_t *list_tiny, *list_warp, *list_cta;   // slot ids per DP class
+    int64_t list_cap;
+};
+
+// ---- stage 1
+size_t stage1_small_smem(int key_bytes, uint32_t cap, int words, int maxq);
+cudaError_t launch_stage1_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count,
+                                int k, uint32_t cap, int words, int maxq, bool full, int32_t *status,
+                                int32_t *aof, uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st);
+cudaError_t launch_stage1_large(const uint8_t *seqs, const PairDesc *pairs, const LargeDesc *ld,
+                                const int32_t *list, int count, int max_n, int k, bool full,
+                                uint32_t *packed, void *table, size_t table_bytes, int32_t *status,
+                                int32_t *aof, uint8_t *nd0, uint8_t *nd1, cudaStream_t st, int *launches);
+
+// ---- stage 2
+cudaError_t launch_stage2(const PairDesc *pairs, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
+                          const int32_t *aof, int32_t *status, PairOut *out, Pools pools, Counters *ctr,
+                          int threads, int num_sms, int max_abs_score, int go_raw, int ge_raw, cudaStream_t st);
+
+// ---- stage 3
+// count_dev: device pointer to the number of list entries (no host round trip needed)
+cudaError_t launch_dp_tiny(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                           const unsigned int *count_dev, int64_t max_items, DpParams prm,
+                           uint8_t *strbuf, int num_sms, cudaStream_t st);
+// bnd: per-CTA double-buffered boundary rows, int4 per column, bnd_stride columns each
+cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                                const unsigned int *count_dev, int grid, bool cta_class, DpParams prm,
+                                uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);
+
+// ---- assembly
+cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
+                            const int32_t *status, const int32_t *runs, const Slot *slots, const uint8_t *strbuf,
+                            int64_t *aln_len, int64_t *aln_off, int64_t *run_cnt, int64_t *run_off,
+                            int64_t *scan_tmp, uint8_t *aln0, uint8_t *aln1, int32_t *runs_out,
+                            int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
+                            Counters *ctr, int num_sms, cudaStream_t st, int *launches);
+
+// ---- integer-pipe microbenchmark
+cudaError_t launch_int_peak(int which, int iters, int *sink, int num_sms, cudaStream_t st);
+
+}  // namespace dbga

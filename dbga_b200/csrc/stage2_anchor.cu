@@ -1,0 +1,236 @@
+// Stage 2: merge-node (shared anchor) detection and ordering.
+//
+// Replaces the reference's Python graph walk: merge_node_idx in seq-2 order
+// (src/dbga/debruijn_pairwise.py:94-98), extract_bubble (:277-300, the O(N*M) list scan),
+// debruijn_merge_correctness (src/dbga/utils.py:266-291) and the segment bookkeeping of
+// alignment() (:463-538).  Input: aof[q] from stage 1.  Per pair (one CTA):
+//   * ordered stream compaction (warp ballot + block scan) of the *runs* of consecutive
+//     anchors (a+u, b+u) -- inside a run every inter-anchor segment is the reference's
+//     shortcut (:384-388), so only run boundaries produce DP work;
+//   * colinearity ("cycle") check by adjacent difference over the compacted runs;
+//   * the segment slots [first, mid_1 .. mid_{R-1}, tail] with their DP class, scratch
+//     placement and work-list entries.
+#include "kernels.cuh"
+
+namespace dbga {
+
+struct ScanSmem {
+    int warpS[32], warpE[32];
+    int totS, totE;
+    long long red[32];
+    long long bcast[4];
+    int flag_cycle, flag_big;
+};
+
+__device__ __forceinline__ long long block_sum(long long v, ScanSmem &sm) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if (lane == 0) sm.red[wid] = v;
+    __syncthreads();
+    long long t = 0;
+    for (int w = 0; w < nw; ++w) t += sm.red[w];
+    return t;
+}
+
+__global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pairs, int k, int no_anchors,
+                              int want_segments, const int32_t *__restrict__ aof, const int32_t *__restrict__ status,
+                              PairOut *__restrict__ pout, Pools pools, Counters *__restrict__ ctr,
+                              int max_abs_score, int go_raw, int ge_raw) {
+    __shared__ ScanSmem sm;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
+    unsigned long long my_cells = 0, my_nseg = 0;
+
+    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        const PairDesc pd = pairs[pair];
+        int st = status[pair];
+        PairOut po;
+        po.status = st; po.n_runs = 0; po.run_base = 0; po.slot_base = 0; po.n_slots = 0; po.pad = 0;
+        po.n_anchors = 0; po.aln_len = 0;
+        if (st != DBGA_OK) {
+            if (tid == 0) pout[pair] = po;
+            continue;
+        }
+        const int N1 = no_anchors ? 0 : pd.n1 - k + 1;
+        const int32_t *a_of = aof + pd.q_base;
+        // ---- pass 1: count run starts and anchors
+        long long cS = 0, cA = 0;
+        for (int q = tid; q < N1; q += T) {
+            const int a = a_of[q];
+            if (a >= 0) {
+                ++cA;
+                const int pv = q > 0 ? a_of[q - 1] : -1;
+                cS += !(pv >= 0 && pv + 1 == a);
+            }
+        }
+        const int R = (int)block_sum(cS, sm);
+        const long long M = block_sum(cA, sm);
+        if (tid == 0) {
+            sm.flag_cycle = 0; sm.flag_big = 0;
+            long long base = 0;
+            if (R > 0) {
+                base = (long long)atomicAdd(&ctr->runs_used, (unsigned long long)R);
+                if (base + R > pools.runs_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
+            }
+            sm.bcast[0] = base;
+        }
+        __syncthreads();
+        const long long run_base = sm.bcast[0];
+        if (run_base < 0) {      // pool exhausted: host grows the pool and re-runs stage 2
+            if (tid == 0) { po.status = DBGA_TOO_LARGE; pout[pair] = po; }
+            __syncthreads();
+            continue;
+        }
+        int32_t *runs = pools.runs + 3 * run_base;
+        // ---- pass 2: ordered compaction of run starts (a, b) and run ends (b)
+        int runS = 0, runE = 0;
+        for (int base = 0; base < N1; base += T) {
+            const int q = base + tid;
+            int a = -1;
+            bool isS = false, isE = false;
+            if (q < N1) {
+                a = a_of[q];
+                if (a >= 0) {
+                    const int pv = q > 0 ? a_of[q - 1] : -1;
+                    const int nx = q + 1 < N1 ? a_of[q + 1] : -1;
+                    isS = !(pv >= 0 && pv + 1 == a);
+                    isE = !(nx >= 0 && nx == a + 1);
+                }
+            }
+            const unsigned bS = __ballot_sync(0xffffffffu, isS), bE = __ballot_sync(0xffffffffu, isE);
+            const unsigned lt = (1u << lane) - 1u;
+            if (lane == 0) { sm.warpS[wid] = __popc(bS); sm.warpE[wid] = __popc(bE); }
+            __syncthreads();
+            int offS = runS, offE = runE, totS = 0, totE = 0;
+            for (int w = 0; w < nw; ++w) {
+                const int s = sm.warpS[w], e = sm.warpE[w];
+                if (w < wid) { offS += s; offE += e; }
+                totS += s; totE += e;
+            }
+            if (isS) {
+                const int idx = offS + __popc(bS & lt);
+                runs[3 * (int64_t)idx] = a;
+                runs[3 * (int64_t)idx + 1] = q;
+            }
+            if (isE) runs[3 * (int64_t)(offE + __popc(bE & lt)) + 2] = q;   // end b, turned into len below
+            runS += totS; runE += totE;
+            __syncthreads();
+        }
+        // ---- run lengths, then the colinearity check (utils.py:266-291): seq-1 positions of
+        //      the merge nodes must be strictly increasing along seq 2
+        for (int r = tid; r < R; r += T) runs[3 * (int64_t)r + 2] = runs[3 * (int64_t)r + 2] - runs[3 * (int64_t)r + 1] + 1;
+        __syncthreads();
+        for (int r = tid + 1; r < R; r += T) {
+            const int prev_end = runs[3 * (int64_t)(r - 1)] + runs[3 * (int64_t)(r - 1) + 2] - 1;
+            if (runs[3 * (int64_t)r] <= prev_end) sm.flag_cycle = 1;
+        }
+        __syncthreads();
+        po.n_runs = R; po.run_base = run_base; po.n_anchors = M;
+        if (sm.flag_cycle) {
+            if (tid == 0) { po.status = DBGA_CYCLE; pout[pair] = po; }
+            __syncthreads();
+            continue;
+        }
+        if (!want_segments) {
+            if (tid == 0) pout[pair] = po;
+            __syncthreads();
+            continue;
+        }
+        // ---- segment slots (debruijn_pairwise.py:453-457, 463-538)
+        const int n_slots = R == 0 ? 1 : R + 1;
+        if (tid == 0) {
+            long long base = (long long)atomicAdd(&ctr->slots_used, (unsigned long long)n_slots);
+            if (base + n_slots > pools.slots_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
+            sm.bcast[1] = base;
+        }
+        __syncthreads();
+        const long long slot_base = sm.bcast[1];
+        if (slot_base < 0) {
+            if (tid == 0) { po.status = DBGA_TOO_LARGE; pout[pair] = po; }
+            __syncthreads();
+            continue;
+        }
+        const int64_t str_base = 2 * pd.off0;
+        const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;   // >= n0 + n1 (alignment padding allowed)
+        for (int base = 0; base < n_slots; base += T) {
+            const int t = base + tid;
+            int cls = CLS_NONE;
+            Slot s;
+            if (t < n_slots) {
+                int x0, x1, y0, y1;
+                if (R == 0) { x0 = 0; x1 = pd.n0; y0 = 0; y1 = pd.n1; }
+                else {
+                    if (t == 0) { x0 = 0; y0 = 0; }
+                    else {
+                        const int len = runs[3 * (int64_t)(t - 1) + 2];
+                        x0 = runs[3 * (int64_t)(t - 1)] + len - 1;
+                        y0 = runs[3 * (int64_t)(t - 1) + 1] + len - 1;
+                    }
+                    if (t == R) { x1 = pd.n0; y1 = pd.n1; }
+                    else { x1 = runs[3 * (int64_t)t]; y1 = runs[3 * (int64_t)t + 1]; }
+                }
+                s.x0 = x0; s.m = x1 - x0; s.y0 = y0; s.n = y1 - y0;
+                s.score = 0; s.len = 0; s.pair = (int32_t)pair; s.tb_off = 0;
+                s.str_off = str_base + x0 + y0;     // row x; row y at + row_len
+                if (s.m > 0 && s.n > 0) {
+                    const long long cells = (long long)s.m * s.n;
+                    my_cells += (unsigned long long)cells; my_nseg += 1;
+                    const long long mag = (long long)max_abs_score * (s.m < s.n ? s.m : s.n) + go_raw + (long long)ge_raw * ((long long)s.m + s.n);
+                    if (mag >= MAX_ABS_SCORE) { sm.flag_big = 1; }
+                    else if (s.m <= TINY_MAX_M && s.n <= TINY_MAX_N) cls = CLS_TINY;
+                    else {
+                        cls = cells <= WARP_CLASS_MAX_CELLS ? CLS_WARP : CLS_CTA;
+                        const long long need = (tb_bytes_wavefront(s.m, s.n, cls == CLS_WARP ? 1 : WF_CTA_WARPS) + 255) & ~255LL;
+                        const long long off = (long long)atomicAdd(&ctr->tb_used, (unsigned long long)need);
+                        if (off + need > pools.tb_cap) { sm.flag_big = 1; cls = CLS_NONE; }
+                        s.tb_off = off;
+                    }
+                } else {
+                    s.len = s.m + s.n;      // utils.py:187-192: one side empty -> all-gap row
+                }
+                s.cls = cls;
+            }
+            // warp-aggregated work-list append per DP class
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned b = __ballot_sync(0xffffffffu, cls == c);
+                if (b) {
+                    unsigned int *cnt = c == 0 ? &ctr->n_tiny : (c == 1 ? &ctr->n_warp : &ctr->n_cta);
+                    int32_t *list = c == 0 ? pools.list_tiny : (c == 1 ? pools.list_warp : pools.list_cta);
+                    unsigned int pos = 0;
+                    const int leader = __ffs(b) - 1;
+                    if (lane == leader) pos = atomicAdd(cnt, (unsigned)__popc(b));
+                    pos = __shfl_sync(0xffffffffu, pos, leader);
+                    if (cls == c) list[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(slot_base + t);
+                }
+            }
+            if (t < n_slots) pools.slots[slot_base + t] = s;
+        }
+        __syncthreads();
+        po.slot_base = slot_base; po.n_slots = n_slots;
+        if (tid == 0) {
+            if (sm.flag_big) po.status = DBGA_TOO_LARGE;
+            pout[pair] = po;
+        }
+        (void)row_len;
+        __syncthreads();
+    }
+    // per-CTA totals
+    const unsigned long long c = (unsigned long long)block_sum((long long)my_cells, sm);
+    const unsigned long long s = (unsigned long long)block_sum((long long)my_nseg, sm);
+    if (tid == 0 && (c | s)) { atomicAdd(&ctr->cells, c); atomicAdd(&ctr->nseg, s); }
+}
+
+cudaError_t launch_stage2(const PairDesc *pairs, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
+                          const int32_t *aof, int32_t *status, PairOut *out, Pools pools, Counters *ctr,
+                          int threads, int num_sms, int max_abs_score, int go_raw, int ge_raw, cudaStream_t st) {
+    if (num_pairs <= 0) return cudaSuccess;
+    int64_t grid = (int64_t)num_sms * (2048 / threads);
+    if (grid > num_pairs) grid = num_pairs;
+    stage2_kernel<<<(int)grid, threads, 0, st>>>(pairs, num_pairs, k, no_anchors ? 1 : 0, want_segments ? 1 : 0, aof,
+                                                status, out, pools, ctr, max_abs_score, go_raw, ge_raw);
+    return cudaGetLastError();
+}
+
+}  // namespace dbga

@@ -1,0 +1,394 @@
+// Stage 3: affine-gap (Gotoh) global alignment of every inter-anchor segment, batched
+// across segments and pairs.
+//
+// Replaces cogent3.align.global_pairwise as called from dna_global_aln
+// (reference src/dbga/utils.py:157-192, call site :185) for every segment the reference's
+// bubble_aln (src/dbga/debruijn_pairwise.py:345-395) hands to it.  Integer three-state
+// recurrence, bit-exact against oracle/ (conventions: SURVEY.md 8c):
+//     M[i][j] = S(x_i, y_j) + max(M, X, Y)[i-1][j-1]
+//     X[i][j] = max(M[i-1][j] - go, X[i-1][j] - ge [, Y[i-1][j] - go])     (x_i vs gap)
+//     Y[i][j] = max(M[i][j-1] - go, Y[i][j-1] - ge [, X[i][j-1] - go])     (gap vs y_j)
+// Scores live in registers as 64*V + 21*prio(state): one integer max (VIMNMX3 /
+// VIADDMNMX) both selects the best predecessor under the configured first-wins tie order
+// and leaves the winner's identity in the low bits, which become the traceback byte
+// (bits 0-1: predecessor of M, 2-3: of X, 4-5: of Y) with two LOP3s.
+//
+// Kernels:
+//   dp_tiny_kernel      8 lanes per segment (m <= 32, n <= 32), four segments per warp,
+//                       traceback bytes in shared memory;
+//   dp_wf_kernel<W>     anti-diagonal wavefront, 8 rows per lane, 32 lanes per warp, W
+//                       warps pipelined through shared-memory boundary rings (a warp per
+//                       segment for W=1, a CTA per long segment for W=8); row strips of
+//                       256*W rows, boundary rows between strips staged through HBM;
+//                       traceback bytes in HBM in a step-major (skewed) layout so that
+//                       every warp step writes one contiguous 256-byte row.
+#include "kernels.cuh"
+
+namespace dbga {
+
+__device__ __forceinline__ int strip(int v) { return v & ~63; }
+
+// One cell.  (Ml,Xl,Yl): in = (i, j-1), out = (i, j).  d*: (i-1, j-1).  u*: (i-1, j).
+template <bool XY>
+__device__ __forceinline__ uint32_t dp_cell(int &Ml, int &Xl, int &Yl, int dM, int dX, int dY, int uM,
+                                            int uX, int uY, int sprime, int go, int ge, int tagX, int tagY) {
+    const int t = __vimax3_s32(dM, dX, dY);
+    int u = __viaddmax_s32(uM, -go, uX - ge);
+    int v = __viaddmax_s32(Ml, -go, Yl - ge);
+    if (XY) {
+        u = max(u, uY - go);
+        v = max(v, Xl - go);
+    }
+    Ml = strip(t) + sprime;
+    Xl = strip(u) | tagX;
+    Yl = strip(v) | tagY;
+    // bit-select: low 2 bits of t, bits 2-3 of u, bits 4-5 of v
+    uint32_t d = ((uint32_t)t & 3u) | ((uint32_t)u & ~3u);
+    d = (d & 15u) | ((uint32_t)v & ~15u);
+    return d & 0xFFu;
+}
+
+// int16 score LUT for the row's seq1 base, indexed by the seq2 base through PRMT
+// (__byte_perm masks the selector with 0x7777, which would drop the sign-replicate bits)
+__device__ __forceinline__ int lut_score(uint32_t lo, uint32_t hi, uint32_t sel) {
+    int r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lo), "r"(hi), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint32_t lut_sel(int ycode) { return 0x9910u + 0x2222u * (uint32_t)ycode; }
+
+__device__ __forceinline__ int prio_to_state(int prio, const DpParams &p) {
+    // 0 = M, 1 = X, 2 = Y
+    const int t = prio * TAGMUL;
+    return t == p.tagM ? 0 : (t == p.tagX ? 1 : 2);
+}
+
+// terminal-cell choice under end_order (first wins, strict >)
+__device__ __forceinline__ void pick_end(int Mv, int Xv, int Yv, const DpParams &p, int &state, int &score) {
+    const long long cm = (long long)strip(Mv) + p.endM, cx = (long long)strip(Xv) + p.endX, cy = (long long)strip(Yv) + p.endY;
+    long long b = cm; state = 0;
+    if (cx > b) { b = cx; state = 1; }
+    if (cy > b) { b = cy; state = 2; }
+    score = (int)(b >> 6);
+}
+
+// ============================================================================ tiny segments
+constexpr int TINY_STEPS = TINY_MAX_N + TINY_G - 1;   // 39
+constexpr int TINY_ROWB = TINY_MAX_M;                 // 32 bytes per step row
+
+template <bool XY>
+__global__ void __launch_bounds__(256)
+dp_tiny_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+               const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
+               uint8_t *__restrict__ strbuf) {
+    __shared__ __align__(16) uint8_t s_tb[32][TINY_STEPS + 1][TINY_ROWB];
+    __shared__ uint8_t s_y[32][TINY_MAX_N];
+    const int tid = threadIdx.x, lane = tid & 31, gl = lane & (TINY_G - 1), grp = tid / TINY_G;
+    const unsigned int count = *count_dev;
+    const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
+    const int NEG = NEG_V * SCALE;
+
+    for (unsigned int base = blockIdx.x * 32u; base < count; base += gridDim.x * 32u) {
+        const unsigned int item = base + grp;
+        const bool have = item < count;
+        int m = 0, n = 0, sid = 0;
+        const uint8_t *xs = nullptr, *ys = nullptr;
+        int64_t str_off = 0, row_len = 0;
+        if (have) {
+            sid = list[item];
+            const Slot s = slots[sid];
+            const PairDesc pd = pairs[s.pair];
+            m = s.m; n = s.n;
+            xs = seqs + pd.off0 + s.x0;
+            ys = seqs + pd.off1 + s.y0;
+            str_off = s.str_off;
+            row_len = (pd.off1 - pd.off0) + pd.n1;
+        }
+        // stage y codes; per-row score LUTs and column-0 state
+        for (int j = gl; j < n; j += TINY_G) s_y[grp][j] = (uint8_t)base_code(ys[j]);
+        int Mr[TINY_R], Xr[TINY_R], Yr[TINY_R];
+        uint32_t slo[TINY_R], shi[TINY_R];
+#pragma unroll
+        for (int r = 0; r < TINY_R; ++r) {
+            const int i = gl * TINY_R + r + 1;              // 1-based row
+            const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
+            slo[r] = prm.lut_lo[xc]; shi[r] = prm.lut_hi[xc];
+            Mr[r] = NEG | tagM;
+            Xr[r] = (-(go + (i - 1) * ge)) | tagX;
+            Yr[r] = NEG | tagY;
+        }
+        int dgM = 0, dgX = 0, dgY = 0;
+        // warp-uniform step count
+        int steps = have ? n + TINY_G - 1 : 0;
+        steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, 8));
+        steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, 16));
+        __syncwarp();
+        const int own_gl = (m - 1) / TINY_R, own_r = (m - 1) % TINY_R;
+        int endM = 0, endX = 0, endY = 0;
+        for (int s = 0; s < steps; ++s) {
+            const int j = s - gl + 1;                        // column this lane works on
+            int uM = __shfl_up_sync(0xffffffffu, Mr[TINY_R - 1], 1, TINY_G);
+            int uX = __shfl_up_sync(0xffffffffu, Xr[TINY_R - 1], 1, TINY_G);
+            int uY = __shfl_up_sync(0xffffffffu, Yr[TINY_R - 1], 1, TINY_G);
+            if (gl == 0) {                                   // row 0 boundary, synthesized
+                uM = NEG | tagM; uX = NEG | tagX; uY = (-(go + (j - 1) * ge)) | tagY;
+                dgM = (j == 1 ? 0 : NEG) | tagM; dgX = NEG | tagX;
+                dgY = (j == 1 ? NEG : -(go + (j - 2) * ge)) | tagY;
+            }
+            if (j >= 1 && j <= n) {
+                const uint32_t sel = lut_sel(s_y[grp][j - 1]);
+                int dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
+                uint32_t word = 0;
+#pragma unroll
+                for (int r = 0; r < TINY_R; ++r) {
+                    const int oM = Mr[r], oX = Xr[r], oY = Yr[r];
+                    const uint32_t d = dp_cell<XY>(Mr[r], Xr[r], Yr[r], dM, dX, dY, aM, aX, aY,
+                                                   lut_score(slo[r], shi[r], sel), go, ge, tagX, tagY);
+                    word |= d << (8 * r);
+                    dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
+                }
+                *reinterpret_cast<uint32_t *>(&s_tb[grp][s][gl * TINY_R]) = word;
+                if (j == n && gl == own_gl) {
+#pragma unroll
+                    for (int r = 0; r < TINY_R; ++r)
+                        if (r == own_r) { endM = Mr[r]; endX = Xr[r]; endY = Yr[r]; }
+                }
+            }
+            dgM = uM; dgX = uX; dgY = uY;
+        }
+        __syncwarp();
+        // traceback by the lane that owns row m; rows are written reversed into scratch
+        if (have && gl == own_gl) {
+            int st, score;
+            pick_end(endM, endX, endY, prm, st, score);
+            int i = m, j = n, len = 0;
+            uint8_t *ox = strbuf + str_off, *oy = ox + row_len;
+            while (i > 0 || j > 0) {
+                if (i == 0) st = 2;
+                else if (j == 0) st = 1;
+                uint32_t d = 0;
+                if (i > 0 && j > 0) d = s_tb[grp][j - 1 + (i - 1) / TINY_R][i - 1];
+                if (st == 0) {
+                    ox[len] = xs[i - 1]; oy[len] = ys[j - 1];
+                    st = prio_to_state(d & 3, prm); --i; --j;
+                } else if (st == 1) {
+                    ox[len] = xs[i - 1]; oy[len] = '-';
+                    st = prio_to_state((d >> 2) & 3, prm); --i;
+                } else {
+                    ox[len] = '-'; oy[len] = ys[j - 1];
+                    st = prio_to_state((d >> 4) & 3, prm); --j;
+                }
+                ++len;
+            }
+            slots[sid].score = score;
+            slots[sid].len = len;
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_dp_tiny(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                           const unsigned int *count_dev, int64_t max_items, DpParams prm,
+                           uint8_t *strbuf, int num_sms, cudaStream_t st) {
+    if (max_items <= 0) return cudaSuccess;
+    int64_t grid = (max_items + 31) / 32;
+    const int64_t cap = (int64_t)num_sms * 5;     // 256 threads, ~41 KB smem -> 5 CTAs / SM
+    if (grid > cap) grid = cap;
+    if (prm.xy) dp_tiny_kernel<true><<<(int)grid, 256, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
+    else dp_tiny_kernel<false><<<(int)grid, 256, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
+    return cudaGetLastError();
+}
+
+// ======================================================================= wavefront kernel
+struct WfShared {
+    int endM, endX, endY, have_end;
+};
+
+template <int W, bool XY>
+__global__ void __launch_bounds__(W * 32)
+dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+             const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
+             uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool, int4 *__restrict__ bnd_pool,
+             int64_t bnd_stride) {
+    constexpr int R = WF_R, D = WF_D, C = WF_C, RING = WF_RING;
+    constexpr int ROWS_PASS = W * 32 * R;
+    __shared__ int4 ring[W + 1][RING];
+    __shared__ WfShared sh;
+    __shared__ __align__(16) uint8_t win[32][64];      // traceback window
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const unsigned int count = *count_dev;
+    const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
+    const int NEG = NEG_V * SCALE;
+    int4 *bndA = bnd_pool + (int64_t)blockIdx.x * 2 * bnd_stride, *bndB = bndA + bnd_stride;
+
+    for (unsigned int item = blockIdx.x; item < count; item += gridDim.x) {
+        const int sid = list[item];
+        const Slot s = slots[sid];
+        const PairDesc pd = pairs[s.pair];
+        const int m = s.m, n = s.n;
+        const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
+        uint8_t *tb = tb_pool + s.tb_off;
+        const int passes = (m + ROWS_PASS - 1) / ROWS_PASS;
+        const int64_t tb_rows = (int64_t)n + 32;           // step rows per (pass, warp) block
+        if (tid == 0) sh.have_end = 0;
+        __syncthreads();
+
+        for (int pass = 0; pass < passes; ++pass) {
+            const int base = pass * ROWS_PASS;
+            const int4 *bin = (pass & 1) ? bndB : bndA;
+            int4 *bout = (pass & 1) ? bndA : bndB;
+            const bool need_out = pass + 1 < passes;
+            int Mr[R], Xr[R], Yr[R];
+            uint32_t slo[R], shi[R];
+            const int row0 = base + (w * 32 + lane) * R;     // 0-based index of this lane's first row
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int i = row0 + r + 1;
+                const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
+                slo[r] = prm.lut_lo[xc]; shi[r] = prm.lut_hi[xc];
+                Mr[r] = NEG | tagM;
+                Xr[r] = (-(go + (i - 1) * ge)) | tagX;
+                Yr[r] = NEG | tagY;
+            }
+            int dgM = 0, dgX = 0, dgY = 0, my_yc = 0;
+            const int own = m - 1 - base;                    // row m inside this pass?
+            const bool i_own = own >= 0 && own < ROWS_PASS && (own / R) == (w * 32 + lane);
+            const int own_r = own >= 0 ? own % R : 0;
+            uint8_t *tbw = tb + ((int64_t)(pass * W + w) * tb_rows) * (32 * R) + lane * R;
+            const int off_last = (W - 1) * D + 31;
+            const int S = n + 1 + off_last;                  // steps in this pass
+            const int NB = (S + C - 1) / C;
+
+            auto fill = [&](int c) {                         // ring[0] entry for column c
+                if (c < 0 || c > n) return;
+                int4 e;
+                if (pass == 0) {
+                    e.x = (c == 0 ? 0 : NEG) | tagM; e.y = NEG | tagX;
+                    e.z = (c == 0 ? NEG : -(go + (c - 1) * ge)) | tagY;
+                } else {
+                    e = bin[c];
+                }
+                e.w = c >= 1 ? base_code(ys[c - 1]) : 0;
+                ring[0][c & (RING - 1)] = e;
+            };
+            if (w == 0) fill(lane);
+            __syncthreads();
+
+            for (int blk = 0; blk < NB; ++blk) {
+                const int s0 = blk * C;
+                if (w == 0) fill(s0 + C + lane);             // next chunk, visible after the barrier
+                if (need_out && w == W - 1) {                // drain what lane 31 produced last block
+                    const int c = s0 - C - off_last + lane;
+                    if (c >= 0 && c <= n) bout[c] = ring[W][c & (RING - 1)];
+                }
+#pragma unroll 1
+                for (int st = 0; st < C; ++st) {
+                    const int sidx = s0 + st;
+                    const int j = sidx - w * D - lane;       // column (0 = init column)
+                    int uM = __shfl_up_sync(0xffffffffu, Mr[R - 1], 1);
+                    int uX = __shfl_up_sync(0xffffffffu, Xr[R - 1], 1);
+                    int uY = __shfl_up_sync(0xffffffffu, Yr[R - 1], 1);
+                    int yc = __shfl_up_sync(0xffffffffu, my_yc, 1);
+                    if (lane == 0 && j >= 0 && j <= n) {
+                        const int4 e = ring[w][j & (RING - 1)];
+                        uM = e.x; uX = e.y; uY = e.z; yc = e.w;
+                    }
+                    if (j >= 1 && j <= n) {
+                        const uint32_t sel = lut_sel(yc);
+                        int dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
+                        uint32_t wlo = 0, whi = 0;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            const int oM = Mr[r], oX = Xr[r], oY = Yr[r];
+                            const uint32_t d = dp_cell<XY>(Mr[r], Xr[r], Yr[r], dM, dX, dY, aM, aX, aY,
+                                                           lut_score(slo[r], shi[r], sel), go, ge, tagX, tagY);
+                            if (r < 4) wlo |= d << (8 * r); else whi |= d << (8 * (r - 4));
+                            dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
+                        }
+                        *reinterpret_cast<uint2 *>(tbw + (int64_t)(j + lane) * (32 * R)) = make_uint2(wlo, whi);
+                        my_yc = yc;
+                        if (j == n && i_own) {
+#pragma unroll
+                            for (int r = 0; r < R; ++r)
+                                if (r == own_r) { sh.endM = Mr[r]; sh.endX = Xr[r]; sh.endY = Yr[r]; sh.have_end = 1; }
+                        }
+                    }
+                    dgM = uM; dgX = uX; dgY = uY;
+                    if (lane == 31 && j >= 0 && j <= n && (w + 1 < W || need_out))
+                        ring[w + 1][j & (RING - 1)] = make_int4(Mr[R - 1], Xr[R - 1], Yr[R - 1], my_yc);
+                }
+                __syncthreads();
+            }
+            if (need_out && w == W - 1) {                    // final drain
+                for (int c = NB * C - C - off_last + lane; c <= n; c += 32)
+                    if (c >= 0) bout[c] = ring[W][c & (RING - 1)];
+            }
+            __syncthreads();
+        }
+        // ---------------------------------------------------------------- traceback (warp 0)
+        if (w == 0) {
+            int st = 0, score = 0;
+            pick_end(sh.endM, sh.endX, sh.endY, prm, st, score);
+            int i = m, j = n, len = 0;
+            const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
+            uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
+            // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block
+            int64_t win_blk = -1; int win_row_hi = 0, win_col_lo = 0;
+            while (i > 0 || j > 0) {
+                if (i == 0) st = 2;
+                else if (j == 0) st = 1;
+                uint32_t d = 0;
+                if (i > 0 && j > 0) {
+                    const int i0 = i - 1;
+                    const int ps = i0 / ROWS_PASS, rem = i0 % ROWS_PASS;
+                    const int ww = rem / (32 * R), cb = rem % (32 * R);     // cb = l*R + r
+                    const int row = j + cb / R;
+                    const int64_t blk = (int64_t)ps * W + ww;
+                    if (blk != win_blk || row > win_row_hi || row <= win_row_hi - 32 || cb < win_col_lo || cb >= win_col_lo + 64) {
+                        __syncwarp();
+                        win_blk = blk; win_row_hi = row;
+                        win_col_lo = max(0, (cb & ~31) - 32);
+                        const int rr = row - lane;
+                        const uint8_t *src = tb + (blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo;
+                        uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
+                        if (rr >= 1) {
+                            const uint4 *p = reinterpret_cast<const uint4 *>(src);
+                            a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
+                        }
+                        uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
+                        dst[0] = a; dst[1] = b; dst[2] = c4; dst[3] = d4;
+                        __syncwarp();
+                    }
+                    d = win[win_row_hi - row][cb - win_col_lo];
+                }
+                if (lane == 0) {
+                    if (st == 0) { ox[len] = xs[i - 1]; oy[len] = ys[j - 1]; }
+                    else if (st == 1) { ox[len] = xs[i - 1]; oy[len] = '-'; }
+                    else { ox[len] = '-'; oy[len] = ys[j - 1]; }
+                }
+                if (st == 0) { st = prio_to_state(d & 3, prm); --i; --j; }
+                else if (st == 1) { st = prio_to_state((d >> 2) & 3, prm); --i; }
+                else { st = prio_to_state((d >> 4) & 3, prm); --j; }
+                ++len;
+            }
+            if (lane == 0) { slots[sid].score = score; slots[sid].len = len; }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                                const unsigned int *count_dev, int grid, bool cta_class, DpParams prm,
+                                uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st) {
+    if (grid <= 0) return cudaSuccess;
+    if (cta_class) {
+        if (prm.xy) dp_wf_kernel<WF_CTA_WARPS, true><<<grid, WF_CTA_WARPS * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+        else dp_wf_kernel<WF_CTA_WARPS, false><<<grid, WF_CTA_WARPS * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+    } else {
+        if (prm.xy) dp_wf_kernel<1, true><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+        else dp_wf_kernel<1, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace dbga

@@ -1,0 +1,130 @@
+/* dbga_b200 -- C ABI of the B200-native DBGA pairwise alignment hot path.
+ *
+ * The reference (xingjianleng/DBGA) is pure Python and has no FFI; these entry points are
+ * what a maintainer would bind from `src/dbga/debruijn_pairwise.py` to replace, for a
+ * batch of independent sequence pairs:
+ *
+ *   stages 1-2  DeBruijnPairwise.__init__            src/dbga/debruijn_pairwise.py:42-76
+ *               (get_kmers / duplicate_kmers          src/dbga/utils.py:108-154,
+ *                add_debruijn / extract_bubble        debruijn_pairwise.py:206-225, 277-300,
+ *                debruijn_merge_correctness           utils.py:266-291)
+ *   stage 3     DeBruijnPairwise.alignment            debruijn_pairwise.py:418-543
+ *               (bubble_aln -> dna_global_aln ->      :345-395, utils.py:157-192,
+ *                cogent3.align.global_pairwise         utils.py:185)
+ *
+ * Plain pointers and sizes only; no exceptions cross the boundary.  Per-pair outcomes are
+ * status codes which the Python layer turns into the reference's exact exceptions
+ * (INTEGRATION.md).  All calls on one context are synchronous on that context's stream;
+ * use one context per GPU / per host thread.
+ */
+#ifndef DBGA_B200_H
+#define DBGA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- per-pair status ---------------------------------------------------------------- */
+#define DBGA_OK 0        /* aligned */
+#define DBGA_CYCLE 1     /* ValueError("Cycles detected in de Bruijn graph, ...")  debruijn_pairwise.py:73-76 */
+#define DBGA_K_INVALID 2 /* ValueError("Invalid k size for kmers")                 utils.py:129-130 */
+#define DBGA_BAD_CHAR 3  /* a character outside ACGT (the DP alphabet, utils.py:184) */
+#define DBGA_TOO_LARGE 4 /* exceeds a workspace or numeric limit of this build; never silent */
+
+/* ---- call-level return codes -------------------------------------------------------- */
+#define DBGA_SUCCESS 0
+#define DBGA_ERR_CUDA (-1)
+#define DBGA_ERR_ARG (-2)
+#define DBGA_ERR_NOMEM (-3)
+
+/* Tie-order encoding shared with oracle/: index into XMY, XYM, MXY, MYX, YXM, YMX
+ * (first state wins ties; X consumes a seq1 character, Y a seq2 character). */
+typedef struct dbga_params {
+    int32_t k;            /* k-mer size, 1..31 (larger: DBGA_ERR_ARG)                   */
+    int32_t score[16];    /* substitution scores, row-major over ACGT x ACGT            */
+    int32_t gap_open;     /* d  (debruijn_pairwise.py:423)                              */
+    int32_t gap_extend;   /* e  (:424)                                                  */
+    int32_t gap_len_mode; /* 0: gap(L) = d + (L-1) e (default)   1: d + L e             */
+    int32_t xy_allowed;   /* 0 (default): no X<->Y transitions                          */
+    int32_t pred_order;   /* default 0 = X,M,Y                                          */
+    int32_t end_order;    /* default 0 = X,M,Y                                          */
+    int32_t stages;       /* 2: stop after stages 1-2 (constructor)   3: full alignment */
+    int32_t want_graph;   /* 1: also return per-k-mer "non-duplicate" flags (node ids)  */
+} dbga_params;
+
+typedef struct dbga_ctx dbga_ctx;
+
+/* Results of one batch.  Every array is host memory owned by the context (pinned) and
+ * stays valid until the next dbga_align_batch / dbga_plan_fetch on the same context or
+ * dbga_destroy. */
+typedef struct dbga_result {
+    int64_t num_pairs;
+    const int32_t *status;      /* [P]                                                    */
+    const int64_t *score;       /* [P] sum of DP scores of the segments handed to the DP  */
+    const int64_t *dp_cells;    /* [P] sum |x|*|y| over those segments        */
+    const int32_t *dp_segments; /* [P]                                                    */
+    const int64_t *n_anchors;   /* [P] number of merge nodes M                            */
+    const int64_t *run_off;     /* [P+1] offsets (in runs) into `runs`                    */
+    const int32_t *runs;        /* [3*run_off[P]] (a, b, len): anchors (a+u, b+u), u<len,
+                                   in ascending b -- the merge nodes in seq-2 order       */
+    const int64_t *aln_off;     /* [P+1] byte offsets into aln0 / aln1                    */
+    const uint8_t *aln0;        /* gapped seq1 rows, concatenated                         */
+    const uint8_t *aln1;        /* gapped seq2 rows                                       */
+    /* want_graph only: per k-mer position, 1 = not a duplicate k-mer (utils.py:148-154).
+       Node ids follow by prefix sums (DESIGN.md "Node ids").                              */
+    const int64_t *p_off;       /* [P+1] offsets into nondup0 (seq1 k-mer positions)      */
+    const uint8_t *nondup0;
+    const int64_t *q_off;       /* [P+1] offsets into nondup1 (seq2 k-mer positions)      */
+    const uint8_t *nondup1;
+    /* device-side timing of the last run, milliseconds (CUDA events on the ctx stream)  */
+    float ms_h2d, ms_stage1, ms_stage2, ms_stage3, ms_assemble, ms_d2h, ms_total;
+    int64_t dp_cells_total;
+    int64_t dp_segments_total;
+    int64_t kernel_launches;    /* kernels of this library launched for the batch         */
+} dbga_result;
+
+/* Context: one CUDA device, one stream, grow-only workspaces. */
+int dbga_create(int device, dbga_ctx **out);
+void dbga_destroy(dbga_ctx *ctx);
+const char *dbga_last_error(dbga_ctx *ctx);
+/* Use an existing stream (e.g. torch's current stream) instead of the context's own. */
+int dbga_set_stream(dbga_ctx *ctx, void *cuda_stream);
+/* Upper bound on device scratch for traceback matrices, bytes (default 8 GiB). */
+int dbga_set_scratch_limit(dbga_ctx *ctx, int64_t bytes);
+
+/* Pinned host buffers for callers that want full-speed host<->device copies. */
+void *dbga_host_alloc(int64_t bytes);
+void dbga_host_free(void *p);
+
+/* One call = the reference's  [DeBruijnPairwise(pair, k).alignment(...) for pair in batch].
+ * seqs    : concatenated ASCII sequences (host memory)
+ * offsets : [2P+1]; sequence j of pair i is seqs[offsets[2i+j] : offsets[2i+j+1]] */
+int dbga_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets,
+                     int64_t num_pairs, const dbga_params *params, dbga_result *out);
+
+/* Split form: plan (host-side sizing + metadata upload), run on device-resident
+ * sequences (kernels only, nothing copied), fetch (device -> host). */
+int dbga_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t num_pairs, const dbga_params *params);
+/* same, for dbga_global_align_batch's workload (every pair is one whole-sequence segment) */
+int dbga_plan_global(dbga_ctx *ctx, const int64_t *offsets, int64_t num_pairs, const dbga_params *params);
+int dbga_plan_run(dbga_ctx *ctx, const uint8_t *device_seqs);
+int dbga_plan_fetch(dbga_ctx *ctx, dbga_result *out);
+
+/* Measured integer-pipe peaks used as the DP roofline denominator:
+ * out[0] = int32 add ops/s, out[1] = int32 max ops/s, out[2] = ops/s of the DP's own
+ * 5 add : 4 max mix, all over the whole chip. */
+int dbga_measure_int_peak(dbga_ctx *ctx, double out[3]);
+
+/* Stand-alone stage-3 entry: P independent global alignments (the batched equivalent of
+ * utils.py:157-192 dna_global_aln); same offsets convention; results in out->aln*. */
+int dbga_global_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets,
+                            int64_t num_pairs, const dbga_params *params, dbga_result *out);
+
+int dbga_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBGA_B200_H */

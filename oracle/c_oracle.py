@@ -104,6 +104,25 @@ def align_pair(s0: str, s1: str, k: int, match=10, transition=-1, transversion=-
     return out
 
 
+def gotoh(x: str, y: str, match=10, transition=-1, transversion=-8, d=10, e=2,
+          conv: pyo.Convention = pyo.DEFAULT, s=None):
+    """oracle_gotoh on two non-empty strings -> (score, aligned_x, aligned_y)."""
+    L = lib()
+    code = {65: 0, 67: 1, 71: 2, 84: 3}
+    xb = bytes(code[c] for c in x.encode())
+    yb = bytes(code[c] for c in y.encode())
+    ox = C.create_string_buffer(len(x) + len(y) + 1)
+    oy = C.create_string_buffer(len(x) + len(y) + 1)
+    n = C.c_int64(0)
+    cv = conv_struct(conv)
+    L.oracle_gotoh.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.POINTER(C.c_int32),
+                               C.c_int32, C.c_int32, C.POINTER(Conv), C.c_char_p, C.c_char_p,
+                               C.POINTER(C.c_int64)]
+    sc = L.oracle_gotoh(xb, len(xb), yb, len(yb), score_array(match, transition, transversion, s),
+                        d, e, C.byref(cv), ox, oy, C.byref(n))
+    return int(sc), ox.raw[:n.value].decode(), oy.raw[:n.value].decode()
+
+
 def align_batch(seqs: np.ndarray, offsets: np.ndarray, k: int, match=10, transition=-1,
                 transversion=-8, d=10, e=2, conv: pyo.Convention = pyo.DEFAULT, s=None, threads: int = 0):
     """Summary-only batch (status, score, aligned length, DP cells, anchors per pair);

@@ -1,0 +1,199 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle.  Needs a B200."""
+import itertools
+import random
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as CO
+from oracle import dbga_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aligner():
+    from dbga_b200 import Aligner
+    a = Aligner(0)
+    yield a
+    a.close()
+
+
+def rand_seq(rng, n, alpha="ACGT"):
+    return "".join(rng.choice(alpha) for _ in range(n))
+
+
+def mutate(rng, s, ps, pi):
+    out, i = [], 0
+    while i < len(s):
+        r = rng.random()
+        if r < pi:
+            if rng.random() < 0.5:
+                out.append(rand_seq(rng, rng.randint(1, 4)))
+                out.append(s[i]); i += 1
+            else:
+                i += rng.randint(1, 4)
+        elif r < pi + ps:
+            out.append(rng.choice([c for c in "ACGT" if c != s[i]])); i += 1
+        else:
+            out.append(s[i]); i += 1
+    return "".join(out)
+
+
+def check_batch(aligner, pairs, k, conv=O.DEFAULT, oracle=CO.align_pair, **score):
+    res = aligner.align_pairs(pairs, k, gap_len_mode=conv.gap_len_mode, xy_allowed=conv.xy_allowed,
+                              pred_order=conv.pred_order, end_order=conv.end_order, **score)
+    n_ok = 0
+    for i, (s0, s1) in enumerate(pairs):
+        ref = oracle(s0, s1, k, conv=conv, **score)
+        assert res.status[i] == ref.status, (i, s0, s1, k, res.status[i], ref.status)
+        if ref.status in (O.OK, O.CYCLE):
+            anchors = [tuple(x) for x in np.asarray(ref.anchors).reshape(-1, 2).tolist()]
+            assert [tuple(x) for x in res.anchors(i).tolist()] == anchors, (i, s0, s1, k)
+        if ref.status == O.OK:
+            a0, a1 = res.alignment(i)
+            assert (a0, a1) == (ref.aln0, ref.aln1), (i, s0, s1, k, conv, a0, a1, ref.aln0, ref.aln1)
+            assert res.score[i] == ref.score, (i, s0, s1, k)
+            assert res.dp_cells[i] == ref.dp_cells and res.dp_segments[i] == ref.dp_segments
+            n_ok += 1
+    return n_ok
+
+
+def test_reference_goldens(aligner, ref_fixtures):
+    # reference tests/test_debruijn_pairwise.py:50-214 through the CUDA path
+    for fx in ref_fixtures["e2e"]:
+        res = aligner.align_pairs([tuple(fx["seqs"])], fx["k"], want_graph=True)
+        assert res.status[0] == O.OK
+        assert list(res.alignment(0)) == fx["aln"], fx["fixture"]
+        nd0, nd1 = res.graph_flags(0)
+        ids = [1 + int(nd0[:a].sum()) for a, _ in res.anchors(0).tolist()]
+        assert ids == fx["merge_node_idx"], fx["fixture"]
+    for fx in ref_fixtures["cycles"]:
+        res = aligner.align_pairs([tuple(fx["seqs"])], fx["k"])
+        assert res.status[0] == O.CYCLE
+
+
+def test_recorded_reference_fuzz(aligner, ref_fuzz):
+    # 400 inputs recorded from the reference's own code (tests/golden/ref_graph_fuzz.json)
+    by_k = {}
+    for c in ref_fuzz:
+        by_k.setdefault(c["k"], []).append(c)
+    for k, cases in by_k.items():
+        res = aligner.align_pairs([tuple(c["seqs"]) for c in cases], k, want_graph=True)
+        for i, c in enumerate(cases):
+            ref = c["ref"]
+            if "error" in ref:
+                assert res.status[i] == O.CYCLE
+                continue
+            assert res.status[i] == O.OK
+            assert list(res.alignment(i)) == ref["aln"]
+            nd0, nd1 = res.graph_flags(i)
+            anchors = res.anchors(i).tolist()
+            assert [1 + int(nd0[:a].sum()) for a, _ in anchors] == ref["merge_node_idx"]
+            # id_count = 4 terminal nodes + non-duplicate k-mers of both - merge nodes
+            assert 4 + int(nd0.sum()) + int(nd1.sum()) - len(anchors) == ref["id_count"]
+            assert res.dp_segments[i] == len(ref["dp_calls"])
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 9, 15, 16, 21, 31])
+def test_small_pairs_vs_oracle(aligner, k):
+    rng = random.Random(1000 + k)
+    pairs = []
+    for _ in range(300):
+        n = rng.choice([k, k + 1, 40, 90, 200, 600])
+        n = max(n, k)
+        s0 = rand_seq(rng, n, rng.choice(["ACGT", "ACGT", "AC"]))
+        if rng.random() < 0.8:
+            s1 = mutate(rng, s0, rng.choice([0, 0.02, 0.1]), rng.choice([0, 0.01, 0.05]))
+        else:
+            s1 = rand_seq(rng, rng.randint(k, n + 5))
+        if len(s1) < k:
+            s1 = s0
+        pairs.append((s0, s1))
+    assert check_batch(aligner, pairs, k) > 50
+
+
+def test_all_conventions(aligner):
+    rng = random.Random(5)
+    pairs = []
+    for _ in range(60):
+        s0 = rand_seq(rng, rng.choice([30, 80, 150]))
+        pairs.append((s0, mutate(rng, s0, 0.08, 0.05) or "A"))
+    pairs = [(a, b) for a, b in pairs if len(b) >= 5]
+    for g, xy, po, eo in itertools.product((0, 1), (False, True), O.ORDERS, ("XMY", "MYX", "YMX")):
+        check_batch(aligner, pairs, 5, conv=O.Convention(g, xy, po, eo))
+    check_batch(aligner, pairs, 5, match=5, transition=-4, transversion=-4, d=7, e=1)
+    check_batch(aligner, pairs, 5, match=1, transition=0, transversion=-1, d=0, e=0)
+
+
+def test_status_codes(aligner):
+    res = aligner.align_pairs([("ACGT", "ACGTA"), ("ACGNACGT", "ACGTACGT"), ("ACGTACGTAC", "ACGTTCGTAC"),
+                               ("acgtacgt", "ACGTACGT")], 5)
+    assert res.status.tolist() == [O.K_INVALID, O.BAD_CHAR, O.OK, O.BAD_CHAR]
+
+
+def test_global_align_classes(aligner):
+    """dna_global_aln through every DP kernel class: tiny, warp (1 and >1 row strips),
+    CTA wavefront (1 and >1 strips), plus empty sides (utils.py:187-192)."""
+    rng = random.Random(11)
+    shapes = [(1, 1), (5, 7), (32, 32), (33, 20), (20, 33), (100, 90), (256, 300), (257, 301), (700, 650),
+              (40, 3000), (3000, 40), (600, 600), (2100, 2300), (513, 520), (0, 5), (6, 0)]
+    pairs = []
+    for m, n in shapes:
+        x = rand_seq(rng, m)
+        if m and n and rng.random() < 0.7:
+            y = (mutate(rng, x, 0.1, 0.05) + rand_seq(rng, n))[:n]
+        else:
+            y = rand_seq(rng, n)
+        pairs.append((x, y))
+    for conv in (O.DEFAULT, O.Convention(1, True, "MYX", "YMX")):
+        res = aligner.global_align_pairs(pairs, gap_len_mode=conv.gap_len_mode, xy_allowed=conv.xy_allowed,
+                                         pred_order=conv.pred_order, end_order=conv.end_order)
+        s = O.make_dna_scoring_dict(10, -1, -8)
+        for i, (x, y) in enumerate(pairs):
+            assert res.status[i] == O.OK
+            if x and y:
+                sc, ax, ay = CO.gotoh(x, y, conv=conv)
+                assert res.score[i] == sc, (i, len(x), len(y))
+            else:
+                ax, ay = O.dna_global_aln(x, y, s, 10, 2)
+            assert res.alignment(i) == (ax, ay), (i, len(x), len(y), conv)
+
+
+def test_large_path_vs_oracle(aligner):
+    """Pairs too big for the shared-memory table take the global-memory stage-1 path."""
+    pairs = [O.synth_pair(30000, 0.004, 0.001, 3), O.synth_pair(12000, 0.01, 0.002, 4),
+             O.synth_pair(60000, 0.002, 0.0005, 5)]
+    n_ok = check_batch(aligner, pairs, 11) + check_batch(aligner, pairs, 17)
+    assert n_ok >= 1
+    # mixed small + large in one batch, and graph flags on the large path
+    small = [O.synth_pair(300, 0.02, 0.004, s) for s in range(20)]
+    check_batch(aligner, small + pairs[:1] + small, 11)
+    res = aligner.align_pairs(pairs[:1], 11, want_graph=True, stages=2)
+    ref = CO.align_pair(*pairs[0], 11, want_graph=True, stages=2)
+    nd0, nd1 = res.graph_flags(0)
+    assert np.array_equal(nd0, ref.nondup0) and np.array_equal(nd1, ref.nondup1)
+
+
+def test_cfg3_sample_vs_oracle(aligner):
+    """BASELINE config 3 shape (1.5 kb, 2 % divergence, k=9): 2000 pairs bit-exact."""
+    pairs = [O.synth_pair(1500, 0.018, 0.002, 100 + s) for s in range(2000)]
+    n_ok = check_batch(aligner, pairs, 9)
+    assert n_ok > 1000
+
+
+def test_full_size_properties(aligner):
+    """Size-independent properties at a larger batch: degapped rows == inputs, equal row
+    lengths, no all-gap column, idempotent across two calls."""
+    pairs = [O.synth_pair(1500, 0.018, 0.002, 50000 + s) for s in range(20000)]
+    r1 = aligner.align_pairs(pairs, 9)
+    r2 = aligner.align_pairs(pairs, 9)
+    assert np.array_equal(r1.status, r2.status) and np.array_equal(r1.aln0, r2.aln0) and np.array_equal(r1.aln1, r2.aln1)
+    assert (r1.status == O.OK).sum() > 10000
+    for i in range(0, len(pairs), 37):
+        if r1.status[i] != O.OK:
+            continue
+        a0, a1 = r1.alignment(i)
+        assert len(a0) == len(a1)
+        assert a0.replace("-", "") == pairs[i][0] and a1.replace("-", "") == pairs[i][1]
+        assert not any(x == "-" and y == "-" for x, y in zip(a0, a1))
