@@ -1,0 +1,179 @@
+"""CPU-side tests: host logic, the C-ABI library's exports, error behaviour without a GPU,
+and the 2-rank sharding logic over gloo.  No compute calls (there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    from dbga_b200 import build
+    return build.build_library()
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "dbga_b200.h")).read()
+    declared = set(re.findall(r"\b(dbga_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(built)
+    for name in declared:
+        assert hasattr(lib, name), name
+    from dbga_b200 import _lib
+    assert declared == set(_lib.EXPORTS)
+    assert lib.dbga_version() >= 100
+
+
+def test_struct_layouts_match_header(built):
+    from dbga_b200 import _lib
+    assert ctypes.sizeof(_lib.Params) == 4 * (1 + 16 + 2 + 4 + 2)
+    # 15 pointers/int64 + 7 floats (+pad) + 3 int64
+    assert ctypes.sizeof(_lib.Result) == 8 * 15 + 4 * 8 + 8 * 3
+
+
+def test_no_cpu_fallback_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dbga_b200 import Aligner
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Aligner(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dbga_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"(from|import)\s+oracle|liboracle|oracle_[a-z]|c_oracle", text), f
+
+
+def test_utils_mirror_reference_behaviour():
+    from dbga_b200 import utils
+    # reference tests/test_utils.py:20-37
+    assert utils.read_nucleotide_from_kmers("", 3) == ""
+    assert utils.read_nucleotide_from_kmers("AOPKFNLSDOEPKPOWSEGH", 4) == "AFDKS"
+    assert utils.read_nucleotide_from_kmers("1092831790", 2) == "19819"
+    with pytest.raises(AssertionError):
+        utils.read_nucleotide_from_kmers("ACMDANFGL", 4)
+    # :113-145
+    assert utils.get_kmers("GTACACGTATG", 3) == ["GTA", "TAC", "ACA", "CAC", "ACG", "CGT", "GTA", "TAT", "ATG"]
+    with pytest.raises(ValueError) as e:
+        utils.get_kmers("TACCACGTAAT", 16)
+    assert e.value.args[0] == "Invalid k size for kmers"
+    # :148-155
+    assert utils.duplicate_kmers([["AG", "CT", "CA", "AC", "CT"], ["CT", "AC", "GT", "AG"]]) == {"CT"}
+    assert utils.duplicate_kmers([["AG", "CT", "CA", "AG", "CT"], ["CT", "AG", "CT", "AG", "AC"]]) == {"AG", "CT"}
+    # :98-110
+    assert utils.debruijn_merge_correctness([[0, [1, 2], 3], [0, 3]]) is False
+    assert utils.debruijn_merge_correctness([[0, [1, 2], 3], [0, 4, 3]]) is False
+    assert utils.debruijn_merge_correctness([[0, [1, 2], 3], [0, [6, 7], 4]]) is False
+    assert utils.debruijn_merge_correctness([[0, [1, 2], 3], [0, [6, 7], 3]]) is True
+    assert utils.get_closest_odd(3, True) == 3 and utils.get_closest_odd(4, True) == 5 and utils.get_closest_odd(4, False) == 3
+
+
+def test_load_sequences(data_dir):
+    from dbga_b200 import utils, seqcoll
+    sc = utils.load_sequences(os.path.join(data_dir, "gap_at_end.fasta"), moltype="dna")
+    assert [str(s) for s in sc.seqs] == ["GTACAAGCGATG", "GTACAAGCGA"] and sc.names == ["seq1", "seq2"]
+    sc = utils.load_sequences(["ACGTCAG", "GACTGTGA"], moltype="dna")
+    assert sc.names == [0, 1]
+    assert utils.load_sequences(sc, moltype="dna") is sc
+    with pytest.raises(ValueError) as e:
+        utils.load_sequences({1: "ACGTGTA"}, moltype="dna")
+    assert e.value.args[0] == "Invalid input for sequence argument"
+    with pytest.raises(ValueError):
+        utils.load_sequences("data/not_a_file", moltype="dna")
+    with pytest.raises(seqcoll.AlphabetError):
+        utils.load_sequences(["ACTGA", "TACGE"], moltype="dna")
+
+
+def test_alignment_container():
+    from dbga_b200 import seqcoll
+    aln = seqcoll.make_aligned_seqs({"seq1": "AC-T", "seq2": "ACGT"}, moltype="dna")
+    assert aln == {"seq1": "AC-T", "seq2": "ACGT"}
+    assert aln.to_fasta() == ">seq1\nAC-T\n>seq2\nACGT\n"
+    assert aln.to_dict() == {"seq1": "AC-T", "seq2": "ACGT"} and aln.seq_len == 4
+
+
+def test_pack_pairs_and_synth():
+    from dbga_b200.batch import pack_pairs
+    from dbga_b200.synth import synth_batch, pairs_from_buffers
+    buf, offs = pack_pairs([("ACGT", "AC"), ("", "GGG")])
+    assert buf.tobytes() == b"ACGTACGGG" and offs.tolist() == [0, 4, 6, 6, 9]
+    buf, offs = synth_batch(50, 200, 0.02, 0.01, seed=3)
+    assert len(offs) == 101 and offs[-1] == len(buf)
+    pairs = pairs_from_buffers(buf, offs, range(50))
+    assert all(len(a) == 200 and set(a + b) <= set("ACGT") for a, b in pairs)
+    assert any(len(b) != 200 for _, b in pairs) and any(a != b for a, b in pairs)
+    b2, o2 = synth_batch(50, 200, 0.02, 0.01, seed=3)
+    assert np.array_equal(buf, b2) and np.array_equal(offs, o2)
+
+
+def test_batch_result_anchor_expansion():
+    from dbga_b200.batch import BatchResult
+    z = np.zeros(0)
+    r = BatchResult(status=np.zeros(2, np.int32), score=z, dp_cells=z, dp_segments=z, n_anchors=z,
+                    run_off=np.array([0, 2, 2]), runs=np.array([[3, 1, 3], [9, 8, 1]], np.int32),
+                    aln_off=np.array([0, 0, 0]), aln0=np.zeros(0, np.uint8), aln1=np.zeros(0, np.uint8))
+    assert r.anchors(0).tolist() == [[3, 1], [4, 2], [5, 3], [9, 8]]
+    assert r.anchors(1).shape == (0, 2)
+
+
+def test_cli_rejects_non_fasta(tmp_path):
+    from click.testing import CliRunner
+    from dbga_b200.cli import main
+    p = tmp_path / "in.txt"
+    p.write_text(">a\nACGT\n>b\nACGT\n")
+    res = CliRunner().invoke(main, ["-i", str(p), "-o", str(tmp_path / "o.fasta"), "-k", "3", "-m", "dna"])
+    assert res.exit_code == 0 and "Expect input and output files to be `fasta` format!" in res.output
+    one = tmp_path / "one.fasta"
+    one.write_text(">a\nACGT\n")
+    res = CliRunner().invoke(main, ["-i", str(one), "-o", str(tmp_path / "o.fasta"), "-k", "3", "-m", "dna"])
+    assert "Too few sequences for alignment, should be at least 2!" in res.output
+
+
+SHARD_SCRIPT = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from dbga_b200.sharding import shard_range, gather_results
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+lo, hi = shard_range(11, rank, 2)
+local = [("pair%d" % i, i * i) for i in range(lo, hi)]
+allr = gather_results(local)
+if rank == 0:
+    assert [x[0] for x in allr] == ["pair%d" % i for i in range(11)], allr
+    assert [x[1] for x in allr] == [i * i for i in range(11)]
+    print("SHARD_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sharding_gloo(tmp_path):
+    script = tmp_path / "shard.py"
+    script.write_text(SHARD_SCRIPT.format(root=ROOT, port=29611))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARD_OK" in outs[0][0]
+
+
+def test_shard_range_partitions():
+    from dbga_b200.sharding import shard_range
+    for n in (0, 1, 7, 100_000):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
