@@ -60,12 +60,13 @@ struct dbga_ctx {
     int64_t runs_cap = 0, slots_cap = 0, tb_cap = 0;
     int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
     int grid_warp = 0, grid_cta = 0;
+    int tiny_bound[NUM_TINY] = {8, 16, 24, 32};
     int launches = 0;
     const uint8_t *d_seqs_run = nullptr;
 
     // ---- device buffers (grow only)
-    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_slots, d_lt, d_lw,
-        d_lc, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_len, d_aln_off, d_run_cnt,
+    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_slots, d_lists,
+        d_tt, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_len, d_aln_off, d_run_cnt,
         d_run_off, d_scan_tmp, d_aln0, d_aln1, d_runs_out, d_score, d_cells, d_nseg, d_nanch, d_status_out,
         d_sink;
     // ---- pinned host result buffers
@@ -297,6 +298,13 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     ctx->slots_cap = std::max<int64_t>(ctx->slots_cap, ctx->runs_cap + P + 16);
     ctx->tb_cap = std::max<int64_t>(ctx->tb_cap, std::min<int64_t>(ctx->scratch_limit, 64LL << 20));
     ctx->stage2_threads = mx1 <= 4096 ? 128 : (mx1 <= 65536 ? 256 : 1024);
+    {   // tiny DP classes: a substitution bubble is (k+1) x (k+1), so bucket around multiples of it
+        const int b0 = std::min(TINY_MAX, no_anchors ? 8 : k + 1);
+        ctx->tiny_bound[0] = b0;
+        ctx->tiny_bound[1] = std::min(TINY_MAX, std::max(b0, (3 * b0 + 1) / 2));
+        ctx->tiny_bound[2] = std::min(TINY_MAX, std::max(b0, 2 * b0 + 2));
+        ctx->tiny_bound[3] = TINY_MAX;
+    }
     // boundary rows for multi-pass wavefronts
     ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, WARP_CLASS_MAX_CELLS / (WF_ROWS_PER_WARP + 1) + 2);
     ctx->bnd_stride_cta = (int64_t)mx1 + 1;
@@ -306,7 +314,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         int64_t g = (1LL << 30) / std::max<int64_t>(per, 1);
         ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, g));
     }
-    const bool any_non_tiny = (mx0 > TINY_MAX_M) || (mx1 > TINY_MAX_N);
+    const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
     const bool any_cta = (int64_t)mx0 * mx1 > WARP_CLASS_MAX_CELLS;
     if (!any_non_tiny) ctx->grid_warp = 0;
     if (!any_cta) ctx->grid_cta = 0;
@@ -331,7 +339,8 @@ int reserve_pools(dbga_ctx *ctx) {
     RESERVE(d_runs_out, 12 * ctx->runs_cap);
     if (ctx->prm.stages == 3) {
         RESERVE(d_slots, sizeof(Slot) * ctx->slots_cap);
-        RESERVE(d_lt, 4 * ctx->slots_cap); RESERVE(d_lw, 4 * ctx->slots_cap); RESERVE(d_lc, 4 * ctx->slots_cap);
+        RESERVE(d_lists, 4 * ctx->slots_cap * NUM_CLS);
+        RESERVE(d_tt, dp_thread_scratch_bytes(TINY_MAX, ctx->num_sms));
         if (ctx->grid_warp || ctx->grid_cta) RESERVE(d_tb, ctx->tb_cap);
     }
     return DBGA_SUCCESS;
@@ -349,7 +358,8 @@ int run_from_stage2(dbga_ctx *ctx) {
     pools.runs = (int32_t *)ctx->d_runs.p; pools.runs_cap = ctx->runs_cap;
     pools.slots = (Slot *)ctx->d_slots.p; pools.slots_cap = ctx->slots_cap;
     pools.tb_cap = (ctx->grid_warp || ctx->grid_cta) ? ctx->tb_cap : 0;
-    pools.list_tiny = (int32_t *)ctx->d_lt.p; pools.list_warp = (int32_t *)ctx->d_lw.p; pools.list_cta = (int32_t *)ctx->d_lc.p;
+    pools.lists = (int32_t *)ctx->d_lists.p;
+    for (int c = 0; c < NUM_TINY; ++c) pools.tiny_bound[c] = ctx->tiny_bound[c];
     pools.list_cap = ctx->slots_cap;
     Counters *ctr = (Counters *)ctx->d_ctr.p;
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[2], st));
@@ -360,17 +370,21 @@ int run_from_stage2(dbga_ctx *ctx) {
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));
     if (seg) {
         const uint8_t *seqs = ctx->d_seqs_run;
-        DBGA_CUDA_CHECK(launch_dp_tiny(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.list_tiny, &ctr->n_tiny,
-                                       ctx->slots_cap, ctx->dp, (uint8_t *)ctx->d_str.p, ctx->num_sms, st));
-        ctx->launches += 1;
+        for (int c = 0; c < NUM_TINY; ++c) {
+            if (c > 0 && ctx->tiny_bound[c] == ctx->tiny_bound[c - 1]) continue;   // empty class
+            DBGA_CUDA_CHECK(launch_dp_thread(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots,
+                                             pools.lists + (int64_t)c * pools.list_cap, &ctr->n_cls[c], ctx->tiny_bound[c],
+                                             ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
+            ctx->launches += 1;
+        }
         if (ctx->grid_warp) {
-            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.list_warp, &ctr->n_warp,
+            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.lists + (int64_t)CLS_WARP * pools.list_cap, &ctr->n_cls[CLS_WARP],
                                                 ctx->grid_warp, false, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
                                                 (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
             ctx->launches += 1;
         }
         if (ctx->grid_cta) {
-            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.list_cta, &ctr->n_cta,
+            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap, &ctr->n_cls[CLS_CTA],
                                                 ctx->grid_cta, true, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
                                                 (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
             ctx->launches += 1;
@@ -549,7 +563,7 @@ void dbga_destroy(dbga_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *dbs[] = {&ctx->d_seqs, &ctx->d_pairs, &ctx->d_list, &ctx->d_large, &ctx->d_status, &ctx->d_aof, &ctx->d_nd0,
-                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_slots, &ctx->d_lt, &ctx->d_lw, &ctx->d_lc, &ctx->d_ctr,
+                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_slots, &ctx->d_lists, &ctx->d_tt, &ctx->d_ctr,
                      &ctx->d_tb, &ctx->d_bnd_w, &ctx->d_bnd_c, &ctx->d_str, &ctx->d_packed, &ctx->d_table, &ctx->d_aln_len,
                      &ctx->d_aln_off, &ctx->d_run_cnt, &ctx->d_run_off, &ctx->d_scan_tmp, &ctx->d_aln0, &ctx->d_aln1,
                      &ctx->d_runs_out, &ctx->d_score, &ctx->d_cells, &ctx->d_nseg, &ctx->d_nanch, &ctx->d_status_out,

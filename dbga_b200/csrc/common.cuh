@@ -41,13 +41,13 @@ struct Slot {
     int32_t cls;          // DP class: -1 none, 0 tiny, 1 warp, 2 cta
 };
 
-enum : int32_t { CLS_NONE = -1, CLS_TINY = 0, CLS_WARP = 1, CLS_CTA = 2 };
+// DP classes: 0..3 = thread-per-segment ("tiny", bucketed by max(m, n) so that the segments of
+// a warp have similar loop bounds), 4 = warp wavefront, 5 = CTA wavefront.
+enum : int32_t { CLS_NONE = -1, CLS_TINY0 = 0, NUM_TINY = 4, CLS_WARP = 4, CLS_CTA = 5, NUM_CLS = 6 };
 
 // DP geometry (shared by host sizing and kernels)
-constexpr int TINY_G = 8;        // lanes per tiny segment
-constexpr int TINY_R = 4;        // rows per lane  -> m <= 32
-constexpr int TINY_MAX_M = TINY_G * TINY_R;
-constexpr int TINY_MAX_N = 32;
+constexpr int TINY_MAX = 32;     // thread-per-segment kernel: m, n <= 32
+constexpr int TINY_THREADS = 128;
 constexpr int WF_R = 8;          // rows per lane in the wavefront kernels
 constexpr int WF_ROWS_PER_WARP = 32 * WF_R;   // 256
 constexpr int WF_CTA_WARPS = 8;  // warps per CTA in the long-segment kernel

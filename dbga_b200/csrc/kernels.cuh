@@ -17,7 +17,7 @@ struct Counters {
     unsigned long long runs_used;      // in runs
     unsigned long long slots_used;     // in slots
     unsigned long long tb_used;        // bytes of traceback scratch
-    unsigned int n_tiny, n_warp, n_cta;
+    unsigned int n_cls[NUM_CLS];       // work-list lengths per DP class
     unsigned int overflow;             // a pool was exhausted (host grows and re-runs)
     unsigned long long cells;          // sum of DP cells
     unsigned long long nseg;           // DP segments
@@ -29,8 +29,9 @@ struct Pools {
     int32_t *runs;   int64_t runs_cap;     // (a, b, len) triples
     Slot *slots;     int64_t slots_cap;
     int64_t tb_cap;                        // bytes
-    int32_t *list_tiny, *list_warp, *list_cta;   // slot ids per DP class
+    int32_t *lists;                        // NUM_CLS work lists of list_cap slot ids each
     int64_t list_cap;
+    int32_t tiny_bound[NUM_TINY];          // class c holds segments with max(m, n) <= tiny_bound[c]
 };
 
 // ---- stage 1
@@ -50,9 +51,11 @@ cudaError_t launch_stage2(const PairDesc *pairs, int64_t num_pairs, int k, bool 
 
 // ---- stage 3
 // count_dev: device pointer to the number of list entries (no host round trip needed)
-cudaError_t launch_dp_tiny(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
-                           const unsigned int *count_dev, int64_t max_items, DpParams prm,
-                           uint8_t *strbuf, int num_sms, cudaStream_t st);
+// thread-per-segment kernel for one tiny class (segments with max(m, n) <= bound)
+size_t dp_thread_scratch_bytes(int bound, int num_sms);
+cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                             const unsigned int *count_dev, int bound, DpParams prm, uint8_t *strbuf,
+                             uint32_t *tb_scratch, int num_sms, cudaStream_t st);
 // bnd: per-CTA double-buffered boundary rows, int4 per column, bnd_stride columns each
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                 const unsigned int *count_dev, int grid, bool cta_class, DpParams prm,

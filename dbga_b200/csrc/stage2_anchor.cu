@@ -178,8 +178,12 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pa
                     my_cells += (unsigned long long)cells; my_nseg += 1;
                     const long long mag = (long long)max_abs_score * (s.m < s.n ? s.m : s.n) + go_raw + (long long)ge_raw * ((long long)s.m + s.n);
                     if (mag >= MAX_ABS_SCORE) { sm.flag_big = 1; }
-                    else if (s.m <= TINY_MAX_M && s.n <= TINY_MAX_N) cls = CLS_TINY;
-                    else {
+                    else if (s.m <= TINY_MAX && s.n <= TINY_MAX) {
+                        const int mx = s.m > s.n ? s.m : s.n;
+                        cls = NUM_TINY - 1;
+#pragma unroll
+                        for (int c = NUM_TINY - 2; c >= 0; --c) if (mx <= pools.tiny_bound[c]) cls = c;
+                    } else {
                         cls = cells <= WARP_CLASS_MAX_CELLS ? CLS_WARP : CLS_CTA;
                         const long long need = (tb_bytes_wavefront(s.m, s.n, cls == CLS_WARP ? 1 : WF_CTA_WARPS) + 255) & ~255LL;
                         const long long off = (long long)atomicAdd(&ctr->tb_used, (unsigned long long)need);
@@ -192,12 +196,11 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pa
                 s.cls = cls;
             }
             // warp-aggregated work-list append per DP class
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < NUM_CLS; ++c) {
                 const unsigned b = __ballot_sync(0xffffffffu, cls == c);
                 if (b) {
-                    unsigned int *cnt = c == 0 ? &ctr->n_tiny : (c == 1 ? &ctr->n_warp : &ctr->n_cta);
-                    int32_t *list = c == 0 ? pools.list_tiny : (c == 1 ? pools.list_warp : pools.list_cta);
+                    unsigned int *cnt = &ctr->n_cls[c];
+                    int32_t *list = pools.lists + (int64_t)c * pools.list_cap;
                     unsigned int pos = 0;
                     const int leader = __ffs(b) - 1;
                     if (lane == leader) pos = atomicAdd(cnt, (unsigned)__popc(b));

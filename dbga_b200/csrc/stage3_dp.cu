@@ -14,8 +14,8 @@
 // (bits 0-1: predecessor of M, 2-3: of X, 4-5: of Y) with two LOP3s.
 //
 // Kernels:
-//   dp_tiny_kernel      8 lanes per segment (m <= 32, n <= 32), four segments per warp,
-//                       traceback bytes in shared memory;
+//   dp_thread_kernel    one thread per tiny segment (m, n <= 32), previous row in shared
+//                       memory, work lists bucketed by size;
 //   dp_wf_kernel<W>     anti-diagonal wavefront, 8 rows per lane, 32 lanes per warp, W
 //                       warps pipelined through shared-memory boundary rings (a warp per
 //                       segment for W=1, a CTA per long segment for W=8); row strips of
@@ -73,26 +73,39 @@ __device__ __forceinline__ void pick_end(int Mv, int Xv, int Yv, const DpParams 
 }
 
 // ============================================================================ tiny segments
-constexpr int TINY_STEPS = TINY_MAX_N + TINY_G - 1;   // 39
-constexpr int TINY_ROWB = TINY_MAX_M;                 // 32 bytes per step row
-
+// One THREAD per segment (m, n <= 32).  Measured on cfg3 (round 1, profiles/r01_*): with 8
+// lanes per ~10x10 segment the forward pass ran at 6 % lane efficiency and the serial
+// traceback idled 30 of 32 lanes; a thread per segment keeps every lane busy in both phases.
+// Row sweep: the previous row lives in shared memory as two values per column,
+//   T[j] = max(M, X, Y)[i-1][j]   (tagged; the diagonal candidate of row i) and
+//   U[j] = max(M[i-1][j] - go, X[i-1][j] - ge [, Y[i-1][j] - go])   (the X state of row i),
+// laid out [column][thread] (bank = thread: conflict free).  Loops run to the warp-wide
+// maximum of (m, n) and are branch-free: lanes outside their own segment compute and
+// store garbage into their private columns.  Work lists are bucketed by max(m, n) in
+// stage 2, so the bounds inside a warp are similar.  Traceback bytes go to a per-CTA
+// scratch in HBM/L2, four columns per 32-bit word, [word][thread] (coalesced).
 template <bool XY>
-__global__ void __launch_bounds__(256)
-dp_tiny_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
-               const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
-               uint8_t *__restrict__ strbuf) {
-    __shared__ __align__(16) uint8_t s_tb[32][TINY_STEPS + 1][TINY_ROWB];
-    __shared__ uint8_t s_y[32][TINY_MAX_N];
-    const int tid = threadIdx.x, lane = tid & 31, gl = lane & (TINY_G - 1), grp = tid / TINY_G;
+__global__ void __launch_bounds__(TINY_THREADS)
+dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+                 const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, int bound,
+                 DpParams prm, uint8_t *__restrict__ strbuf, uint32_t *__restrict__ tb_scratch) {
+    extern __shared__ int smem_i[];
+    constexpr int TH = TINY_THREADS;
+    const int tid = threadIdx.x;
+    int *Tc = smem_i + tid;                                   // Tc[j * TH], j = 0..bound
+    int *Uc = Tc + (bound + 1) * TH;
+    uint16_t *selc = reinterpret_cast<uint16_t *>(smem_i + 2 * (bound + 1) * TH) + tid;   // selc[(j-1) * TH]
+    const int wpr = (bound + 3) >> 2;                         // traceback words per row
+    uint32_t *tbw = tb_scratch + (size_t)blockIdx.x * ((size_t)bound * wpr * TH) + tid;
     const unsigned int count = *count_dev;
     const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
 
-    for (unsigned int base = blockIdx.x * 32u; base < count; base += gridDim.x * 32u) {
-        const unsigned int item = base + grp;
+    for (unsigned int base = blockIdx.x * TH; base < count; base += gridDim.x * TH) {
+        const unsigned int item = base + tid;
         const bool have = item < count;
         int m = 0, n = 0, sid = 0;
-        const uint8_t *xs = nullptr, *ys = nullptr;
+        const uint8_t *xs = seqs, *ys = seqs;
         int64_t str_off = 0, row_len = 0;
         if (have) {
             sid = list[item];
@@ -104,70 +117,65 @@ dp_tiny_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
             str_off = s.str_off;
             row_len = (pd.off1 - pd.off0) + pd.n1;
         }
-        // stage y codes; per-row score LUTs and column-0 state
-        for (int j = gl; j < n; j += TINY_G) s_y[grp][j] = (uint8_t)base_code(ys[j]);
-        int Mr[TINY_R], Xr[TINY_R], Yr[TINY_R];
-        uint32_t slo[TINY_R], shi[TINY_R];
+        // row 0 and the per-column score selectors
+        Tc[0] = 0 | tagM;
+        Uc[0] = (-go) | tagM;
+        for (int j = 1; j <= n; ++j) {
+            selc[(j - 1) * TH] = (uint16_t)lut_sel(base_code(ys[j - 1]));
+            const int y0 = (-(go + (j - 1) * ge)) | tagY;
+            Tc[j * TH] = y0;
+            int u = __viaddmax_s32(NEG | tagM, -go, (NEG | tagX) - ge);
+            if (XY) u = max(u, y0 - go);
+            Uc[j * TH] = u;
+        }
+        int mmax = m, nmax = n;
 #pragma unroll
-        for (int r = 0; r < TINY_R; ++r) {
-            const int i = gl * TINY_R + r + 1;              // 1-based row
+        for (int o = 16; o > 0; o >>= 1) {
+            mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        }
+        int eM = 0, eX = 0, eY = 0;
+        for (int i = 1; i <= mmax; ++i) {
             const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
-            slo[r] = prm.lut_lo[xc]; shi[r] = prm.lut_hi[xc];
-            Mr[r] = NEG | tagM;
-            Xr[r] = (-(go + (i - 1) * ge)) | tagX;
-            Yr[r] = NEG | tagY;
-        }
-        int dgM = 0, dgX = 0, dgY = 0;
-        // warp-uniform step count
-        int steps = have ? n + TINY_G - 1 : 0;
-        steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, 8));
-        steps = max(steps, __shfl_xor_sync(0xffffffffu, steps, 16));
-        __syncwarp();
-        const int own_gl = (m - 1) / TINY_R, own_r = (m - 1) % TINY_R;
-        int endM = 0, endX = 0, endY = 0;
-        for (int s = 0; s < steps; ++s) {
-            const int j = s - gl + 1;                        // column this lane works on
-            int uM = __shfl_up_sync(0xffffffffu, Mr[TINY_R - 1], 1, TINY_G);
-            int uX = __shfl_up_sync(0xffffffffu, Xr[TINY_R - 1], 1, TINY_G);
-            int uY = __shfl_up_sync(0xffffffffu, Yr[TINY_R - 1], 1, TINY_G);
-            if (gl == 0) {                                   // row 0 boundary, synthesized
-                uM = NEG | tagM; uX = NEG | tagX; uY = (-(go + (j - 1) * ge)) | tagY;
-                dgM = (j == 1 ? 0 : NEG) | tagM; dgX = NEG | tagX;
-                dgY = (j == 1 ? NEG : -(go + (j - 2) * ge)) | tagY;
+            const uint32_t slo = prm.lut_lo[xc], shi = prm.lut_hi[xc];
+            const int xi0 = (-(go + (i - 1) * ge)) | tagX;       // X[i][0]
+            int Ml = NEG | tagM, Yl = NEG | tagY, Xl = xi0;
+            int diag = Tc[0];
+            Tc[0] = xi0;                                         // max(M, X, Y)[i][0]
+            Uc[0] = xi0 - ge;                                    // X candidate of row i+1, column 0
+            uint32_t word = 0;
+            uint32_t *tbrow = tbw + (size_t)(i - 1) * wpr * TH;
+            for (int j = 1; j <= nmax; ++j) {
+                const int Tj = Tc[j * TH], Uj = Uc[j * TH];
+                const uint32_t sel = selc[(j - 1) * TH];
+                const int Mn = strip(diag) + lut_score(slo, shi, sel);
+                const int Xn = strip(Uj) | tagX;
+                int v = __viaddmax_s32(Ml, -go, Yl - ge);
+                if (XY) v = max(v, Xl - go);
+                const int Yn = strip(v) | tagY;
+                uint32_t d = ((uint32_t)diag & 3u) | ((uint32_t)Uj & ~3u);
+                d = (d & 15u) | ((uint32_t)v & ~15u);
+                word |= (d & 0xFFu) << (8 * ((j - 1) & 3));
+                int un = __viaddmax_s32(Mn, -go, Xn - ge);
+                if (XY) un = max(un, Yn - go);
+                Tc[j * TH] = __vimax3_s32(Mn, Xn, Yn);
+                Uc[j * TH] = un;
+                if (i == m && j == n) { eM = Mn; eX = Xn; eY = Yn; }
+                diag = Tj; Ml = Mn; Yl = Yn; Xl = Xn;
+                if ((j & 3) == 0 || j == nmax) { tbrow[((j - 1) >> 2) * TH] = word; word = 0; }
             }
-            if (j >= 1 && j <= n) {
-                const uint32_t sel = lut_sel(s_y[grp][j - 1]);
-                int dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
-                uint32_t word = 0;
-#pragma unroll
-                for (int r = 0; r < TINY_R; ++r) {
-                    const int oM = Mr[r], oX = Xr[r], oY = Yr[r];
-                    const uint32_t d = dp_cell<XY>(Mr[r], Xr[r], Yr[r], dM, dX, dY, aM, aX, aY,
-                                                   lut_score(slo[r], shi[r], sel), go, ge, tagX, tagY);
-                    word |= d << (8 * r);
-                    dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
-                }
-                *reinterpret_cast<uint32_t *>(&s_tb[grp][s][gl * TINY_R]) = word;
-                if (j == n && gl == own_gl) {
-#pragma unroll
-                    for (int r = 0; r < TINY_R; ++r)
-                        if (r == own_r) { endM = Mr[r]; endX = Xr[r]; endY = Yr[r]; }
-                }
-            }
-            dgM = uM; dgX = uX; dgY = uY;
         }
-        __syncwarp();
-        // traceback by the lane that owns row m; rows are written reversed into scratch
-        if (have && gl == own_gl) {
+        // traceback: every lane walks its own segment; rows are written reversed
+        if (have) {
             int st, score;
-            pick_end(endM, endX, endY, prm, st, score);
+            pick_end(eM, eX, eY, prm, st, score);
             int i = m, j = n, len = 0;
             uint8_t *ox = strbuf + str_off, *oy = ox + row_len;
             while (i > 0 || j > 0) {
                 if (i == 0) st = 2;
                 else if (j == 0) st = 1;
                 uint32_t d = 0;
-                if (i > 0 && j > 0) d = s_tb[grp][j - 1 + (i - 1) / TINY_R][i - 1];
+                if (i > 0 && j > 0) d = tbw[((size_t)(i - 1) * wpr + ((j - 1) >> 2)) * TH] >> (8 * ((j - 1) & 3));
                 if (st == 0) {
                     ox[len] = xs[i - 1]; oy[len] = ys[j - 1];
                     st = prio_to_state(d & 3, prm); --i; --j;
@@ -183,19 +191,27 @@ dp_tiny_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
             slots[sid].score = score;
             slots[sid].len = len;
         }
-        __syncwarp();
     }
 }
 
-cudaError_t launch_dp_tiny(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
-                           const unsigned int *count_dev, int64_t max_items, DpParams prm,
-                           uint8_t *strbuf, int num_sms, cudaStream_t st) {
-    if (max_items <= 0) return cudaSuccess;
-    int64_t grid = (max_items + 31) / 32;
-    const int64_t cap = (int64_t)num_sms * 5;     // 256 threads, ~41 KB smem -> 5 CTAs / SM
-    if (grid > cap) grid = cap;
-    if (prm.xy) dp_tiny_kernel<true><<<(int)grid, 256, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
-    else dp_tiny_kernel<false><<<(int)grid, 256, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
+static size_t dp_thread_smem(int bound) { return (size_t)(2 * (bound + 1) * 4 + bound * 2) * TINY_THREADS; }
+static int dp_thread_grid(int num_sms) { return num_sms * 8; }
+size_t dp_thread_scratch_bytes(int bound, int num_sms) {
+    return (size_t)dp_thread_grid(num_sms) * bound * ((bound + 3) / 4) * TINY_THREADS * 4;
+}
+
+cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                             const unsigned int *count_dev, int bound, DpParams prm, uint8_t *strbuf,
+                             uint32_t *tb_scratch, int num_sms, cudaStream_t st) {
+    const size_t smem = dp_thread_smem(bound);
+    const int grid = dp_thread_grid(num_sms);
+    if (prm.xy) {
+        cudaFuncSetAttribute(dp_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dp_thread_kernel<true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, bound, prm, strbuf, tb_scratch);
+    } else {
+        cudaFuncSetAttribute(dp_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dp_thread_kernel<false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, bound, prm, strbuf, tb_scratch);
+    }
     return cudaGetLastError();
 }
 
