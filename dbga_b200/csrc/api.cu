@@ -209,7 +209,8 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             const uint32_t cap = pow2_at_least(keys + keys / 2 + 1, 256);
             const int nmax = std::max(pd.n0, pd.n1);
             const int words = (((nmax + 15) / 16 + 3) + 1) & ~1;
-            const bool fits = cap <= 32768 && stage1_small_smem(key_bytes, cap, words, (int)N1) <= SMEM_LIMIT;
+            const bool fits = cap <= 32768 && N0 < 65000 && N1 < 65000 &&   // 16-bit positions in shared memory
+                              stage12_small_smem(key_bytes, cap, words, (int)N1) <= SMEM_LIMIT;
             if (fits) {
                 int lg = 0;
                 while ((1u << lg) < cap) ++lg;
@@ -231,7 +232,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             }
             c.words = (((nmax + 15) / 16 + 3) + 1) & ~1;
             c.maxq = qmax;
-            if (stage1_small_smem(key_bytes, c.cap, c.words, c.maxq) > SMEM_LIMIT) {
+            if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq) > SMEM_LIMIT) {
                 // mixed extremes inside one class: fall back to the large path for this class
                 ctx->h_list.resize((size_t)c.begin);
                 for (int32_t i : by_cap[lg]) large.push_back(i);
@@ -346,14 +347,19 @@ int reserve_pools(dbga_ctx *ctx) {
     return DBGA_SUCCESS;
 }
 
-// stages 2..assemble; may be re-run after growing pools
-int run_from_stage2(dbga_ctx *ctx) {
+// the whole kernel pipeline on the context stream; re-run by do_fetch after growing pools
+int run_pipeline(dbga_ctx *ctx) {
     cudaStream_t st = ctx->stream;
     const int64_t P = ctx->P;
     const bool seg = ctx->prm.stages == 3;
+    const bool full = ctx->prm.want_graph != 0 && !ctx->no_anchors;
+    const uint8_t *seqs = ctx->d_seqs_run;
     int rc = reserve_pools(ctx);
     if (rc != DBGA_SUCCESS) return rc;
+    ctx->launches = 0;
+    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], st));
     DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(Counters), st));
+    DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_status.p, 0, 4 * std::max<int64_t>(P, 1), st));
     Pools pools;
     pools.runs = (int32_t *)ctx->d_runs.p; pools.runs_cap = ctx->runs_cap;
     pools.slots = (Slot *)ctx->d_slots.p; pools.slots_cap = ctx->slots_cap;
@@ -362,42 +368,69 @@ int run_from_stage2(dbga_ctx *ctx) {
     for (int c = 0; c < NUM_TINY; ++c) pools.tiny_bound[c] = ctx->tiny_bound[c];
     pools.list_cap = ctx->slots_cap;
     Counters *ctr = (Counters *)ctx->d_ctr.p;
+    PairDesc *pairs = (PairDesc *)ctx->d_pairs.p;
+    PairOut *pout = (PairOut *)ctx->d_pout.p;
+    // ---- stages 1+2 fused (shared-memory tables) and stage 1 with global tables
+    if (!ctx->no_anchors) {
+        for (const SmallClass &c : ctx->classes) {
+            DBGA_CUDA_CHECK(launch_stage12_small(seqs, pairs, (int32_t *)ctx->d_list.p + c.begin, c.count, ctx->prm.k, c.cap,
+                                                 c.words, c.maxq, full, seg, pout, pools, ctr, ctx->max_abs_score,
+                                                 ctx->dp.go_raw, ctx->dp.ge_raw, (uint8_t *)ctx->d_nd0.p,
+                                                 (uint8_t *)ctx->d_nd1.p, ctx->num_sms, st));
+            ctx->launches += 1;
+        }
+        for (const LargeWave &w : ctx->waves) {
+            DBGA_CUDA_CHECK(launch_stage1_large(seqs, pairs, (LargeDesc *)ctx->d_large.p + w.begin,
+                                                (int32_t *)ctx->d_list.p + ctx->large_begin + w.begin, w.count, w.max_n,
+                                                ctx->prm.k, full, (uint32_t *)ctx->d_packed.p, ctx->d_table.p, w.table_bytes,
+                                                (int32_t *)ctx->d_status.p, (int32_t *)ctx->d_aof.p, (uint8_t *)ctx->d_nd0.p,
+                                                (uint8_t *)ctx->d_nd1.p, st, &ctx->launches));
+        }
+    }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[2], st));
-    DBGA_CUDA_CHECK(launch_stage2((PairDesc *)ctx->d_pairs.p, P, ctx->no_anchors ? 1 : ctx->prm.k, ctx->no_anchors, seg,
-                                  (int32_t *)ctx->d_aof.p, (int32_t *)ctx->d_status.p, (PairOut *)ctx->d_pout.p, pools, ctr,
-                                  ctx->stage2_threads, ctx->num_sms, ctx->max_abs_score, ctx->dp.go_raw, ctx->dp.ge_raw, st));
-    ctx->launches += 1;
+    // ---- generic stage 2: pairs that went through the global-table path, or every pair
+    //      when there is no anchoring at all (dbga_global_align_batch)
+    {
+        const int64_t n_large = (int64_t)ctx->h_list.size() - ctx->large_begin;
+        const int64_t cnt = ctx->no_anchors ? P : n_large;
+        const int32_t *lst = ctx->no_anchors ? nullptr : (int32_t *)ctx->d_list.p + ctx->large_begin;
+        if (cnt > 0) {
+            DBGA_CUDA_CHECK(launch_stage2(pairs, lst, cnt, ctx->no_anchors ? 1 : ctx->prm.k, ctx->no_anchors, seg,
+                                          (int32_t *)ctx->d_aof.p, (int32_t *)ctx->d_status.p, pout, pools, ctr,
+                                          ctx->stage2_threads, ctx->num_sms, ctx->max_abs_score, ctx->dp.go_raw,
+                                          ctx->dp.ge_raw, st));
+            ctx->launches += 1;
+        }
+    }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));
     if (seg) {
-        const uint8_t *seqs = ctx->d_seqs_run;
         for (int c = 0; c < NUM_TINY; ++c) {
             if (c > 0 && ctx->tiny_bound[c] == ctx->tiny_bound[c - 1]) continue;   // empty class
-            DBGA_CUDA_CHECK(launch_dp_thread(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots,
-                                             pools.lists + (int64_t)c * pools.list_cap, &ctr->n_cls[c], ctx->tiny_bound[c],
-                                             ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
+            DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists + (int64_t)c * pools.list_cap,
+                                             &ctr->n_cls[c], ctx->tiny_bound[c], ctx->dp, (uint8_t *)ctx->d_str.p,
+                                             (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
             ctx->launches += 1;
         }
         if (ctx->grid_warp) {
-            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.lists + (int64_t)CLS_WARP * pools.list_cap, &ctr->n_cls[CLS_WARP],
-                                                ctx->grid_warp, false, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
-                                                (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
+            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_WARP * pools.list_cap,
+                                                &ctr->n_cls[CLS_WARP], ctx->grid_warp, false, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
             ctx->launches += 1;
         }
         if (ctx->grid_cta) {
-            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, (PairDesc *)ctx->d_pairs.p, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap, &ctr->n_cls[CLS_CTA],
-                                                ctx->grid_cta, true, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
-                                                (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
+            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
+                                                &ctr->n_cls[CLS_CTA], ctx->grid_cta, true, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
             ctx->launches += 1;
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[4], st));
-    DBGA_CUDA_CHECK(launch_assemble(ctx->d_seqs_run, (PairDesc *)ctx->d_pairs.p, P, (PairOut *)ctx->d_pout.p,
-                                    (int32_t *)ctx->d_status_out.p, (int32_t *)ctx->d_runs.p, (Slot *)ctx->d_slots.p,
-                                    (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p, (int64_t *)ctx->d_aln_off.p,
-                                    (int64_t *)ctx->d_run_cnt.p, (int64_t *)ctx->d_run_off.p, (int64_t *)ctx->d_scan_tmp.p,
-                                    (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p, (int32_t *)ctx->d_runs_out.p,
-                                    (int64_t *)ctx->d_score.p, (int64_t *)ctx->d_cells.p, (int32_t *)ctx->d_nseg.p,
-                                    (int64_t *)ctx->d_nanch.p, ctr, ctx->num_sms, st, &ctx->launches));
+    DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, (int32_t *)ctx->d_status_out.p, (int32_t *)ctx->d_runs.p,
+                                    (Slot *)ctx->d_slots.p, (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p,
+                                    (int64_t *)ctx->d_aln_off.p, (int64_t *)ctx->d_run_cnt.p, (int64_t *)ctx->d_run_off.p,
+                                    (int64_t *)ctx->d_scan_tmp.p, (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p,
+                                    (int32_t *)ctx->d_runs_out.p, (int64_t *)ctx->d_score.p, (int64_t *)ctx->d_cells.p,
+                                    (int32_t *)ctx->d_nseg.p, (int64_t *)ctx->d_nanch.p, ctr, ctx->num_sms, st, &ctx->launches));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
     return DBGA_SUCCESS;
 }
@@ -405,29 +438,8 @@ int run_from_stage2(dbga_ctx *ctx) {
 int do_run(dbga_ctx *ctx, const uint8_t *d_seqs) {
     if (!ctx->planned) return fail(ctx, DBGA_ERR_ARG, "dbga_plan_run without a plan");
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
     ctx->d_seqs_run = d_seqs;
-    ctx->launches = 0;
-    const bool full = ctx->prm.want_graph != 0 && !ctx->no_anchors;
-    DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], st));
-    DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_status.p, 0, 4 * std::max<int64_t>(ctx->P, 1), st));
-    if (!ctx->no_anchors) {
-        for (const SmallClass &c : ctx->classes) {
-            DBGA_CUDA_CHECK(launch_stage1_small(d_seqs, (PairDesc *)ctx->d_pairs.p, (int32_t *)ctx->d_list.p + c.begin, c.count,
-                                                ctx->prm.k, c.cap, c.words, c.maxq, full, (int32_t *)ctx->d_status.p,
-                                                (int32_t *)ctx->d_aof.p, (uint8_t *)ctx->d_nd0.p, (uint8_t *)ctx->d_nd1.p,
-                                                ctx->num_sms, st));
-            ctx->launches += 1;
-        }
-        for (const LargeWave &w : ctx->waves) {
-            DBGA_CUDA_CHECK(launch_stage1_large(d_seqs, (PairDesc *)ctx->d_pairs.p, (LargeDesc *)ctx->d_large.p + w.begin,
-                                                (int32_t *)ctx->d_list.p + ctx->large_begin + w.begin, w.count, w.max_n,
-                                                ctx->prm.k, full, (uint32_t *)ctx->d_packed.p, ctx->d_table.p, w.table_bytes,
-                                                (int32_t *)ctx->d_status.p, (int32_t *)ctx->d_aof.p, (uint8_t *)ctx->d_nd0.p,
-                                                (uint8_t *)ctx->d_nd1.p, st, &ctx->launches));
-        }
-    }
-    int rc = run_from_stage2(ctx);
+    int rc = run_pipeline(ctx);
     if (rc != DBGA_SUCCESS) return rc;
     ctx->ran = true;
     return DBGA_SUCCESS;
@@ -440,7 +452,7 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     const int64_t P = ctx->P;
     HRESERVE(h_ctr, sizeof(Counters));
     Counters *hc = (Counters *)ctx->h_ctr.p;
-    // pool overflow: grow to the measured need and re-run stages 2.. (stage 1 output is kept)
+    // pool overflow: grow to the measured need and re-run the pipeline
     for (int attempt = 0; attempt < 4; ++attempt) {
         DBGA_CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -453,7 +465,7 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
             grow = true;
         }
         if (!grow) break;
-        int rc = run_from_stage2(ctx);
+        int rc = run_pipeline(ctx);
         if (rc != DBGA_SUCCESS) return rc;
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[6], st));

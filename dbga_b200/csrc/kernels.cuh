@@ -34,18 +34,21 @@ struct Pools {
     int32_t tiny_bound[NUM_TINY];          // class c holds segments with max(m, n) <= tiny_bound[c]
 };
 
-// ---- stage 1
-size_t stage1_small_smem(int key_bytes, uint32_t cap, int words, int maxq);
-cudaError_t launch_stage1_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count,
-                                int k, uint32_t cap, int words, int maxq, bool full, int32_t *status,
-                                int32_t *aof, uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st);
+// ---- stages 1+2 fused (pairs whose table fits in shared memory)
+size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq);
+cudaError_t launch_stage12_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
+                                 uint32_t cap, int words, int maxq, bool full, bool want_segments, PairOut *pout,
+                                 Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,
+                                 uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st);
+// ---- stage 1, global-memory table (large pairs)
 cudaError_t launch_stage1_large(const uint8_t *seqs, const PairDesc *pairs, const LargeDesc *ld,
                                 const int32_t *list, int count, int max_n, int k, bool full,
                                 uint32_t *packed, void *table, size_t table_bytes, int32_t *status,
                                 int32_t *aof, uint8_t *nd0, uint8_t *nd1, cudaStream_t st, int *launches);
 
 // ---- stage 2
-cudaError_t launch_stage2(const PairDesc *pairs, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
+// pair_list == nullptr: all pairs 0..num_pairs-1
+cudaError_t launch_stage2(const PairDesc *pairs, const int32_t *pair_list, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
                           const int32_t *aof, int32_t *status, PairOut *out, Pools pools, Counters *ctr,
                           int threads, int num_sms, int max_abs_score, int go_raw, int ge_raw, cudaStream_t st);
 

@@ -1,0 +1,422 @@
+// Stages 1 + 2 fused for pairs whose k-mer table fits in shared memory: ONE CTA per pair,
+// nothing but the sequences is read from HBM and nothing but runs / slots is written.
+//
+// Stage 1 (reference get_kmers / duplicate_kmers, src/dbga/utils.py:108-154, and the dict walk
+// of debruijn_pairwise.py:78-204):
+//   * 128-bit loads, 4 bases at a time turned into 2-bit codes with byte-SIMD integer ops
+//     (validation included), packed 16 bases per word in shared memory;
+//   * open-addressing table in shared memory, bucketized: one 128-bit LDS fetches a whole
+//     bucket (4 x 32-bit or 2 x 64-bit keys), so almost every probe finishes in one
+//     iteration and the warp does not diverge; a slot is claimed with one atomicCAS, all
+//     occurrence bookkeeping is plain stores split over barriers:
+//         A   seq1: claim/find; claimer stores pos0, later finders store dup0 = 1
+//         B1  seq2: find (graph mode: claim); last1[slot] = q (racy store, one q survives)
+//         B15 every q that did not survive marks dup1[slot] = 1
+//         B2  q is an anchor iff pos0 valid and !dup0 and !dup1  ->  a = pos0[slot]
+// Stage 2 (merge_node_idx order, extract_bubble :277-300, debruijn_merge_correctness
+// utils.py:266-291): run starts/ends are rare (a few per hundred positions), so they are
+// appended unordered with shared-memory atomics and then rank-sorted by seq-2 position
+// (bitonic sort beyond 1024 runs); adjacent-difference cycle check; slots (slots.cuh).
+#include "slots.cuh"
+
+namespace dbga {
+
+static constexpr uint16_t NONE16 = 0xFFFFu;
+static constexpr int RANK_SORT_MAX = 1024;
+
+__device__ __forceinline__ uint4 lds_v4(const void *p) {
+    uint4 v;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
+// ---- 4 ASCII bases (one 32-bit word) -> 8 bits of 2-bit codes; sets bad on non-ACGT
+__device__ __forceinline__ uint32_t pack4(uint32_t w, bool &bad) {
+    const uint32_t codes = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+    const uint32_t t = codes | (codes >> 4);
+    const uint32_t sel = __byte_perm(t, 0u, 0x4420u);            // nibble i = code of byte i
+    const uint32_t expect = __byte_perm(0x54474341u, 0u, sel);  // "ACGT"[code]
+    bad |= (expect != w);
+    return (codes * 0x01041040u) >> 24;                          // c0 | c1<<2 | c2<<4 | c3<<6
+}
+
+__device__ __forceinline__ uint32_t pack16_fast(const uint8_t *src, int64_t valid, bool aligned, bool &bad) {
+    if (valid >= 16 && aligned) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
+        return pack4(v.x, bad) | (pack4(v.y, bad) << 8) | (pack4(v.z, bad) << 16) | (pack4(v.w, bad) << 24);
+    }
+    uint32_t w = 0;
+    for (int i = 0; i < 16 && i < valid; ++i) {
+        const uint8_t c = src[i];
+        bad |= !is_acgt(c);
+        w |= (uint32_t)base_code(c) << (2 * i);
+    }
+    return w;
+}
+
+template <typename KeyT> struct Bucket;
+template <> struct Bucket<uint32_t> {
+    static constexpr int W = 4;
+    static constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+    static __device__ __forceinline__ uint32_t hash(uint32_t k, int shift) { return (k * 0x9E3779B1u) >> shift; }
+    static __device__ __forceinline__ uint32_t kmer(const uint32_t *pk, int p, uint32_t kmask) {
+        const int w = p >> 4, sh = (p & 15) * 2;
+        return __funnelshift_r(pk[w], pk[w + 1], sh) & kmask;
+    }
+    // position of key / of the first EMPTY in the bucket (-1: none)
+    static __device__ __forceinline__ void scan(const uint32_t *base, uint32_t key, int &hit, int &emp) {
+        const uint4 kk = lds_v4(base);
+        hit = kk.x == key ? 0 : (kk.y == key ? 1 : (kk.z == key ? 2 : (kk.w == key ? 3 : -1)));
+        emp = kk.x == EMPTY ? 0 : (kk.y == EMPTY ? 1 : (kk.z == EMPTY ? 2 : (kk.w == EMPTY ? 3 : -1)));
+    }
+    static __device__ __forceinline__ uint32_t cas(uint32_t *a, uint32_t v) { return atomicCAS(a, EMPTY, v); }
+};
+template <> struct Bucket<uint64_t> {
+    static constexpr int W = 2;
+    static constexpr uint64_t EMPTY = ~0ULL;
+    static __device__ __forceinline__ uint32_t hash(uint64_t k, int shift) {
+        return (uint32_t)((k * 0x9E3779B97F4A7C15ULL) >> 32) >> shift;
+    }
+    static __device__ __forceinline__ uint64_t kmer(const uint32_t *pk, int p, uint64_t kmask) {
+        const int w = p >> 4, sh = (p & 15) * 2;
+        const uint32_t a = pk[w], b = pk[w + 1], c = pk[w + 2];
+        return (((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh)) & kmask;
+    }
+    static __device__ __forceinline__ void scan(const uint64_t *base, uint64_t key, int &hit, int &emp) {
+        const uint4 kk = lds_v4(base);
+        const uint64_t k0 = ((uint64_t)kk.y << 32) | kk.x, k1 = ((uint64_t)kk.w << 32) | kk.z;
+        hit = k0 == key ? 0 : (k1 == key ? 1 : -1);
+        emp = k0 == EMPTY ? 0 : (k1 == EMPTY ? 1 : -1);
+    }
+    static __device__ __forceinline__ uint64_t cas(uint64_t *a, uint64_t v) {
+        return (uint64_t)atomicCAS(reinterpret_cast<unsigned long long *>(a), ~0ULL, (unsigned long long)v);
+    }
+};
+
+// find-or-claim; `claimed` tells whether this call inserted the key
+template <typename KeyT>
+__device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb_mask, int shift, KeyT key, bool &claimed) {
+    using B = Bucket<KeyT>;
+    uint32_t b = B::hash(key, shift);
+    for (;;) {
+        KeyT *base = keys + b * B::W;
+        int hit, emp;
+        B::scan(base, key, hit, emp);
+        if (hit >= 0) { claimed = false; return b * B::W + hit; }
+        if (emp >= 0) {
+            const KeyT old = B::cas(base + emp, key);
+            if (old == B::EMPTY) { claimed = true; return b * B::W + emp; }
+            if (old == key) { claimed = false; return b * B::W + emp; }
+            continue;                       // somebody else took the slot: look at the bucket again
+        }
+        b = (b + 1) & nb_mask;
+    }
+}
+template <typename KeyT>
+__device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb_mask, int shift, KeyT key) {
+    using B = Bucket<KeyT>;
+    uint32_t b = B::hash(key, shift);
+    for (;;) {
+        int hit, emp;
+        B::scan(keys + b * B::W, key, hit, emp);
+        if (hit >= 0) return b * B::W + hit;
+        if (emp >= 0) return 0xFFFFFFFFu;
+        b = (b + 1) & nb_mask;
+    }
+}
+
+struct S12Shared {
+    int bad, nS, nE, nA, cycle, big;
+    long long bcast[2];
+    long long red[8];
+};
+
+template <typename KeyT, bool FULL>
+__global__ void __launch_bounds__(256)
+stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs,
+                     const int32_t *__restrict__ pair_list, int count, int k, uint32_t cap, int lognb,
+                     int words, int maxq, int want_segments, PairOut *__restrict__ pout, Pools pools,
+                     Counters *__restrict__ ctr, SlotCfg cfg, uint8_t *__restrict__ nd0, uint8_t *__restrict__ nd1) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    using B = Bucket<KeyT>;
+    uint32_t *pk0 = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *pk1 = pk0 + words;
+    KeyT *keys = reinterpret_cast<KeyT *>(pk1 + words);
+    uint16_t *pos0 = reinterpret_cast<uint16_t *>(keys + cap);
+    uint16_t *last1 = pos0 + cap;
+    uint8_t *dup0 = reinterpret_cast<uint8_t *>(last1 + cap);
+    uint8_t *dup1 = dup0 + cap;
+    uint16_t *memo = reinterpret_cast<uint16_t *>(dup1 + cap);      // later: aof in shared memory
+    // aliases valid once the table is dead (after phase B2)
+    uint32_t *ska = reinterpret_cast<uint32_t *>(keys);             // unordered run starts (b<<16 | a), cap entries
+    uint16_t *ske = pos0;                                           // unordered run ends (b), cap entries
+    uint32_t *srt_s = reinterpret_cast<uint32_t *>(last1);          // rank-sorted starts (4*cap bytes: last1+dup0+dup1)
+    uint16_t *srt_e = memo;                                         // rank-sorted ends
+    __shared__ S12Shared sh;
+
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t nb_mask = (cap / B::W) - 1;
+    const int shift = 32 - lognb;
+    const KeyT kmask = (2 * k >= (int)(8 * sizeof(KeyT))) ? ~(KeyT)0 : (((KeyT)1 << (2 * k)) - 1);
+    unsigned long long my_cells = 0, my_nseg = 0;
+
+    for (int it = blockIdx.x; it < count; it += gridDim.x) {
+        const int pair = pair_list[it];
+        const PairDesc pd = pairs[pair];
+        PairOut po;
+        po.status = DBGA_OK; po.n_runs = 0; po.run_base = 0; po.slot_base = 0; po.n_slots = 0; po.pad = 0;
+        po.n_anchors = 0; po.aln_len = 0;
+        if (k > pd.n0 || k > pd.n1) {                                  // utils.py:129-130
+            if (tid == 0) { po.status = DBGA_K_INVALID; pout[pair] = po; }
+            continue;
+        }
+        __syncthreads();            // previous pair's shared state is no longer in use
+        if (tid == 0) { sh.bad = 0; sh.nS = 0; sh.nE = 0; sh.nA = 0; sh.cycle = 0; sh.big = 0; }
+        // ---- pack + table init
+        bool bad = false;
+        {
+            const uint8_t *s0 = seqs + pd.off0, *s1 = seqs + pd.off1;
+            const bool al0 = (reinterpret_cast<uintptr_t>(s0) & 15) == 0;
+            const bool al1 = (reinterpret_cast<uintptr_t>(s1) & 15) == 0;
+            for (int w = tid; w < words; w += T) {
+                const int64_t r0 = (int64_t)pd.n0 - 16 * w, r1 = (int64_t)pd.n1 - 16 * w;
+                pk0[w] = r0 > 0 ? pack16_fast(s0 + 16 * w, r0, al0, bad) : 0u;
+                pk1[w] = r1 > 0 ? pack16_fast(s1 + 16 * w, r1, al1, bad) : 0u;
+            }
+            uint4 *t4 = reinterpret_cast<uint4 *>(keys);                // keys + pos0 + last1 = all ones
+            const int n_ff = (int)((cap * (sizeof(KeyT) + 4)) / 16), n_00 = (int)(cap * 2 / 16);
+            for (int i = tid; i < n_ff; i += T) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+            uint4 *z4 = reinterpret_cast<uint4 *>(dup0);                // dup0 + dup1 = 0
+            for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        if (bad) sh.bad = 1;
+        __syncthreads();
+        if (sh.bad) {
+            if (tid == 0) { po.status = DBGA_BAD_CHAR; pout[pair] = po; }
+            continue;
+        }
+        const int N0 = pd.n0 - k + 1, N1 = pd.n1 - k + 1;
+        // ---- A: seq1 k-mers
+        for (int p = tid; p < N0; p += T) {
+            bool claimed;
+            const uint32_t h = bkt_insert<KeyT>(keys, nb_mask, shift, B::kmer(pk0, p, kmask), claimed);
+            if (claimed) pos0[h] = (uint16_t)p;
+            else dup0[h] = 1;
+        }
+        __syncthreads();
+        // ---- B1: seq2 k-mers
+        for (int q = tid; q < N1; q += T) {
+            const KeyT key = B::kmer(pk1, q, kmask);
+            uint32_t h;
+            if (FULL) {
+                bool claimed;
+                h = bkt_insert<KeyT>(keys, nb_mask, shift, key, claimed);
+            } else {
+                h = bkt_find<KeyT>(keys, nb_mask, shift, key);
+                if (h != 0xFFFFFFFFu && dup0[h]) h = 0xFFFFFFFFu;
+            }
+            if (h != 0xFFFFFFFFu) last1[h] = (uint16_t)q;
+            memo[q] = h != 0xFFFFFFFFu ? (uint16_t)h : NONE16;
+        }
+        __syncthreads();
+        // ---- B1.5: whoever did not survive in last1 proves a duplicate in seq2
+        for (int q = tid; q < N1; q += T) {
+            const uint16_t h = memo[q];
+            if (h != NONE16 && last1[h] != (uint16_t)q) dup1[h] = 1;
+        }
+        __syncthreads();
+        // ---- B2: anchors; memo[q] becomes aof[q] (position in seq1 or NONE16)
+        for (int q = tid; q < N1; q += T) {
+            const uint16_t h = memo[q];
+            uint16_t a = NONE16;
+            if (h != NONE16) {
+                const bool d = dup0[h] | dup1[h];
+                if (!d) a = pos0[h];                 // NONE16 when the k-mer is private to seq2 (graph mode)
+                if (FULL) nd1[pd.q_base + q] = !d;
+            }
+            memo[q] = a;
+        }
+        if (FULL) {
+            for (int p = tid; p < N0; p += T) {
+                const uint32_t h = bkt_find<KeyT>(keys, nb_mask, shift, B::kmer(pk0, p, kmask));
+                nd0[pd.p_base + p] = !(dup0[h] | dup1[h]);
+            }
+        }
+        __syncthreads();                              // table dead from here on
+        // ---- stage 2: run starts / ends (rare) appended unordered
+        int cA = 0;
+        for (int q = tid; q < N1; q += T) {
+            const uint16_t a = memo[q];
+            if (a != NONE16) {
+                ++cA;
+                const uint16_t pv = q > 0 ? memo[q - 1] : NONE16;
+                const uint16_t nx = q + 1 < N1 ? memo[q + 1] : NONE16;
+                if (!(pv != NONE16 && (uint16_t)(pv + 1) == a)) ska[atomicAdd(&sh.nS, 1)] = ((uint32_t)q << 16) | a;
+                if (!(nx != NONE16 && nx == (uint16_t)(a + 1))) ske[atomicAdd(&sh.nE, 1)] = (uint16_t)q;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cA += __shfl_xor_sync(0xffffffffu, cA, o);
+        if (lane == 0 && cA) atomicAdd(&sh.nA, cA);
+        __syncthreads();
+        const int R = sh.nS;
+        const uint32_t *S = srt_s;
+        const uint16_t *E = srt_e;
+        if (R <= RANK_SORT_MAX) {
+            for (int t = tid; t < R; t += T) {
+                const uint32_t ks = ska[t];
+                const uint16_t ke = ske[t];
+                int rs = 0, re = 0;
+                for (int u = 0; u < R; ++u) { rs += ska[u] < ks; re += ske[u] < ke; }
+                srt_s[rs] = ks; srt_e[re] = ke;
+            }
+        } else {                                       // in-place bitonic sort, padded to a power of two
+            int n2 = 1;
+            while (n2 < R) n2 <<= 1;
+            for (int i = R + tid; i < n2; i += T) { ska[i] = 0xFFFFFFFFu; ske[i] = 0xFFFFu; }
+            __syncthreads();
+            for (int k2 = 2; k2 <= n2; k2 <<= 1) {
+                for (int j = k2 >> 1; j > 0; j >>= 1) {
+                    for (int i = tid; i < n2; i += T) {
+                        const int x = i ^ j;
+                        if (x > i) {
+                            const bool asc = (i & k2) == 0;
+                            const uint32_t a0 = ska[i], a1 = ska[x];
+                            if ((a0 > a1) == asc) { ska[i] = a1; ska[x] = a0; }
+                            const uint16_t e0 = ske[i], e1 = ske[x];
+                            if ((e0 > e1) == asc) { ske[i] = e1; ske[x] = e0; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            S = ska; E = ske;
+        }
+        __syncthreads();
+        auto run = [&](int r, int &a, int &b, int &len) {
+            const uint32_t key = S[r];
+            a = (int)(key & 0xFFFFu); b = (int)(key >> 16); len = (int)E[r] - b + 1;
+        };
+        // ---- colinearity (utils.py:266-291) and the runs pool
+        for (int r = tid + 1; r < R; r += T) {
+            int a0, b0, l0, a1, b1, l1;
+            run(r - 1, a0, b0, l0); run(r, a1, b1, l1);
+            if (a1 <= a0 + l0 - 1) sh.cycle = 1;
+        }
+        if (tid == 0) {
+            long long base = 0;
+            if (R > 0) {
+                base = (long long)atomicAdd(&ctr->runs_used, (unsigned long long)R);
+                if (base + R > pools.runs_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
+            }
+            sh.bcast[0] = base;
+        }
+        __syncthreads();
+        const long long run_base = sh.bcast[0];
+        if (run_base < 0) {
+            if (tid == 0) { po.status = DBGA_TOO_LARGE; pout[pair] = po; }
+            continue;
+        }
+        {
+            int32_t *gr = pools.runs + 3 * run_base;
+            for (int r = tid; r < R; r += T) {
+                int a, b, len;
+                run(r, a, b, len);
+                gr[3 * r] = a; gr[3 * r + 1] = b; gr[3 * r + 2] = len;
+            }
+        }
+        po.n_runs = R; po.run_base = run_base; po.n_anchors = sh.nA;
+        if (sh.cycle) {
+            if (tid == 0) { po.status = DBGA_CYCLE; pout[pair] = po; }
+            continue;
+        }
+        if (!want_segments) {
+            if (tid == 0) pout[pair] = po;
+            continue;
+        }
+        const int n_slots = R == 0 ? 1 : R + 1;
+        if (tid == 0) {
+            long long base = (long long)atomicAdd(&ctr->slots_used, (unsigned long long)n_slots);
+            if (base + n_slots > pools.slots_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
+            sh.bcast[1] = base;
+        }
+        __syncthreads();
+        const long long slot_base = sh.bcast[1];
+        if (slot_base < 0) {
+            if (tid == 0) { po.status = DBGA_TOO_LARGE; pout[pair] = po; }
+            continue;
+        }
+        build_slots(pair, pd, R, run, slot_base, pools, ctr, cfg, &sh.big, my_cells, my_nseg);
+        __syncthreads();
+        po.slot_base = slot_base; po.n_slots = n_slots;
+        if (tid == 0) {
+            if (sh.big) po.status = DBGA_TOO_LARGE;
+            pout[pair] = po;
+        }
+    }
+    // per-CTA totals of DP work
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_cells += __shfl_xor_sync(0xffffffffu, my_cells, o);
+        my_nseg += __shfl_xor_sync(0xffffffffu, my_nseg, o);
+    }
+    if (lane == 0) { sh.red[wid] = (long long)my_cells; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long c = 0;
+        for (int w = 0; w < (T >> 5); ++w) c += (unsigned long long)sh.red[w];
+        if (c) atomicAdd(&ctr->cells, c);
+    }
+    __syncthreads();
+    if (lane == 0) { sh.red[wid] = (long long)my_nseg; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long c = 0;
+        for (int w = 0; w < (T >> 5); ++w) c += (unsigned long long)sh.red[w];
+        if (c) atomicAdd(&ctr->nseg, c);
+    }
+}
+
+size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq) {
+    return (size_t)words * 8 + (size_t)cap * (key_bytes + 6) + (size_t)((maxq + 7) / 8 * 8) * 2 + 16;
+}
+
+template <typename KeyT, bool FULL>
+static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
+                            uint32_t cap, int words, int maxq, bool want_segments, PairOut *pout, Pools pools,
+                            Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st) {
+    const size_t smem = stage12_small_smem(sizeof(KeyT), cap, words, maxq);
+    auto kern = stage12_small_kernel<KeyT, FULL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    int grid = num_sms * occ;
+    if (grid > count) grid = count;
+    int lognb = 0;
+    while ((1u << lognb) < cap / Bucket<KeyT>::W) ++lognb;
+    kern<<<grid, 256, smem, st>>>(seqs, pairs, list, count, k, cap, lognb, words, maxq, want_segments ? 1 : 0, pout,
+                                  pools, ctr, cfg, nd0, nd1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage12_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
+                                 uint32_t cap, int words, int maxq, bool full, bool want_segments, PairOut *pout,
+                                 Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,
+                                 uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    const SlotCfg cfg{max_abs_score, go_raw, ge_raw};
+    if (k <= 15) {
+        return full ? launch_t<uint32_t, true>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st)
+                    : launch_t<uint32_t, false>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st);
+    }
+    return full ? launch_t<uint64_t, true>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st)
+                : launch_t<uint64_t, false>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st);
+}
+
+}  // namespace dbga

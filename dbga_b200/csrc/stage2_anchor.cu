@@ -10,7 +10,7 @@
 //   * colinearity ("cycle") check by adjacent difference over the compacted runs;
 //   * the segment slots [first, mid_1 .. mid_{R-1}, tail] with their DP class, scratch
 //     placement and work-list entries.
-#include "kernels.cuh"
+#include "slots.cuh"
 
 namespace dbga {
 
@@ -34,7 +34,7 @@ __device__ __forceinline__ long long block_sum(long long v, ScanSmem &sm) {
     return t;
 }
 
-__global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pairs, int k, int no_anchors,
+__global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t *__restrict__ pair_list, int64_t num_pairs, int k, int no_anchors,
                               int want_segments, const int32_t *__restrict__ aof, const int32_t *__restrict__ status,
                               PairOut *__restrict__ pout, Pools pools, Counters *__restrict__ ctr,
                               int max_abs_score, int go_raw, int ge_raw) {
@@ -42,7 +42,8 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pa
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
     unsigned long long my_cells = 0, my_nseg = 0;
 
-    for (int64_t pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+    for (int64_t it = blockIdx.x; it < num_pairs; it += gridDim.x) {
+        const int64_t pair = pair_list ? pair_list[it] : it;
         const PairDesc pd = pairs[pair];
         int st = status[pair];
         PairOut po;
@@ -151,72 +152,17 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pa
             __syncthreads();
             continue;
         }
-        const int64_t str_base = 2 * pd.off0;
-        const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;   // >= n0 + n1 (alignment padding allowed)
-        for (int base = 0; base < n_slots; base += T) {
-            const int t = base + tid;
-            int cls = CLS_NONE;
-            Slot s;
-            if (t < n_slots) {
-                int x0, x1, y0, y1;
-                if (R == 0) { x0 = 0; x1 = pd.n0; y0 = 0; y1 = pd.n1; }
-                else {
-                    if (t == 0) { x0 = 0; y0 = 0; }
-                    else {
-                        const int len = runs[3 * (int64_t)(t - 1) + 2];
-                        x0 = runs[3 * (int64_t)(t - 1)] + len - 1;
-                        y0 = runs[3 * (int64_t)(t - 1) + 1] + len - 1;
-                    }
-                    if (t == R) { x1 = pd.n0; y1 = pd.n1; }
-                    else { x1 = runs[3 * (int64_t)t]; y1 = runs[3 * (int64_t)t + 1]; }
-                }
-                s.x0 = x0; s.m = x1 - x0; s.y0 = y0; s.n = y1 - y0;
-                s.score = 0; s.len = 0; s.pair = (int32_t)pair; s.tb_off = 0;
-                s.str_off = str_base + x0 + y0;     // row x; row y at + row_len
-                if (s.m > 0 && s.n > 0) {
-                    const long long cells = (long long)s.m * s.n;
-                    my_cells += (unsigned long long)cells; my_nseg += 1;
-                    const long long mag = (long long)max_abs_score * (s.m < s.n ? s.m : s.n) + go_raw + (long long)ge_raw * ((long long)s.m + s.n);
-                    if (mag >= MAX_ABS_SCORE) { sm.flag_big = 1; }
-                    else if (s.m <= TINY_MAX && s.n <= TINY_MAX) {
-                        const int mx = s.m > s.n ? s.m : s.n;
-                        cls = NUM_TINY - 1;
-#pragma unroll
-                        for (int c = NUM_TINY - 2; c >= 0; --c) if (mx <= pools.tiny_bound[c]) cls = c;
-                    } else {
-                        cls = cells <= WARP_CLASS_MAX_CELLS ? CLS_WARP : CLS_CTA;
-                        const long long need = (tb_bytes_wavefront(s.m, s.n, cls == CLS_WARP ? 1 : WF_CTA_WARPS) + 255) & ~255LL;
-                        const long long off = (long long)atomicAdd(&ctr->tb_used, (unsigned long long)need);
-                        if (off + need > pools.tb_cap) { sm.flag_big = 1; cls = CLS_NONE; }
-                        s.tb_off = off;
-                    }
-                } else {
-                    s.len = s.m + s.n;      // utils.py:187-192: one side empty -> all-gap row
-                }
-                s.cls = cls;
-            }
-            // warp-aggregated work-list append per DP class
-            for (int c = 0; c < NUM_CLS; ++c) {
-                const unsigned b = __ballot_sync(0xffffffffu, cls == c);
-                if (b) {
-                    unsigned int *cnt = &ctr->n_cls[c];
-                    int32_t *list = pools.lists + (int64_t)c * pools.list_cap;
-                    unsigned int pos = 0;
-                    const int leader = __ffs(b) - 1;
-                    if (lane == leader) pos = atomicAdd(cnt, (unsigned)__popc(b));
-                    pos = __shfl_sync(0xffffffffu, pos, leader);
-                    if (cls == c) list[pos + __popc(b & ((1u << lane) - 1u))] = (int32_t)(slot_base + t);
-                }
-            }
-            if (t < n_slots) pools.slots[slot_base + t] = s;
-        }
+        build_slots(pair, pd, R,
+                    [&](int r, int &a, int &b, int &len) {
+                        a = runs[3 * (int64_t)r]; b = runs[3 * (int64_t)r + 1]; len = runs[3 * (int64_t)r + 2];
+                    },
+                    slot_base, pools, ctr, SlotCfg{max_abs_score, go_raw, ge_raw}, &sm.flag_big, my_cells, my_nseg);
         __syncthreads();
         po.slot_base = slot_base; po.n_slots = n_slots;
         if (tid == 0) {
             if (sm.flag_big) po.status = DBGA_TOO_LARGE;
             pout[pair] = po;
         }
-        (void)row_len;
         __syncthreads();
     }
     // per-CTA totals
@@ -225,13 +171,13 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, int64_t num_pa
     if (tid == 0 && (c | s)) { atomicAdd(&ctr->cells, c); atomicAdd(&ctr->nseg, s); }
 }
 
-cudaError_t launch_stage2(const PairDesc *pairs, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
+cudaError_t launch_stage2(const PairDesc *pairs, const int32_t *pair_list, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
                           const int32_t *aof, int32_t *status, PairOut *out, Pools pools, Counters *ctr,
                           int threads, int num_sms, int max_abs_score, int go_raw, int ge_raw, cudaStream_t st) {
     if (num_pairs <= 0) return cudaSuccess;
     int64_t grid = (int64_t)num_sms * (2048 / threads);
     if (grid > num_pairs) grid = num_pairs;
-    stage2_kernel<<<(int)grid, threads, 0, st>>>(pairs, num_pairs, k, no_anchors ? 1 : 0, want_segments ? 1 : 0, aof,
+    stage2_kernel<<<(int)grid, threads, 0, st>>>(pairs, pair_list, num_pairs, k, no_anchors ? 1 : 0, want_segments ? 1 : 0, aof,
                                                 status, out, pools, ctr, max_abs_score, go_raw, ge_raw);
     return cudaGetLastError();
 }
