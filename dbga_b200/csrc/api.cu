@@ -1,6 +1,7 @@
 // C-ABI host side: plan (sizing, classing, metadata upload), run (kernel pipeline on one
 // stream, no host round trips), fetch (device -> pinned host).  See include/dbga_b200.h.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -71,7 +72,10 @@ struct dbga_ctx {
         d_sink;
     // ---- pinned host result buffers
     HostBuf h_status, h_score, h_cells, h_nseg, h_nanch, h_aln_off, h_run_off, h_aln0, h_aln1, h_runs, h_nd0,
-        h_nd1, h_poff, h_qoff, h_ctr;
+        h_nd1, h_poff, h_qoff, h_ctr, h_meta;
+    // ---- pipelined dbga_align_batch: child contexts (own stream + workspaces) used round-robin
+    dbga_ctx *lanes[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_ready = nullptr;
 };
 
 namespace {
@@ -165,7 +169,8 @@ int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr size_t L2_TABLE_BUDGET = 64u << 20;
 
-int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params *params, bool no_anchors) {
+int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params *params, bool no_anchors,
+            int64_t off_base = 0) {
     ctx->planned = false; ctx->ran = false;
     if (!offsets || !params || P < 0) return fail(ctx, DBGA_ERR_ARG, "null argument");
     if (P > 0x7fffff00LL) return fail(ctx, DBGA_ERR_ARG, "too many pairs in one batch");
@@ -180,11 +185,11 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     const bool full = params->want_graph != 0 && !no_anchors;
     ctx->P = P;
     ctx->h_pairs.resize((size_t)P);
-    ctx->total_bytes = P > 0 ? offsets[2 * P] : 0;
+    ctx->total_bytes = P > 0 ? offsets[2 * P] - off_base : 0;
     int64_t qb = 0, pb = 0;
     int mx0 = 0, mx1 = 0;
     for (int64_t i = 0; i < P; ++i) {
-        const int64_t o0 = offsets[2 * i], o1 = offsets[2 * i + 1], o2 = offsets[2 * i + 2];
+        const int64_t o0 = offsets[2 * i] - off_base, o1 = offsets[2 * i + 1] - off_base, o2 = offsets[2 * i + 2] - off_base;
         if (o0 < 0 || o1 < o0 || o2 < o1) return fail(ctx, DBGA_ERR_ARG, "offsets must be non-decreasing");
         if (o1 - o0 > 0x7ffffff0LL || o2 - o1 > 0x7ffffff0LL) return fail(ctx, DBGA_ERR_ARG, "sequence longer than 2^31");
         PairDesc &pd = ctx->h_pairs[(size_t)i];
@@ -273,9 +278,17 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     RESERVE(d_pairs, sizeof(PairDesc) * std::max<int64_t>(P, 1));
     RESERVE(d_list, sizeof(int32_t) * std::max<size_t>(ctx->h_list.size(), 1));
     RESERVE(d_large, sizeof(LargeDesc) * std::max<size_t>(ctx->h_large.size(), 1));
-    if (P) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pairs.p, ctx->h_pairs.data(), sizeof(PairDesc) * P, cudaMemcpyHostToDevice, ctx->stream));
-    if (!ctx->h_list.empty()) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_list.p, ctx->h_list.data(), sizeof(int32_t) * ctx->h_list.size(), cudaMemcpyHostToDevice, ctx->stream));
-    if (!ctx->h_large.empty()) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_large.p, ctx->h_large.data(), sizeof(LargeDesc) * ctx->h_large.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {   // metadata goes through one pinned staging buffer so that the uploads are truly asynchronous
+        const size_t b0 = sizeof(PairDesc) * (size_t)P, b1 = sizeof(int32_t) * ctx->h_list.size(),
+                     b2 = sizeof(LargeDesc) * ctx->h_large.size();
+        const size_t o1 = (b0 + 15) & ~(size_t)15, o2 = (o1 + b1 + 15) & ~(size_t)15;
+        DBGA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));     // previous use of the staging buffer is over
+        HRESERVE(h_meta, o2 + b2 + 16);
+        char *m = (char *)ctx->h_meta.p;
+        if (b0) { memcpy(m, ctx->h_pairs.data(), b0); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pairs.p, m, b0, cudaMemcpyHostToDevice, ctx->stream)); }
+        if (b1) { memcpy(m + o1, ctx->h_list.data(), b1); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_list.p, m + o1, b1, cudaMemcpyHostToDevice, ctx->stream)); }
+        if (b2) { memcpy(m + o2, ctx->h_large.data(), b2); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_large.p, m + o2, b2, cudaMemcpyHostToDevice, ctx->stream)); }
+    }
     size_t max_tbl = 0, max_pk = 0;
     for (size_t wi = 0; wi < ctx->waves.size(); ++wi) {
         const LargeWave &w = ctx->waves[wi];
@@ -445,21 +458,24 @@ int do_run(dbga_ctx *ctx, const uint8_t *d_seqs) {
     return DBGA_SUCCESS;
 }
 
-int do_fetch(dbga_ctx *ctx, dbga_result *out) {
-    if (!ctx->ran) return fail(ctx, DBGA_ERR_ARG, "dbga_plan_fetch before dbga_plan_run");
-    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+struct HostDst {
+    int32_t *status; int64_t *score; int64_t *cells; int32_t *nseg; int64_t *nanch;
+    int64_t *aln_off; int64_t *run_off; uint8_t *aln0; uint8_t *aln1; int32_t *runs;
+};
+
+// counters -> host; on pool overflow grow to the measured need and re-run the pipeline
+int fetch_resolve(dbga_ctx *ctx, bool counters_already_copied) {
     cudaStream_t st = ctx->stream;
-    const int64_t P = ctx->P;
-    HRESERVE(h_ctr, sizeof(Counters));
     Counters *hc = (Counters *)ctx->h_ctr.p;
-    // pool overflow: grow to the measured need and re-run the pipeline
     for (int attempt = 0; attempt < 4; ++attempt) {
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (!(attempt == 0 && counters_already_copied)) {
+            DBGA_CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+            DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+        }
         bool grow = false;
         if ((int64_t)hc->runs_used > ctx->runs_cap) { ctx->runs_cap = (int64_t)hc->runs_used + 1024; grow = true; }
         if ((int64_t)hc->slots_used > ctx->slots_cap) { ctx->slots_cap = (int64_t)hc->slots_used + 1024; grow = true; }
-        ctx->slots_cap = std::max(ctx->slots_cap, ctx->runs_cap + P + 16);
+        ctx->slots_cap = std::max(ctx->slots_cap, ctx->runs_cap + ctx->P + 16);
         if ((int64_t)hc->tb_used > ctx->tb_cap && ctx->tb_cap < ctx->scratch_limit) {
             ctx->tb_cap = std::min<int64_t>(ctx->scratch_limit, (int64_t)hc->tb_used + (1 << 20));
             grow = true;
@@ -468,6 +484,38 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
         int rc = run_pipeline(ctx);
         if (rc != DBGA_SUCCESS) return rc;
     }
+    return DBGA_SUCCESS;
+}
+
+// asynchronous device -> host copies of one batch's results (offsets are batch-local)
+int fetch_enqueue(dbga_ctx *ctx, const HostDst &d, int64_t total_aln, int64_t total_runs) {
+    cudaStream_t st = ctx->stream;
+    const int64_t P = ctx->P;
+    if (!P) return DBGA_SUCCESS;
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.status, ctx->d_status_out.p, 4 * P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.score, ctx->d_score.p, 8 * P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.cells, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.nseg, ctx->d_nseg.p, 4 * P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.nanch, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln_off, ctx->d_aln_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(d.run_off, ctx->d_run_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    if (total_aln) {
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln0, ctx->d_aln0.p, total_aln, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln1, ctx->d_aln1.p, total_aln, cudaMemcpyDeviceToHost, st));
+    }
+    if (total_runs) DBGA_CUDA_CHECK(cudaMemcpyAsync(d.runs, ctx->d_runs_out.p, 12 * total_runs, cudaMemcpyDeviceToHost, st));
+    return DBGA_SUCCESS;
+}
+
+int do_fetch(dbga_ctx *ctx, dbga_result *out) {
+    if (!ctx->ran) return fail(ctx, DBGA_ERR_ARG, "dbga_plan_fetch before dbga_plan_run");
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t P = ctx->P;
+    HRESERVE(h_ctr, sizeof(Counters));
+    Counters *hc = (Counters *)ctx->h_ctr.p;
+    int rc = fetch_resolve(ctx, false);
+    if (rc != DBGA_SUCCESS) return rc;
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[6], st));
     const bool seg = ctx->prm.stages == 3;
     const bool full = ctx->prm.want_graph != 0 && !ctx->no_anchors;
@@ -477,19 +525,12 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     const int64_t total_aln = seg ? (int64_t)hc->total_aln : 0, total_runs = (int64_t)hc->total_runs;
     HRESERVE(h_aln0, std::max<int64_t>(total_aln, 1)); HRESERVE(h_aln1, std::max<int64_t>(total_aln, 1));
     HRESERVE(h_runs, 12 * std::max<int64_t>(total_runs, 1));
+    HostDst d{(int32_t *)ctx->h_status.p, (int64_t *)ctx->h_score.p, (int64_t *)ctx->h_cells.p, (int32_t *)ctx->h_nseg.p,
+              (int64_t *)ctx->h_nanch.p, (int64_t *)ctx->h_aln_off.p, (int64_t *)ctx->h_run_off.p,
+              (uint8_t *)ctx->h_aln0.p, (uint8_t *)ctx->h_aln1.p, (int32_t *)ctx->h_runs.p};
     if (P) {
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status_out.p, 4 * P, cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_score.p, ctx->d_score.p, 8 * P, cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cells.p, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nseg.p, ctx->d_nseg.p, 4 * P, cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nanch.p, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_aln_off.p, ctx->d_aln_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_run_off.p, ctx->d_run_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
-        if (total_aln) {
-            DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_aln0.p, ctx->d_aln0.p, total_aln, cudaMemcpyDeviceToHost, st));
-            DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_aln1.p, ctx->d_aln1.p, total_aln, cudaMemcpyDeviceToHost, st));
-        }
-        if (total_runs) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_runs.p, ctx->d_runs_out.p, 12 * total_runs, cudaMemcpyDeviceToHost, st));
+        rc = fetch_enqueue(ctx, d, total_aln, total_runs);
+        if (rc != DBGA_SUCCESS) return rc;
     } else {
         ((int64_t *)ctx->h_aln_off.p)[0] = 0; ((int64_t *)ctx->h_run_off.p)[0] = 0;
     }
@@ -506,12 +547,10 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
     memset(out, 0, sizeof(*out));
     out->num_pairs = P;
-    out->status = (int32_t *)ctx->h_status.p; out->score = (int64_t *)ctx->h_score.p;
-    out->dp_cells = (int64_t *)ctx->h_cells.p; out->dp_segments = (int32_t *)ctx->h_nseg.p;
-    out->n_anchors = (int64_t *)ctx->h_nanch.p; out->run_off = (int64_t *)ctx->h_run_off.p;
-    out->runs = (int32_t *)ctx->h_runs.p; out->aln_off = (int64_t *)ctx->h_aln_off.p;
-    out->aln0 = (uint8_t *)ctx->h_aln0.p; out->aln1 = (uint8_t *)ctx->h_aln1.p;
-    if (!seg && P) { for (int64_t i = 0; i <= P; ++i) ((int64_t *)ctx->h_aln_off.p)[i] = 0; }
+    out->status = d.status; out->score = d.score; out->dp_cells = d.cells; out->dp_segments = d.nseg;
+    out->n_anchors = d.nanch; out->run_off = d.run_off; out->runs = d.runs; out->aln_off = d.aln_off;
+    out->aln0 = d.aln0; out->aln1 = d.aln1;
+    if (!seg && P) { for (int64_t i = 0; i <= P; ++i) d.aln_off[i] = 0; }
     if (full) {
         out->p_off = (int64_t *)ctx->h_poff.p; out->nondup0 = (uint8_t *)ctx->h_nd0.p;
         out->q_off = (int64_t *)ctx->h_qoff.p; out->nondup1 = (uint8_t *)ctx->h_nd1.p;
@@ -528,10 +567,135 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     return DBGA_SUCCESS;
 }
 
+int create_ctx(int device, dbga_ctx **out);
+
+// Pipelined whole-batch call: the batch is cut into chunks that flow through three child
+// contexts (lanes).  Each lane's stream carries H2D -> kernels -> D2H of its chunk in order,
+// so at any time one lane uploads, one computes and one downloads.  The host never waits
+// for anything but the small counters of the previous chunk (needed to size its D2H).
+int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P,
+                    const dbga_params *params, dbga_result *out, bool no_anchors, int nchunks) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    const int64_t total_bytes = offsets[2 * P] - offsets[0];
+    const bool seg = params->stages == 3;
+    for (int i = 0; i < 3; ++i) {
+        if (!ctx->lanes[i]) {
+            int rc = create_ctx(ctx->device, &ctx->lanes[i]);
+            if (rc != DBGA_SUCCESS) return fail(ctx, rc, "could not create a pipeline lane");
+            if (cudaEventCreateWithFlags(&ctx->lanes[i]->ev_ready, cudaEventDisableTiming) != cudaSuccess)
+                return fail(ctx, DBGA_ERR_CUDA, "cudaEventCreate failed");
+        }
+        ctx->lanes[i]->scratch_limit = ctx->scratch_limit;
+    }
+    // chunk boundaries: equal bytes
+    std::vector<int64_t> lo((size_t)nchunks + 1, P);
+    lo[0] = 0;
+    {
+        int c = 1;
+        for (int64_t i = 0; i < P && c < nchunks; ++i) {
+            if (offsets[2 * i] - offsets[0] >= total_bytes * c / nchunks) lo[(size_t)c++] = i;
+        }
+        for (; c < nchunks; ++c) lo[(size_t)c] = P;
+    }
+    HRESERVE(h_status, 4 * (P + 1)); HRESERVE(h_score, 8 * (P + 1)); HRESERVE(h_cells, 8 * (P + 1));
+    HRESERVE(h_nseg, 4 * (P + 1)); HRESERVE(h_nanch, 8 * (P + 1));
+    HRESERVE(h_aln_off, 8 * (P + 2 + nchunks)); HRESERVE(h_run_off, 8 * (P + 2 + nchunks));
+    if (seg) { HRESERVE(h_aln0, total_bytes + 16); HRESERVE(h_aln1, total_bytes + 16); }
+    HRESERVE(h_runs, std::max<int64_t>((int64_t)ctx->h_runs.cap, total_bytes / 4 + 4096));
+    int64_t *aln_off = (int64_t *)ctx->h_aln_off.p, *run_off = (int64_t *)ctx->h_run_off.p;
+    std::vector<int64_t> aln_base((size_t)nchunks + 1, 0), run_base((size_t)nchunks + 1, 0);
+    float ms[4] = {0, 0, 0, 0};
+    int64_t cells = 0, nsegs = 0, launches = 0;
+    auto fail_lane = [&](dbga_ctx *l, int rc) { snprintf(ctx->err, sizeof(ctx->err), "%s", l->err); return rc; };
+
+    for (int step = 0; step <= nchunks; ++step) {
+        if (step < nchunks) {
+            dbga_ctx *l = ctx->lanes[step % 3];
+            const int64_t a = lo[(size_t)step], b = lo[(size_t)step + 1];
+            const int64_t base = offsets[2 * a];
+            int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
+            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
+            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            if (l->total_bytes && cudaMemcpyAsync(l->d_seqs.p, seqs + base, (size_t)l->total_bytes, cudaMemcpyHostToDevice, l->stream) != cudaSuccess)
+                return fail(ctx, DBGA_ERR_CUDA, "H2D copy failed");
+            rc = do_run(l, (const uint8_t *)l->d_seqs.p);
+            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            rc = host_reserve(l, l->h_ctr, sizeof(Counters));
+            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            if (cudaMemcpyAsync(l->h_ctr.p, l->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, l->stream) != cudaSuccess ||
+                cudaEventRecord(l->ev_ready, l->stream) != cudaSuccess)
+                return fail(ctx, DBGA_ERR_CUDA, "counter copy failed");
+        }
+        if (step >= 1) {
+            const int c = step - 1;
+            dbga_ctx *l = ctx->lanes[c % 3];
+            const int64_t a = lo[(size_t)c];
+            if (cudaEventSynchronize(l->ev_ready) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventSynchronize failed");
+            int rc = fetch_resolve(l, true);
+            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            const Counters *hc = (const Counters *)l->h_ctr.p;
+            const int64_t ta = seg ? (int64_t)hc->total_aln : 0, tr = (int64_t)hc->total_runs;
+            aln_base[(size_t)c + 1] = aln_base[(size_t)c] + ta;
+            run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
+            if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
+                for (int i = 0; i < 3; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
+                HostBuf old = ctx->h_runs;
+                ctx->h_runs = HostBuf();
+                rc = host_reserve(ctx, ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]) * 2);
+                if (rc != DBGA_SUCCESS) return rc;
+                memcpy(ctx->h_runs.p, old.p, (size_t)(12 * run_base[(size_t)c]));
+                cudaFreeHost(old.p);
+            }
+            float t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+            cudaEventElapsedTime(&t1, l->ev[1], l->ev[2]); cudaEventElapsedTime(&t2, l->ev[2], l->ev[3]);
+            cudaEventElapsedTime(&t3, l->ev[3], l->ev[4]); cudaEventElapsedTime(&t4, l->ev[4], l->ev[5]);
+            ms[0] += t1; ms[1] += t2; ms[2] += t3; ms[3] += t4;
+            cells += (int64_t)hc->cells; nsegs += (int64_t)hc->nseg; launches += l->launches;
+            // offsets of chunk c land at [a + c, a + c + n + 1) (one extra slot per chunk), fixed up below
+            HostDst d{(int32_t *)ctx->h_status.p + a, (int64_t *)ctx->h_score.p + a, (int64_t *)ctx->h_cells.p + a,
+                      (int32_t *)ctx->h_nseg.p + a, (int64_t *)ctx->h_nanch.p + a, aln_off + a + c, run_off + a + c,
+                      (uint8_t *)ctx->h_aln0.p + aln_base[(size_t)c], (uint8_t *)ctx->h_aln1.p + aln_base[(size_t)c],
+                      (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c]};
+            rc = fetch_enqueue(l, d, ta, tr);
+            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+        }
+    }
+    for (int i = 0; i < 3; ++i)
+        if (cudaStreamSynchronize(ctx->lanes[i]->stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "stream sync failed");
+    // compact the per-chunk offset arrays in place and add the chunk bases
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t a = lo[(size_t)c], n = lo[(size_t)c + 1] - a;
+        for (int64_t i = 0; i < n; ++i) {
+            aln_off[a + i] = (seg ? aln_off[a + c + i] : 0) + aln_base[(size_t)c];
+            run_off[a + i] = run_off[a + c + i] + run_base[(size_t)c];
+        }
+    }
+    aln_off[P] = aln_base[(size_t)nchunks];
+    run_off[P] = run_base[(size_t)nchunks];
+    memset(out, 0, sizeof(*out));
+    out->num_pairs = P;
+    out->status = (int32_t *)ctx->h_status.p; out->score = (int64_t *)ctx->h_score.p;
+    out->dp_cells = (int64_t *)ctx->h_cells.p; out->dp_segments = (int32_t *)ctx->h_nseg.p;
+    out->n_anchors = (int64_t *)ctx->h_nanch.p; out->run_off = run_off; out->runs = (int32_t *)ctx->h_runs.p;
+    out->aln_off = aln_off; out->aln0 = (uint8_t *)ctx->h_aln0.p; out->aln1 = (uint8_t *)ctx->h_aln1.p;
+    out->ms_stage1 = ms[0]; out->ms_stage2 = ms[1]; out->ms_stage3 = ms[2]; out->ms_assemble = ms[3];
+    out->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    out->dp_cells_total = cells; out->dp_segments_total = nsegs; out->kernel_launches = launches;
+    return DBGA_SUCCESS;
+}
+
 int align_common(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P, const dbga_params *params,
                  dbga_result *out, bool no_anchors) {
-    if (!ctx || !out || (!seqs && P > 0)) return DBGA_ERR_ARG;
+    if (!ctx || !out || !offsets || !params || (!seqs && P > 0)) return DBGA_ERR_ARG;
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (P >= 64 && !params->want_graph && ctx->own_stream) {
+        const int64_t total = offsets[2 * P] - offsets[0];
+        if (total >= (16LL << 20)) {
+            const int nchunks = (int)std::min<int64_t>(64, std::max<int64_t>(3, (total + (32LL << 20) - 1) / (32LL << 20)));
+            return align_pipelined(ctx, seqs, offsets, P, params, out, no_anchors, nchunks);
+        }
+    }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
     int rc = do_plan(ctx, offsets, P, params, no_anchors);
     if (rc != DBGA_SUCCESS) return rc;
@@ -553,7 +717,12 @@ extern "C" {
 
 int dbga_version(void) { return 100; }
 
-int dbga_create(int device, dbga_ctx **out) {
+int dbga_create(int device, dbga_ctx **out) { return create_ctx(device, out); }
+
+}  // extern "C"
+
+namespace {
+int create_ctx(int device, dbga_ctx **out) {
     if (!out) return DBGA_ERR_ARG;
     *out = nullptr;
     int ndev = 0;
@@ -569,9 +738,13 @@ int dbga_create(int device, dbga_ctx **out) {
     *out = ctx;
     return DBGA_SUCCESS;
 }
+}  // namespace
+
+extern "C" {
 
 void dbga_destroy(dbga_ctx *ctx) {
     if (!ctx) return;
+    for (auto &l : ctx->lanes) if (l) { if (l->ev_ready) cudaEventDestroy(l->ev_ready); dbga_destroy(l); l = nullptr; }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *dbs[] = {&ctx->d_seqs, &ctx->d_pairs, &ctx->d_list, &ctx->d_large, &ctx->d_status, &ctx->d_aof, &ctx->d_nd0,
@@ -583,7 +756,7 @@ void dbga_destroy(dbga_ctx *ctx) {
     for (DevBuf *b : dbs) if (b->p) cudaFree(b->p);
     HostBuf *hbs[] = {&ctx->h_status, &ctx->h_score, &ctx->h_cells, &ctx->h_nseg, &ctx->h_nanch, &ctx->h_aln_off,
                       &ctx->h_run_off, &ctx->h_aln0, &ctx->h_aln1, &ctx->h_runs, &ctx->h_nd0, &ctx->h_nd1, &ctx->h_poff,
-                      &ctx->h_qoff, &ctx->h_ctr};
+                      &ctx->h_qoff, &ctx->h_ctr, &ctx->h_meta};
     for (HostBuf *b : hbs) if (b->p) cudaFreeHost(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

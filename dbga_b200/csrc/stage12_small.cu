@@ -41,18 +41,37 @@ __device__ __forceinline__ uint32_t pack4(uint32_t w, bool &bad) {
     return (codes * 0x01041040u) >> 24;                          // c0 | c1<<2 | c2<<4 | c3<<6
 }
 
-__device__ __forceinline__ uint32_t pack16_fast(const uint8_t *src, int64_t valid, bool aligned, bool &bad) {
-    if (valid >= 16 && aligned) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src));
-        return pack4(v.x, bad) | (pack4(v.y, bad) << 8) | (pack4(v.z, bad) << 16) | (pack4(v.w, bad) << 24);
+// 16 bases starting at src (any alignment) -> one packed word.  Two aligned 128-bit loads
+// and a byte-granular funnel shift replace 16 byte loads; `off` = src & 15 is the same for
+// every word of a sequence, so the shift selection is warp-uniform.  The second load is
+// only issued when it contains a byte of the sequence (never reads past the allocation's
+// last 16-byte block).  Bytes beyond `valid` are replaced by 'A' (code 0, not an error).
+__device__ __forceinline__ uint32_t pack16_fast(const uint8_t *src, int64_t valid, bool &bad) {
+    const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15);
+    const uint4 *p = reinterpret_cast<const uint4 *>(src - off);
+    const int nv = valid < 16 ? (int)valid : 16;
+    const uint4 a = __ldg(p);
+    uint4 b = make_uint4(0x41414141u, 0x41414141u, 0x41414141u, 0x41414141u);
+    if (off + nv > 16) b = __ldg(p + 1);
+    uint32_t w0, w1, w2, w3;
+    const uint32_t sh = (off & 3) * 8;
+    switch (off >> 2) {
+    case 0: w0 = __funnelshift_r(a.x, a.y, sh); w1 = __funnelshift_r(a.y, a.z, sh); w2 = __funnelshift_r(a.z, a.w, sh); w3 = __funnelshift_r(a.w, b.x, sh); break;
+    case 1: w0 = __funnelshift_r(a.y, a.z, sh); w1 = __funnelshift_r(a.z, a.w, sh); w2 = __funnelshift_r(a.w, b.x, sh); w3 = __funnelshift_r(b.x, b.y, sh); break;
+    case 2: w0 = __funnelshift_r(a.z, a.w, sh); w1 = __funnelshift_r(a.w, b.x, sh); w2 = __funnelshift_r(b.x, b.y, sh); w3 = __funnelshift_r(b.y, b.z, sh); break;
+    default: w0 = __funnelshift_r(a.w, b.x, sh); w1 = __funnelshift_r(b.x, b.y, sh); w2 = __funnelshift_r(b.y, b.z, sh); w3 = __funnelshift_r(b.z, b.w, sh); break;
     }
-    uint32_t w = 0;
-    for (int i = 0; i < 16 && i < valid; ++i) {
-        const uint8_t c = src[i];
-        bad |= !is_acgt(c);
-        w |= (uint32_t)base_code(c) << (2 * i);
+    if (nv < 16) {                 // tail word: neutralise bytes past the end of the sequence
+        uint32_t w[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = nv - 4 * j;                       // valid bytes in word j
+            const uint32_t m = c >= 4 ? 0xFFFFFFFFu : (c <= 0 ? 0u : ((1u << (8 * c)) - 1u));
+            w[j] = (w[j] & m) | (0x41414141u & ~m);
+        }
+        w0 = w[0]; w1 = w[1]; w2 = w[2]; w3 = w[3];
     }
-    return w;
+    return pack4(w0, bad) | (pack4(w1, bad) << 8) | (pack4(w2, bad) << 16) | (pack4(w3, bad) << 24);
 }
 
 template <typename KeyT> struct Bucket;
@@ -177,12 +196,10 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         bool bad = false;
         {
             const uint8_t *s0 = seqs + pd.off0, *s1 = seqs + pd.off1;
-            const bool al0 = (reinterpret_cast<uintptr_t>(s0) & 15) == 0;
-            const bool al1 = (reinterpret_cast<uintptr_t>(s1) & 15) == 0;
             for (int w = tid; w < words; w += T) {
                 const int64_t r0 = (int64_t)pd.n0 - 16 * w, r1 = (int64_t)pd.n1 - 16 * w;
-                pk0[w] = r0 > 0 ? pack16_fast(s0 + 16 * w, r0, al0, bad) : 0u;
-                pk1[w] = r1 > 0 ? pack16_fast(s1 + 16 * w, r1, al1, bad) : 0u;
+                pk0[w] = r0 > 0 ? pack16_fast(s0 + 16 * w, r0, bad) : 0u;
+                pk1[w] = r1 > 0 ? pack16_fast(s1 + 16 * w, r1, bad) : 0u;
             }
             uint4 *t4 = reinterpret_cast<uint4 *>(keys);                // keys + pos0 + last1 = all ones
             const int n_ff = (int)((cap * (sizeof(KeyT) + 4)) / 16), n_00 = (int)(cap * 2 / 16);

@@ -197,3 +197,23 @@ def test_full_size_properties(aligner):
         assert len(a0) == len(a1)
         assert a0.replace("-", "") == pairs[i][0] and a1.replace("-", "") == pairs[i][1]
         assert not any(x == "-" and y == "-" for x, y in zip(a0, a1))
+
+
+def test_pipelined_batch_equals_direct(aligner):
+    """Batches >= 16 MB go through the chunked 3-lane copy/compute pipeline of
+    dbga_align_batch; the result must be identical to aligning the halves directly."""
+    pairs = [O.synth_pair(1500, 0.018, 0.002, 7000 + s) for s in range(7000)]     # ~21 MB
+    big = aligner.align_pairs(pairs, 9)
+    parts = [aligner.align_pairs(pairs[i:i + 3500], 9) for i in (0, 3500)]         # ~10 MB each: direct path
+    assert big.timing["launches"] > parts[0].timing["launches"]                     # several chunks ran
+    status = np.concatenate([p.status for p in parts])
+    assert np.array_equal(big.status, status)
+    assert np.array_equal(big.score, np.concatenate([p.score for p in parts]))
+    assert np.array_equal(big.n_anchors, np.concatenate([p.n_anchors for p in parts]))
+    assert np.array_equal(big.aln0, np.concatenate([p.aln0 for p in parts]))
+    assert np.array_equal(big.aln1, np.concatenate([p.aln1 for p in parts]))
+    assert np.array_equal(big.runs, np.concatenate([p.runs for p in parts]))
+    for i in (0, 1, 3499, 3500, 6999):
+        j, part = (i, parts[0]) if i < 3500 else (i - 3500, parts[1])
+        assert big.alignment(i) == part.alignment(j)
+        assert np.array_equal(big.anchors(i), part.anchors(j))
