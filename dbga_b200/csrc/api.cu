@@ -62,6 +62,7 @@ struct dbga_ctx {
     int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
     int grid_warp = 0, grid_cta = 0;
     int tiny_bound[NUM_TINY] = {8, 16, 24, 32};
+    bool seen_warp_work = true, seen_cta_work = true;   // adaptive grid for the (often empty) wavefront launches
     int launches = 0;
     const uint8_t *d_seqs_run = nullptr;
 
@@ -74,7 +75,8 @@ struct dbga_ctx {
     HostBuf h_status, h_score, h_cells, h_nseg, h_nanch, h_aln_off, h_run_off, h_aln0, h_aln1, h_runs, h_nd0,
         h_nd1, h_poff, h_qoff, h_ctr, h_meta;
     // ---- pipelined dbga_align_batch: child contexts (own stream + workspaces) used round-robin
-    dbga_ctx *lanes[3] = {nullptr, nullptr, nullptr};
+    static constexpr int NL = 4;
+    dbga_ctx *lanes[NL] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_ready = nullptr;
 };
 
@@ -417,22 +419,28 @@ int run_pipeline(dbga_ctx *ctx) {
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));
     if (seg) {
-        for (int c = 0; c < NUM_TINY; ++c) {
-            if (c > 0 && ctx->tiny_bound[c] == ctx->tiny_bound[c - 1]) continue;   // empty class
-            DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists + (int64_t)c * pools.list_cap,
-                                             &ctr->n_cls[c], ctx->tiny_bound[c], ctx->dp, (uint8_t *)ctx->d_str.p,
-                                             (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
+        {   // tiny classes: two launches (small / large shared-memory footprint)
+            TinyBounds tbnd;
+            for (int c = 0; c < NUM_TINY; ++c) tbnd.b[c] = ctx->tiny_bound[c];
+            const int split = NUM_TINY / 2;
+            DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, 0, split, tbnd,
+                                             ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
             ctx->launches += 1;
+            if (tbnd.b[NUM_TINY - 1] > tbnd.b[split - 1]) {
+                DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, split, NUM_TINY,
+                                                 tbnd, ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
+                ctx->launches += 1;
+            }
         }
         if (ctx->grid_warp) {
             DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_WARP * pools.list_cap,
-                                                &ctr->n_cls[CLS_WARP], ctx->grid_warp, false, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                &ctr->n_cls[CLS_WARP], ctx->seen_warp_work ? ctx->grid_warp : std::min(ctx->grid_warp, ctx->num_sms), false, ctx->dp, (uint8_t *)ctx->d_str.p,
                                                 (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
             ctx->launches += 1;
         }
         if (ctx->grid_cta) {
             DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
-                                                &ctr->n_cls[CLS_CTA], ctx->grid_cta, true, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                &ctr->n_cls[CLS_CTA], ctx->seen_cta_work ? ctx->grid_cta : std::min(ctx->grid_cta, 8), true, ctx->dp, (uint8_t *)ctx->d_str.p,
                                                 (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
             ctx->launches += 1;
         }
@@ -484,6 +492,10 @@ int fetch_resolve(dbga_ctx *ctx, bool counters_already_copied) {
         int rc = run_pipeline(ctx);
         if (rc != DBGA_SUCCESS) return rc;
     }
+    // the wavefront kernels are persistent, so any grid is correct; keep it small while the
+    // workload has no segment for them (most closely related pairs)
+    ctx->seen_warp_work = hc->n_cls[CLS_WARP] > 0;
+    ctx->seen_cta_work = hc->n_cls[CLS_CTA] > 0;
     return DBGA_SUCCESS;
 }
 
@@ -569,7 +581,7 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
 
 int create_ctx(int device, dbga_ctx **out);
 
-// Pipelined whole-batch call: the batch is cut into chunks that flow through three child
+// Pipelined whole-batch call: the batch is cut into chunks that flow through NL child
 // contexts (lanes).  Each lane's stream carries H2D -> kernels -> D2H of its chunk in order,
 // so at any time one lane uploads, one computes and one downloads.  The host never waits
 // for anything but the small counters of the previous chunk (needed to size its D2H).
@@ -578,7 +590,10 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     const auto t_begin = std::chrono::steady_clock::now();
     const int64_t total_bytes = offsets[2 * P] - offsets[0];
     const bool seg = params->stages == 3;
-    for (int i = 0; i < 3; ++i) {
+    constexpr int NL = dbga_ctx::NL;
+    int lag = 2;                       // chunks kept in flight before the oldest is committed
+    if (const char *e = getenv("DBGA_LAG")) lag = std::max(1, std::min(NL - 1, atoi(e)));
+    for (int i = 0; i < NL; ++i) {
         if (!ctx->lanes[i]) {
             int rc = create_ctx(ctx->device, &ctx->lanes[i]);
             if (rc != DBGA_SUCCESS) return fail(ctx, rc, "could not create a pipeline lane");
@@ -608,13 +623,18 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     int64_t cells = 0, nsegs = 0, launches = 0;
     auto fail_lane = [&](dbga_ctx *l, int rc) { snprintf(ctx->err, sizeof(ctx->err), "%s", l->err); return rc; };
 
-    for (int step = 0; step <= nchunks; ++step) {
+    const bool trace = getenv("DBGA_TRACE") != nullptr;
+    auto now_ms = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+    for (int step = 0; step < nchunks + lag; ++step) {
+        const float t_s0 = now_ms();
+        float t_plan = 0, t_enq = 0, t_sync = 0;
         if (step < nchunks) {
-            dbga_ctx *l = ctx->lanes[step % 3];
+            dbga_ctx *l = ctx->lanes[step % NL];
             const int64_t a = lo[(size_t)step], b = lo[(size_t)step + 1];
             const int64_t base = offsets[2 * a];
             int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            t_plan = now_ms() - t_s0;
             rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
             if (l->total_bytes && cudaMemcpyAsync(l->d_seqs.p, seqs + base, (size_t)l->total_bytes, cudaMemcpyHostToDevice, l->stream) != cudaSuccess)
@@ -626,12 +646,15 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
             if (cudaMemcpyAsync(l->h_ctr.p, l->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, l->stream) != cudaSuccess ||
                 cudaEventRecord(l->ev_ready, l->stream) != cudaSuccess)
                 return fail(ctx, DBGA_ERR_CUDA, "counter copy failed");
+            t_enq = now_ms() - t_s0;
         }
-        if (step >= 1) {
-            const int c = step - 1;
-            dbga_ctx *l = ctx->lanes[c % 3];
+        if (step >= lag) {
+            const int c = step - lag;
+            dbga_ctx *l = ctx->lanes[c % NL];
             const int64_t a = lo[(size_t)c];
+            const float t_b = now_ms();
             if (cudaEventSynchronize(l->ev_ready) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventSynchronize failed");
+            t_sync = now_ms() - t_b;
             int rc = fetch_resolve(l, true);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
             const Counters *hc = (const Counters *)l->h_ctr.p;
@@ -639,7 +662,7 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
             aln_base[(size_t)c + 1] = aln_base[(size_t)c] + ta;
             run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
             if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
-                for (int i = 0; i < 3; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
+                for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
                 HostBuf old = ctx->h_runs;
                 ctx->h_runs = HostBuf();
                 rc = host_reserve(ctx, ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]) * 2);
@@ -660,8 +683,9 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
             rc = fetch_enqueue(l, d, ta, tr);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
         }
+        if (trace) fprintf(stderr, "[dbga] step %d start %.3f plan %.3f enq %.3f sync %.3f end %.3f\n", step, t_s0, t_plan, t_enq, t_sync, now_ms());
     }
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < NL; ++i)
         if (cudaStreamSynchronize(ctx->lanes[i]->stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "stream sync failed");
     // compact the per-chunk offset arrays in place and add the chunk bases
     for (int c = 0; c < nchunks; ++c) {
@@ -692,7 +716,10 @@ int align_common(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int
     if (P >= 64 && !params->want_graph && ctx->own_stream) {
         const int64_t total = offsets[2 * P] - offsets[0];
         if (total >= (16LL << 20)) {
-            const int nchunks = (int)std::min<int64_t>(64, std::max<int64_t>(3, (total + (32LL << 20) - 1) / (32LL << 20)));
+            int64_t chunk_mb = 32;
+            if (const char *e = getenv("DBGA_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
+            const int64_t cb = chunk_mb << 20;
+            const int nchunks = (int)std::min<int64_t>(256, std::max<int64_t>(3, (total + cb - 1) / cb));
             return align_pipelined(ctx, seqs, offsets, P, params, out, no_anchors, nchunks);
         }
     }

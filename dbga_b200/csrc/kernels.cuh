@@ -54,11 +54,12 @@ cudaError_t launch_stage2(const PairDesc *pairs, const int32_t *pair_list, int64
 
 // ---- stage 3
 // count_dev: device pointer to the number of list entries (no host round trip needed)
-// thread-per-segment kernel for one tiny class (segments with max(m, n) <= bound)
+// thread-per-segment kernel over the tiny classes c0..c1-1 (one launch)
+struct TinyBounds { int b[NUM_TINY]; };
 size_t dp_thread_scratch_bytes(int bound, int num_sms);
-cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
-                             const unsigned int *count_dev, int bound, DpParams prm, uint8_t *strbuf,
-                             uint32_t *tb_scratch, int num_sms, cudaStream_t st);
+cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
+                             int64_t list_cap, const unsigned int *counts_dev, int c0, int c1, TinyBounds tb,
+                             DpParams prm, uint8_t *strbuf, uint32_t *tb_scratch, int num_sms, cudaStream_t st);
 // bnd: per-CTA double-buffered boundary rows, int4 per column, bnd_stride columns each
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                 const unsigned int *count_dev, int grid, bool cta_class, DpParams prm,

@@ -87,20 +87,28 @@ __device__ __forceinline__ void pick_end(int Mv, int Xv, int Yv, const DpParams 
 template <bool XY>
 __global__ void __launch_bounds__(TINY_THREADS)
 dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
-                 const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, int bound,
-                 DpParams prm, uint8_t *__restrict__ strbuf, uint32_t *__restrict__ tb_scratch) {
+                 const int32_t *__restrict__ lists, int64_t list_cap, const unsigned int *__restrict__ counts_dev,
+                 int c0, int c1, TinyBounds tb, DpParams prm, uint8_t *__restrict__ strbuf,
+                 uint32_t *__restrict__ tb_scratch) {
     extern __shared__ int smem_i[];
     constexpr int TH = TINY_THREADS;
     const int tid = threadIdx.x;
-    int *Tc = smem_i + tid;                                   // Tc[j * TH], j = 0..bound
-    int *Uc = Tc + (bound + 1) * TH;
-    uint16_t *selc = reinterpret_cast<uint16_t *>(smem_i + 2 * (bound + 1) * TH) + tid;   // selc[(j-1) * TH]
-    const int wpr = (bound + 3) >> 2;                         // traceback words per row
-    uint32_t *tbw = tb_scratch + (size_t)blockIdx.x * ((size_t)bound * wpr * TH) + tid;
-    const unsigned int count = *count_dev;
+    const int bmax = tb.b[c1 - 1];                            // shared memory is sized for the largest class
+    int *Tc = smem_i + tid;                                   // Tc[j * TH], j = 0..bmax
+    int *Uc = Tc + (bmax + 1) * TH;
+    uint16_t *selc = reinterpret_cast<uint16_t *>(smem_i + 2 * (bmax + 1) * TH) + tid;   // selc[(j-1) * TH]
     const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
 
+  // one launch walks the work lists of classes c0..c1-1 back to back: a CTA that runs out of
+  // items in one class moves on to the next, so the classes' tails overlap
+  for (int cls = c0; cls < c1; ++cls) {
+    if (cls > 0 && tb.b[cls] == tb.b[cls - 1]) continue;     // empty class
+    const int bound = tb.b[cls];
+    const int32_t *list = lists + (int64_t)cls * list_cap;
+    const unsigned int count = counts_dev[cls];
+    const int wpr = (bound + 3) >> 2;                         // traceback words per row
+    uint32_t *tbw = tb_scratch + (size_t)blockIdx.x * ((size_t)bmax * ((bmax + 3) >> 2) * TH) + tid;
     for (unsigned int base = blockIdx.x * TH; base < count; base += gridDim.x * TH) {
         const unsigned int item = base + tid;
         const bool have = item < count;
@@ -192,6 +200,7 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
             slots[sid].len = len;
         }
     }
+  }
 }
 
 static size_t dp_thread_smem(int bound) { return (size_t)(2 * (bound + 1) * 4 + bound * 2) * TINY_THREADS; }
@@ -200,17 +209,17 @@ size_t dp_thread_scratch_bytes(int bound, int num_sms) {
     return (size_t)dp_thread_grid(num_sms) * bound * ((bound + 3) / 4) * TINY_THREADS * 4;
 }
 
-cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
-                             const unsigned int *count_dev, int bound, DpParams prm, uint8_t *strbuf,
-                             uint32_t *tb_scratch, int num_sms, cudaStream_t st) {
-    const size_t smem = dp_thread_smem(bound);
+cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
+                             int64_t list_cap, const unsigned int *counts_dev, int c0, int c1, TinyBounds tb,
+                             DpParams prm, uint8_t *strbuf, uint32_t *tb_scratch, int num_sms, cudaStream_t st) {
+    const size_t smem = dp_thread_smem(tb.b[c1 - 1]);
     const int grid = dp_thread_grid(num_sms);
     if (prm.xy) {
         cudaFuncSetAttribute(dp_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dp_thread_kernel<true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, bound, prm, strbuf, tb_scratch);
+        dp_thread_kernel<true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch);
     } else {
         cudaFuncSetAttribute(dp_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dp_thread_kernel<false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, bound, prm, strbuf, tb_scratch);
+        dp_thread_kernel<false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch);
     }
     return cudaGetLastError();
 }
