@@ -67,7 +67,7 @@ struct dbga_ctx {
     const uint8_t *d_seqs_run = nullptr;
 
     // ---- device buffers (grow only)
-    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_slots, d_lists,
+    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_run_meta, d_slots, d_lists,
         d_tt, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_len, d_aln_off, d_run_cnt,
         d_run_off, d_scan_tmp, d_aln0, d_aln1, d_runs_out, d_score, d_cells, d_nseg, d_nanch, d_status_out,
         d_sink;
@@ -352,6 +352,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
 
 int reserve_pools(dbga_ctx *ctx) {
     RESERVE(d_runs, 12 * ctx->runs_cap);
+    RESERVE(d_run_meta, 8 * ctx->runs_cap);
     RESERVE(d_runs_out, 12 * ctx->runs_cap);
     if (ctx->prm.stages == 3) {
         RESERVE(d_slots, sizeof(Slot) * ctx->slots_cap);
@@ -447,11 +448,12 @@ int run_pipeline(dbga_ctx *ctx) {
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[4], st));
     DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, (int32_t *)ctx->d_status_out.p, (int32_t *)ctx->d_runs.p,
-                                    (Slot *)ctx->d_slots.p, (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p,
-                                    (int64_t *)ctx->d_aln_off.p, (int64_t *)ctx->d_run_cnt.p, (int64_t *)ctx->d_run_off.p,
-                                    (int64_t *)ctx->d_scan_tmp.p, (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p,
-                                    (int32_t *)ctx->d_runs_out.p, (int64_t *)ctx->d_score.p, (int64_t *)ctx->d_cells.p,
-                                    (int32_t *)ctx->d_nseg.p, (int64_t *)ctx->d_nanch.p, ctr, ctx->num_sms, st, &ctx->launches));
+                                    ctx->runs_cap, (int2 *)ctx->d_run_meta.p, (Slot *)ctx->d_slots.p, ctx->slots_cap,
+                                    (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p, (int64_t *)ctx->d_aln_off.p,
+                                    (int64_t *)ctx->d_run_cnt.p, (int64_t *)ctx->d_run_off.p, (int64_t *)ctx->d_scan_tmp.p,
+                                    (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p, (int32_t *)ctx->d_runs_out.p,
+                                    (int64_t *)ctx->d_score.p, (int64_t *)ctx->d_cells.p, (int32_t *)ctx->d_nseg.p,
+                                    (int64_t *)ctx->d_nanch.p, ctr, seg, ctx->num_sms, st, &ctx->launches));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
     return DBGA_SUCCESS;
 }
@@ -775,7 +777,7 @@ void dbga_destroy(dbga_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *dbs[] = {&ctx->d_seqs, &ctx->d_pairs, &ctx->d_list, &ctx->d_large, &ctx->d_status, &ctx->d_aof, &ctx->d_nd0,
-                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_slots, &ctx->d_lists, &ctx->d_tt, &ctx->d_ctr,
+                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_run_meta, &ctx->d_slots, &ctx->d_lists, &ctx->d_tt, &ctx->d_ctr,
                      &ctx->d_tb, &ctx->d_bnd_w, &ctx->d_bnd_c, &ctx->d_str, &ctx->d_packed, &ctx->d_table, &ctx->d_aln_len,
                      &ctx->d_aln_off, &ctx->d_run_cnt, &ctx->d_run_off, &ctx->d_scan_tmp, &ctx->d_aln0, &ctx->d_aln1,
                      &ctx->d_runs_out, &ctx->d_score, &ctx->d_cells, &ctx->d_nseg, &ctx->d_nanch, &ctx->d_status_out,

@@ -8,42 +8,74 @@
 
 namespace dbga {
 
-// ---------------------------------------------------------------- per-pair lengths
+// ---------------------------------------------------------------- per-pair layout
+// One warp per pair walks the pair's items in output order (slot 0, run 0, slot 1, run 1, ...,
+// run R-1, slot R) 32 at a time, scans their lengths and records where every slot and run
+// starts inside the pair's rows.  The copy kernels below are then item-parallel, so a pair
+// with a million columns is assembled by the whole chip, not by one warp.
 __global__ void __launch_bounds__(256)
-pair_len_kernel(const PairOut *__restrict__ pout, int64_t num_pairs, const Slot *__restrict__ slots,
-                int64_t *__restrict__ aln_len, int64_t *__restrict__ run_cnt, int64_t *__restrict__ score,
-                int64_t *__restrict__ cells, int32_t *__restrict__ nseg, int64_t *__restrict__ n_anchors,
-                int32_t *__restrict__ status_out) {
+pair_layout_kernel(const PairOut *__restrict__ pout, int64_t num_pairs, Slot *__restrict__ slots,
+                   const int32_t *__restrict__ runs, int2 *__restrict__ run_meta, int64_t *__restrict__ aln_len,
+                   int64_t *__restrict__ run_cnt, int64_t *__restrict__ score, int64_t *__restrict__ cells,
+                   int32_t *__restrict__ nseg, int64_t *__restrict__ n_anchors, int32_t *__restrict__ status_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t pair = warp; pair < num_pairs; pair += nwarps) {
         const PairOut po = pout[pair];
-        long long len = 0, sc = 0, ce = 0;
+        const bool ok = po.status == DBGA_OK, report = ok || po.status == DBGA_CYCLE;
+        const int R = po.n_runs;
+        long long carry = 0, sc = 0, ce = 0;
         int ns = 0;
-        if (po.status == DBGA_OK) {
-            for (int t = lane; t < po.n_slots; t += 32) {
-                const Slot s = slots[po.slot_base + t];
-                const bool mid = po.n_runs > 0 && t > 0 && t < po.n_slots - 1;
-                len += s.len - (mid && s.len > 0 ? 1 : 0);
-                if (s.m > 0 && s.n > 0) { sc += s.score; ce += (long long)s.m * s.n; ++ns; }
+        if (ok && po.n_slots > 0) {
+            const int n_items = po.n_slots + R;
+            for (int ib = 0; ib < n_items; ib += 32) {
+                const int it = ib + lane;
+                long long len = 0;
+                bool is_slot = false;
+                int t = 0;
+                if (it < n_items) {
+                    is_slot = (R == 0) || (it % 2 == 0);
+                    t = it / 2;
+                    if (is_slot) {
+                        const Slot s = slots[po.slot_base + t];
+                        const bool mid = R > 0 && t > 0 && t < po.n_slots - 1;
+                        const int skip = (mid && s.len > 0) ? 1 : 0;
+                        len = s.len - skip;
+                        slots[po.slot_base + t].skip = skip;
+                        if (s.m > 0 && s.n > 0) { sc += s.score; ce += (long long)s.m * s.n; ++ns; }
+                    } else {
+                        len = runs[3 * (po.run_base + t) + 2] - (t == R - 1 ? 1 : 0);   // last merge node is left to the tail
+                    }
+                }
+                long long inc = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const long long off = carry + inc - len;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+                if (it < n_items) {
+                    if (is_slot) slots[po.slot_base + t].out_off = (int32_t)off;
+                    else run_meta[po.run_base + t] = make_int2((int)off, (int)pair);
+                }
             }
+        } else if (R > 0 && po.run_base >= 0) {
+            // no alignment (cycle, or a limit was hit): runs are only reported / ignored
+            for (int r = lane; r < R; r += 32) run_meta[po.run_base + r] = make_int2(-1, report ? (int)pair : -1);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            len += __shfl_xor_sync(0xffffffffu, len, o);
             sc += __shfl_xor_sync(0xffffffffu, sc, o);
             ce += __shfl_xor_sync(0xffffffffu, ce, o);
             ns += __shfl_xor_sync(0xffffffffu, ns, o);
         }
         if (lane == 0) {
-            const bool ok = po.status == DBGA_OK;
-            if (ok && po.n_slots > 0 && po.n_anchors > 0) len += po.n_anchors - 1;
-            aln_len[pair] = ok ? len : 0;
-            // runs are reported for aligned pairs and for cycle pairs (the anchors that cycle)
-            run_cnt[pair] = (ok || po.status == DBGA_CYCLE) ? po.n_runs : 0;
+            aln_len[pair] = ok ? carry : 0;
+            run_cnt[pair] = report ? R : 0;       // cycle pairs still report the anchors that cycle
             score[pair] = sc; cells[pair] = ce; nseg[pair] = ns;
-            n_anchors[pair] = (ok || po.status == DBGA_CYCLE) ? po.n_anchors : 0;
+            n_anchors[pair] = report ? po.n_anchors : 0;
             status_out[pair] = po.status;
         }
     }
@@ -129,115 +161,98 @@ static cudaError_t exclusive_scan(const int64_t *in, int64_t n, int64_t *out, in
 }
 
 // ---------------------------------------------------------------- row assembly
-// One warp per pair.  Items in output order: slot 0, run 0, slot 1, run 1, ..., run R-1,
-// slot R (tail).  Lengths are scanned 32 items at a time; every item is then copied by the
-// whole warp.
+// Item-parallel copies, 8 lanes per item (a slot is ~10 columns, a run ~40): one kernel
+// over the slot pool, one over the run pool.  An entry is trusted only if the pair it names
+// currently owns that pool index (pools are not cleared between runs).
+constexpr int ASM_G = 8;
+
 __global__ void __launch_bounds__(256)
-assemble_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, int64_t num_pairs,
-                const PairOut *__restrict__ pout, const int32_t *__restrict__ runs, const Slot *__restrict__ slots,
-                const uint8_t *__restrict__ strbuf, const int64_t *__restrict__ aln_off,
-                const int64_t *__restrict__ run_off, uint8_t *__restrict__ aln0, uint8_t *__restrict__ aln1,
-                int32_t *__restrict__ runs_out) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t pair = warp; pair < num_pairs; pair += nwarps) {
-        const PairOut po = pout[pair];
-        if (po.status != DBGA_OK && po.status != DBGA_CYCLE) continue;
-        const int R = po.n_runs;
-        const int32_t *pr = runs + 3 * po.run_base;
-        {   // compact copy of the runs (anchors)
-            int32_t *dst = runs_out + 3 * run_off[pair];
-            for (int i = lane; i < 3 * R; i += 32) dst[i] = pr[i];
-        }
-        if (po.status != DBGA_OK || po.n_slots == 0) continue;
-        const PairDesc pd = pairs[pair];
-        const uint8_t *s0 = seqs + pd.off0, *s1 = seqs + pd.off1;
-        const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
-        uint8_t *o0 = aln0 + aln_off[pair], *o1 = aln1 + aln_off[pair];
-        const int n_items = po.n_slots + R;          // R == 0 -> just the one slot
-        long long carry = 0;
-        for (int ib = 0; ib < n_items; ib += 32) {
-            const int it = ib + lane;
-            // item description
-            int kind = -1;       // 0: DP slot (reversed rows in scratch) 1: gap slot 2: run copy
-            long long len = 0, src = 0;
-            int skip = 0, sm_ = 0, sn_ = 0, sx0 = 0, sy0 = 0;
-            if (it < n_items) {
-                const bool is_slot = (R == 0) || (it % 2 == 0);
-                const int t = it / 2;
-                if (is_slot) {
-                    const Slot s = slots[po.slot_base + t];
-                    const bool mid = R > 0 && t > 0 && t < po.n_slots - 1;
-                    skip = (mid && s.len > 0) ? 1 : 0;
-                    len = s.len - skip;
-                    sm_ = s.m; sn_ = s.n; sx0 = s.x0; sy0 = s.y0;
-                    if (s.m > 0 && s.n > 0) { kind = 0; src = s.str_off; len = s.len - skip; sm_ = s.len; }
-                    else kind = 1;
-                } else {
-                    kind = 2;
-                    sx0 = pr[3 * t]; sy0 = pr[3 * t + 1];
-                    len = pr[3 * t + 2] - (t == R - 1 ? 1 : 0);   // last merge node is left to the tail
-                }
+assemble_slots_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, int64_t num_pairs,
+                      const PairOut *__restrict__ pout, const Slot *__restrict__ slots, int64_t slots_cap,
+                      const Counters *__restrict__ ctr, const uint8_t *__restrict__ strbuf,
+                      const int64_t *__restrict__ aln_off, uint8_t *__restrict__ aln0, uint8_t *__restrict__ aln1) {
+    const int gl = threadIdx.x & (ASM_G - 1);
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / ASM_G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / ASM_G;
+    int64_t total = (int64_t)ctr->slots_used;
+    if (total > slots_cap) total = slots_cap;
+    for (int64_t idx = grp; idx < total; idx += ngrp) {
+        const Slot s = slots[idx];
+        if (s.pair < 0 || s.pair >= num_pairs) continue;
+        const PairOut po = pout[s.pair];
+        if (po.status != DBGA_OK || idx < po.slot_base || idx >= po.slot_base + po.n_slots) continue;
+        const int len = s.len - s.skip;
+        if (len <= 0) continue;
+        const PairDesc pd = pairs[s.pair];
+        uint8_t *o0 = aln0 + aln_off[s.pair] + s.out_off, *o1 = aln1 + aln_off[s.pair] + s.out_off;
+        if (s.m > 0 && s.n > 0) {        // reversed rows in scratch: column c is at [len_full - 1 - c]
+            const uint8_t *rx = strbuf + s.str_off, *ry = rx + ((pd.off1 - pd.off0) + pd.n1);
+            for (int c = gl; c < len; c += ASM_G) {
+                o0[c] = rx[s.len - 1 - (c + s.skip)];
+                o1[c] = ry[s.len - 1 - (c + s.skip)];
             }
-            // exclusive scan of len over the 32 items
-            long long inc = len;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            const long long off = carry + inc - len;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-            const int cnt = min(32, n_items - ib);
-            for (int u = 0; u < cnt; ++u) {
-                const int kd = __shfl_sync(0xffffffffu, kind, u);
-                const long long ln = __shfl_sync(0xffffffffu, len, u);
-                const long long of = __shfl_sync(0xffffffffu, off, u);
-                const long long sr = __shfl_sync(0xffffffffu, src, u);
-                const int sk = __shfl_sync(0xffffffffu, skip, u);
-                const int a0 = __shfl_sync(0xffffffffu, sx0, u), b0 = __shfl_sync(0xffffffffu, sy0, u);
-                const int mm = __shfl_sync(0xffffffffu, sm_, u);
-                if (kd == 0) {           // reversed rows: column c of the segment is at [full_len-1-c]
-                    const uint8_t *rx = strbuf + sr, *ry = rx + row_len;
-                    for (long long c = lane; c < ln; c += 32) {
-                        o0[of + c] = rx[mm - 1 - (c + sk)];
-                        o1[of + c] = ry[mm - 1 - (c + sk)];
-                    }
-                } else if (kd == 1) {    // one side empty (utils.py:187-190)
-                    for (long long c = lane; c < ln; c += 32) {
-                        o0[of + c] = mm > 0 ? s0[a0 + c + sk] : (uint8_t)'-';
-                        o1[of + c] = mm > 0 ? (uint8_t)'-' : s1[b0 + c + sk];
-                    }
-                } else if (kd == 2) {
-                    for (long long c = lane; c < ln; c += 32) {
-                        o0[of + c] = s0[a0 + c];
-                        o1[of + c] = s1[b0 + c];
-                    }
-                }
+        } else {                         // one side empty (utils.py:187-190)
+            const uint8_t *s0 = seqs + pd.off0 + s.x0, *s1 = seqs + pd.off1 + s.y0;
+            for (int c = gl; c < len; c += ASM_G) {
+                o0[c] = s.m > 0 ? s0[c + s.skip] : (uint8_t)'-';
+                o1[c] = s.m > 0 ? (uint8_t)'-' : s1[c + s.skip];
             }
         }
     }
 }
 
+__global__ void __launch_bounds__(256)
+assemble_runs_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, int64_t num_pairs,
+                     const PairOut *__restrict__ pout, const int32_t *__restrict__ runs, const int2 *__restrict__ run_meta,
+                     int64_t runs_cap, const Counters *__restrict__ ctr, const int64_t *__restrict__ aln_off,
+                     const int64_t *__restrict__ run_off, uint8_t *__restrict__ aln0, uint8_t *__restrict__ aln1,
+                     int32_t *__restrict__ runs_out) {
+    const int gl = threadIdx.x & (ASM_G - 1);
+    const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / ASM_G;
+    const int64_t ngrp = ((int64_t)gridDim.x * blockDim.x) / ASM_G;
+    int64_t total = (int64_t)ctr->runs_used;
+    if (total > runs_cap) total = runs_cap;
+    for (int64_t idx = grp; idx < total; idx += ngrp) {
+        const int2 meta = run_meta[idx];
+        const int pair = meta.y;
+        if (pair < 0 || pair >= num_pairs) continue;
+        const PairOut po = pout[pair];
+        if (idx < po.run_base || idx >= po.run_base + po.n_runs) continue;
+        if (po.status != DBGA_OK && po.status != DBGA_CYCLE) continue;
+        const int a = runs[3 * idx], b = runs[3 * idx + 1], len = runs[3 * idx + 2];
+        if (gl < 3) runs_out[3 * (run_off[pair] + (idx - po.run_base)) + gl] = gl == 0 ? a : (gl == 1 ? b : len);
+        if (po.status != DBGA_OK || meta.x < 0) continue;
+        const int n = len - (idx == po.run_base + po.n_runs - 1 ? 1 : 0);
+        const PairDesc pd = pairs[pair];
+        const uint8_t *s0 = seqs + pd.off0 + a, *s1 = seqs + pd.off1 + b;
+        uint8_t *o0 = aln0 + aln_off[pair] + meta.x, *o1 = aln1 + aln_off[pair] + meta.x;
+        for (int c = gl; c < n; c += ASM_G) { o0[c] = s0[c]; o1[c] = s1[c]; }
+    }
+}
+
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
-                            const int32_t *status, const int32_t *runs, const Slot *slots, const uint8_t *strbuf,
-                            int64_t *aln_len, int64_t *aln_off, int64_t *run_cnt, int64_t *run_off,
-                            int64_t *scan_tmp, uint8_t *aln0, uint8_t *aln1, int32_t *runs_out,
-                            int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
-                            Counters *ctr, int num_sms, cudaStream_t st, int *launches) {
+                            const int32_t *status, const int32_t *runs, int64_t runs_cap, int2 *run_meta, Slot *slots,
+                            int64_t slots_cap, const uint8_t *strbuf, int64_t *aln_len, int64_t *aln_off,
+                            int64_t *run_cnt, int64_t *run_off, int64_t *scan_tmp, uint8_t *aln0, uint8_t *aln1,
+                            int32_t *runs_out, int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
+                            Counters *ctr, bool want_rows, int num_sms, cudaStream_t st, int *launches) {
     if (num_pairs <= 0) return cudaSuccess;
     int64_t grid = (num_pairs + 7) / 8;
     if (grid > (int64_t)num_sms * 8) grid = (int64_t)num_sms * 8;
-    pair_len_kernel<<<(int)grid, 256, 0, st>>>(pout, num_pairs, slots, aln_len, run_cnt, score, cells, nseg,
-                                              n_anchors, const_cast<int32_t *>(status));
+    pair_layout_kernel<<<(int)grid, 256, 0, st>>>(pout, num_pairs, slots, runs, run_meta, aln_len, run_cnt, score, cells,
+                                                 nseg, n_anchors, const_cast<int32_t *>(status));
     *launches += 1;
     cudaError_t e = exclusive_scan(aln_len, num_pairs, aln_off, scan_tmp, reinterpret_cast<int64_t *>(&ctr->total_aln), st, launches);
     if (e != cudaSuccess) return e;
     e = exclusive_scan(run_cnt, num_pairs, run_off, scan_tmp, reinterpret_cast<int64_t *>(&ctr->total_runs), st, launches);
     if (e != cudaSuccess) return e;
-    assemble_kernel<<<(int)grid, 256, 0, st>>>(seqs, pairs, num_pairs, pout, runs, slots, strbuf, aln_off, run_off,
-                                              aln0, aln1, runs_out);
+    const int cgrid = num_sms * 8;
+    if (want_rows) {
+        assemble_slots_kernel<<<cgrid, 256, 0, st>>>(seqs, pairs, num_pairs, pout, slots, slots_cap, ctr, strbuf, aln_off, aln0, aln1);
+        *launches += 1;
+    }
+    assemble_runs_kernel<<<cgrid, 256, 0, st>>>(seqs, pairs, num_pairs, pout, runs, run_meta, runs_cap, ctr, aln_off, run_off,
+                                               aln0, aln1, runs_out);
     *launches += 1;
     return cudaGetLastError();
 }

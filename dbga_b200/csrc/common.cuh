@@ -38,8 +38,12 @@ struct Slot {
     int64_t str_off;      // scratch: reversed rows; row x at [str_off, +m+n), row y after
     int64_t tb_off;       // scratch: traceback bytes (warp / cta classes)
     int32_t pair;
-    int32_t cls;          // DP class: -1 none, 0 tiny, 1 warp, 2 cta
+    int32_t cls;          // DP class (CLS_*)
+    int32_t out_off;      // assembly: first output column of this slot, relative to the pair
+    int32_t skip;         // assembly: 1 = drop the first column (mid segments, debruijn_pairwise.py:499-500)
+    int32_t pad[2];
 };
+static_assert(sizeof(Slot) == 64, "Slot is four 16-byte words");
 
 // DP classes: 0..3 = thread-per-segment ("tiny", bucketed by max(m, n) so that the segments of
 // a warp have similar loop bounds), 4 = warp wavefront, 5 = CTA wavefront.

@@ -67,11 +67,11 @@ cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot
 
 // ---- assembly
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
-                            const int32_t *status, const int32_t *runs, const Slot *slots, const uint8_t *strbuf,
-                            int64_t *aln_len, int64_t *aln_off, int64_t *run_cnt, int64_t *run_off,
-                            int64_t *scan_tmp, uint8_t *aln0, uint8_t *aln1, int32_t *runs_out,
-                            int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
-                            Counters *ctr, int num_sms, cudaStream_t st, int *launches);
+                            const int32_t *status, const int32_t *runs, int64_t runs_cap, int2 *run_meta, Slot *slots,
+                            int64_t slots_cap, const uint8_t *strbuf, int64_t *aln_len, int64_t *aln_off,
+                            int64_t *run_cnt, int64_t *run_off, int64_t *scan_tmp, uint8_t *aln0, uint8_t *aln1,
+                            int32_t *runs_out, int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
+                            Counters *ctr, bool want_rows, int num_sms, cudaStream_t st, int *launches);
 
 // ---- integer-pipe microbenchmark
 cudaError_t launch_int_peak(int which, int iters, int *sink, int num_sms, cudaStream_t st);
