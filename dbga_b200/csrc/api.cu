@@ -61,6 +61,7 @@ struct dbga_ctx {
     int64_t runs_cap = 0, slots_cap = 0, tb_cap = 0;
     int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
     int grid_warp = 0, grid_cta = 0;
+    int64_t warp_max_cells = WARP_CLASS_MAX_CELLS_FEW;
     int tiny_bound[NUM_TINY] = {8, 16, 24, 32};
     bool seen_warp_work = true, seen_cta_work = true;   // adaptive grid for the (often empty) wavefront launches
     int launches = 0;
@@ -322,16 +323,17 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         ctx->tiny_bound[3] = TINY_MAX;
     }
     // boundary rows for multi-pass wavefronts
-    ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, WARP_CLASS_MAX_CELLS / (WF_ROWS_PER_WARP + 1) + 2);
+    ctx->warp_max_cells = P >= MANY_PAIRS ? WARP_CLASS_MAX_CELLS_MANY : WARP_CLASS_MAX_CELLS_FEW;
+    ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, ctx->warp_max_cells / (WF_ROWS_PER_WARP + 1) + 2);
     ctx->bnd_stride_cta = (int64_t)mx1 + 1;
-    ctx->grid_warp = ctx->num_sms * 16;
+    ctx->grid_warp = (int)std::max<int64_t>(ctx->num_sms, std::min<int64_t>(ctx->num_sms * 16, (512LL << 20) / (32 * ctx->bnd_stride_warp)));
     {
         const int64_t per = 2 * ctx->bnd_stride_cta * 16;
         int64_t g = (1LL << 30) / std::max<int64_t>(per, 1);
         ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, g));
     }
     const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
-    const bool any_cta = (int64_t)mx0 * mx1 > WARP_CLASS_MAX_CELLS;
+    const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells;
     if (!any_non_tiny) ctx->grid_warp = 0;
     if (!any_cta) ctx->grid_cta = 0;
     if (params->stages == 3) {
@@ -383,6 +385,7 @@ int run_pipeline(dbga_ctx *ctx) {
     pools.lists = (int32_t *)ctx->d_lists.p;
     for (int c = 0; c < NUM_TINY; ++c) pools.tiny_bound[c] = ctx->tiny_bound[c];
     pools.list_cap = ctx->slots_cap;
+    pools.warp_max_cells = ctx->warp_max_cells;
     Counters *ctr = (Counters *)ctx->d_ctr.p;
     PairDesc *pairs = (PairDesc *)ctx->d_pairs.p;
     PairOut *pout = (PairOut *)ctx->d_pout.p;

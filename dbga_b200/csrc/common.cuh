@@ -58,7 +58,12 @@ constexpr int WF_CTA_WARPS = 8;  // warps per CTA in the long-segment kernel
 constexpr int WF_D = 64;         // step delay between consecutive warps
 constexpr int WF_C = 32;         // steps per barrier
 constexpr int WF_RING = 128;     // ring entries (columns) per warp boundary
-constexpr int64_t WARP_CLASS_MAX_CELLS = 1 << 18;   // above this a segment gets a CTA
+// A segment above warp_max_cells gets a whole CTA (8 pipelined warps), below it one warp.
+// With few pairs in the batch a big segment needs the CTA's parallelism; with many pairs
+// there are enough segments to fill the chip warp by warp, which wastes no pipeline fill.
+constexpr int64_t WARP_CLASS_MAX_CELLS_FEW = 1 << 18;
+constexpr int64_t WARP_CLASS_MAX_CELLS_MANY = 1 << 24;
+constexpr int64_t MANY_PAIRS = 592;
 
 // Scores are kept as 64*V + 21*tag(state): the three 2-bit tag fields make every max()
 // break ties in the configured state order and leave the winner's identity in the low

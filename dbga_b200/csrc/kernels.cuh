@@ -32,6 +32,7 @@ struct Pools {
     int32_t *lists;                        // NUM_CLS work lists of list_cap slot ids each
     int64_t list_cap;
     int32_t tiny_bound[NUM_TINY];          // class c holds segments with max(m, n) <= tiny_bound[c]
+    int64_t warp_max_cells;                // larger segments get a whole CTA
 };
 
 // ---- stages 1+2 fused (pairs whose table fits in shared memory)

@@ -51,7 +51,7 @@ __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, in
 #pragma unroll
                     for (int c = NUM_TINY - 2; c >= 0; --c) if (mx <= pools.tiny_bound[c]) cls = c;
                 } else {
-                    cls = cells <= WARP_CLASS_MAX_CELLS ? CLS_WARP : CLS_CTA;
+                    cls = cells <= pools.warp_max_cells ? CLS_WARP : CLS_CTA;
                     const long long need = (tb_bytes_wavefront(s.m, s.n, cls == CLS_WARP ? 1 : WF_CTA_WARPS) + 255) & ~255LL;
                     const long long off = (long long)atomicAdd(&ctr->tb_used, (unsigned long long)need);
                     if (off + need > pools.tb_cap) { *flag_big = 1; cls = CLS_NONE; }

@@ -93,18 +93,30 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
     extern __shared__ int smem_i[];
     constexpr int TH = TINY_THREADS;
     const int tid = threadIdx.x;
-    const int bmax = tb.b[c1 - 1];                            // shared memory is sized for the largest class
+    int bmax = 0;
+#pragma unroll
+    for (int c = 0; c < NUM_TINY; ++c) if (c == c1 - 1) bmax = (tb.b[c] + 3) & ~3;   // shared memory is sized for the largest class
     int *Tc = smem_i + tid;                                   // Tc[j * TH], j = 0..bmax
     int *Uc = Tc + (bmax + 1) * TH;
     uint16_t *selc = reinterpret_cast<uint16_t *>(smem_i + 2 * (bmax + 1) * TH) + tid;   // selc[(j-1) * TH]
     const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
+    // score LUT in shared memory: indexing kernel parameters with a run-time base code would
+    // compile into a long predicated cascade
+    __shared__ uint32_t s_lut[8];
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_lut[c] = prm.lut_lo[c]; s_lut[4 + c] = prm.lut_hi[c]; }
+    }
+    __syncthreads();
 
   // one launch walks the work lists of classes c0..c1-1 back to back: a CTA that runs out of
   // items in one class moves on to the next, so the classes' tails overlap
   for (int cls = c0; cls < c1; ++cls) {
-    if (cls > 0 && tb.b[cls] == tb.b[cls - 1]) continue;     // empty class
-    const int bound = tb.b[cls];
+    int bound = 0, prev_bound = -1;
+#pragma unroll
+    for (int c = 0; c < NUM_TINY; ++c) { if (c == cls) bound = tb.b[c]; if (c + 1 == cls) prev_bound = tb.b[c]; }
+    if (bound == prev_bound) continue;                        // empty class
     const int32_t *list = lists + (int64_t)cls * list_cap;
     const unsigned int count = counts_dev[cls];
     const int wpr = (bound + 3) >> 2;                         // traceback words per row
@@ -142,41 +154,56 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
             mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
             nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
         }
+        // columns are processed four at a time (one traceback word); columns past a lane's own
+        // n, and rows past its m, compute garbage into the lane's private shared-memory columns
+        const int ngrp = (nmax + 3) >> 2;
         int eM = 0, eX = 0, eY = 0;
+        int xi0 = (-go) | tagX;                                   // X[i][0], i = 1
+        uint32_t *tbrow = tbw;
         for (int i = 1; i <= mmax; ++i) {
             const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
-            const uint32_t slo = prm.lut_lo[xc], shi = prm.lut_hi[xc];
-            const int xi0 = (-(go + (i - 1) * ge)) | tagX;       // X[i][0]
+            const uint32_t slo = s_lut[xc], shi = s_lut[4 + xc];
             int Ml = NEG | tagM, Yl = NEG | tagY, Xl = xi0;
             int diag = Tc[0];
             Tc[0] = xi0;                                         // max(M, X, Y)[i][0]
             Uc[0] = xi0 - ge;                                    // X candidate of row i+1, column 0
-            uint32_t word = 0;
-            uint32_t *tbrow = tbw + (size_t)(i - 1) * wpr * TH;
-            for (int j = 1; j <= nmax; ++j) {
-                const int Tj = Tc[j * TH], Uj = Uc[j * TH];
-                const uint32_t sel = selc[(j - 1) * TH];
-                const int Mn = strip(diag) + lut_score(slo, shi, sel);
-                const int Xn = strip(Uj) | tagX;
-                int v = __viaddmax_s32(Ml, -go, Yl - ge);
-                if (XY) v = max(v, Xl - go);
-                const int Yn = strip(v) | tagY;
-                uint32_t d = ((uint32_t)diag & 3u) | ((uint32_t)Uj & ~3u);
-                d = (d & 15u) | ((uint32_t)v & ~15u);
-                word |= (d & 0xFFu) << (8 * ((j - 1) & 3));
-                int un = __viaddmax_s32(Mn, -go, Xn - ge);
-                if (XY) un = max(un, Yn - go);
-                Tc[j * TH] = __vimax3_s32(Mn, Xn, Yn);
-                Uc[j * TH] = un;
-                if (i == m && j == n) { eM = Mn; eX = Xn; eY = Yn; }
-                diag = Tj; Ml = Mn; Yl = Yn; Xl = Xn;
-                if ((j & 3) == 0 || j == nmax) { tbrow[((j - 1) >> 2) * TH] = word; word = 0; }
+            xi0 -= ge;
+            const bool last_row = (i == m);
+            int *Tp = Tc + TH, *Up = Uc + TH;
+            const uint16_t *sp = selc;
+            for (int g = 0; g < ngrp; ++g) {
+                uint32_t word = 0;
+                const int capg = last_row ? n - 4 * g : -1;       // terminal cell is column capg of this group
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int Tj = Tp[u4 * TH], Uj = Up[u4 * TH];
+                    const uint32_t sel = sp[u4 * TH];
+                    const int Mn = strip(diag) + lut_score(slo, shi, sel);
+                    const int Xn = strip(Uj) | tagX;
+                    int v = __viaddmax_s32(Ml, -go, Yl - ge);
+                    if (XY) v = max(v, Xl - go);
+                    const int Yn = strip(v) | tagY;
+                    uint32_t d = ((uint32_t)diag & 3u) | ((uint32_t)Uj & ~3u);
+                    d = (d & 15u) | ((uint32_t)v & ~15u);
+                    word |= (d & 0xFFu) << (8 * u4);
+                    int un = __viaddmax_s32(Mn, -go, Xn - ge);
+                    if (XY) un = max(un, Yn - go);
+                    Tp[u4 * TH] = __vimax3_s32(Mn, Xn, Yn);
+                    Up[u4 * TH] = un;
+                    if (capg == u4 + 1) { eM = Mn; eX = Xn; eY = Yn; }
+                    diag = Tj; Ml = Mn; Yl = Yn; Xl = Xn;
+                }
+                tbrow[g * TH] = word;
+                Tp += 4 * TH; Up += 4 * TH; sp += 4 * TH;
             }
+            tbrow += wpr * TH;
         }
         // traceback: every lane walks its own segment; rows are written reversed
         if (have) {
             int st, score;
             pick_end(eM, eX, eY, prm, st, score);
+            const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
+                                  ((uint32_t)prio_to_state(2, prm) << 4);
             int i = m, j = n, len = 0;
             uint8_t *ox = strbuf + str_off, *oy = ox + row_len;
             while (i > 0 || j > 0) {
@@ -184,16 +211,11 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
                 else if (j == 0) st = 1;
                 uint32_t d = 0;
                 if (i > 0 && j > 0) d = tbw[((size_t)(i - 1) * wpr + ((j - 1) >> 2)) * TH] >> (8 * ((j - 1) & 3));
-                if (st == 0) {
-                    ox[len] = xs[i - 1]; oy[len] = ys[j - 1];
-                    st = prio_to_state(d & 3, prm); --i; --j;
-                } else if (st == 1) {
-                    ox[len] = xs[i - 1]; oy[len] = '-';
-                    st = prio_to_state((d >> 2) & 3, prm); --i;
-                } else {
-                    ox[len] = '-'; oy[len] = ys[j - 1];
-                    st = prio_to_state((d >> 4) & 3, prm); --j;
-                }
+                ox[len] = st == 2 ? (uint8_t)'-' : xs[i - 1];
+                oy[len] = st == 1 ? (uint8_t)'-' : ys[j - 1];
+                const uint32_t tag = (d >> (2 * st)) & 3u;
+                i -= (st != 2); j -= (st != 1);
+                st = (int)((pmap >> (2 * tag)) & 3u);
                 ++len;
             }
             slots[sid].score = score;
@@ -203,7 +225,10 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
   }
 }
 
-static size_t dp_thread_smem(int bound) { return (size_t)(2 * (bound + 1) * 4 + bound * 2) * TINY_THREADS; }
+static size_t dp_thread_smem(int bound) {
+    const int b4 = (bound + 3) & ~3;                   // columns are processed in groups of four
+    return (size_t)(2 * (b4 + 1) * 4 + b4 * 2) * TINY_THREADS;
+}
 static int dp_thread_grid(int num_sms) { return num_sms * 8; }
 size_t dp_thread_scratch_bytes(int bound, int num_sms) {
     return (size_t)dp_thread_grid(num_sms) * bound * ((bound + 3) / 4) * TINY_THREADS * 4;
@@ -240,6 +265,12 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     __shared__ int4 ring[W + 1][RING];
     __shared__ WfShared sh;
     __shared__ __align__(16) uint8_t win[32][64];      // traceback window
+    __shared__ uint32_t s_lut[8];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_lut[c] = prm.lut_lo[c]; s_lut[4 + c] = prm.lut_hi[c]; }
+    }
+    __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned int count = *count_dev;
     const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
@@ -270,7 +301,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             for (int r = 0; r < R; ++r) {
                 const int i = row0 + r + 1;
                 const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
-                slo[r] = prm.lut_lo[xc]; shi[r] = prm.lut_hi[xc];
+                slo[r] = s_lut[xc]; shi[r] = s_lut[4 + xc];
                 Mr[r] = NEG | tagM;
                 Xr[r] = (-(go + (i - 1) * ge)) | tagX;
                 Yr[r] = NEG | tagY;
@@ -357,27 +388,30 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             int i = m, j = n, len = 0;
             const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
             uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
-            // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block
-            int64_t win_blk = -1; int win_row_hi = 0, win_col_lo = 0;
+            // state reached through a traceback tag: packed table prio -> state (0 = M, 1 = X, 2 = Y)
+            const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
+                                  ((uint32_t)prio_to_state(2, prm) << 4);
+            // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
+            // runs the same walk (uniform control flow); lane (len & 31) keeps the column's two
+            // characters and the warp flushes 32 columns with one coalesced store per row.
+            int win_blk = -1, win_row_hi = 0, win_col_lo = 0;
+            uint32_t cx = 0, cy = 0;
             while (i > 0 || j > 0) {
                 if (i == 0) st = 2;
                 else if (j == 0) st = 1;
                 uint32_t d = 0;
                 if (i > 0 && j > 0) {
                     const int i0 = i - 1;
-                    const int ps = i0 / ROWS_PASS, rem = i0 % ROWS_PASS;
-                    const int ww = rem / (32 * R), cb = rem % (32 * R);     // cb = l*R + r
+                    const int blk = i0 / (32 * R), cb = i0 % (32 * R);      // (pass * W + warp), l * R + r
                     const int row = j + cb / R;
-                    const int64_t blk = (int64_t)ps * W + ww;
-                    if (blk != win_blk || row > win_row_hi || row <= win_row_hi - 32 || cb < win_col_lo || cb >= win_col_lo + 64) {
+                    if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= 64u) {
                         __syncwarp();
                         win_blk = blk; win_row_hi = row;
                         win_col_lo = max(0, (cb & ~31) - 32);
                         const int rr = row - lane;
-                        const uint8_t *src = tb + (blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo;
                         uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
                         if (rr >= 1) {
-                            const uint4 *p = reinterpret_cast<const uint4 *>(src);
+                            const uint4 *p = reinterpret_cast<const uint4 *>(tb + ((int64_t)blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo);
                             a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
                         }
                         uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
@@ -386,16 +420,16 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                     }
                     d = win[win_row_hi - row][cb - win_col_lo];
                 }
-                if (lane == 0) {
-                    if (st == 0) { ox[len] = xs[i - 1]; oy[len] = ys[j - 1]; }
-                    else if (st == 1) { ox[len] = xs[i - 1]; oy[len] = '-'; }
-                    else { ox[len] = '-'; oy[len] = ys[j - 1]; }
-                }
-                if (st == 0) { st = prio_to_state(d & 3, prm); --i; --j; }
-                else if (st == 1) { st = prio_to_state((d >> 2) & 3, prm); --i; }
-                else { st = prio_to_state((d >> 4) & 3, prm); --j; }
+                const uint32_t chx = st == 2 ? (uint32_t)'-' : (uint32_t)xs[i - 1];
+                const uint32_t chy = st == 1 ? (uint32_t)'-' : (uint32_t)ys[j - 1];
+                if ((len & 31) == lane) { cx = chx; cy = chy; }
+                if ((len & 31) == 31) { ox[len - 31 + lane] = (uint8_t)cx; oy[len - 31 + lane] = (uint8_t)cy; }
+                const uint32_t tag = (d >> (2 * st)) & 3u;
+                i -= (st != 2); j -= (st != 1);
+                st = (int)((pmap >> (2 * tag)) & 3u);
                 ++len;
             }
+            if (lane < (len & 31)) { ox[(len & ~31) + lane] = (uint8_t)cx; oy[(len & ~31) + lane] = (uint8_t)cy; }
             if (lane == 0) { slots[sid].score = score; slots[sid].len = len; }
         }
         __syncthreads();

@@ -217,3 +217,18 @@ def test_pipelined_batch_equals_direct(aligner):
         j, part = (i, parts[0]) if i < 3500 else (i - 3500, parts[1])
         assert big.alignment(i) == part.alignment(j)
         assert np.array_equal(big.anchors(i), part.anchors(j))
+
+
+def test_big_segments_in_big_batch(aligner):
+    """With >= 592 pairs in the batch, segments up to 2^24 cells go to the warp-per-segment
+    wavefront (many row strips) instead of the CTA kernel."""
+    rng = random.Random(21)
+    pairs = [(rand_seq(rng, 12), rand_seq(rng, 12)) for _ in range(600)]
+    x = rand_seq(rng, 2100)
+    pairs += [(x, (mutate(rng, x, 0.1, 0.05) + rand_seq(rng, 2300))[:2300]), (rand_seq(rng, 700), rand_seq(rng, 650)),
+              (rand_seq(rng, 3000), rand_seq(rng, 40)), (rand_seq(rng, 40), rand_seq(rng, 3000))]
+    res = aligner.global_align_pairs(pairs)
+    for i in list(range(0, 600, 97)) + [600, 601, 602, 603]:
+        sc, ax, ay = CO.gotoh(*pairs[i])
+        assert res.status[i] == O.OK and res.score[i] == sc, i
+        assert res.alignment(i) == (ax, ay), i
