@@ -76,7 +76,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.002)
 
     def start(self):
         if self.nv is not None:
