@@ -134,6 +134,33 @@ def main():
     fixtures["kmers"].append({"seq": "GTACACGTATG", "k": 3, "kmers": get_kmers("GTACACGTATG", 3)})
     fixtures["kmers"].append({"seq": "TACCACGTAAT", "k": 4, "kmers": get_kmers("TACCACGTAAT", 4)})
     assert duplicate_kmers([["AG", "CT", "CA", "AC", "CT"], ["CT", "AC", "GT", "AG"]]) == {"CT"}
+    # adaptive aligner goldens (reference tests/test_adaptive_debruijn.py:19-48)
+    from dbga.adaptive_debruijn import adpt_dbg_alignment_recursive
+    ADAPT = [("gap_bubble_duplicate", (3, 2), ("GTACACGTATG", "GTACACG-ATG")),
+             ("gap_bubble_duplicate", (7, 5, 3, 2), ("GTACACGTATG", "GTACACG-ATG")),
+             ("duplicate_unbalanced_end", (3,), ("TGTACGTCAATGTCG", "TGTAAGTCAATG---")),
+             ("duplicate_in_stem", (3,), ("GTACACGTATG", "GTACTCGTATG"))]
+    fixtures["adaptive"] = []
+    for name, kc, aln in ADAPT:
+        _, seqs = read_fasta(os.path.join(REF, "tests", "data", name + ".fasta"))
+        got = adpt_dbg_alignment_recursive(seqs, 0, kc, s, 10, 2)
+        assert tuple(got) == aln, (name, got)
+        fixtures["adaptive"].append({"seqs": seqs, "k_choice": list(kc), "aln": list(aln),
+                                     "ref": "tests/test_adaptive_debruijn.py:19-48"})
+    # recorded outputs of the reference's adaptive recursion on random related pairs
+    arng = random.Random(77)
+    fixtures["adaptive_fuzz"] = []
+    while len(fixtures["adaptive_fuzz"]) < 40:
+        n = arng.choice([60, 150, 400])
+        s0 = "".join(arng.choice("ACGT") for _ in range(n))
+        s1 = mutate(arng, s0, 0.03, 0.01)
+        kc = arng.choice([(9, 5, 3), (7, 4), (11, 7, 5, 3)])
+        try:
+            got = adpt_dbg_alignment_recursive((s0, s1), 0, kc, s, 10, 2)
+        except Exception as ex:  # cycles at some level: the reference raises
+            fixtures["adaptive_fuzz"].append({"seqs": [s0, s1], "k_choice": list(kc), "error": type(ex).__name__})
+            continue
+        fixtures["adaptive_fuzz"].append({"seqs": [s0, s1], "k_choice": list(kc), "aln": list(got)})
     json.dump(fixtures, open(os.path.join(ROOT, "tests", "golden", "ref_fixtures.json"), "w"), indent=1)
 
     rng = random.Random(20261019)

@@ -137,3 +137,24 @@ def test_baseline_config2_is_a_cycle_error():
         break
     else:
         pytest.fail("no colinear seed found")
+
+
+def test_adaptive_recursive_goldens(ref_fixtures):
+    # reference tests/test_adaptive_debruijn.py:19-48, plus recorded outputs of the reference's
+    # own adpt_dbg_alignment_recursive on random related pairs (oracle/make_golden.py)
+    from dbga_b200 import make_dna_scoring_dict
+    from dbga_b200.adaptive_debruijn import adpt_dbg_alignment_recursive
+    s = make_dna_scoring_dict(10, -1, -8)
+    for fx in ref_fixtures["adaptive"]:
+        got = adpt_dbg_alignment_recursive(fx["seqs"], 0, tuple(fx["k_choice"]), s, 10, 2)
+        assert list(got) == fx["aln"]
+    n_ok = 0
+    for fx in ref_fixtures["adaptive_fuzz"]:
+        if "error" in fx:
+            with pytest.raises(Exception):
+                adpt_dbg_alignment_recursive(tuple(fx["seqs"]), 0, tuple(fx["k_choice"]), s, 10, 2)
+            continue
+        got = adpt_dbg_alignment_recursive(tuple(fx["seqs"]), 0, tuple(fx["k_choice"]), s, 10, 2)
+        assert list(got) == fx["aln"]
+        n_ok += 1
+    assert n_ok >= 10
