@@ -17,6 +17,8 @@ integer-pipe rate), `stages_ms`, `cycle_frac`.
 from __future__ import annotations
 
 import argparse
+import os as _os
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: one hardware queue per stream
 import json
 import os
 import sys

@@ -79,6 +79,18 @@ struct dbga_ctx {
     static constexpr int NL = 4;
     dbga_ctx *lanes[NL] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_ready = nullptr;
+    // sub-chunked upload of a lane's sequences: piece s is complete when ev_sub[s] fires;
+    // stage 1+2 for the pairs of piece s is launched right behind it
+    static constexpr int MAX_SUB = 16;
+    cudaStream_t meta_stream = nullptr;   // lanes: upload plan metadata on the shared upload stream
+    cudaEvent_t ev_meta = nullptr;
+    cudaStream_t copy_stream = nullptr;   // parent only: one upload stream shared by all lanes (uploads are serial on
+                                          // the H2D engine anyway, and every extra stream risks aliasing onto one of the
+                                          // CUDA_DEVICE_MAX_CONNECTIONS hardware queues, which creates false dependencies)
+    cudaEvent_t ev_sub[MAX_SUB] = {};
+    int n_sub = 0;
+    int64_t sub_pair_lo[MAX_SUB + 1] = {};
+    cudaEvent_t dbg_ev[4] = {};       // DBGA_TRACE: upload begin / end, download begin / end
 };
 
 namespace {
@@ -288,9 +300,17 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         DBGA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));     // previous use of the staging buffer is over
         HRESERVE(h_meta, o2 + b2 + 16);
         char *m = (char *)ctx->h_meta.p;
-        if (b0) { memcpy(m, ctx->h_pairs.data(), b0); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pairs.p, m, b0, cudaMemcpyHostToDevice, ctx->stream)); }
-        if (b1) { memcpy(m + o1, ctx->h_list.data(), b1); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_list.p, m + o1, b1, cudaMemcpyHostToDevice, ctx->stream)); }
-        if (b2) { memcpy(m + o2, ctx->h_large.data(), b2); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_large.p, m + o2, b2, cudaMemcpyHostToDevice, ctx->stream)); }
+        // a lane of the pipelined path uploads through the shared upload stream, so that its own
+        // stream never touches the host-to-device copy engine (which is busy with sequence data)
+        cudaStream_t ms = ctx->meta_stream ? ctx->meta_stream : ctx->stream;
+        if (ctx->meta_stream) DBGA_CUDA_CHECK(cudaStreamWaitEvent(ms, ctx->ev_ready, 0));   // old metadata no longer in use
+        if (b0) { memcpy(m, ctx->h_pairs.data(), b0); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pairs.p, m, b0, cudaMemcpyHostToDevice, ms)); }
+        if (b1) { memcpy(m + o1, ctx->h_list.data(), b1); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_list.p, m + o1, b1, cudaMemcpyHostToDevice, ms)); }
+        if (b2) { memcpy(m + o2, ctx->h_large.data(), b2); DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_large.p, m + o2, b2, cudaMemcpyHostToDevice, ms)); }
+        if (ctx->meta_stream) {
+            DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev_meta, ms));
+            DBGA_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_meta, 0));
+        }
     }
     size_t max_tbl = 0, max_pk = 0;
     for (size_t wi = 0; wi < ctx->waves.size(); ++wi) {
@@ -376,8 +396,9 @@ int run_pipeline(dbga_ctx *ctx) {
     if (rc != DBGA_SUCCESS) return rc;
     ctx->launches = 0;
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], st));
-    DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_ctr.p, 0, sizeof(Counters), st));
-    DBGA_CUDA_CHECK(cudaMemsetAsync(ctx->d_status.p, 0, 4 * std::max<int64_t>(P, 1), st));
+    DBGA_CUDA_CHECK(launch_clear((Counters *)ctx->d_ctr.p, (int32_t *)ctx->d_status.p, P, st));
+    ctx->launches += 1;
+    static const bool skip_kernels = getenv("DBGA_SKIP_KERNELS") != nullptr;   // diagnosis: copies only
     Pools pools;
     pools.runs = (int32_t *)ctx->d_runs.p; pools.runs_cap = ctx->runs_cap;
     pools.slots = (Slot *)ctx->d_slots.p; pools.slots_cap = ctx->slots_cap;
@@ -390,13 +411,31 @@ int run_pipeline(dbga_ctx *ctx) {
     PairDesc *pairs = (PairDesc *)ctx->d_pairs.p;
     PairOut *pout = (PairOut *)ctx->d_pout.p;
     // ---- stages 1+2 fused (shared-memory tables) and stage 1 with global tables
+    if (skip_kernels) {
+        for (int sb = 0; sb < ctx->n_sub; ++sb) DBGA_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sub[sb], 0));
+        for (int e = 2; e <= 5; ++e) DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[e], st));
+        return DBGA_SUCCESS;
+    }
     if (!ctx->no_anchors) {
-        for (const SmallClass &c : ctx->classes) {
-            DBGA_CUDA_CHECK(launch_stage12_small(seqs, pairs, (int32_t *)ctx->d_list.p + c.begin, c.count, ctx->prm.k, c.cap,
-                                                 c.words, c.maxq, full, seg, pout, pools, ctr, ctx->max_abs_score,
-                                                 ctx->dp.go_raw, ctx->dp.ge_raw, (uint8_t *)ctx->d_nd0.p,
-                                                 (uint8_t *)ctx->d_nd1.p, ctx->num_sms, st));
-            ctx->launches += 1;
+        const bool piecewise = ctx->n_sub > 1 && ctx->waves.empty();
+        if (ctx->n_sub > 0 && !piecewise)
+            for (int sb = 0; sb < ctx->n_sub; ++sb) DBGA_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sub[sb], 0));
+        for (int sb = 0; sb < (piecewise ? ctx->n_sub : 1); ++sb) {
+            if (piecewise) DBGA_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sub[sb], 0));
+            for (const SmallClass &c : ctx->classes) {
+                int lo = 0, hi = c.count;
+                if (piecewise) {       // class lists are ascending in pair index
+                    const int32_t *b = ctx->h_list.data() + c.begin;
+                    lo = (int)(std::lower_bound(b, b + c.count, (int32_t)ctx->sub_pair_lo[sb]) - b);
+                    hi = (int)(std::lower_bound(b, b + c.count, (int32_t)ctx->sub_pair_lo[sb + 1]) - b);
+                }
+                if (hi <= lo) continue;
+                DBGA_CUDA_CHECK(launch_stage12_small(seqs, pairs, (int32_t *)ctx->d_list.p + c.begin + lo, hi - lo, ctx->prm.k,
+                                                     c.cap, c.words, c.maxq, full, seg, pout, pools, ctr, ctx->max_abs_score,
+                                                     ctx->dp.go_raw, ctx->dp.ge_raw, (uint8_t *)ctx->d_nd0.p,
+                                                     (uint8_t *)ctx->d_nd1.p, ctx->num_sms, st));
+                ctx->launches += 1;
+            }
         }
         for (const LargeWave &w : ctx->waves) {
             DBGA_CUDA_CHECK(launch_stage1_large(seqs, pairs, (LargeDesc *)ctx->d_large.p + w.begin,
@@ -406,6 +445,8 @@ int run_pipeline(dbga_ctx *ctx) {
                                                 (uint8_t *)ctx->d_nd1.p, st, &ctx->launches));
         }
     }
+    if (ctx->no_anchors)
+        for (int sb = 0; sb < ctx->n_sub; ++sb) DBGA_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sub[sb], 0));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[2], st));
     // ---- generic stage 2: pairs that went through the global-table path, or every pair
     //      when there is no anchoring at all (dbga_global_align_batch)
@@ -461,8 +502,9 @@ int run_pipeline(dbga_ctx *ctx) {
     return DBGA_SUCCESS;
 }
 
-int do_run(dbga_ctx *ctx, const uint8_t *d_seqs) {
+int do_run(dbga_ctx *ctx, const uint8_t *d_seqs, bool keep_sub = false) {
     if (!ctx->planned) return fail(ctx, DBGA_ERR_ARG, "dbga_plan_run without a plan");
+    if (!keep_sub) ctx->n_sub = 0;
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
     ctx->d_seqs_run = d_seqs;
     int rc = run_pipeline(ctx);
@@ -591,32 +633,54 @@ int create_ctx(int device, dbga_ctx **out);
 // so at any time one lane uploads, one computes and one downloads.  The host never waits
 // for anything but the small counters of the previous chunk (needed to size its D2H).
 int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P,
-                    const dbga_params *params, dbga_result *out, bool no_anchors, int nchunks) {
+                    const dbga_params *params, dbga_result *out, bool no_anchors, int64_t chunk_bytes) {
     const auto t_begin = std::chrono::steady_clock::now();
     const int64_t total_bytes = offsets[2 * P] - offsets[0];
     const bool seg = params->stages == 3;
     constexpr int NL = dbga_ctx::NL;
     int lag = 2;                       // chunks kept in flight before the oldest is committed
+    int64_t sub_bytes = 16LL << 20;    // upload piece size
+    if (const char *e = getenv("DBGA_SUB_MB")) sub_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("DBGA_LAG")) lag = std::max(1, std::min(NL - 1, atoi(e)));
+    if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(ctx, DBGA_ERR_CUDA, "could not create the upload stream");
     for (int i = 0; i < NL; ++i) {
         if (!ctx->lanes[i]) {
             int rc = create_ctx(ctx->device, &ctx->lanes[i]);
             if (rc != DBGA_SUCCESS) return fail(ctx, rc, "could not create a pipeline lane");
-            if (cudaEventCreateWithFlags(&ctx->lanes[i]->ev_ready, cudaEventDisableTiming) != cudaSuccess)
-                return fail(ctx, DBGA_ERR_CUDA, "cudaEventCreate failed");
+            dbga_ctx *l = ctx->lanes[i];
+            bool okc = cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&l->ev_meta, cudaEventDisableTiming) == cudaSuccess;
+            l->meta_stream = ctx->copy_stream;
+            for (int sb = 0; okc && sb < dbga_ctx::MAX_SUB; ++sb)
+                okc = cudaEventCreateWithFlags(&l->ev_sub[sb], cudaEventDisableTiming) == cudaSuccess;
+            for (auto &e : l->dbg_ev) okc = okc && cudaEventCreate(&e) == cudaSuccess;
+            if (!okc) return fail(ctx, DBGA_ERR_CUDA, "could not create lane streams / events");
         }
         ctx->lanes[i]->scratch_limit = ctx->scratch_limit;
     }
-    // chunk boundaries: equal bytes
-    std::vector<int64_t> lo((size_t)nchunks + 1, P);
-    lo[0] = 0;
+    // Chunk boundaries.  The download engine is the busiest resource of the pipeline (results
+    // are as large as the input and share the link with the uploads), so the first chunks are
+    // small -- results start flowing back almost immediately -- and grow geometrically up to
+    // the requested chunk size.
+    std::vector<int64_t> lo;
+    lo.push_back(0);
     {
-        int c = 1;
-        for (int64_t i = 0; i < P && c < nchunks; ++i) {
-            if (offsets[2 * i] - offsets[0] >= total_bytes * c / nchunks) lo[(size_t)c++] = i;
+        int64_t first_mb = 8;
+        if (const char *e = getenv("DBGA_FIRST_MB")) first_mb = std::max(1, atoi(e));
+        int64_t want = std::min<int64_t>(first_mb << 20, chunk_bytes), next_cut = want;
+        for (int64_t i = 1; i < P; ++i) {
+            if (offsets[2 * i] - offsets[0] >= next_cut) {
+                lo.push_back(i);
+                want = std::min<int64_t>(want * 2, chunk_bytes);
+                next_cut = (offsets[2 * i] - offsets[0]) + want;
+            }
         }
-        for (; c < nchunks; ++c) lo[(size_t)c] = P;
+        // a tiny tail chunk is merged into its predecessor
+        if (lo.size() > 1 && total_bytes - (offsets[2 * lo.back()] - offsets[0]) < (4LL << 20)) lo.pop_back();
+        lo.push_back(P);
     }
+    const int nchunks = (int)lo.size() - 1;
     HRESERVE(h_status, 4 * (P + 1)); HRESERVE(h_score, 8 * (P + 1)); HRESERVE(h_cells, 8 * (P + 1));
     HRESERVE(h_nseg, 4 * (P + 1)); HRESERVE(h_nanch, 8 * (P + 1));
     HRESERVE(h_aln_off, 8 * (P + 2 + nchunks)); HRESERVE(h_run_off, 8 * (P + 2 + nchunks));
@@ -629,6 +693,7 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     auto fail_lane = [&](dbga_ctx *l, int rc) { snprintf(ctx->err, sizeof(ctx->err), "%s", l->err); return rc; };
 
     const bool trace = getenv("DBGA_TRACE") != nullptr;
+    if (trace) { cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventSynchronize(ctx->ev[0]); }
     auto now_ms = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     for (int step = 0; step < nchunks + lag; ++step) {
         const float t_s0 = now_ms();
@@ -640,11 +705,40 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
             int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
             t_plan = now_ms() - t_s0;
+            if ((size_t)std::max<int64_t>(l->total_bytes, 16) + 64 > l->d_seqs.cap) cudaStreamSynchronize(ctx->copy_stream);
             rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            if (l->total_bytes && cudaMemcpyAsync(l->d_seqs.p, seqs + base, (size_t)l->total_bytes, cudaMemcpyHostToDevice, l->stream) != cudaSuccess)
-                return fail(ctx, DBGA_ERR_CUDA, "H2D copy failed");
-            rc = do_run(l, (const uint8_t *)l->d_seqs.p);
+            {   // upload in pieces on the lane's copy stream (after the lane's previous kernels are done
+                // with d_seqs); stage 1+2 of each piece starts as soon as the piece has landed
+                if (cudaStreamWaitEvent(ctx->copy_stream, l->ev_ready, 0) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaStreamWaitEvent failed");
+                if (trace) cudaEventRecord(l->dbg_ev[0], ctx->copy_stream);
+                const int64_t nb = l->total_bytes, np = b - a;
+                int ns = (int)std::max<int64_t>(1, std::min<int64_t>(dbga_ctx::MAX_SUB, (nb + sub_bytes - 1) / sub_bytes));
+                if (np < ns) ns = (int)std::max<int64_t>(1, np);
+                l->n_sub = ns;
+                l->sub_pair_lo[0] = 0;
+                int64_t prev_off = 0;
+                for (int sb = 0; sb < ns; ++sb) {
+                    int64_t pe = np;                                   // first pair of the next piece (chunk-relative)
+                    if (sb + 1 < ns) {
+                        const int64_t target = base + nb * (sb + 1) / ns;
+                        const int64_t *o = offsets + 2 * a;
+                        int64_t lo2 = l->sub_pair_lo[sb], hi2 = np;
+                        while (lo2 < hi2) { const int64_t mid = (lo2 + hi2) / 2; if (o[2 * mid] < target) lo2 = mid + 1; else hi2 = mid; }
+                        pe = lo2;
+                    }
+                    l->sub_pair_lo[sb + 1] = pe;
+                    const int64_t end_off = (pe == np ? offsets[2 * b] : offsets[2 * (a + pe)]) - base;
+                    if (end_off > prev_off &&
+                        cudaMemcpyAsync((uint8_t *)l->d_seqs.p + prev_off, seqs + base + prev_off, (size_t)(end_off - prev_off),
+                                        cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
+                        return fail(ctx, DBGA_ERR_CUDA, "H2D copy failed");
+                    if (cudaEventRecord(l->ev_sub[sb], ctx->copy_stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventRecord failed");
+                    prev_off = end_off;
+                }
+                if (trace) cudaEventRecord(l->dbg_ev[1], ctx->copy_stream);
+            }
+            rc = do_run(l, (const uint8_t *)l->d_seqs.p, true);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
             rc = host_reserve(l, l->h_ctr, sizeof(Counters));
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
@@ -663,7 +757,8 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
             int rc = fetch_resolve(l, true);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
             const Counters *hc = (const Counters *)l->h_ctr.p;
-            const int64_t ta = seg ? (int64_t)hc->total_aln : 0, tr = (int64_t)hc->total_runs;
+            int64_t ta = seg ? (int64_t)hc->total_aln : 0, tr = (int64_t)hc->total_runs;
+            if (getenv("DBGA_SKIP_KERNELS")) { ta = (int64_t)(l->total_bytes * 0.415); tr = l->total_bytes / 85; }
             aln_base[(size_t)c + 1] = aln_base[(size_t)c] + ta;
             run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
             if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
@@ -685,8 +780,20 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
                       (int32_t *)ctx->h_nseg.p + a, (int64_t *)ctx->h_nanch.p + a, aln_off + a + c, run_off + a + c,
                       (uint8_t *)ctx->h_aln0.p + aln_base[(size_t)c], (uint8_t *)ctx->h_aln1.p + aln_base[(size_t)c],
                       (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c]};
+            if (trace) cudaEventRecord(l->dbg_ev[2], l->stream);
             rc = fetch_enqueue(l, d, ta, tr);
             if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+            if (trace) {
+                cudaEventRecord(l->dbg_ev[3], l->stream);
+                cudaEventSynchronize(l->dbg_ev[3]);
+                float a0, a1, k0, k1, d0, d1;
+                dbga_ctx *l0 = ctx->lanes[0];
+                cudaEventElapsedTime(&a0, ctx->ev[0], l->dbg_ev[0]); cudaEventElapsedTime(&a1, ctx->ev[0], l->dbg_ev[1]);
+                cudaEventElapsedTime(&k0, ctx->ev[0], l->ev[1]); cudaEventElapsedTime(&k1, ctx->ev[0], l->ev[5]);
+                cudaEventElapsedTime(&d0, ctx->ev[0], l->dbg_ev[2]); cudaEventElapsedTime(&d1, ctx->ev[0], l->dbg_ev[3]);
+                (void)l0;
+                fprintf(stderr, "[dbga] chunk %d gpu: h2d %.2f-%.2f kernels %.2f-%.2f (s12 %.2f s3 %.2f asm %.2f) d2h %.2f-%.2f\n", c, a0, a1, k0, k1, t1, t3, t4, d0, d1);
+            }
         }
         if (trace) fprintf(stderr, "[dbga] step %d start %.3f plan %.3f enq %.3f sync %.3f end %.3f\n", step, t_s0, t_plan, t_enq, t_sync, now_ms());
     }
@@ -723,9 +830,7 @@ int align_common(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int
         if (total >= (16LL << 20)) {
             int64_t chunk_mb = 32;
             if (const char *e = getenv("DBGA_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
-            const int64_t cb = chunk_mb << 20;
-            const int nchunks = (int)std::min<int64_t>(256, std::max<int64_t>(3, (total + cb - 1) / cb));
-            return align_pipelined(ctx, seqs, offsets, P, params, out, no_anchors, nchunks);
+            return align_pipelined(ctx, seqs, offsets, P, params, out, no_anchors, std::max<int64_t>(chunk_mb << 20, total / 200));
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -756,6 +861,7 @@ int dbga_create(int device, dbga_ctx **out) { return create_ctx(device, out); }
 namespace {
 int create_ctx(int device, dbga_ctx **out) {
     if (!out) return DBGA_ERR_ARG;
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);   // only effective before the CUDA context exists
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return DBGA_ERR_CUDA;
@@ -776,7 +882,15 @@ extern "C" {
 
 void dbga_destroy(dbga_ctx *ctx) {
     if (!ctx) return;
-    for (auto &l : ctx->lanes) if (l) { if (l->ev_ready) cudaEventDestroy(l->ev_ready); dbga_destroy(l); l = nullptr; }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
+    for (auto &l : ctx->lanes) if (l) {
+        if (l->ev_ready) cudaEventDestroy(l->ev_ready);
+        if (l->ev_meta) cudaEventDestroy(l->ev_meta);
+        for (auto &e : l->ev_sub) if (e) cudaEventDestroy(e);
+        for (auto &e : l->dbg_ev) if (e) cudaEventDestroy(e);
+        if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+        dbga_destroy(l); l = nullptr;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *dbs[] = {&ctx->d_seqs, &ctx->d_pairs, &ctx->d_list, &ctx->d_large, &ctx->d_status, &ctx->d_aof, &ctx->d_nd0,

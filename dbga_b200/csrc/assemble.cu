@@ -230,6 +230,21 @@ assemble_runs_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     }
 }
 
+// Clears the per-run counters and the status array with a kernel: a cudaMemsetAsync would go
+// through a copy engine and queue behind the (large) sequence uploads of other lanes.
+__global__ void __launch_bounds__(256) clear_kernel(Counters *ctr, int32_t *status, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)(sizeof(Counters) / 4)) reinterpret_cast<uint32_t *>(ctr)[i] = 0u;
+    for (int64_t j = i; j < n; j += (int64_t)gridDim.x * blockDim.x) status[j] = 0;
+}
+cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, cudaStream_t st) {
+    int64_t grid = (n + 255) / 256;
+    if (grid < 1) grid = 1;
+    if (grid > 1024) grid = 1024;
+    clear_kernel<<<(int)grid, 256, 0, st>>>(ctr, status, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
                             const int32_t *status, const int32_t *runs, int64_t runs_cap, int2 *run_meta, Slot *slots,
                             int64_t slots_cap, const uint8_t *strbuf, int64_t *aln_len, int64_t *aln_off,

@@ -74,6 +74,8 @@ cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t 
                             int32_t *runs_out, int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
                             Counters *ctr, bool want_rows, int num_sms, cudaStream_t st, int *launches);
 
+cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, cudaStream_t st);
+
 // ---- integer-pipe microbenchmark
 cudaError_t launch_int_peak(int which, int iters, int *sink, int num_sms, cudaStream_t st);
 

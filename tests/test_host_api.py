@@ -177,3 +177,50 @@ def test_shard_range_partitions():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_fasta_batch_reader_and_writer(tmp_path):
+    from dbga_b200 import fasta
+    from dbga_b200.batch import BatchResult
+    p = tmp_path / "pairs.fasta"
+    p.write_text(">a1 desc\nACGT\nacg\n>b1\nAC\r\nGT\n\n>a2\n\n>b2\nTTTT")
+    names, buf, offs = fasta.read_pairs(p)
+    assert names == ["a1", "b1", "a2", "b2"]
+    assert buf.tobytes() == b"ACGTACGACGTTTTT" and offs.tolist() == [0, 7, 11, 11, 15]
+    odd = tmp_path / "odd.fasta"
+    odd.write_text(">x\nAC\n")
+    with pytest.raises(ValueError):
+        fasta.read_pairs(odd)
+    z = np.zeros(0)
+    res = BatchResult(status=np.array([0, 1], np.int32), score=z, dp_cells=z, dp_segments=z, n_anchors=z,
+                      run_off=np.zeros(3, np.int64), runs=np.zeros((0, 3), np.int32), aln_off=np.array([0, 5, 5]),
+                      aln0=np.frombuffer(b"AC-GT", np.uint8), aln1=np.frombuffer(b"ACGGT", np.uint8))
+    out = tmp_path / "aln.fasta"
+    assert fasta.write_alignments(out, names, res, width=3) == 1
+    assert out.read_text() == ">a1\nAC-\nGT\n>b1\nACG\nGT\n"
+
+
+def test_sop_reference_goldens():
+    # reference tests/test_utils.py:158-215
+    from dbga_b200.quality import sop, pairwise_alignment_score
+    assert sop({"seq1": "AGTCCAGTGA", "seq2": "A--C-ATGGA"}) == {"match": 5, "mismatch": 2, "gap_open": 2, "gap_extend": 1}
+    assert sop({"seq1": "AACTTCTTCGTGT", "seq2": "AAC--C--CGTGT"}) == {"match": 9, "mismatch": 0, "gap_open": 2, "gap_extend": 2}
+    assert sop({"seq1": "AACTTCTTCGTGT", "seq2": "AAC--C--CGTGT", "seq3": "AAC-----CGTGT"}) == \
+        {"match": 25, "mismatch": 0, "gap_open": 4, "gap_extend": 6}
+    assert sop({"seq1": "AAGTCGATGGTCA", "seq2": "AAC-CCA---TGA", "seq3": "ATCT---T--CCA"}) == \
+        {"match": 14, "mismatch": 9, "gap_open": 7, "gap_extend": 7}
+    assert pairwise_alignment_score({"a": "A-C", "b": "AG-"}) == {"match": 1, "mismatch": 0, "gap_open": 2, "gap_extend": 0}
+
+
+def test_sop_matches_reference_loop():
+    """Property check against a direct transcription-free re-derivation: random alignments,
+    counts must satisfy columns = match + mismatch + gap_open + gap_extend + both-gap columns."""
+    from dbga_b200.quality import score_rows
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        n = int(rng.integers(1, 60))
+        r1 = rng.choice(np.frombuffer(b"ACGT-", np.uint8), n)
+        r2 = rng.choice(np.frombuffer(b"ACGT-", np.uint8), n)
+        s = score_rows(r1, r2)
+        both_gap = int(((r1 == 45) & (r2 == 45)).sum())
+        assert sum(s.values()) + both_gap == n
