@@ -1,7 +1,9 @@
 // C-ABI host side: plan (sizing, classing, metadata upload), run (kernel pipeline on one
 // stream, no host round trips), fetch (device -> pinned host).  See include/dbga_b200.h.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -398,7 +400,6 @@ int run_pipeline(dbga_ctx *ctx) {
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], st));
     DBGA_CUDA_CHECK(launch_clear((Counters *)ctx->d_ctr.p, (int32_t *)ctx->d_status.p, P, st));
     ctx->launches += 1;
-    static const bool skip_kernels = getenv("DBGA_SKIP_KERNELS") != nullptr;   // diagnosis: copies only
     Pools pools;
     pools.runs = (int32_t *)ctx->d_runs.p; pools.runs_cap = ctx->runs_cap;
     pools.slots = (Slot *)ctx->d_slots.p; pools.slots_cap = ctx->slots_cap;
@@ -411,11 +412,6 @@ int run_pipeline(dbga_ctx *ctx) {
     PairDesc *pairs = (PairDesc *)ctx->d_pairs.p;
     PairOut *pout = (PairOut *)ctx->d_pout.p;
     // ---- stages 1+2 fused (shared-memory tables) and stage 1 with global tables
-    if (skip_kernels) {
-        for (int sb = 0; sb < ctx->n_sub; ++sb) DBGA_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_sub[sb], 0));
-        for (int e = 2; e <= 5; ++e) DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[e], st));
-        return DBGA_SUCCESS;
-    }
     if (!ctx->no_anchors) {
         const bool piecewise = ctx->n_sub > 1 && ctx->waves.empty();
         if (ctx->n_sub > 0 && !piecewise)
@@ -638,10 +634,9 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     const int64_t total_bytes = offsets[2 * P] - offsets[0];
     const bool seg = params->stages == 3;
     constexpr int NL = dbga_ctx::NL;
-    int lag = 2;                       // chunks kept in flight before the oldest is committed
+    int lag = 0;
     int64_t sub_bytes = 16LL << 20;    // upload piece size
     if (const char *e = getenv("DBGA_SUB_MB")) sub_bytes = (int64_t)std::max(1, atoi(e)) << 20;
-    if (const char *e = getenv("DBGA_LAG")) lag = std::max(1, std::min(NL - 1, atoi(e)));
     if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(ctx, DBGA_ERR_CUDA, "could not create the upload stream");
     for (int i = 0; i < NL; ++i) {
@@ -695,107 +690,136 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     const bool trace = getenv("DBGA_TRACE") != nullptr;
     if (trace) { cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventSynchronize(ctx->ev[0]); }
     auto now_ms = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-    for (int step = 0; step < nchunks + lag; ++step) {
-        const float t_s0 = now_ms();
-        float t_plan = 0, t_enq = 0, t_sync = 0;
-        if (step < nchunks) {
-            dbga_ctx *l = ctx->lanes[step % NL];
-            const int64_t a = lo[(size_t)step], b = lo[(size_t)step + 1];
-            const int64_t base = offsets[2 * a];
-            int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
-            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            t_plan = now_ms() - t_s0;
-            if ((size_t)std::max<int64_t>(l->total_bytes, 16) + 64 > l->d_seqs.cap) cudaStreamSynchronize(ctx->copy_stream);
-            rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
-            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            {   // upload in pieces on the lane's copy stream (after the lane's previous kernels are done
-                // with d_seqs); stage 1+2 of each piece starts as soon as the piece has landed
-                if (cudaStreamWaitEvent(ctx->copy_stream, l->ev_ready, 0) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaStreamWaitEvent failed");
-                if (trace) cudaEventRecord(l->dbg_ev[0], ctx->copy_stream);
-                const int64_t nb = l->total_bytes, np = b - a;
-                int ns = (int)std::max<int64_t>(1, std::min<int64_t>(dbga_ctx::MAX_SUB, (nb + sub_bytes - 1) / sub_bytes));
-                if (np < ns) ns = (int)std::max<int64_t>(1, np);
-                l->n_sub = ns;
-                l->sub_pair_lo[0] = 0;
-                int64_t prev_off = 0;
-                for (int sb = 0; sb < ns; ++sb) {
-                    int64_t pe = np;                                   // first pair of the next piece (chunk-relative)
-                    if (sb + 1 < ns) {
-                        const int64_t target = base + nb * (sb + 1) / ns;
-                        const int64_t *o = offsets + 2 * a;
-                        int64_t lo2 = l->sub_pair_lo[sb], hi2 = np;
-                        while (lo2 < hi2) { const int64_t mid = (lo2 + hi2) / 2; if (o[2 * mid] < target) lo2 = mid + 1; else hi2 = mid; }
-                        pe = lo2;
-                    }
-                    l->sub_pair_lo[sb + 1] = pe;
-                    const int64_t end_off = (pe == np ? offsets[2 * b] : offsets[2 * (a + pe)]) - base;
-                    if (end_off > prev_off &&
-                        cudaMemcpyAsync((uint8_t *)l->d_seqs.p + prev_off, seqs + base + prev_off, (size_t)(end_off - prev_off),
-                                        cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
-                        return fail(ctx, DBGA_ERR_CUDA, "H2D copy failed");
-                    if (cudaEventRecord(l->ev_sub[sb], ctx->copy_stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventRecord failed");
-                    prev_off = end_off;
-                }
-                if (trace) cudaEventRecord(l->dbg_ev[1], ctx->copy_stream);
+
+    // ---- producer: plan chunk c, queue its upload pieces and its kernels (lane c % NL)
+    auto issue = [&](int c) -> int {
+        dbga_ctx *l = ctx->lanes[c % NL];
+        const int64_t a = lo[(size_t)c], b = lo[(size_t)c + 1];
+        const int64_t base = offsets[2 * a];
+        if (cudaSetDevice(ctx->device) != cudaSuccess) return DBGA_ERR_CUDA;
+        int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
+        if (rc != DBGA_SUCCESS) return rc;
+        if ((size_t)std::max<int64_t>(l->total_bytes, 16) + 64 > l->d_seqs.cap) cudaStreamSynchronize(ctx->copy_stream);
+        rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
+        if (rc != DBGA_SUCCESS) return rc;
+        // upload in pieces on the shared upload stream (after the lane's previous kernels are done with
+        // d_seqs); stage 1+2 of each piece starts as soon as the piece has landed
+        if (cudaStreamWaitEvent(ctx->copy_stream, l->ev_ready, 0) != cudaSuccess) return DBGA_ERR_CUDA;
+        if (trace) cudaEventRecord(l->dbg_ev[0], ctx->copy_stream);
+        const int64_t nb = l->total_bytes, np = b - a;
+        int ns = (int)std::max<int64_t>(1, std::min<int64_t>(dbga_ctx::MAX_SUB, (nb + sub_bytes - 1) / sub_bytes));
+        if (np < ns) ns = (int)std::max<int64_t>(1, np);
+        l->n_sub = ns;
+        l->sub_pair_lo[0] = 0;
+        int64_t prev_off = 0;
+        for (int sb = 0; sb < ns; ++sb) {
+            int64_t pe = np;                                   // first pair of the next piece (chunk-relative)
+            if (sb + 1 < ns) {
+                const int64_t target = base + nb * (sb + 1) / ns;
+                const int64_t *o = offsets + 2 * a;
+                int64_t lo2 = l->sub_pair_lo[sb], hi2 = np;
+                while (lo2 < hi2) { const int64_t mid = (lo2 + hi2) / 2; if (o[2 * mid] < target) lo2 = mid + 1; else hi2 = mid; }
+                pe = lo2;
             }
-            rc = do_run(l, (const uint8_t *)l->d_seqs.p, true);
-            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            rc = host_reserve(l, l->h_ctr, sizeof(Counters));
-            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            if (cudaMemcpyAsync(l->h_ctr.p, l->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, l->stream) != cudaSuccess ||
-                cudaEventRecord(l->ev_ready, l->stream) != cudaSuccess)
-                return fail(ctx, DBGA_ERR_CUDA, "counter copy failed");
-            t_enq = now_ms() - t_s0;
+            l->sub_pair_lo[sb + 1] = pe;
+            const int64_t end_off = (pe == np ? offsets[2 * b] : offsets[2 * (a + pe)]) - base;
+            if (end_off > prev_off &&
+                cudaMemcpyAsync((uint8_t *)l->d_seqs.p + prev_off, seqs + base + prev_off, (size_t)(end_off - prev_off),
+                                cudaMemcpyHostToDevice, ctx->copy_stream) != cudaSuccess)
+                return DBGA_ERR_CUDA;
+            if (cudaEventRecord(l->ev_sub[sb], ctx->copy_stream) != cudaSuccess) return DBGA_ERR_CUDA;
+            prev_off = end_off;
         }
-        if (step >= lag) {
-            const int c = step - lag;
-            dbga_ctx *l = ctx->lanes[c % NL];
-            const int64_t a = lo[(size_t)c];
-            const float t_b = now_ms();
-            if (cudaEventSynchronize(l->ev_ready) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventSynchronize failed");
-            t_sync = now_ms() - t_b;
-            int rc = fetch_resolve(l, true);
-            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            const Counters *hc = (const Counters *)l->h_ctr.p;
-            int64_t ta = seg ? (int64_t)hc->total_aln : 0, tr = (int64_t)hc->total_runs;
-            if (getenv("DBGA_SKIP_KERNELS")) { ta = (int64_t)(l->total_bytes * 0.415); tr = l->total_bytes / 85; }
-            aln_base[(size_t)c + 1] = aln_base[(size_t)c] + ta;
-            run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
-            if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
-                for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
-                HostBuf old = ctx->h_runs;
-                ctx->h_runs = HostBuf();
-                rc = host_reserve(ctx, ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]) * 2);
-                if (rc != DBGA_SUCCESS) return rc;
-                memcpy(ctx->h_runs.p, old.p, (size_t)(12 * run_base[(size_t)c]));
-                cudaFreeHost(old.p);
-            }
-            float t1 = 0, t2 = 0, t3 = 0, t4 = 0;
-            cudaEventElapsedTime(&t1, l->ev[1], l->ev[2]); cudaEventElapsedTime(&t2, l->ev[2], l->ev[3]);
-            cudaEventElapsedTime(&t3, l->ev[3], l->ev[4]); cudaEventElapsedTime(&t4, l->ev[4], l->ev[5]);
-            ms[0] += t1; ms[1] += t2; ms[2] += t3; ms[3] += t4;
-            cells += (int64_t)hc->cells; nsegs += (int64_t)hc->nseg; launches += l->launches;
-            // offsets of chunk c land at [a + c, a + c + n + 1) (one extra slot per chunk), fixed up below
-            HostDst d{(int32_t *)ctx->h_status.p + a, (int64_t *)ctx->h_score.p + a, (int64_t *)ctx->h_cells.p + a,
-                      (int32_t *)ctx->h_nseg.p + a, (int64_t *)ctx->h_nanch.p + a, aln_off + a + c, run_off + a + c,
-                      (uint8_t *)ctx->h_aln0.p + aln_base[(size_t)c], (uint8_t *)ctx->h_aln1.p + aln_base[(size_t)c],
-                      (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c]};
-            if (trace) cudaEventRecord(l->dbg_ev[2], l->stream);
-            rc = fetch_enqueue(l, d, ta, tr);
-            if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
-            if (trace) {
-                cudaEventRecord(l->dbg_ev[3], l->stream);
-                cudaEventSynchronize(l->dbg_ev[3]);
-                float a0, a1, k0, k1, d0, d1;
-                dbga_ctx *l0 = ctx->lanes[0];
-                cudaEventElapsedTime(&a0, ctx->ev[0], l->dbg_ev[0]); cudaEventElapsedTime(&a1, ctx->ev[0], l->dbg_ev[1]);
-                cudaEventElapsedTime(&k0, ctx->ev[0], l->ev[1]); cudaEventElapsedTime(&k1, ctx->ev[0], l->ev[5]);
-                cudaEventElapsedTime(&d0, ctx->ev[0], l->dbg_ev[2]); cudaEventElapsedTime(&d1, ctx->ev[0], l->dbg_ev[3]);
-                (void)l0;
-                fprintf(stderr, "[dbga] chunk %d gpu: h2d %.2f-%.2f kernels %.2f-%.2f (s12 %.2f s3 %.2f asm %.2f) d2h %.2f-%.2f\n", c, a0, a1, k0, k1, t1, t3, t4, d0, d1);
-            }
+        if (trace) cudaEventRecord(l->dbg_ev[1], ctx->copy_stream);
+        rc = do_run(l, (const uint8_t *)l->d_seqs.p, true);
+        if (rc != DBGA_SUCCESS) return rc;
+        rc = host_reserve(l, l->h_ctr, sizeof(Counters));
+        if (rc != DBGA_SUCCESS) return rc;
+        if (cudaMemcpyAsync(l->h_ctr.p, l->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, l->stream) != cudaSuccess ||
+            cudaEventRecord(l->ev_ready, l->stream) != cudaSuccess)
+            return DBGA_ERR_CUDA;
+        return DBGA_SUCCESS;
+    };
+
+    // ---- consumer: once chunk c's counters are on the host, queue its (exactly sized) download
+    auto commit = [&](int c) -> int {
+        dbga_ctx *l = ctx->lanes[c % NL];
+        const int64_t a = lo[(size_t)c];
+        if (cudaEventSynchronize(l->ev_ready) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventSynchronize failed");
+        int rc = fetch_resolve(l, true);
+        if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+        const Counters *hc = (const Counters *)l->h_ctr.p;
+        int64_t ta = seg ? (int64_t)hc->total_aln : 0, tr = (int64_t)hc->total_runs;
+        aln_base[(size_t)c + 1] = aln_base[(size_t)c] + ta;
+        run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
+        if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
+            for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
+            HostBuf old = ctx->h_runs;
+            ctx->h_runs = HostBuf();
+            rc = host_reserve(ctx, ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]) * 2);
+            if (rc != DBGA_SUCCESS) return rc;
+            memcpy(ctx->h_runs.p, old.p, (size_t)(12 * run_base[(size_t)c]));
+            cudaFreeHost(old.p);
         }
-        if (trace) fprintf(stderr, "[dbga] step %d start %.3f plan %.3f enq %.3f sync %.3f end %.3f\n", step, t_s0, t_plan, t_enq, t_sync, now_ms());
+        float t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        cudaEventElapsedTime(&t1, l->ev[1], l->ev[2]); cudaEventElapsedTime(&t2, l->ev[2], l->ev[3]);
+        cudaEventElapsedTime(&t3, l->ev[3], l->ev[4]); cudaEventElapsedTime(&t4, l->ev[4], l->ev[5]);
+        ms[0] += t1; ms[1] += t2; ms[2] += t3; ms[3] += t4;
+        cells += (int64_t)hc->cells; nsegs += (int64_t)hc->nseg; launches += l->launches;
+        // offsets of chunk c land at [a + c, a + c + n + 1) (one extra slot per chunk), fixed up below
+        HostDst d{(int32_t *)ctx->h_status.p + a, (int64_t *)ctx->h_score.p + a, (int64_t *)ctx->h_cells.p + a,
+                  (int32_t *)ctx->h_nseg.p + a, (int64_t *)ctx->h_nanch.p + a, aln_off + a + c, run_off + a + c,
+                  (uint8_t *)ctx->h_aln0.p + aln_base[(size_t)c], (uint8_t *)ctx->h_aln1.p + aln_base[(size_t)c],
+                  (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c]};
+        if (trace) cudaEventRecord(l->dbg_ev[2], l->stream);
+        rc = fetch_enqueue(l, d, ta, tr);
+        if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+        if (trace) {
+            cudaEventRecord(l->dbg_ev[3], l->stream);
+            cudaEventSynchronize(l->dbg_ev[3]);
+            float a0, a1, k0, k1, d0, d1;
+            cudaEventElapsedTime(&a0, ctx->ev[0], l->dbg_ev[0]); cudaEventElapsedTime(&a1, ctx->ev[0], l->dbg_ev[1]);
+            cudaEventElapsedTime(&k0, ctx->ev[0], l->ev[1]); cudaEventElapsedTime(&k1, ctx->ev[0], l->ev[5]);
+            cudaEventElapsedTime(&d0, ctx->ev[0], l->dbg_ev[2]); cudaEventElapsedTime(&d1, ctx->ev[0], l->dbg_ev[3]);
+            fprintf(stderr, "[dbga] chunk %d gpu: h2d %.2f-%.2f kernels %.2f-%.2f (s12 %.2f s3 %.2f asm %.2f) d2h %.2f-%.2f  host now %.2f\n",
+                    c, a0, a1, k0, k1, t1, t3, t4, d0, d1, now_ms());
+        }
+        return DBGA_SUCCESS;
+    };
+
+    // The producer runs on its own host thread so that planning the next chunk never delays the
+    // download of a finished one.  It may run at most NL - 1 chunks ahead of the consumer (a lane
+    // is reused only after its previous chunk has been committed).
+    std::atomic<int> issued{0}, committed{0}, prod_rc{DBGA_SUCCESS};
+    std::atomic<bool> stop{false};
+    (void)lag;
+    std::thread producer([&]() {
+        for (int c = 0; c < nchunks && !stop.load(); ++c) {
+            while (c - committed.load(std::memory_order_acquire) >= NL && !stop.load()) std::this_thread::yield();
+            if (stop.load()) break;
+            const int rc = issue(c);
+            if (rc != DBGA_SUCCESS) {
+                snprintf(ctx->err, sizeof(ctx->err), "pipeline producer: %s", ctx->lanes[c % NL]->err);
+                prod_rc.store(rc);
+                break;
+            }
+            issued.store(c + 1, std::memory_order_release);
+        }
+    });
+    int main_rc = DBGA_SUCCESS;
+    for (int c = 0; c < nchunks; ++c) {
+        while (issued.load(std::memory_order_acquire) <= c && prod_rc.load() == DBGA_SUCCESS) std::this_thread::yield();
+        if (issued.load(std::memory_order_acquire) <= c) { main_rc = prod_rc.load(); break; }
+        main_rc = commit(c);
+        if (main_rc != DBGA_SUCCESS) break;
+        committed.store(c + 1, std::memory_order_release);
+    }
+    stop.store(true);
+    producer.join();
+    if (main_rc != DBGA_SUCCESS) {
+        for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        return main_rc;
     }
     for (int i = 0; i < NL; ++i)
         if (cudaStreamSynchronize(ctx->lanes[i]->stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "stream sync failed");
