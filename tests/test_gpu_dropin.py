@@ -158,3 +158,12 @@ def test_adaptive_recursive_goldens(ref_fixtures):
         assert list(got) == fx["aln"]
         n_ok += 1
     assert n_ok >= 10
+
+
+def test_k_zero_means_no_anchors():
+    """k = 0 is legal in the reference (utils.py:129: only k < 0 or k > len is rejected): every
+    k-mer is the empty string, hence a duplicate; no merge node; plain global alignment."""
+    from dbga_b200 import DeBruijnPairwise
+    db = DeBruijnPairwise(["ACGTAGTATC", "ACCTACAGCA"], 0, "dna")
+    assert db.merge_node_idx == [] and db.seq_node_idx == {0: [0, 1], 1: [2, 3]} and db.id_count == 4
+    assert db.alignment() == {0: "ACGT--AGTATC", 1: "ACCTACAGCA--"}

@@ -232,3 +232,63 @@ def test_big_segments_in_big_batch(aligner):
         sc, ax, ay = CO.gotoh(*pairs[i])
         assert res.status[i] == O.OK and res.score[i] == sc, i
         assert res.alignment(i) == (ax, ay), i
+
+
+def test_edge_cases(aligner):
+    """Empty batch, single-base sequences, k == len, very unbalanced lengths, homopolymers
+    (every k-mer duplicate -> whole-sequence DP), identical pairs (only the tail reaches the DP)."""
+    empty = aligner.align_pairs([], 3)
+    assert len(empty) == 0 and empty.aln_off.tolist() == [0]
+    rng = random.Random(31)
+    s = rand_seq(rng, 2000)
+    pairs = [("A", "A"), ("A", "C"), ("ACGTACG", "ACGTACG"), (s, s[990:1002]), (s[5:25], s), ("A" * 300, "A" * 280),
+             ("AC" * 200, "AC" * 190 + "G"), (s, s), (s[:1200], s[:600] + "T" + s[600:1200]), ("ACGT" * 50, "TGCA" * 50)]
+    for k in (1, 3, 7):
+        use = [(a, b) for a, b in pairs if len(a) >= k and len(b) >= k]
+        check_batch(aligner, use, k)
+    check_batch(aligner, [("ACGTACG", "ACGTACG"), ("ACGTACG", "ACGTTCG")], 7)          # k == len
+
+
+def test_extreme_scores_and_limits(aligner):
+    rng = random.Random(32)
+    pairs = []
+    for _ in range(40):
+        a = rand_seq(rng, rng.choice([30, 120, 400]))
+        pairs.append((a, mutate(rng, a, 0.1, 0.05) or "ACGT"))
+    pairs = [(a, b) for a, b in pairs if len(b) >= 4]
+    check_batch(aligner, pairs, 4, match=500, transition=-500, transversion=-499, d=1000, e=999)
+    check_batch(aligner, pairs, 4, match=0, transition=0, transversion=0, d=0, e=0)
+    check_batch(aligner, pairs, 4, match=-3, transition=2, transversion=5, d=3, e=7)   # unusual but legal
+    with pytest.raises(RuntimeError, match="substitution score"):
+        aligner.align_pairs(pairs, 4, match=501)
+    with pytest.raises(RuntimeError, match="k must be"):
+        aligner.align_pairs(pairs, 32)
+
+
+def test_scratch_limit_is_an_explicit_status():
+    """A segment whose traceback does not fit the scratch limit is reported as TOO_LARGE,
+    never silently dropped; the others in the batch are unaffected."""
+    from dbga_b200 import Aligner
+    al = Aligner(0)
+    al.set_scratch_limit(1 << 20)
+    rng = random.Random(33)
+    big = (rand_seq(rng, 3000), rand_seq(rng, 3000))          # no shared 15-mer: one 9 M-cell segment
+    small = O.synth_pair(400, 0.02, 0.004, 1)
+    res = al.align_pairs([small, big, small], 15)
+    ref = CO.align_pair(*small, 15)
+    assert res.status.tolist() == [ref.status, O.TOO_LARGE, ref.status]
+    if ref.status == O.OK:
+        assert res.alignment(0) == (ref.aln0, ref.aln1) == res.alignment(2)
+    assert res.alignment(1) == ("", "")
+    al.close()
+
+
+def test_graph_flags_in_a_batch(aligner):
+    pairs = [O.synth_pair(200, 0.05, 0.01, s) for s in range(30)]
+    res = aligner.align_pairs(pairs, 5, want_graph=True, stages=2)
+    for i, (a, b) in enumerate(pairs):
+        ref = CO.align_pair(a, b, 5, want_graph=True, stages=2)
+        assert res.status[i] == ref.status
+        nd0, nd1 = res.graph_flags(i)
+        assert np.array_equal(nd0, ref.nondup0) and np.array_equal(nd1, ref.nondup1)
+        assert [tuple(x) for x in res.anchors(i).tolist()] == [tuple(x) for x in ref.anchors.tolist()]
