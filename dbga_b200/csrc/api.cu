@@ -6,6 +6,7 @@
 #include <thread>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <vector>
 
 #include "kernels.cuh"
@@ -222,31 +223,44 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     ctx->classes.clear(); ctx->h_list.clear(); ctx->h_large.clear(); ctx->waves.clear();
     if (!no_anchors) {
         const int key_bytes = k <= 15 ? 4 : 8;
-        std::vector<std::vector<int32_t>> by_cap(32);
+        std::map<uint32_t, std::vector<int32_t>> by_cap;
+        const uint64_t cap_lo = 150, cap_hi = 275;
         std::vector<int32_t> large;
         for (int64_t i = 0; i < P; ++i) {
             const PairDesc &pd = ctx->h_pairs[(size_t)i];
             const int64_t N0 = std::max(0, pd.n0 - k + 1), N1 = std::max(0, pd.n1 - k + 1);
             const uint64_t keys = full ? (uint64_t)(N0 + N1) : (uint64_t)N0;
-            const uint32_t cap = pow2_at_least(keys + keys / 2 + 1, 256);
+            // Table capacity (measured on cfg3, tools/cap_sweep.sh): probing cost falls with the load
+            // factor until the table costs occupancy, so take the largest table that still lets five
+            // CTAs share an SM, within [1.5, 2.75] x the key count; never below the power of two the
+            // run sort may need (>= min(N0, N1) runs).  Rounded to a granule so that similar pairs
+            // share a launch.
+            const int nmax0 = std::max(pd.n0, pd.n1);
+            const int words0 = (((nmax0 + 15) / 16 + 3) + 1) & ~1;
+            const int64_t fixed = (int64_t)words0 * 8 + ((N1 + 7) / 8 * 8) * 2 + 1024;
+            const int64_t fit5 = ((int64_t)SMEM_LIMIT / 5 - fixed) / (key_bytes + 6);
+            uint64_t want = (uint64_t)std::max<int64_t>((int64_t)(keys * cap_lo / 100 + 16), std::min<int64_t>((int64_t)(keys * cap_hi / 100), fit5));
+            want = std::max<uint64_t>(want, pow2_at_least((uint64_t)std::min(N0, N1) + 1, 64));
+            uint32_t gran = 256;
+            while ((uint64_t)gran * 16 < want) gran <<= 1;             // <= 16 classes per octave
+            const uint32_t cap = (uint32_t)(want / gran * gran >= keys * cap_lo / 100 + 16 && want / gran * gran >= pow2_at_least((uint64_t)std::min(N0, N1) + 1, 64)
+                                                ? want / gran * gran : (want + gran - 1) / gran * gran);
             const int nmax = std::max(pd.n0, pd.n1);
             const int words = (((nmax + 15) / 16 + 3) + 1) & ~1;
             const bool fits = cap <= 32768 && N0 < 65000 && N1 < 65000 &&   // 16-bit positions in shared memory
                               stage12_small_smem(key_bytes, cap, words, (int)N1) <= SMEM_LIMIT;
             if (fits) {
-                int lg = 0;
-                while ((1u << lg) < cap) ++lg;
-                by_cap[lg].push_back((int32_t)i);
+                by_cap[cap].push_back((int32_t)i);
             } else {
                 large.push_back((int32_t)i);
             }
         }
-        for (int lg = 0; lg < 32; ++lg) {
-            if (by_cap[lg].empty()) continue;
+        for (auto &kv : by_cap) {
+            const std::vector<int32_t> &members = kv.second;
             SmallClass c;
-            c.cap = 1u << lg; c.begin = (int)ctx->h_list.size(); c.count = (int)by_cap[lg].size();
+            c.cap = kv.first; c.begin = (int)ctx->h_list.size(); c.count = (int)members.size();
             int nmax = 0, qmax = 0;
-            for (int32_t i : by_cap[lg]) {
+            for (int32_t i : members) {
                 const PairDesc &pd = ctx->h_pairs[(size_t)i];
                 nmax = std::max(nmax, std::max(pd.n0, pd.n1));
                 qmax = std::max(qmax, std::max(0, pd.n1 - k + 1));
@@ -257,7 +271,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq) > SMEM_LIMIT) {
                 // mixed extremes inside one class: fall back to the large path for this class
                 ctx->h_list.resize((size_t)c.begin);
-                for (int32_t i : by_cap[lg]) large.push_back(i);
+                for (int32_t i : members) large.push_back(i);
                 continue;
             }
             ctx->classes.push_back(c);

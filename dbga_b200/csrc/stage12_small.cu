@@ -78,7 +78,7 @@ template <typename KeyT> struct Bucket;
 template <> struct Bucket<uint32_t> {
     static constexpr int W = 4;
     static constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-    static __device__ __forceinline__ uint32_t hash(uint32_t k, int shift) { return (k * 0x9E3779B1u) >> shift; }
+    static __device__ __forceinline__ uint32_t hash(uint32_t k, uint32_t nb) { return __umulhi(k * 0x9E3779B1u, nb); }
     static __device__ __forceinline__ uint32_t kmer(const uint32_t *pk, int p, uint32_t kmask) {
         const int w = p >> 4, sh = (p & 15) * 2;
         return __funnelshift_r(pk[w], pk[w + 1], sh) & kmask;
@@ -94,8 +94,8 @@ template <> struct Bucket<uint32_t> {
 template <> struct Bucket<uint64_t> {
     static constexpr int W = 2;
     static constexpr uint64_t EMPTY = ~0ULL;
-    static __device__ __forceinline__ uint32_t hash(uint64_t k, int shift) {
-        return (uint32_t)((k * 0x9E3779B97F4A7C15ULL) >> 32) >> shift;
+    static __device__ __forceinline__ uint32_t hash(uint64_t k, uint32_t nb) {
+        return __umulhi((uint32_t)((k * 0x9E3779B97F4A7C15ULL) >> 32), nb);
     }
     static __device__ __forceinline__ uint64_t kmer(const uint32_t *pk, int p, uint64_t kmask) {
         const int w = p >> 4, sh = (p & 15) * 2;
@@ -115,9 +115,9 @@ template <> struct Bucket<uint64_t> {
 
 // find-or-claim; `claimed` tells whether this call inserted the key
 template <typename KeyT>
-__device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb_mask, int shift, KeyT key, bool &claimed) {
+__device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb, KeyT key, bool &claimed) {
     using B = Bucket<KeyT>;
-    uint32_t b = B::hash(key, shift);
+    uint32_t b = B::hash(key, nb);
     for (;;) {
         KeyT *base = keys + b * B::W;
         int hit, emp;
@@ -129,19 +129,19 @@ __device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb_mask, int
             if (old == key) { claimed = false; return b * B::W + emp; }
             continue;                       // somebody else took the slot: look at the bucket again
         }
-        b = (b + 1) & nb_mask;
+        b = b + 1 == nb ? 0 : b + 1;
     }
 }
 template <typename KeyT>
-__device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb_mask, int shift, KeyT key) {
+__device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT key) {
     using B = Bucket<KeyT>;
-    uint32_t b = B::hash(key, shift);
+    uint32_t b = B::hash(key, nb);
     for (;;) {
         int hit, emp;
         B::scan(keys + b * B::W, key, hit, emp);
         if (hit >= 0) return b * B::W + hit;
         if (emp >= 0) return 0xFFFFFFFFu;
-        b = (b + 1) & nb_mask;
+        b = b + 1 == nb ? 0 : b + 1;
     }
 }
 
@@ -154,7 +154,7 @@ struct S12Shared {
 template <typename KeyT, bool FULL>
 __global__ void __launch_bounds__(256)
 stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs,
-                     const int32_t *__restrict__ pair_list, int count, int k, uint32_t cap, int lognb,
+                     const int32_t *__restrict__ pair_list, int count, int k, uint32_t cap,
                      int words, int maxq, int want_segments, PairOut *__restrict__ pout, Pools pools,
                      Counters *__restrict__ ctr, SlotCfg cfg, uint8_t *__restrict__ nd0, uint8_t *__restrict__ nd1) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -175,8 +175,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     __shared__ S12Shared sh;
 
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t nb_mask = (cap / B::W) - 1;
-    const int shift = 32 - lognb;
+    const uint32_t nb = cap / B::W;             // buckets; cap is a multiple of 16, not necessarily a power of two
     const KeyT kmask = (2 * k >= (int)(8 * sizeof(KeyT))) ? ~(KeyT)0 : (((KeyT)1 << (2 * k)) - 1);
     unsigned long long my_cells = 0, my_nseg = 0;
 
@@ -218,7 +217,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         // ---- A: seq1 k-mers
         for (int p = tid; p < N0; p += T) {
             bool claimed;
-            const uint32_t h = bkt_insert<KeyT>(keys, nb_mask, shift, B::kmer(pk0, p, kmask), claimed);
+            const uint32_t h = bkt_insert<KeyT>(keys, nb, B::kmer(pk0, p, kmask), claimed);
             if (claimed) pos0[h] = (uint16_t)p;
             else dup0[h] = 1;
         }
@@ -229,9 +228,9 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             uint32_t h;
             if (FULL) {
                 bool claimed;
-                h = bkt_insert<KeyT>(keys, nb_mask, shift, key, claimed);
+                h = bkt_insert<KeyT>(keys, nb, key, claimed);
             } else {
-                h = bkt_find<KeyT>(keys, nb_mask, shift, key);
+                h = bkt_find<KeyT>(keys, nb, key);
                 if (h != 0xFFFFFFFFu && dup0[h]) h = 0xFFFFFFFFu;
             }
             if (h != 0xFFFFFFFFu) last1[h] = (uint16_t)q;
@@ -257,7 +256,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         }
         if (FULL) {
             for (int p = tid; p < N0; p += T) {
-                const uint32_t h = bkt_find<KeyT>(keys, nb_mask, shift, B::kmer(pk0, p, kmask));
+                const uint32_t h = bkt_find<KeyT>(keys, nb, B::kmer(pk0, p, kmask));
                 nd0[pd.p_base + p] = !(dup0[h] | dup1[h]);
             }
         }
@@ -415,9 +414,7 @@ static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const in
     if (occ < 1) occ = 1;
     int grid = num_sms * occ;
     if (grid > count) grid = count;
-    int lognb = 0;
-    while ((1u << lognb) < cap / Bucket<KeyT>::W) ++lognb;
-    kern<<<grid, 256, smem, st>>>(seqs, pairs, list, count, k, cap, lognb, words, maxq, want_segments ? 1 : 0, pout,
+    kern<<<grid, 256, smem, st>>>(seqs, pairs, list, count, k, cap, words, maxq, want_segments ? 1 : 0, pout,
                                   pools, ctr, cfg, nd0, nd1);
     return cudaGetLastError();
 }
