@@ -113,7 +113,9 @@ template <> struct Bucket<uint64_t> {
     }
 };
 
-// find-or-claim; `claimed` tells whether this call inserted the key
+// find-or-claim; `claimed` tells whether this call inserted the key.  Slots of a bucket fill in
+// order; after a lost race for one slot the later slots that were empty at scan time are
+// tried straight from registers (no second bucket load).
 template <typename KeyT>
 __device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb, KeyT key, bool &claimed) {
     using B = Bucket<KeyT>;
@@ -124,10 +126,12 @@ __device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb, KeyT key
         B::scan(base, key, hit, emp);
         if (hit >= 0) { claimed = false; return b * B::W + hit; }
         if (emp >= 0) {
-            const KeyT old = B::cas(base + emp, key);
-            if (old == B::EMPTY) { claimed = true; return b * B::W + emp; }
-            if (old == key) { claimed = false; return b * B::W + emp; }
-            continue;                       // somebody else took the slot: look at the bucket again
+            // slots emp .. W-1 were empty when the bucket was read (slots fill in order)
+            for (int e = emp; e < B::W; ++e) {
+                const KeyT old = B::cas(base + e, key);
+                if (old == B::EMPTY) { claimed = true; return b * B::W + e; }
+                if (old == key) { claimed = false; return b * B::W + e; }
+            }
         }
         b = b + 1 == nb ? 0 : b + 1;
     }
