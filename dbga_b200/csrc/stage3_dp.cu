@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(TINY_THREADS)
 dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                  const int32_t *__restrict__ lists, int64_t list_cap, const unsigned int *__restrict__ counts_dev,
                  int c0, int c1, TinyBounds tb, DpParams prm, uint8_t *__restrict__ strbuf,
-                 uint32_t *__restrict__ tb_scratch) {
+                 uint32_t *__restrict__ tb_scratch, int tb_in_smem) {
     extern __shared__ int smem_i[];
     constexpr int TH = TINY_THREADS;
     const int tid = threadIdx.x;
@@ -120,7 +120,10 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
     const int32_t *list = lists + (int64_t)cls * list_cap;
     const unsigned int count = counts_dev[cls];
     const int wpr = (bound + 3) >> 2;                         // traceback words per row
-    uint32_t *tbw = tb_scratch + (size_t)blockIdx.x * ((size_t)bmax * ((bmax + 3) >> 2) * TH) + tid;
+    // traceback words: shared memory for the small classes (a dependent chain of L2 round trips
+    // per traceback step was the top stall), per-CTA scratch in HBM/L2 otherwise
+    uint32_t *tbw = tb_in_smem ? reinterpret_cast<uint32_t *>(smem_i + 2 * (bmax + 1) * TH) + (bmax * TH) / 2 + tid
+                               : tb_scratch + (size_t)blockIdx.x * ((size_t)bmax * ((bmax + 3) >> 2) * TH) + tid;
     for (unsigned int base = blockIdx.x * TH; base < count; base += gridDim.x * TH) {
         const unsigned int item = base + tid;
         const bool have = item < count;
@@ -137,6 +140,9 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
             str_off = s.str_off;
             row_len = (pd.off1 - pd.off0) + pd.n1;
         }
+        // seq1 codes of the segment, 2 bits each, loaded back to back (independent loads)
+        unsigned long long xcodes = 0;
+        for (int i = 0; i < m; ++i) xcodes |= (unsigned long long)base_code(xs[i]) << (2 * i);
         // row 0 and the per-column score selectors
         Tc[0] = 0 | tagM;
         Uc[0] = (-go) | tagM;
@@ -161,7 +167,7 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
         int xi0 = (-go) | tagX;                                   // X[i][0], i = 1
         uint32_t *tbrow = tbw;
         for (int i = 1; i <= mmax; ++i) {
-            const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
+            const int xc = (int)(xcodes >> (2 * (i - 1))) & 3;
             const uint32_t slo = s_lut[xc], shi = s_lut[4 + xc];
             int Ml = NEG | tagM, Yl = NEG | tagY, Xl = xi0;
             int diag = Tc[0];
@@ -225,9 +231,11 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
   }
 }
 
-static size_t dp_thread_smem(int bound) {
+static size_t dp_thread_smem(int bound, bool tb_in_smem) {
     const int b4 = (bound + 3) & ~3;                   // columns are processed in groups of four
-    return (size_t)(2 * (b4 + 1) * 4 + b4 * 2) * TINY_THREADS;
+    size_t bytes = (size_t)(2 * (b4 + 1) * 4 + b4 * 2) * TINY_THREADS;
+    if (tb_in_smem) bytes += (size_t)b4 * (b4 / 4) * 4 * TINY_THREADS;      // b4 rows x b4/4 words per thread
+    return bytes;
 }
 static int dp_thread_grid(int num_sms) { return num_sms * 8; }
 size_t dp_thread_scratch_bytes(int bound, int num_sms) {
@@ -237,14 +245,16 @@ size_t dp_thread_scratch_bytes(int bound, int num_sms) {
 cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
                              int64_t list_cap, const unsigned int *counts_dev, int c0, int c1, TinyBounds tb,
                              DpParams prm, uint8_t *strbuf, uint32_t *tb_scratch, int num_sms, cudaStream_t st) {
-    const size_t smem = dp_thread_smem(tb.b[c1 - 1]);
+    // traceback in shared memory when that leaves at least four CTAs per SM
+    const bool tbs = dp_thread_smem(tb.b[c1 - 1], true) <= 56 * 1024;
+    const size_t smem = dp_thread_smem(tb.b[c1 - 1], tbs);
     const int grid = dp_thread_grid(num_sms);
     if (prm.xy) {
         cudaFuncSetAttribute(dp_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dp_thread_kernel<true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch);
+        dp_thread_kernel<true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch, tbs ? 1 : 0);
     } else {
         cudaFuncSetAttribute(dp_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dp_thread_kernel<false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch);
+        dp_thread_kernel<false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch, tbs ? 1 : 0);
     }
     return cudaGetLastError();
 }
