@@ -66,7 +66,7 @@ struct dbga_ctx {
     int grid_warp = 0, grid_cta = 0;
     int64_t warp_max_cells = WARP_CLASS_MAX_CELLS_FEW;
     int tiny_bound[NUM_TINY] = {8, 16, 24, 32};
-    bool seen_warp_work = true, seen_cta_work = true;   // adaptive grid for the (often empty) wavefront launches
+    bool seen_work[NUM_CLS] = {true, true, true, true, true, true, true, true};   // adaptive grids for the (often empty) wavefront launches
     int launches = 0;
     const uint8_t *d_seqs_run = nullptr;
 
@@ -360,7 +360,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     }
     // boundary rows for multi-pass wavefronts
     ctx->warp_max_cells = P >= MANY_PAIRS ? WARP_CLASS_MAX_CELLS_MANY : WARP_CLASS_MAX_CELLS_FEW;
-    ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, ctx->warp_max_cells / (WF_ROWS_PER_WARP + 1) + 2);
+    ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, ctx->warp_max_cells / 65 + 2);
     ctx->bnd_stride_cta = (int64_t)mx1 + 1;
     ctx->grid_warp = (int)std::max<int64_t>(ctx->num_sms, std::min<int64_t>(ctx->num_sms * 16, (512LL << 20) / (32 * ctx->bnd_stride_warp)));
     {
@@ -488,15 +488,19 @@ int run_pipeline(dbga_ctx *ctx) {
             }
         }
         if (ctx->grid_warp) {
-            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_WARP * pools.list_cap,
-                                                &ctr->n_cls[CLS_WARP], ctx->seen_warp_work ? ctx->grid_warp : std::min(ctx->grid_warp, ctx->num_sms), false, ctx->dp, (uint8_t *)ctx->d_str.p,
-                                                (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
-            ctx->launches += 1;
+            for (int cls = CLS_WARP2; cls <= CLS_WARP8; ++cls) {
+                const int g = ctx->seen_work[cls] ? ctx->grid_warp : std::min(ctx->grid_warp, ctx->num_sms);
+                DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
+                                                    &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                    (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));
+                ctx->launches += 1;
+            }
         }
         if (ctx->grid_cta) {
             DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
-                                                &ctr->n_cls[CLS_CTA], ctx->seen_cta_work ? ctx->grid_cta : std::min(ctx->grid_cta, 8), true, ctx->dp, (uint8_t *)ctx->d_str.p,
-                                                (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
+                                                &ctr->n_cls[CLS_CTA], ctx->seen_work[CLS_CTA] ? ctx->grid_cta : std::min(ctx->grid_cta, 8),
+                                                CLS_CTA, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
+                                                (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
             ctx->launches += 1;
         }
     }
@@ -551,8 +555,7 @@ int fetch_resolve(dbga_ctx *ctx, bool counters_already_copied) {
     }
     // the wavefront kernels are persistent, so any grid is correct; keep it small while the
     // workload has no segment for them (most closely related pairs)
-    ctx->seen_warp_work = hc->n_cls[CLS_WARP] > 0;
-    ctx->seen_cta_work = hc->n_cls[CLS_CTA] > 0;
+    for (int c = 0; c < NUM_CLS; ++c) ctx->seen_work[c] = hc->n_cls[c] > 0;
     return DBGA_SUCCESS;
 }
 

@@ -46,14 +46,17 @@ struct Slot {
 static_assert(sizeof(Slot) == 64, "Slot is four 16-byte words");
 
 // DP classes: 0..3 = thread-per-segment ("tiny", bucketed by max(m, n) so that the segments of
-// a warp have similar loop bounds), 4 = warp wavefront, 5 = CTA wavefront.
-enum : int32_t { CLS_NONE = -1, CLS_TINY0 = 0, NUM_TINY = 4, CLS_WARP = 4, CLS_CTA = 5, NUM_CLS = 6 };
+// a warp have similar loop bounds),
+// 4..6 = warp wavefront with 2 / 4 / 8 rows per lane (segments of up to 64 / 128 / any rows),
+// 7 = CTA wavefront (8 rows per lane, 8 warps).
+enum : int32_t { CLS_NONE = -1, CLS_TINY0 = 0, NUM_TINY = 4, CLS_WARP2 = 4, CLS_WARP4 = 5, CLS_WARP8 = 6, CLS_CTA = 7, NUM_CLS = 8 };
 
 // DP geometry (shared by host sizing and kernels)
 constexpr int TINY_MAX = 32;     // thread-per-segment kernel: m, n <= 32
 constexpr int TINY_THREADS = 128;
-constexpr int WF_R = 8;          // rows per lane in the wavefront kernels
+constexpr int WF_R = 8;          // rows per lane in the widest wavefront kernels
 constexpr int WF_ROWS_PER_WARP = 32 * WF_R;   // 256
+__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 ? 4 : 8); }
 constexpr int WF_CTA_WARPS = 8;  // warps per CTA in the long-segment kernel
 constexpr int WF_D = 64;         // step delay between consecutive warps
 constexpr int WF_C = 32;         // steps per barrier
@@ -83,10 +86,11 @@ struct DpParams {
     int32_t go_raw, ge_raw;
 };
 
-__host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int warps) {
-    const int64_t rows_per_pass = (int64_t)warps * WF_ROWS_PER_WARP;
+__host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int warps, int rows_per_lane) {
+    const int64_t rows_per_warp = 32 * rows_per_lane;
+    const int64_t rows_per_pass = (int64_t)warps * rows_per_warp;
     const int64_t passes = (m + rows_per_pass - 1) / rows_per_pass;
-    return passes * warps * (n + 32) * WF_ROWS_PER_WARP;
+    return passes * warps * (n + 32) * rows_per_warp;
 }
 
 // ------------------------------------------------------------------ small device utils

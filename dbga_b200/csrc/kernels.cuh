@@ -63,7 +63,7 @@ cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *s
                              DpParams prm, uint8_t *strbuf, uint32_t *tb_scratch, int num_sms, cudaStream_t st);
 // bnd: per-CTA double-buffered boundary rows, int4 per column, bnd_stride columns each
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
-                                const unsigned int *count_dev, int grid, bool cta_class, DpParams prm,
+                                const unsigned int *count_dev, int grid, int cls, DpParams prm,
                                 uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);
 
 // ---- assembly

@@ -264,14 +264,15 @@ struct WfShared {
     int endM, endX, endY, have_end;
 };
 
-template <int W, bool XY>
+template <int W, int R, bool XY>
 __global__ void __launch_bounds__(W * 32)
 dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
              const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
              uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool, int4 *__restrict__ bnd_pool,
              int64_t bnd_stride) {
-    constexpr int R = WF_R, D = WF_D, C = WF_C, RING = WF_RING;
+    constexpr int D = WF_D, C = WF_C, RING = WF_RING;
     constexpr int ROWS_PASS = W * 32 * R;
+    constexpr int WIN_W = (32 * R >= 64) ? 64 : 32 * R;       // traceback window width in bytes
     __shared__ int4 ring[W + 1][RING];
     __shared__ WfShared sh;
     __shared__ __align__(16) uint8_t win[32][64];      // traceback window
@@ -371,7 +372,10 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                             if (r < 4) wlo |= d << (8 * r); else whi |= d << (8 * (r - 4));
                             dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
                         }
-                        *reinterpret_cast<uint2 *>(tbw + (int64_t)(j + lane) * (32 * R)) = make_uint2(wlo, whi);
+                        uint8_t *tbp = tbw + (int64_t)(j + lane) * (32 * R);
+                        if constexpr (R == 8) *reinterpret_cast<uint2 *>(tbp) = make_uint2(wlo, whi);
+                        else if constexpr (R == 4) *reinterpret_cast<uint32_t *>(tbp) = wlo;
+                        else *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)wlo;
                         my_yc = yc;
                         if (j == n && i_own) {
 #pragma unroll
@@ -414,18 +418,20 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                     const int i0 = i - 1;
                     const int blk = i0 / (32 * R), cb = i0 % (32 * R);      // (pass * W + warp), l * R + r
                     const int row = j + cb / R;
-                    if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= 64u) {
+                    if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= (unsigned)WIN_W) {
                         __syncwarp();
                         win_blk = blk; win_row_hi = row;
-                        win_col_lo = max(0, (cb & ~31) - 32);
+                        win_col_lo = (WIN_W == 64) ? max(0, (cb & ~31) - 32) : 0;
                         const int rr = row - lane;
                         uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
                         if (rr >= 1) {
                             const uint4 *p = reinterpret_cast<const uint4 *>(tb + ((int64_t)blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo);
-                            a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
+                            a = p[0]; b = p[1];
+                            if constexpr (WIN_W == 64) { c4 = p[2]; d4 = p[3]; }
                         }
                         uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
-                        dst[0] = a; dst[1] = b; dst[2] = c4; dst[3] = d4;
+                        dst[0] = a; dst[1] = b;
+                        if constexpr (WIN_W == 64) { dst[2] = c4; dst[3] = d4; }
                         __syncwarp();
                     }
                     d = win[win_row_hi - row][cb - win_col_lo];
@@ -446,17 +452,23 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     }
 }
 
+template <int W, int R>
+static void launch_wf_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                        const unsigned int *count_dev, DpParams prm, uint8_t *strbuf, uint8_t *tb, int4 *bnd,
+                        int64_t bnd_stride, cudaStream_t st) {
+    if (prm.xy) dp_wf_kernel<W, R, true><<<grid, W * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+    else dp_wf_kernel<W, R, false><<<grid, W * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+}
+
+// cls: CLS_WARP2 / CLS_WARP4 / CLS_WARP8 (one warp per segment) or CLS_CTA
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
-                                const unsigned int *count_dev, int grid, bool cta_class, DpParams prm,
+                                const unsigned int *count_dev, int grid, int cls, DpParams prm,
                                 uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (cta_class) {
-        if (prm.xy) dp_wf_kernel<WF_CTA_WARPS, true><<<grid, WF_CTA_WARPS * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
-        else dp_wf_kernel<WF_CTA_WARPS, false><<<grid, WF_CTA_WARPS * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
-    } else {
-        if (prm.xy) dp_wf_kernel<1, true><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
-        else dp_wf_kernel<1, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
-    }
+    if (cls == CLS_CTA) launch_wf_t<WF_CTA_WARPS, 8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    else if (cls == CLS_WARP2) launch_wf_t<1, 2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    else if (cls == CLS_WARP4) launch_wf_t<1, 4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    else launch_wf_t<1, 8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     return cudaGetLastError();
 }
 
