@@ -44,7 +44,7 @@ __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, in
                 my_cells += (unsigned long long)cells; my_nseg += 1;
                 const long long mag = (long long)cfg.max_abs_score * (s.m < s.n ? s.m : s.n) + cfg.go_raw +
                                       (long long)cfg.ge_raw * ((long long)s.m + s.n);
-                if (mag >= MAX_ABS_SCORE) { *flag_big = 1; }
+                if (2 * mag >= MAX_ABS_SCORE) { *flag_big = 1; }      // real score + the ge*(i+j) offset
                 else if (s.m <= TINY_MAX && s.n <= TINY_MAX) {
                     const int mx = s.m > s.n ? s.m : s.n;
                     cls = NUM_TINY - 1;

@@ -8,6 +8,9 @@
 //     M[i][j] = S(x_i, y_j) + max(M, X, Y)[i-1][j-1]
 //     X[i][j] = max(M[i-1][j] - go, X[i-1][j] - ge [, Y[i-1][j] - go])     (x_i vs gap)
 //     Y[i][j] = max(M[i][j-1] - go, Y[i][j-1] - ge [, X[i][j-1] - go])     (gap vs y_j)
+// All three states are stored with the same offset ge*(i+j) added (H^ = H + ge*(i+j)): a gap
+// extension then costs nothing and a gap open costs go - ge, so X and Y are one fused
+// add-max each (no separate subtraction); the match state absorbs 2*ge into its score add.
 // Scores live in registers as 64*V + 21*prio(state): one integer max (VIMNMX3 /
 // VIADDMNMX) both selects the best predecessor under the configured first-wins tie order
 // and leaves the winner's identity in the low bits, which become the traceback byte
@@ -31,15 +34,15 @@ __device__ __forceinline__ int strip(int v) { return v & ~63; }
 // One cell.  (Ml,Xl,Yl): in = (i, j-1), out = (i, j).  d*: (i-1, j-1).  u*: (i-1, j).
 template <bool XY>
 __device__ __forceinline__ uint32_t dp_cell(int &Ml, int &Xl, int &Yl, int dM, int dX, int dY, int uM,
-                                            int uX, int uY, int sprime, int go, int ge, int tagX, int tagY) {
+                                            int uX, int uY, int sprime, int gmo, int ge2, int tagX, int tagY) {
     const int t = __vimax3_s32(dM, dX, dY);
-    int u = __viaddmax_s32(uM, -go, uX - ge);
-    int v = __viaddmax_s32(Ml, -go, Yl - ge);
+    int u = __viaddmax_s32(uM, gmo, uX);          // max(M_up + (ge - go), X_up)
+    int v = __viaddmax_s32(Ml, gmo, Yl);
     if (XY) {
-        u = max(u, uY - go);
-        v = max(v, Xl - go);
+        u = max(u, uY + gmo);
+        v = max(v, Xl + gmo);
     }
-    Ml = strip(t) + sprime;
+    Ml = strip(t) + sprime + ge2;
     Xl = strip(u) | tagX;
     Yl = strip(v) | tagY;
     // bit-select: low 2 bits of t, bits 2-3 of u, bits 4-5 of v
@@ -69,7 +72,7 @@ __device__ __forceinline__ void pick_end(int Mv, int Xv, int Yv, const DpParams 
     long long b = cm; state = 0;
     if (cx > b) { b = cx; state = 1; }
     if (cy > b) { b = cy; state = 2; }
-    score = (int)(b >> 6);
+    score = (int)(b >> 6);          // still carries the offset ge*(m+n); the caller removes it
 }
 
 // ============================================================================ tiny segments
@@ -99,7 +102,7 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
     int *Tc = smem_i + tid;                                   // Tc[j * TH], j = 0..bmax
     int *Uc = Tc + (bmax + 1) * TH;
     uint16_t *selc = reinterpret_cast<uint16_t *>(smem_i + 2 * (bmax + 1) * TH) + tid;   // selc[(j-1) * TH]
-    const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
+    const int gmo = prm.ge - prm.go, ge2 = 2 * prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
     // score LUT in shared memory: indexing kernel parameters with a run-time base code would
     // compile into a long predicated cascade
@@ -145,13 +148,13 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
         for (int i = 0; i < m; ++i) xcodes |= (unsigned long long)base_code(xs[i]) << (2 * i);
         // row 0 and the per-column score selectors
         Tc[0] = 0 | tagM;
-        Uc[0] = (-go) | tagM;
+        Uc[0] = gmo | tagM;                                       // X^[1][0] comes from M[0][0]
         for (int j = 1; j <= n; ++j) {
             selc[(j - 1) * TH] = (uint16_t)lut_sel(base_code(ys[j - 1]));
-            const int y0 = (-(go + (j - 1) * ge)) | tagY;
+            const int y0 = gmo | tagY;                            // Y^[0][j] = -(go + (j-1) ge) + ge j
             Tc[j * TH] = y0;
-            int u = __viaddmax_s32(NEG | tagM, -go, (NEG | tagX) - ge);
-            if (XY) u = max(u, y0 - go);
+            int u = __viaddmax_s32(NEG | tagM, gmo, NEG | tagX);
+            if (XY) u = max(u, y0 + gmo);
             Uc[j * TH] = u;
         }
         int mmax = m, nmax = n;
@@ -164,7 +167,7 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
         // n, and rows past its m, compute garbage into the lane's private shared-memory columns
         const int ngrp = (nmax + 3) >> 2;
         int eM = 0, eX = 0, eY = 0;
-        int xi0 = (-go) | tagX;                                   // X[i][0], i = 1
+        const int xi0 = gmo | tagX;                               // X^[i][0] = -(go + (i-1) ge) + ge i
         uint32_t *tbrow = tbw;
         for (int i = 1; i <= mmax; ++i) {
             const int xc = (int)(xcodes >> (2 * (i - 1))) & 3;
@@ -172,8 +175,7 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
             int Ml = NEG | tagM, Yl = NEG | tagY, Xl = xi0;
             int diag = Tc[0];
             Tc[0] = xi0;                                         // max(M, X, Y)[i][0]
-            Uc[0] = xi0 - ge;                                    // X candidate of row i+1, column 0
-            xi0 -= ge;
+            Uc[0] = xi0;                                         // X candidate of row i+1, column 0
             const bool last_row = (i == m);
             int *Tp = Tc + TH, *Up = Uc + TH;
             const uint16_t *sp = selc;
@@ -184,16 +186,16 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
                 for (int u4 = 0; u4 < 4; ++u4) {
                     const int Tj = Tp[u4 * TH], Uj = Up[u4 * TH];
                     const uint32_t sel = sp[u4 * TH];
-                    const int Mn = strip(diag) + lut_score(slo, shi, sel);
+                    const int Mn = strip(diag) + lut_score(slo, shi, sel) + ge2;
                     const int Xn = strip(Uj) | tagX;
-                    int v = __viaddmax_s32(Ml, -go, Yl - ge);
-                    if (XY) v = max(v, Xl - go);
+                    int v = __viaddmax_s32(Ml, gmo, Yl);
+                    if (XY) v = max(v, Xl + gmo);
                     const int Yn = strip(v) | tagY;
                     uint32_t d = ((uint32_t)diag & 3u) | ((uint32_t)Uj & ~3u);
                     d = (d & 15u) | ((uint32_t)v & ~15u);
                     word |= (d & 0xFFu) << (8 * u4);
-                    int un = __viaddmax_s32(Mn, -go, Xn - ge);
-                    if (XY) un = max(un, Yn - go);
+                    int un = __viaddmax_s32(Mn, gmo, Xn);
+                    if (XY) un = max(un, Yn + gmo);
                     Tp[u4 * TH] = __vimax3_s32(Mn, Xn, Yn);
                     Up[u4 * TH] = un;
                     if (capg == u4 + 1) { eM = Mn; eX = Xn; eY = Yn; }
@@ -224,7 +226,7 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
                 st = (int)((pmap >> (2 * tag)) & 3u);
                 ++len;
             }
-            slots[sid].score = score;
+            slots[sid].score = score - prm.ge_raw * (m + n);
             slots[sid].len = len;
         }
     }
@@ -284,7 +286,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned int count = *count_dev;
-    const int go = prm.go, ge = prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
+    const int gmo = prm.ge - prm.go, ge2 = 2 * prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
     int4 *bndA = bnd_pool + (int64_t)blockIdx.x * 2 * bnd_stride, *bndB = bndA + bnd_stride;
 
@@ -314,7 +316,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                 const int xc = (i <= m) ? base_code(xs[i - 1]) : 0;
                 slo[r] = s_lut[xc]; shi[r] = s_lut[4 + xc];
                 Mr[r] = NEG | tagM;
-                Xr[r] = (-(go + (i - 1) * ge)) | tagX;
+                Xr[r] = gmo | tagX;                          // X^[i][0]
                 Yr[r] = NEG | tagY;
             }
             int dgM = 0, dgX = 0, dgY = 0, my_yc = 0;
@@ -331,7 +333,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                 int4 e;
                 if (pass == 0) {
                     e.x = (c == 0 ? 0 : NEG) | tagM; e.y = NEG | tagX;
-                    e.z = (c == 0 ? NEG : -(go + (c - 1) * ge)) | tagY;
+                    e.z = (c == 0 ? NEG : gmo) | tagY;       // Y^[0][c]
                 } else {
                     e = bin[c];
                 }
@@ -368,7 +370,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                         for (int r = 0; r < R; ++r) {
                             const int oM = Mr[r], oX = Xr[r], oY = Yr[r];
                             const uint32_t d = dp_cell<XY>(Mr[r], Xr[r], Yr[r], dM, dX, dY, aM, aX, aY,
-                                                           lut_score(slo[r], shi[r], sel), go, ge, tagX, tagY);
+                                                           lut_score(slo[r], shi[r], sel), gmo, ge2, tagX, tagY);
                             if (r < 4) wlo |= d << (8 * r); else whi |= d << (8 * (r - 4));
                             dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
                         }
@@ -446,7 +448,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                 ++len;
             }
             if (lane < (len & 31)) { ox[(len & ~31) + lane] = (uint8_t)cx; oy[(len & ~31) + lane] = (uint8_t)cy; }
-            if (lane == 0) { slots[sid].score = score; slots[sid].len = len; }
+            if (lane == 0) { slots[sid].score = score - prm.ge_raw * (m + n); slots[sid].len = len; }
         }
         __syncthreads();
     }
