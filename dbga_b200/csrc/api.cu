@@ -26,6 +26,7 @@ struct HostBuf {
 
 struct SmallClass {
     uint32_t cap;
+    int parts;          // 1: fused stages 1+2; > 1: partitioned table, stage 1 only ("medium" pairs)
     int words, maxq;
     int begin, count;   // range in the small pair list
 };
@@ -60,6 +61,7 @@ struct dbga_ctx {
     std::vector<LargeDesc> h_large;
     std::vector<LargeWave> waves;
     int large_begin = 0;
+    int stage2_begin = 0;      // first list entry that needs the generic stage-2 kernel (medium + large pairs)
     int stage2_threads = 128;
     int64_t runs_cap = 0, slots_cap = 0, tb_cap = 0;
     int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
@@ -223,7 +225,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     ctx->classes.clear(); ctx->h_list.clear(); ctx->h_large.clear(); ctx->waves.clear();
     if (!no_anchors) {
         const int key_bytes = k <= 15 ? 4 : 8;
-        std::map<uint32_t, std::vector<int32_t>> by_cap;
+        std::map<std::pair<int, uint32_t>, std::vector<int32_t>> by_cap;   // (partitions, capacity) -> pairs
         const uint64_t cap_lo = 150, cap_hi = 275;
         std::vector<int32_t> large;
         for (int64_t i = 0; i < P; ++i) {
@@ -250,15 +252,29 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             const bool fits = cap <= 32768 && N0 < 65000 && N1 < 65000 &&   // 16-bit positions in shared memory
                               stage12_small_smem(key_bytes, cap, words, (int)N1) <= SMEM_LIMIT;
             if (fits) {
-                by_cap[cap].push_back((int32_t)i);
+                by_cap[{1, cap}].push_back((int32_t)i);
             } else {
-                large.push_back((int32_t)i);
+                // medium: split the keys over 2..8 table partitions that take turns in shared memory
+                int parts = 0;
+                uint32_t pcap = 0;
+                if (N0 < 65000 && N1 < 65000) {
+                    for (int g = 2; g <= 8 && !parts; ++g) {
+                        uint64_t w = keys * 170 / 100 / g + 64;       // 1.7 x the expected keys per partition
+                        uint32_t gr = 256;
+                        while ((uint64_t)gr * 16 < w) gr <<= 1;
+                        const uint32_t c = (uint32_t)((w + gr - 1) / gr * gr);
+                        if (c <= 32768 && stage12_small_smem(key_bytes, c, words0, (int)N1) <= 200 * 1024) { parts = g; pcap = c; }
+                    }
+                }
+                if (parts) by_cap[{parts, pcap}].push_back((int32_t)i);
+                else large.push_back((int32_t)i);
             }
         }
+        int stage2_first = -1;
         for (auto &kv : by_cap) {
             const std::vector<int32_t> &members = kv.second;
             SmallClass c;
-            c.cap = kv.first; c.begin = (int)ctx->h_list.size(); c.count = (int)members.size();
+            c.parts = kv.first.first; c.cap = kv.first.second; c.begin = (int)ctx->h_list.size(); c.count = (int)members.size();
             int nmax = 0, qmax = 0;
             for (int32_t i : members) {
                 const PairDesc &pd = ctx->h_pairs[(size_t)i];
@@ -274,9 +290,11 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                 for (int32_t i : members) large.push_back(i);
                 continue;
             }
+            if (c.parts > 1 && stage2_first < 0) stage2_first = c.begin;
             ctx->classes.push_back(c);
         }
         ctx->large_begin = (int)ctx->h_list.size();
+        ctx->stage2_begin = stage2_first >= 0 ? stage2_first : ctx->large_begin;
         // waves of large pairs whose tables stay L2 resident together
         size_t wave_tbl = 0, wave_pk = 0;
         LargeWave w{(int)ctx->h_large.size(), 0, 0, 0};
@@ -441,9 +459,10 @@ int run_pipeline(dbga_ctx *ctx) {
                 }
                 if (hi <= lo) continue;
                 DBGA_CUDA_CHECK(launch_stage12_small(seqs, pairs, (int32_t *)ctx->d_list.p + c.begin + lo, hi - lo, ctx->prm.k,
-                                                     c.cap, c.words, c.maxq, full, seg, pout, pools, ctr, ctx->max_abs_score,
-                                                     ctx->dp.go_raw, ctx->dp.ge_raw, (uint8_t *)ctx->d_nd0.p,
-                                                     (uint8_t *)ctx->d_nd1.p, ctx->num_sms, st));
+                                                     c.cap, c.parts, c.words, c.maxq, full, seg, pout, pools, ctr,
+                                                     ctx->max_abs_score, ctx->dp.go_raw, ctx->dp.ge_raw, (uint8_t *)ctx->d_nd0.p,
+                                                     (uint8_t *)ctx->d_nd1.p, (int32_t *)ctx->d_status.p, (int32_t *)ctx->d_aof.p,
+                                                     ctx->num_sms, st));
                 ctx->launches += 1;
             }
         }
@@ -461,9 +480,9 @@ int run_pipeline(dbga_ctx *ctx) {
     // ---- generic stage 2: pairs that went through the global-table path, or every pair
     //      when there is no anchoring at all (dbga_global_align_batch)
     {
-        const int64_t n_large = (int64_t)ctx->h_list.size() - ctx->large_begin;
-        const int64_t cnt = ctx->no_anchors ? P : n_large;
-        const int32_t *lst = ctx->no_anchors ? nullptr : (int32_t *)ctx->d_list.p + ctx->large_begin;
+        const int64_t n_generic = (int64_t)ctx->h_list.size() - ctx->stage2_begin;
+        const int64_t cnt = ctx->no_anchors ? P : n_generic;
+        const int32_t *lst = ctx->no_anchors ? nullptr : (int32_t *)ctx->d_list.p + ctx->stage2_begin;
         if (cnt > 0) {
             DBGA_CUDA_CHECK(launch_stage2(pairs, lst, cnt, ctx->no_anchors ? 1 : ctx->prm.k, ctx->no_anchors, seg,
                                           (int32_t *)ctx->d_aof.p, (int32_t *)ctx->d_status.p, pout, pools, ctr,

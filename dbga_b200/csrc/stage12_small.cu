@@ -78,7 +78,7 @@ template <typename KeyT> struct Bucket;
 template <> struct Bucket<uint32_t> {
     static constexpr int W = 4;
     static constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-    static __device__ __forceinline__ uint32_t hash(uint32_t k, uint32_t nb) { return __umulhi(k * 0x9E3779B1u, nb); }
+    static __device__ __forceinline__ uint32_t mix(uint32_t k) { return k * 0x9E3779B1u; }
     static __device__ __forceinline__ uint32_t kmer(const uint32_t *pk, int p, uint32_t kmask) {
         const int w = p >> 4, sh = (p & 15) * 2;
         return __funnelshift_r(pk[w], pk[w + 1], sh) & kmask;
@@ -94,9 +94,7 @@ template <> struct Bucket<uint32_t> {
 template <> struct Bucket<uint64_t> {
     static constexpr int W = 2;
     static constexpr uint64_t EMPTY = ~0ULL;
-    static __device__ __forceinline__ uint32_t hash(uint64_t k, uint32_t nb) {
-        return __umulhi((uint32_t)((k * 0x9E3779B97F4A7C15ULL) >> 32), nb);
-    }
+    static __device__ __forceinline__ uint32_t mix(uint64_t k) { return (uint32_t)((k * 0x9E3779B97F4A7C15ULL) >> 32); }
     static __device__ __forceinline__ uint64_t kmer(const uint32_t *pk, int p, uint64_t kmask) {
         const int w = p >> 4, sh = (p & 15) * 2;
         const uint32_t a = pk[w], b = pk[w + 1], c = pk[w + 2];
@@ -117,9 +115,9 @@ template <> struct Bucket<uint64_t> {
 // order; after a lost race for one slot the later slots that were empty at scan time are
 // tried straight from registers (no second bucket load).
 template <typename KeyT>
-__device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb, KeyT key, bool &claimed) {
+__device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb, KeyT key, uint32_t hv, bool &claimed) {
     using B = Bucket<KeyT>;
-    uint32_t b = B::hash(key, nb);
+    uint32_t b = __umulhi(hv, nb);
     for (;;) {
         KeyT *base = keys + b * B::W;
         int hit, emp;
@@ -137,9 +135,9 @@ __device__ __forceinline__ uint32_t bkt_insert(KeyT *keys, uint32_t nb, KeyT key
     }
 }
 template <typename KeyT>
-__device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT key) {
+__device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT key, uint32_t hv) {
     using B = Bucket<KeyT>;
-    uint32_t b = B::hash(key, nb);
+    uint32_t b = __umulhi(hv, nb);
     for (;;) {
         int hit, emp;
         B::scan(keys + b * B::W, key, hit, emp);
@@ -152,17 +150,25 @@ __device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT
 struct S12Shared {
     int bad, nS, nE, nA, cycle, big;
     long long bcast[2];
-    long long red[8];
+    long long red[32];
 };
 
-template <typename KeyT, bool FULL>
-__global__ void __launch_bounds__(256)
+// parts > 1 ("medium" pairs): the key space is split by hash into `parts` partitions that take
+// turns in one shared-memory table of `cap` slots -- every round re-scans the packed
+// sequences (cheap) but inserts / looks up only its own partition's k-mers (the expensive
+// part stays constant).  Such pairs stop after stage 1: aof[] goes to HBM and the generic
+// stage-2 kernel takes over (their run count is not bounded by the table size).
+template <typename KeyT, bool FULL, int TPB>
+__global__ void __launch_bounds__(TPB, TPB == 256 ? 5 : 1)      // five CTAs per SM for the small-pair case
 stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs,
-                     const int32_t *__restrict__ pair_list, int count, int k, uint32_t cap,
+                     const int32_t *__restrict__ pair_list, int count, int k, uint32_t cap, int parts,
                      int words, int maxq, int want_segments, PairOut *__restrict__ pout, Pools pools,
-                     Counters *__restrict__ ctr, SlotCfg cfg, uint8_t *__restrict__ nd0, uint8_t *__restrict__ nd1) {
+                     Counters *__restrict__ ctr, SlotCfg cfg, uint8_t *__restrict__ nd0, uint8_t *__restrict__ nd1,
+                     int32_t *__restrict__ status, int32_t *__restrict__ aof) {
     extern __shared__ __align__(16) uint8_t smem[];
     using B = Bucket<KeyT>;
+    constexpr bool MEDIUM = TPB > 256;          // the small-pair instantiation compiles without any partition logic
+    if (!MEDIUM) parts = 1;
     uint32_t *pk0 = reinterpret_cast<uint32_t *>(smem);
     uint32_t *pk1 = pk0 + words;
     KeyT *keys = reinterpret_cast<KeyT *>(pk1 + words);
@@ -190,7 +196,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         po.status = DBGA_OK; po.n_runs = 0; po.run_base = 0; po.slot_base = 0; po.n_slots = 0; po.pad = 0;
         po.n_anchors = 0; po.aln_len = 0;
         if (k > pd.n0 || k > pd.n1) {                                  // utils.py:129-130
-            if (tid == 0) { po.status = DBGA_K_INVALID; pout[pair] = po; }
+            if (tid == 0) { po.status = DBGA_K_INVALID; pout[pair] = po; if (MEDIUM) status[pair] = DBGA_K_INVALID; }
             continue;
         }
         __syncthreads();            // previous pair's shared state is no longer in use
@@ -204,65 +210,89 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 pk0[w] = r0 > 0 ? pack16_fast(s0 + 16 * w, r0, bad) : 0u;
                 pk1[w] = r1 > 0 ? pack16_fast(s1 + 16 * w, r1, bad) : 0u;
             }
-            uint4 *t4 = reinterpret_cast<uint4 *>(keys);                // keys + pos0 + last1 = all ones
+        }
+        auto init_table = [&]() {       // keys + pos0 + last1 = all ones, dup0 + dup1 = 0
+            uint4 *t4 = reinterpret_cast<uint4 *>(keys);
             const int n_ff = (int)((cap * (sizeof(KeyT) + 4)) / 16), n_00 = (int)(cap * 2 / 16);
             for (int i = tid; i < n_ff; i += T) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-            uint4 *z4 = reinterpret_cast<uint4 *>(dup0);                // dup0 + dup1 = 0
+            uint4 *z4 = reinterpret_cast<uint4 *>(dup0);
             for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
-        }
+        };
+        init_table();                   // first partition's table, in the same phase as the packing
         __syncthreads();
         if (bad) sh.bad = 1;
         __syncthreads();
         if (sh.bad) {
-            if (tid == 0) { po.status = DBGA_BAD_CHAR; pout[pair] = po; }
+            if (tid == 0) { po.status = DBGA_BAD_CHAR; pout[pair] = po; if (MEDIUM) status[pair] = DBGA_BAD_CHAR; }
             continue;
         }
         const int N0 = pd.n0 - k + 1, N1 = pd.n1 - k + 1;
-        // ---- A: seq1 k-mers
-        for (int p = tid; p < N0; p += T) {
-            bool claimed;
-            const uint32_t h = bkt_insert<KeyT>(keys, nb, B::kmer(pk0, p, kmask), claimed);
-            if (claimed) pos0[h] = (uint16_t)p;
-            else dup0[h] = 1;
-        }
-        __syncthreads();
-        // ---- B1: seq2 k-mers
-        for (int q = tid; q < N1; q += T) {
-            const KeyT key = B::kmer(pk1, q, kmask);
-            uint32_t h;
-            if (FULL) {
-                bool claimed;
-                h = bkt_insert<KeyT>(keys, nb, key, claimed);
-            } else {
-                h = bkt_find<KeyT>(keys, nb, key);
-                if (h != 0xFFFFFFFFu && dup0[h]) h = 0xFFFFFFFFu;
-            }
-            if (h != 0xFFFFFFFFu) last1[h] = (uint16_t)q;
-            memo[q] = h != 0xFFFFFFFFu ? (uint16_t)h : NONE16;
-        }
-        __syncthreads();
-        // ---- B1.5: whoever did not survive in last1 proves a duplicate in seq2
-        for (int q = tid; q < N1; q += T) {
-            const uint16_t h = memo[q];
-            if (h != NONE16 && last1[h] != (uint16_t)q) dup1[h] = 1;
-        }
-        __syncthreads();
-        // ---- B2: anchors; memo[q] becomes aof[q] (position in seq1 or NONE16)
-        for (int q = tid; q < N1; q += T) {
-            const uint16_t h = memo[q];
-            uint16_t a = NONE16;
-            if (h != NONE16) {
-                const bool d = dup0[h] | dup1[h];
-                if (!d) a = pos0[h];                 // NONE16 when the k-mer is private to seq2 (graph mode)
-                if (FULL) nd1[pd.q_base + q] = !d;
-            }
-            memo[q] = a;
-        }
-        if (FULL) {
+        for (int g = 0; g < parts; ++g) {
+            if (g > 0) { __syncthreads(); init_table(); __syncthreads(); }
+            // partition of a k-mer: low 16 bits of its hash (the bucket uses the high bits)
+            auto in_part = [&](uint32_t hv) { return !MEDIUM || (int)(((hv & 0xFFFFu) * (uint32_t)parts) >> 16) == g; };
+            // ---- A: seq1 k-mers
             for (int p = tid; p < N0; p += T) {
-                const uint32_t h = bkt_find<KeyT>(keys, nb, B::kmer(pk0, p, kmask));
-                nd0[pd.p_base + p] = !(dup0[h] | dup1[h]);
+                const KeyT key = B::kmer(pk0, p, kmask);
+                const uint32_t hv = B::mix(key);
+                if (!in_part(hv)) continue;
+                bool claimed;
+                const uint32_t h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
+                if (claimed) pos0[h] = (uint16_t)p;
+                else dup0[h] = 1;
             }
+            __syncthreads();
+            // ---- B1: seq2 k-mers
+            for (int q = tid; q < N1; q += T) {
+                const KeyT key = B::kmer(pk1, q, kmask);
+                const uint32_t hv = B::mix(key);
+                if (!in_part(hv)) continue;
+                uint32_t h;
+                if (FULL) {
+                    bool claimed;
+                    h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
+                } else {
+                    h = bkt_find<KeyT>(keys, nb, key, hv);
+                    if (h != 0xFFFFFFFFu && dup0[h]) h = 0xFFFFFFFFu;
+                }
+                if (h != 0xFFFFFFFFu) last1[h] = (uint16_t)q;
+                memo[q] = h != 0xFFFFFFFFu ? (uint16_t)h : NONE16;
+            }
+            __syncthreads();
+            // ---- B1.5: whoever did not survive in last1 proves a duplicate in seq2
+            for (int q = tid; q < N1; q += T) {
+                if (MEDIUM && !in_part(B::mix(B::kmer(pk1, q, kmask)))) continue;
+                const uint16_t h = memo[q];
+                if (h != NONE16 && last1[h] != (uint16_t)q) dup1[h] = 1;
+            }
+            __syncthreads();
+            // ---- B2: anchors; memo[q] becomes aof[q] (position in seq1 or NONE16)
+            for (int q = tid; q < N1; q += T) {
+                if (MEDIUM && !in_part(B::mix(B::kmer(pk1, q, kmask)))) continue;
+                const uint16_t h = memo[q];
+                uint16_t a = NONE16;
+                if (h != NONE16) {
+                    const bool d = dup0[h] | dup1[h];
+                    if (!d) a = pos0[h];             // NONE16 when the k-mer is private to seq2 (graph mode)
+                    if (FULL) nd1[pd.q_base + q] = !d;
+                }
+                memo[q] = a;
+            }
+            if (FULL) {
+                for (int p = tid; p < N0; p += T) {
+                    const KeyT key = B::kmer(pk0, p, kmask);
+                    const uint32_t hv = B::mix(key);
+                    if (!in_part(hv)) continue;
+                    const uint32_t h = bkt_find<KeyT>(keys, nb, key, hv);
+                    nd0[pd.p_base + p] = !(dup0[h] | dup1[h]);
+                }
+            }
+        }
+        if (MEDIUM) {                                 // medium pair: hand aof[] to the generic stage 2
+            __syncthreads();
+            int32_t *ga = aof + pd.q_base;
+            for (int q = tid; q < N1; q += T) { const uint16_t a = memo[q]; ga[q] = a == NONE16 ? -1 : (int32_t)a; }
+            continue;
         }
         __syncthreads();                              // table dead from here on
         // ---- stage 2: run starts / ends (rare) appended unordered
@@ -404,37 +434,51 @@ size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq) {
     return (size_t)words * 8 + (size_t)cap * (key_bytes + 6) + (size_t)((maxq + 7) / 8 * 8) * 2 + 16;
 }
 
-template <typename KeyT, bool FULL>
+template <typename KeyT, bool FULL, int TPB>
 static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
-                            uint32_t cap, int words, int maxq, bool want_segments, PairOut *pout, Pools pools,
-                            Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st) {
+                            uint32_t cap, int parts, int words, int maxq, bool want_segments, PairOut *pout,
+                            Pools pools, Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int32_t *status,
+                            int32_t *aof, int num_sms, cudaStream_t st) {
     const size_t smem = stage12_small_smem(sizeof(KeyT), cap, words, maxq);
-    auto kern = stage12_small_kernel<KeyT, FULL>;
+    auto kern = stage12_small_kernel<KeyT, FULL, TPB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     int grid = num_sms * occ;
     if (grid > count) grid = count;
-    kern<<<grid, 256, smem, st>>>(seqs, pairs, list, count, k, cap, words, maxq, want_segments ? 1 : 0, pout,
-                                  pools, ctr, cfg, nd0, nd1);
+    kern<<<grid, TPB, smem, st>>>(seqs, pairs, list, count, k, cap, parts, words, maxq, want_segments ? 1 : 0, pout,
+                                  pools, ctr, cfg, nd0, nd1, status, aof);
     return cudaGetLastError();
 }
 
+template <typename KeyT>
+static cudaError_t launch_k(bool full, int parts, const uint8_t *seqs, const PairDesc *pairs, const int32_t *list,
+                            int count, int k, uint32_t cap, int words, int maxq, bool want_segments, PairOut *pout,
+                            Pools pools, Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int32_t *status,
+                            int32_t *aof, int num_sms, cudaStream_t st) {
+#define DBGA_S12_ARGS seqs, pairs, list, count, k, cap, parts, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, status, aof, num_sms, st
+    if (parts > 1) return full ? launch_t<KeyT, true, 1024>(DBGA_S12_ARGS) : launch_t<KeyT, false, 1024>(DBGA_S12_ARGS);
+    return full ? launch_t<KeyT, true, 256>(DBGA_S12_ARGS) : launch_t<KeyT, false, 256>(DBGA_S12_ARGS);
+#undef DBGA_S12_ARGS
+}
+
+// parts == 1: stages 1+2 fused (small pairs).  parts > 1: stage 1 only with a partitioned table
+// (medium pairs); status[] / aof[] feed the generic stage-2 kernel.
 cudaError_t launch_stage12_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
-                                 uint32_t cap, int words, int maxq, bool full, bool want_segments, PairOut *pout,
-                                 Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,
-                                 uint8_t *nd0, uint8_t *nd1, int num_sms, cudaStream_t st) {
+                                 uint32_t cap, int parts, int words, int maxq, bool full, bool want_segments,
+                                 PairOut *pout, Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,
+                                 uint8_t *nd0, uint8_t *nd1, int32_t *status, int32_t *aof, int num_sms,
+                                 cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     const SlotCfg cfg{max_abs_score, go_raw, ge_raw};
-    if (k <= 15) {
-        return full ? launch_t<uint32_t, true>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st)
-                    : launch_t<uint32_t, false>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st);
-    }
-    return full ? launch_t<uint64_t, true>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st)
-                : launch_t<uint64_t, false>(seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, num_sms, st);
+    if (k <= 15)
+        return launch_k<uint32_t>(full, parts, seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr,
+                                  cfg, nd0, nd1, status, aof, num_sms, st);
+    return launch_k<uint64_t>(full, parts, seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg,
+                              nd0, nd1, status, aof, num_sms, st);
 }
 
 }  // namespace dbga
