@@ -68,7 +68,7 @@ struct dbga_ctx {
     int grid_warp = 0, grid_cta = 0;
     int64_t warp_max_cells = WARP_CLASS_MAX_CELLS_FEW;
     int tiny_bound[NUM_TINY] = {8, 16, 24, 32};
-    bool seen_work[NUM_CLS] = {true, true, true, true, true, true, true, true};   // adaptive grids for the (often empty) wavefront launches
+    bool seen_work[NUM_CLS] = {true, true, true, true, true, true, true, true, true};   // adaptive grids for the (often empty) wavefront launches
     int launches = 0;
     const uint8_t *d_seqs_run = nullptr;
 
@@ -507,7 +507,7 @@ int run_pipeline(dbga_ctx *ctx) {
             }
         }
         if (ctx->grid_warp) {
-            for (int cls = CLS_WARP2; cls <= CLS_WARP8; ++cls) {
+            for (int cls = CLS_WARP2; cls <= CLS_WARP16; ++cls) {
                 const int g = ctx->seen_work[cls] ? ctx->grid_warp : std::min(ctx->grid_warp, ctx->num_sms);
                 DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
                                                     &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,

@@ -47,16 +47,17 @@ static_assert(sizeof(Slot) == 64, "Slot is four 16-byte words");
 
 // DP classes: 0..3 = thread-per-segment ("tiny", bucketed by max(m, n) so that the segments of
 // a warp have similar loop bounds),
-// 4..6 = warp wavefront with 2 / 4 / 8 rows per lane (segments of up to 64 / 128 / any rows),
-// 7 = CTA wavefront (8 rows per lane, 8 warps).
-enum : int32_t { CLS_NONE = -1, CLS_TINY0 = 0, NUM_TINY = 4, CLS_WARP2 = 4, CLS_WARP4 = 5, CLS_WARP8 = 6, CLS_CTA = 7, NUM_CLS = 8 };
+// 4..7 = warp wavefront with 2 / 4 / 8 / 16 rows per lane (segments of up to 64 / 128 / 256 / any rows;
+// more rows per lane amortise the per-step shuffles, fewer keep all 32 lanes busy on short segments),
+// 8 = CTA wavefront (8 rows per lane, 8 warps).
+enum : int32_t { CLS_NONE = -1, CLS_TINY0 = 0, NUM_TINY = 4, CLS_WARP2 = 4, CLS_WARP4 = 5, CLS_WARP8 = 6, CLS_WARP16 = 7, CLS_CTA = 8, NUM_CLS = 9 };
 
 // DP geometry (shared by host sizing and kernels)
 constexpr int TINY_MAX = 32;     // thread-per-segment kernel: m, n <= 32
 constexpr int TINY_THREADS = 128;
 constexpr int WF_R = 8;          // rows per lane in the widest wavefront kernels
 constexpr int WF_ROWS_PER_WARP = 32 * WF_R;   // 256
-__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 ? 4 : 8); }
+__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 ? 4 : (cls == CLS_WARP16 ? 16 : 8)); }
 constexpr int WF_CTA_WARPS = 8;  // warps per CTA in the long-segment kernel
 constexpr int WF_D = 64;         // step delay between consecutive warps
 constexpr int WF_C = 32;         // steps per barrier

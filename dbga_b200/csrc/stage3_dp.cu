@@ -25,6 +25,8 @@
 //                       256*W rows, boundary rows between strips staged through HBM;
 //                       traceback bytes in HBM in a step-major (skewed) layout so that
 //                       every warp step writes one contiguous 256-byte row.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace dbga {
@@ -365,19 +367,20 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                     if (j >= 1 && j <= n) {
                         const uint32_t sel = lut_sel(yc);
                         int dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
-                        uint32_t wlo = 0, whi = 0;
+                        uint32_t wv[(R + 3) / 4] = {};
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
                             const int oM = Mr[r], oX = Xr[r], oY = Yr[r];
                             const uint32_t d = dp_cell<XY>(Mr[r], Xr[r], Yr[r], dM, dX, dY, aM, aX, aY,
                                                            lut_score(slo[r], shi[r], sel), gmo, ge2, tagX, tagY);
-                            if (r < 4) wlo |= d << (8 * r); else whi |= d << (8 * (r - 4));
+                            wv[r / 4] |= d << (8 * (r % 4));
                             dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
                         }
                         uint8_t *tbp = tbw + (int64_t)(j + lane) * (32 * R);
-                        if constexpr (R == 8) *reinterpret_cast<uint2 *>(tbp) = make_uint2(wlo, whi);
-                        else if constexpr (R == 4) *reinterpret_cast<uint32_t *>(tbp) = wlo;
-                        else *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)wlo;
+                        if constexpr (R == 16) *reinterpret_cast<uint4 *>(tbp) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                        else if constexpr (R == 8) *reinterpret_cast<uint2 *>(tbp) = make_uint2(wv[0], wv[1]);
+                        else if constexpr (R == 4) *reinterpret_cast<uint32_t *>(tbp) = wv[0];
+                        else *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)wv[0];
                         my_yc = yc;
                         if (j == n && i_own) {
 #pragma unroll
@@ -462,7 +465,7 @@ static void launch_wf_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Sl
     else dp_wf_kernel<W, R, false><<<grid, W * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
 }
 
-// cls: CLS_WARP2 / CLS_WARP4 / CLS_WARP8 (one warp per segment) or CLS_CTA
+// cls: CLS_WARP2 / 4 / 8 / 16 (one warp per segment) or CLS_CTA
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                 const unsigned int *count_dev, int grid, int cls, DpParams prm,
                                 uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st) {
@@ -470,6 +473,7 @@ cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot
     if (cls == CLS_CTA) launch_wf_t<WF_CTA_WARPS, 8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP2) launch_wf_t<1, 2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP4) launch_wf_t<1, 4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    else if (cls == CLS_WARP16) launch_wf_t<1, 16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else launch_wf_t<1, 8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     return cudaGetLastError();
 }
