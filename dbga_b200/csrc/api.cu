@@ -379,12 +379,13 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     // boundary rows for multi-pass wavefronts
     ctx->warp_max_cells = P >= MANY_PAIRS ? WARP_CLASS_MAX_CELLS_MANY : WARP_CLASS_MAX_CELLS_FEW;
     ctx->bnd_stride_warp = std::min<int64_t>((int64_t)mx1 + 1, ctx->warp_max_cells / 65 + 2);
-    ctx->bnd_stride_cta = (int64_t)mx1 + 1;
+    ctx->bnd_stride_cta = (int64_t)mx1 + 2;         // + one entry where the end cell crosses the cluster
     ctx->grid_warp = (int)std::max<int64_t>(ctx->num_sms, std::min<int64_t>(ctx->num_sms * 16, (512LL << 20) / (32 * ctx->bnd_stride_warp)));
     {
         const int64_t per = 2 * ctx->bnd_stride_cta * 16;
         int64_t g = (1LL << 30) / std::max<int64_t>(per, 1);
-        ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, g));
+        // clusters in flight: WF_CLUSTER CTAs of WF_CTA_WARPS warps each, two CTAs per SM
+        ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->num_sms / WF_CLUSTER, g));
     }
     const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
     const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells;
@@ -517,7 +518,7 @@ int run_pipeline(dbga_ctx *ctx) {
         }
         if (ctx->grid_cta) {
             DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
-                                                &ctr->n_cls[CLS_CTA], ctx->seen_work[CLS_CTA] ? ctx->grid_cta : std::min(ctx->grid_cta, 8),
+                                                &ctr->n_cls[CLS_CTA], ctx->seen_work[CLS_CTA] ? ctx->grid_cta : std::min(ctx->grid_cta, 2),
                                                 CLS_CTA, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
                                                 (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
             ctx->launches += 1;

@@ -57,8 +57,9 @@ constexpr int TINY_MAX = 32;     // thread-per-segment kernel: m, n <= 32
 constexpr int TINY_THREADS = 128;
 constexpr int WF_R = 8;          // rows per lane in the widest wavefront kernels
 constexpr int WF_ROWS_PER_WARP = 32 * WF_R;   // 256
-__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 ? 4 : (cls == CLS_WARP16 ? 16 : 8)); }
-constexpr int WF_CTA_WARPS = 8;  // warps per CTA in the long-segment kernel
+__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 || cls == CLS_CTA ? 4 : (cls == CLS_WARP16 ? 16 : 8)); }
+constexpr int WF_CTA_WARPS = 4;  // warps per CTA in the long-segment kernel (one per SM sub-partition, 4 rows per lane)
+constexpr int WF_CLUSTER = 8;    // CTAs per thread-block cluster working on one long segment
 constexpr int WF_D = 64;         // step delay between consecutive warps
 constexpr int WF_C = 32;         // steps per barrier
 constexpr int WF_RING = 128;     // ring entries (columns) per warp boundary
@@ -87,11 +88,11 @@ struct DpParams {
     int32_t go_raw, ge_raw;
 };
 
-__host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int warps, int rows_per_lane) {
+// traceback bytes of one wavefront segment: one block of (n + 32) step rows x 32*R columns per
+// 32*R matrix rows, whatever number of warps shares the segment
+__host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int rows_per_lane) {
     const int64_t rows_per_warp = 32 * rows_per_lane;
-    const int64_t rows_per_pass = (int64_t)warps * rows_per_warp;
-    const int64_t passes = (m + rows_per_pass - 1) / rows_per_pass;
-    return passes * warps * (n + 32) * rows_per_warp;
+    return ((m + rows_per_warp - 1) / rows_per_warp) * (n + 32) * rows_per_warp;
 }
 
 // ------------------------------------------------------------------ small device utils

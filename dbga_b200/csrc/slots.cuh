@@ -54,7 +54,7 @@ __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, in
                     // one warp per segment, rows per lane chosen so that short segments still use
                     // all 32 lanes; huge segments (few pairs in the batch) get a whole CTA
                     cls = cells > pools.warp_max_cells ? CLS_CTA : (s.m <= 64 ? CLS_WARP2 : (s.m <= 128 ? CLS_WARP4 : (s.m <= 256 ? CLS_WARP8 : CLS_WARP16)));
-                    const long long need = (tb_bytes_wavefront(s.m, s.n, cls == CLS_CTA ? WF_CTA_WARPS : 1, wf_rows_per_lane(cls)) + 255) & ~255LL;
+                    const long long need = (tb_bytes_wavefront(s.m, s.n, wf_rows_per_lane(cls)) + 255) & ~255LL;
                     const long long off = (long long)atomicAdd(&ctr->tb_used, (unsigned long long)need);
                     if (off + need > pools.tb_cap) { *flag_big = 1; cls = CLS_NONE; }
                     s.tb_off = off;

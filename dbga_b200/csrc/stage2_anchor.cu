@@ -55,17 +55,41 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
         }
         const int N1 = no_anchors ? 0 : pd.n1 - k + 1;
         const int32_t *a_of = aof + pd.q_base;
-        // ---- pass 1: count run starts and anchors
-        long long cS = 0, cA = 0;
-        for (int q = tid; q < N1; q += T) {
-            const int a = a_of[q];
-            if (a >= 0) {
-                ++cA;
-                const int pv = q > 0 ? a_of[q - 1] : -1;
-                cS += !(pv >= 0 && pv + 1 == a);
+        // ---- pass 1: every warp owns one contiguous chunk of seq-2 positions and counts its
+        //      run starts, run ends and anchors (no block barrier inside the scan loops)
+        const int chunk = (((N1 + nw - 1) / nw) + 31) & ~31;
+        const int q_lo = min(N1, wid * chunk), q_hi = min(N1, q_lo + chunk);
+        auto classify = [&](int q, int &a, bool &isS, bool &isE) {
+            a = -1; isS = false; isE = false;
+            if (q < q_hi) {
+                a = a_of[q];
+                if (a >= 0) {
+                    const int pv = q > 0 ? a_of[q - 1] : -1;
+                    const int nx = q + 1 < N1 ? a_of[q + 1] : -1;
+                    isS = !(pv >= 0 && pv + 1 == a);
+                    isE = !(nx >= 0 && nx == a + 1);
+                }
             }
+        };
+        int cS = 0, cE = 0;
+        long long cA = 0;
+#pragma unroll 4
+        for (int q = q_lo + lane; q < q_hi; q += 32) {
+            int a; bool isS, isE;
+            classify(q, a, isS, isE);
+            cA += a >= 0; cS += isS; cE += isE;
         }
-        const int R = (int)block_sum(cS, sm);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { cS += __shfl_xor_sync(0xffffffffu, cS, o); cE += __shfl_xor_sync(0xffffffffu, cE, o); }
+        __syncthreads();
+        if (lane == 0) { sm.warpS[wid] = cS; sm.warpE[wid] = cE; }
+        __syncthreads();
+        int R = 0, offS = 0, offE = 0;
+        for (int w = 0; w < nw; ++w) {
+            const int s = sm.warpS[w], e = sm.warpE[w];
+            if (w < wid) { offS += s; offE += e; }
+            R += s;
+        }
         const long long M = block_sum(cA, sm);
         if (tid == 0) {
             sm.flag_cycle = 0; sm.flag_big = 0;
@@ -84,40 +108,22 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
             continue;
         }
         int32_t *runs = pools.runs + 3 * run_base;
-        // ---- pass 2: ordered compaction of run starts (a, b) and run ends (b)
-        int runS = 0, runE = 0;
-        for (int base = 0; base < N1; base += T) {
-            const int q = base + tid;
-            int a = -1;
-            bool isS = false, isE = false;
-            if (q < N1) {
-                a = a_of[q];
-                if (a >= 0) {
-                    const int pv = q > 0 ? a_of[q - 1] : -1;
-                    const int nx = q + 1 < N1 ? a_of[q + 1] : -1;
-                    isS = !(pv >= 0 && pv + 1 == a);
-                    isE = !(nx >= 0 && nx == a + 1);
-                }
-            }
+        // ---- pass 2: ordered compaction of run starts (a, b) and run ends (b), per warp chunk
+        for (int base = q_lo; base < q_hi; base += 32) {
+            const int q = base + lane;
+            int a; bool isS, isE;
+            classify(q, a, isS, isE);
             const unsigned bS = __ballot_sync(0xffffffffu, isS), bE = __ballot_sync(0xffffffffu, isE);
             const unsigned lt = (1u << lane) - 1u;
-            if (lane == 0) { sm.warpS[wid] = __popc(bS); sm.warpE[wid] = __popc(bE); }
-            __syncthreads();
-            int offS = runS, offE = runE, totS = 0, totE = 0;
-            for (int w = 0; w < nw; ++w) {
-                const int s = sm.warpS[w], e = sm.warpE[w];
-                if (w < wid) { offS += s; offE += e; }
-                totS += s; totE += e;
-            }
             if (isS) {
                 const int idx = offS + __popc(bS & lt);
                 runs[3 * (int64_t)idx] = a;
                 runs[3 * (int64_t)idx + 1] = q;
             }
             if (isE) runs[3 * (int64_t)(offE + __popc(bE & lt)) + 2] = q;   // end b, turned into len below
-            runS += totS; runE += totE;
-            __syncthreads();
+            offS += __popc(bS); offE += __popc(bE);
         }
+        __syncthreads();
         // ---- run lengths, then the colinearity check (utils.py:266-291): seq-1 positions of
         //      the merge nodes must be strictly increasing along seq 2
         for (int r = tid; r < R; r += T) runs[3 * (int64_t)r + 2] = runs[3 * (int64_t)r + 2] - runs[3 * (int64_t)r + 1] + 1;

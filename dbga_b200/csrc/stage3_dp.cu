@@ -19,17 +19,25 @@
 // Kernels:
 //   dp_thread_kernel    one thread per tiny segment (m, n <= 32), previous row in shared
 //                       memory, work lists bucketed by size;
-//   dp_wf_kernel<W>     anti-diagonal wavefront, 8 rows per lane, 32 lanes per warp, W
-//                       warps pipelined through shared-memory boundary rings (a warp per
-//                       segment for W=1, a CTA per long segment for W=8); row strips of
-//                       256*W rows, boundary rows between strips staged through HBM;
-//                       traceback bytes in HBM in a step-major (skewed) layout so that
-//                       every warp step writes one contiguous 256-byte row.
+//   dp_wf_kernel<W,R,XY,CL>  anti-diagonal wavefront: R rows per lane, 32 lanes per warp,
+//                       W warps per CTA pipelined through shared-memory boundary rings, CL CTAs
+//                       per thread-block cluster with the ring of a CTA's last warp living in
+//                       the next CTA's shared memory (DSMEM).  W = CL = 1, R = 2/4/8/16: one
+//                       warp per segment (throughput classes).  W = 4, R = 4, CL = 8: one
+//                       cluster per long segment, 32 warps on 32 SM sub-partitions -- a single
+//                       warp runs the recurrence at dependent-issue latency, so a lone big
+//                       segment is spread as thin as the wavefront skew allows.  Row strips of
+//                       32*R*W*CL rows, boundary rows between strips staged through HBM;
+//                       traceback bytes in HBM in a step-major (skewed) layout so that every
+//                       warp step writes one contiguous 32*R-byte row.  Traceback: one warp,
+//                       shared-memory window over the table, 32-cell diagonal probes.
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include <cooperative_groups.h>
 
 namespace dbga {
+namespace cg = cooperative_groups;
 
 __device__ __forceinline__ int strip(int v) { return v & ~63; }
 
@@ -268,14 +276,15 @@ struct WfShared {
     int endM, endX, endY, have_end;
 };
 
-template <int W, int R, bool XY>
+template <int W, int R, bool XY, int CL>
 __global__ void __launch_bounds__(W * 32)
 dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
              const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
              uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool, int4 *__restrict__ bnd_pool,
              int64_t bnd_stride) {
     constexpr int D = WF_D, C = WF_C, RING = WF_RING;
-    constexpr int ROWS_PASS = W * 32 * R;
+    constexpr int GW = W * CL;                                // warps working on one segment
+    constexpr int ROWS_PASS = GW * 32 * R;
     constexpr int WIN_W = (32 * R >= 64) ? 64 : 32 * R;       // traceback window width in bytes
     __shared__ int4 ring[W + 1][RING];
     __shared__ WfShared sh;
@@ -287,12 +296,28 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     }
     __syncthreads();
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // CL > 1: a thread-block cluster of CL CTAs shares one segment; the boundary row of a CTA's
+    // last warp goes straight into the next CTA's ring[0] through distributed shared memory.
+    int crank = 0;
+    int4 *ring_next = nullptr;
+    if constexpr (CL > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        crank = (int)cluster.block_rank();
+        if (crank + 1 < CL) ring_next = cluster.map_shared_rank(&ring[0][0], crank + 1);
+    }
+    const int gw = crank * W + w;
+    auto bar = [&]() {
+        if constexpr (CL > 1) cg::this_cluster().sync();
+        else __syncthreads();
+    };
+    const unsigned int group = blockIdx.x / CL, n_groups = gridDim.x / CL;
     const unsigned int count = *count_dev;
     const int gmo = prm.ge - prm.go, ge2 = 2 * prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
-    int4 *bndA = bnd_pool + (int64_t)blockIdx.x * 2 * bnd_stride, *bndB = bndA + bnd_stride;
+    int4 *bndA = bnd_pool + (int64_t)group * 2 * bnd_stride, *bndB = bndA + bnd_stride;
+    int4 *endv = bndA + (bnd_stride - 1);                     // CL > 1: end-cell values cross CTAs here
 
-    for (unsigned int item = blockIdx.x; item < count; item += gridDim.x) {
+    for (unsigned int item = group; item < count; item += n_groups) {
         const int sid = list[item];
         const Slot s = slots[sid];
         const PairDesc pd = pairs[s.pair];
@@ -302,7 +327,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
         const int passes = (m + ROWS_PASS - 1) / ROWS_PASS;
         const int64_t tb_rows = (int64_t)n + 32;           // step rows per (pass, warp) block
         if (tid == 0) sh.have_end = 0;
-        __syncthreads();
+        bar();
 
         for (int pass = 0; pass < passes; ++pass) {
             const int base = pass * ROWS_PASS;
@@ -311,7 +336,10 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             const bool need_out = pass + 1 < passes;
             int Mr[R], Xr[R], Yr[R];
             uint32_t slo[R], shi[R];
-            const int row0 = base + (w * 32 + lane) * R;     // 0-based index of this lane's first row
+            const int row0 = base + (gw * 32 + lane) * R;    // 0-based index of this lane's first row
+            // warps whose rows all lie past m sit the pass out (they only keep the barriers)
+            const int act = min(GW, (m - base + 32 * R - 1) / (32 * R));
+            const bool active = gw < act;
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int i = row0 + r + 1;
@@ -323,10 +351,12 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             }
             int dgM = 0, dgX = 0, dgY = 0, my_yc = 0;
             const int own = m - 1 - base;                    // row m inside this pass?
-            const bool i_own = own >= 0 && own < ROWS_PASS && (own / R) == (w * 32 + lane);
+            const bool i_own = own >= 0 && own < ROWS_PASS && (own / R) == (gw * 32 + lane);
             const int own_r = own >= 0 ? own % R : 0;
-            uint8_t *tbw = tb + ((int64_t)(pass * W + w) * tb_rows) * (32 * R) + lane * R;
-            const int off_last = (W - 1) * D + 31;
+            uint8_t *tbw = tb + ((int64_t)(pass * GW + gw) * tb_rows) * (32 * R) + lane * R;
+            const int off_last = (act - 1) * D + 31;
+            const bool last_warp = gw == act - 1;
+            int4 *ring_out = (w + 1 < W || ring_next == nullptr) ? &ring[w + 1][0] : ring_next;
             const int S = n + 1 + off_last;                  // steps in this pass
             const int NB = (S + C - 1) / C;
 
@@ -342,20 +372,20 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                 e.w = c >= 1 ? base_code(ys[c - 1]) : 0;
                 ring[0][c & (RING - 1)] = e;
             };
-            if (w == 0) fill(lane);
-            __syncthreads();
+            if (gw == 0) fill(lane);
+            bar();
 
             for (int blk = 0; blk < NB; ++blk) {
                 const int s0 = blk * C;
-                if (w == 0) fill(s0 + C + lane);             // next chunk, visible after the barrier
-                if (need_out && w == W - 1) {                // drain what lane 31 produced last block
+                if (gw == 0) fill(s0 + C + lane);            // next chunk, visible after the barrier
+                if (need_out && last_warp) {                 // drain what lane 31 produced last block
                     const int c = s0 - C - off_last + lane;
                     if (c >= 0 && c <= n) bout[c] = ring[W][c & (RING - 1)];
                 }
 #pragma unroll 1
-                for (int st = 0; st < C; ++st) {
+                for (int st = 0; active && st < C; ++st) {
                     const int sidx = s0 + st;
-                    const int j = sidx - w * D - lane;       // column (0 = init column)
+                    const int j = sidx - gw * D - lane;      // column (0 = init column)
                     int uM = __shfl_up_sync(0xffffffffu, Mr[R - 1], 1);
                     int uX = __shfl_up_sync(0xffffffffu, Xr[R - 1], 1);
                     int uY = __shfl_up_sync(0xffffffffu, Yr[R - 1], 1);
@@ -385,25 +415,34 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
                         if (j == n && i_own) {
 #pragma unroll
                             for (int r = 0; r < R; ++r)
-                                if (r == own_r) { sh.endM = Mr[r]; sh.endX = Xr[r]; sh.endY = Yr[r]; sh.have_end = 1; }
+                                if (r == own_r) {
+                                    if constexpr (CL > 1) { *endv = make_int4(Mr[r], Xr[r], Yr[r], 1); __threadfence(); }
+                                    else { sh.endM = Mr[r]; sh.endX = Xr[r]; sh.endY = Yr[r]; sh.have_end = 1; }
+                                }
                         }
                     }
                     dgM = uM; dgX = uX; dgY = uY;
-                    if (lane == 31 && j >= 0 && j <= n && (w + 1 < W || need_out))
-                        ring[w + 1][j & (RING - 1)] = make_int4(Mr[R - 1], Xr[R - 1], Yr[R - 1], my_yc);
+                    if (lane == 31 && j >= 0 && j <= n && (!last_warp || need_out))
+                        ring_out[j & (RING - 1)] = make_int4(Mr[R - 1], Xr[R - 1], Yr[R - 1], my_yc);
                 }
-                __syncthreads();
+                bar();
             }
-            if (need_out && w == W - 1) {                    // final drain
+            if (need_out && last_warp) {                     // final drain
                 for (int c = NB * C - C - off_last + lane; c <= n; c += 32)
                     if (c >= 0) bout[c] = ring[W][c & (RING - 1)];
             }
-            __syncthreads();
+            if constexpr (CL > 1) __threadfence();
+            bar();
         }
         // ---------------------------------------------------------------- traceback (warp 0)
-        if (w == 0) {
+        if (gw == 0) {
             int st = 0, score = 0;
-            pick_end(sh.endM, sh.endX, sh.endY, prm, st, score);
+            if constexpr (CL > 1) {
+                const int4 e = __ldcg(endv);
+                pick_end(e.x, e.y, e.z, prm, st, score);
+            } else {
+                pick_end(sh.endM, sh.endX, sh.endY, prm, st, score);
+            }
             int i = m, j = n, len = 0;
             const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
             uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
@@ -411,58 +450,102 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
                                   ((uint32_t)prio_to_state(2, prm) << 4);
             // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
-            // runs the same walk (uniform control flow); lane (len & 31) keeps the column's two
-            // characters and the warp flushes 32 columns with one coalesced store per row.
+            // runs the same walk (uniform control flow).  Only the kind of each step is kept, as
+            // two bit masks per group of 32 steps (bit t of mY: step t consumes a seq-1 base, of
+            // mX: a seq-2 base); a full group is turned into the two rows' characters by all 32
+            // lanes at once, so the sequence loads stay off the walk's dependency chain.
+            // In state M the 32 lanes probe the next 32 cells of the diagonal together and the
+            // walk jumps over the whole run of M -> M steps (most of the path between similar
+            // sequences); everything else goes one cell at a time.
             int win_blk = -1, win_row_hi = 0, win_col_lo = 0;
-            uint32_t cx = 0, cy = 0;
-            while (i > 0 || j > 0) {
-                if (i == 0) st = 2;
-                else if (j == 0) st = 1;
-                uint32_t d = 0;
-                if (i > 0 && j > 0) {
-                    const int i0 = i - 1;
-                    const int blk = i0 / (32 * R), cb = i0 % (32 * R);      // (pass * W + warp), l * R + r
-                    const int row = j + cb / R;
-                    if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= (unsigned)WIN_W) {
-                        __syncwarp();
-                        win_blk = blk; win_row_hi = row;
-                        win_col_lo = (WIN_W == 64) ? max(0, (cb & ~31) - 32) : 0;
-                        const int rr = row - lane;
-                        uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
-                        if (rr >= 1) {
-                            const uint4 *p = reinterpret_cast<const uint4 *>(tb + ((int64_t)blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo);
-                            a = p[0]; b = p[1];
-                            if constexpr (WIN_W == 64) { c4 = p[2]; d4 = p[3]; }
-                        }
-                        uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
-                        dst[0] = a; dst[1] = b;
-                        if constexpr (WIN_W == 64) { dst[2] = c4; dst[3] = d4; }
-                        __syncwarp();
-                    }
-                    d = win[win_row_hi - row][cb - win_col_lo];
+            uint32_t mY = 0, mX = 0;
+            int pos = 0, gbase = 0;
+            int ib = m, jb = n;                              // (i, j) before the first step of the group
+            const uint32_t lt = (1u << lane) - 1u;
+            auto flush = [&](int cnt) {
+                if (lane < cnt) {
+                    const int it = ib - __popc(mY & lt), jt = jb - __popc(mX & lt);
+                    ox[gbase + lane] = ((mY >> lane) & 1u) ? xs[it - 1] : (uint8_t)'-';
+                    oy[gbase + lane] = ((mX >> lane) & 1u) ? ys[jt - 1] : (uint8_t)'-';
                 }
-                const uint32_t chx = st == 2 ? (uint32_t)'-' : (uint32_t)xs[i - 1];
-                const uint32_t chy = st == 1 ? (uint32_t)'-' : (uint32_t)ys[j - 1];
-                if ((len & 31) == lane) { cx = chx; cy = chy; }
-                if ((len & 31) == 31) { ox[len - 31 + lane] = (uint8_t)cx; oy[len - 31 + lane] = (uint8_t)cy; }
+                ib -= __popc(mY); jb -= __popc(mX);
+                gbase += cnt; mY = 0; mX = 0; pos = 0;
+            };
+            auto emit = [&](int state, int count) {
+                len += count;
+                while (count > 0) {
+                    const int take = min(count, 32 - pos);
+                    const uint32_t bits = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << pos;
+                    if (state != 2) mY |= bits;
+                    if (state != 1) mX |= bits;
+                    pos += take; count -= take;
+                    if (pos == 32) flush(32);
+                }
+            };
+            while (i > 0 || j > 0) {
+                if (i == 0) { emit(2, j); break; }           // first row / column: one long gap
+                if (j == 0) { emit(1, i); break; }
+                const int i0 = i - 1;
+                const int blk = i0 / (32 * R), cb = i0 % (32 * R);      // (pass * GW + warp), l * R + r
+                const int row = j + cb / R;
+                if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= (unsigned)WIN_W) {
+                    __syncwarp();
+                    win_blk = blk; win_row_hi = row;
+                    win_col_lo = (WIN_W == 64) ? max(0, (cb & ~31) - 32) : 0;
+                    const int rr = row - lane;
+                    uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
+                    if (rr >= 1) {
+                        const uint4 *p = reinterpret_cast<const uint4 *>(tb + ((int64_t)blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo);
+                        a = p[0]; b = p[1];
+                        if constexpr (WIN_W == 64) { c4 = p[2]; d4 = p[3]; }
+                    }
+                    uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
+                    dst[0] = a; dst[1] = b;
+                    if constexpr (WIN_W == 64) { dst[2] = c4; dst[3] = d4; }
+                    __syncwarp();
+                }
+                if (st == 0) {
+                    const int il = i0 - lane, jl = j - lane;
+                    bool ok = false;
+                    if (il >= 0 && jl >= 1) {
+                        const int bl = il / (32 * R), cl = il % (32 * R);
+                        const unsigned dr = (unsigned)(win_row_hi - (jl + cl / R)), dc = (unsigned)(cl - win_col_lo);
+                        if (bl == win_blk && dr < 32u && dc < (unsigned)WIN_W)
+                            ok = ((pmap >> (2 * (win[dr][dc] & 3u))) & 3u) == 0u;
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+                    const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
+                    if (c > 0) { emit(0, c); i -= c; j -= c; continue; }
+                }
+                const uint32_t d = win[win_row_hi - row][cb - win_col_lo];
+                emit(st, 1);
                 const uint32_t tag = (d >> (2 * st)) & 3u;
                 i -= (st != 2); j -= (st != 1);
                 st = (int)((pmap >> (2 * tag)) & 3u);
-                ++len;
             }
-            if (lane < (len & 31)) { ox[(len & ~31) + lane] = (uint8_t)cx; oy[(len & ~31) + lane] = (uint8_t)cy; }
+            if (pos) flush(pos);
             if (lane == 0) { slots[sid].score = score - prm.ge_raw * (m + n); slots[sid].len = len; }
         }
         __syncthreads();
     }
 }
 
-template <int W, int R>
+template <int W, int R, int CL = 1>
 static void launch_wf_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                         const unsigned int *count_dev, DpParams prm, uint8_t *strbuf, uint8_t *tb, int4 *bnd,
                         int64_t bnd_stride, cudaStream_t st) {
-    if (prm.xy) dp_wf_kernel<W, R, true><<<grid, W * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
-    else dp_wf_kernel<W, R, false><<<grid, W * 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid * CL);       // grid counts segments in flight (clusters when CL > 1)
+    cfg.blockDim = dim3(W * 32);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (CL > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    if (prm.xy) cudaLaunchKernelEx(&cfg, dp_wf_kernel<W, R, true, CL>, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+    else cudaLaunchKernelEx(&cfg, dp_wf_kernel<W, R, false, CL>, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
 }
 
 // cls: CLS_WARP2 / 4 / 8 / 16 (one warp per segment) or CLS_CTA
@@ -470,7 +553,7 @@ cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot
                                 const unsigned int *count_dev, int grid, int cls, DpParams prm,
                                 uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (cls == CLS_CTA) launch_wf_t<WF_CTA_WARPS, 8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    if (cls == CLS_CTA) launch_wf_t<WF_CTA_WARPS, 4, WF_CLUSTER>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP2) launch_wf_t<1, 2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP4) launch_wf_t<1, 4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP16) launch_wf_t<1, 16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);

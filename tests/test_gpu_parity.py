@@ -134,10 +134,12 @@ def test_status_codes(aligner):
 
 def test_global_align_classes(aligner):
     """dna_global_aln through every DP kernel class: tiny, warp (1 and >1 row strips),
-    CTA wavefront (1 and >1 strips), plus empty sides (utils.py:187-192)."""
+    cluster wavefront (part of a cluster, whole cluster, 2 and 3 row strips), plus empty sides
+    (utils.py:187-192)."""
     rng = random.Random(11)
     shapes = [(1, 1), (5, 7), (32, 32), (33, 20), (20, 33), (100, 90), (256, 300), (257, 301), (700, 650),
-              (40, 3000), (3000, 40), (600, 600), (2100, 2300), (513, 520), (0, 5), (6, 0)]
+              (40, 3000), (3000, 40), (600, 600), (2100, 2300), (513, 520), (0, 5), (6, 0),
+              (9000, 300), (300, 9000), (16500, 70), (8192, 64), (8193, 64)]
     pairs = []
     for m, n in shapes:
         x = rand_seq(rng, m)

@@ -15,7 +15,7 @@ def main():
     out = []
     for L in Ls:
         cells_target = 4e9 if L >= 256 else 1e9
-        P = int(max(8, min(400_000, cells_target / (L * L))))
+        P = int(os.environ.get("DP_PAIRS", 0)) or int(max(8, min(400_000, cells_target / (L * L))))
         buf, offs = synth_batch(P, L, 0.05, 0.01, seed=L)
         d = torch.from_numpy(np.concatenate([buf, np.zeros(64, np.uint8)])).cuda()
         prm = al.params(1)
