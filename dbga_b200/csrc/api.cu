@@ -65,7 +65,7 @@ struct dbga_ctx {
     int stage2_threads = 128;
     int64_t runs_cap = 0, slots_cap = 0, tb_cap = 0;
     int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
-    int grid_warp = 0, grid_cta = 0;
+    int grid_warp = 0, grid_cta = 0, grid_cluster = 0;
     int64_t warp_max_cells = WARP_CLASS_MAX_CELLS_FEW;
     int tiny_bound[NUM_TINY] = {8, 16, 24, 32};
     bool seen_work[NUM_CLS] = {true, true, true, true, true, true, true, true, true};   // adaptive grids for the (often empty) wavefront launches
@@ -384,13 +384,14 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     {
         const int64_t per = 2 * ctx->bnd_stride_cta * 16;
         int64_t g = (1LL << 30) / std::max<int64_t>(per, 1);
-        // clusters in flight: WF_CLUSTER CTAs of WF_CTA_WARPS warps each, two CTAs per SM
-        ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->num_sms / WF_CLUSTER, g));
+        ctx->grid_cta = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->num_sms, g));
+        // clusters in flight: WF_CLUSTER CTAs of WF_CL_WARPS warps each, two CTAs per SM
+        ctx->grid_cluster = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->num_sms / WF_CLUSTER, g));
     }
     const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
     const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells;
     if (!any_non_tiny) ctx->grid_warp = 0;
-    if (!any_cta) ctx->grid_cta = 0;
+    if (!any_cta) ctx->grid_cta = ctx->grid_cluster = 0;
     if (params->stages == 3) {
         RESERVE(d_str, 2 * std::max<int64_t>(ctx->total_bytes, 1));
         if (ctx->grid_warp) RESERVE(d_bnd_w, (size_t)ctx->grid_warp * 2 * ctx->bnd_stride_warp * 16);
@@ -517,11 +518,13 @@ int run_pipeline(dbga_ctx *ctx) {
             }
         }
         if (ctx->grid_cta) {
-            DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
-                                                &ctr->n_cls[CLS_CTA], ctx->seen_work[CLS_CTA] ? ctx->grid_cta : std::min(ctx->grid_cta, 2),
-                                                CLS_CTA, ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
-                                                (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
-            ctx->launches += 1;
+            const bool seen = ctx->seen_work[CLS_CTA];
+            DBGA_CUDA_CHECK(launch_dp_long(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
+                                           &ctr->n_cls[CLS_CTA], seen ? ctx->grid_cluster : std::min(ctx->grid_cluster, 2),
+                                           seen ? ctx->grid_cta : std::min(ctx->grid_cta, 8), 2u * (unsigned)ctx->grid_cluster,
+                                           ctx->dp, (uint8_t *)ctx->d_str.p, (uint8_t *)ctx->d_tb.p,
+                                           (int4 *)ctx->d_bnd_c.p, ctx->bnd_stride_cta, st));
+            ctx->launches += 2;
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[4], st));

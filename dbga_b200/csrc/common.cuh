@@ -57,9 +57,11 @@ constexpr int TINY_MAX = 32;     // thread-per-segment kernel: m, n <= 32
 constexpr int TINY_THREADS = 128;
 constexpr int WF_R = 8;          // rows per lane in the widest wavefront kernels
 constexpr int WF_ROWS_PER_WARP = 32 * WF_R;   // 256
-__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 || cls == CLS_CTA ? 4 : (cls == CLS_WARP16 ? 16 : 8)); }
-constexpr int WF_CTA_WARPS = 4;  // warps per CTA in the long-segment kernel (one per SM sub-partition, 4 rows per lane)
-constexpr int WF_CLUSTER = 8;    // CTAs per thread-block cluster working on one long segment
+__host__ __device__ inline int wf_rows_per_lane(int cls) { return cls == CLS_WARP2 ? 2 : (cls == CLS_WARP4 ? 4 : (cls == CLS_WARP16 ? 16 : 8)); }
+constexpr int WF_CTA_WARPS = 8;  // long segments, many of them: one CTA of 8 warps x 8 rows per lane each
+constexpr int WF_CLUSTER = 8;    // long segments, few of them: a thread-block cluster of 8 CTAs each,
+constexpr int WF_CL_WARPS = 4;   //   4 warps per CTA (one per SM sub-partition),
+constexpr int WF_CL_R = 4;       //   4 rows per lane (traceback storage is sized for 8, which covers both)
 constexpr int WF_D = 64;         // step delay between consecutive warps
 constexpr int WF_C = 32;         // steps per barrier
 constexpr int WF_RING = 128;     // ring entries (columns) per warp boundary

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(W * 32)
 dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
              const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
              uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool, int4 *__restrict__ bnd_pool,
-             int64_t bnd_stride) {
+             int64_t bnd_stride, unsigned int cnt_lo, unsigned int cnt_hi) {
     constexpr int D = WF_D, C = WF_C, RING = WF_RING;
     constexpr int GW = W * CL;                                // warps working on one segment
     constexpr int ROWS_PASS = GW * 32 * R;
@@ -312,6 +312,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     };
     const unsigned int group = blockIdx.x / CL, n_groups = gridDim.x / CL;
     const unsigned int count = *count_dev;
+    if (count < cnt_lo || count > cnt_hi) return;            // the long-segment list goes to one of two kernels
     const int gmo = prm.ge - prm.go, ge2 = 2 * prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
     const int NEG = NEG_V * SCALE;
     int4 *bndA = bnd_pool + (int64_t)group * 2 * bnd_stride, *bndB = bndA + bnd_stride;
@@ -533,7 +534,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
 template <int W, int R, int CL = 1>
 static void launch_wf_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                         const unsigned int *count_dev, DpParams prm, uint8_t *strbuf, uint8_t *tb, int4 *bnd,
-                        int64_t bnd_stride, cudaStream_t st) {
+                        int64_t bnd_stride, cudaStream_t st, unsigned int cnt_lo = 0, unsigned int cnt_hi = 0xffffffffu) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid * CL);       // grid counts segments in flight (clusters when CL > 1)
     cfg.blockDim = dim3(W * 32);
@@ -544,20 +545,32 @@ static void launch_wf_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Sl
         attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
-    if (prm.xy) cudaLaunchKernelEx(&cfg, dp_wf_kernel<W, R, true, CL>, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
-    else cudaLaunchKernelEx(&cfg, dp_wf_kernel<W, R, false, CL>, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride);
+    if (prm.xy) cudaLaunchKernelEx(&cfg, dp_wf_kernel<W, R, true, CL>, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, cnt_lo, cnt_hi);
+    else cudaLaunchKernelEx(&cfg, dp_wf_kernel<W, R, false, CL>, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, cnt_lo, cnt_hi);
 }
 
-// cls: CLS_WARP2 / 4 / 8 / 16 (one warp per segment) or CLS_CTA
+// cls: CLS_WARP2 / 4 / 8 / 16 (one warp per segment)
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                 const unsigned int *count_dev, int grid, int cls, DpParams prm,
                                 uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st) {
     if (grid <= 0) return cudaSuccess;
-    if (cls == CLS_CTA) launch_wf_t<WF_CTA_WARPS, 4, WF_CLUSTER>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
-    else if (cls == CLS_WARP2) launch_wf_t<1, 2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    if (cls == CLS_WARP2) launch_wf_t<1, 2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP4) launch_wf_t<1, 4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else if (cls == CLS_WARP16) launch_wf_t<1, 16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
     else launch_wf_t<1, 8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st);
+    return cudaGetLastError();
+}
+
+// CLS_CTA, the long segments.  Up to `few` of them: a cluster of WF_CLUSTER CTAs each (latency:
+// a lone big segment is all there is to run).  More than that: one CTA of 8 warps x 8 rows per
+// lane each (throughput: less pipeline fill, all SMs busy).  The count lives on the device, so
+// both kernels are launched and one of them returns at once.
+cudaError_t launch_dp_long(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                           const unsigned int *count_dev, int grid_clusters, int grid_ctas, unsigned int few, DpParams prm,
+                           uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st) {
+    if (grid_clusters <= 0 || grid_ctas <= 0) return cudaSuccess;
+    launch_wf_t<WF_CL_WARPS, WF_CL_R, WF_CLUSTER>(grid_clusters, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st, 1u, few);
+    launch_wf_t<WF_CTA_WARPS, 8, 1>(grid_ctas, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, bnd, bnd_stride, st, few + 1u, 0xffffffffu);
     return cudaGetLastError();
 }
 

@@ -162,6 +162,22 @@ def test_global_align_classes(aligner):
             assert res.alignment(i) == (ax, ay), (i, len(x), len(y), conv)
 
 
+def test_many_long_segments_take_the_cta_kernel(aligner):
+    """More long segments than clusters in flight: the list goes to the CTA-per-segment
+    kernel instead of the cluster kernel (same results either way)."""
+    rng = random.Random(23)
+    pairs = []
+    for _ in range(330):
+        m = rng.randrange(520, 760)
+        x = rand_seq(rng, m)
+        pairs.append((x, mutate(rng, x, 0.1, 0.05)))
+    res = aligner.global_align_pairs(pairs)
+    for i, (x, y) in enumerate(pairs):
+        sc, ax, ay = CO.gotoh(x, y)
+        assert res.status[i] == O.OK and res.score[i] == sc
+        assert res.alignment(i) == (ax, ay), i
+
+
 def test_large_path_vs_oracle(aligner):
     """Pairs too big for the shared-memory table take the global-memory stage-1 path."""
     pairs = [O.synth_pair(30000, 0.004, 0.001, 3), O.synth_pair(12000, 0.01, 0.002, 4),
