@@ -7,12 +7,12 @@
 //     (validation included), packed 16 bases per word in shared memory;
 //   * open-addressing table in shared memory, bucketized: one 128-bit LDS fetches a whole
 //     bucket (4 x 32-bit or 2 x 64-bit keys), so almost every probe finishes in one
-//     iteration and the warp does not diverge; a slot is claimed with one atomicCAS, all
-//     occurrence bookkeeping is plain stores split over barriers:
-//         A   seq1: claim/find; claimer stores pos0, later finders store dup0 = 1
-//         B1  seq2: find (graph mode: claim); last1[slot] = q (racy store, one q survives)
-//         B15 every q that did not survive marks dup1[slot] = 1
-//         B2  q is an anchor iff pos0 valid and !dup0 and !dup1  ->  a = pos0[slot]
+//     iteration and the warp does not diverge; a slot is claimed with one atomicCAS; the
+//     occurrence bookkeeping is one 32-bit word per slot:
+//         A   seq1: claim/find; the claimer stores pos0, later finders store cnt = DUP0
+//         B1  seq2: find (graph mode: claim); cnt += 1 (shared-memory add, result unused)
+//         B2  q is an anchor iff cnt == 1 (not repeated in seq1, exactly once in seq2) and
+//             pos0 valid  ->  a = pos0[slot]
 // Stage 2 (merge_node_idx order, extract_bubble :277-300, debruijn_merge_correctness
 // utils.py:266-291): run starts/ends are rare (a few per hundred positions), so they are
 // appended unordered with shared-memory atomics and then rank-sorted by seq-2 position
@@ -83,11 +83,24 @@ template <> struct Bucket<uint32_t> {
         const int w = p >> 4, sh = (p & 15) * 2;
         return __funnelshift_r(pk[w], pk[w + 1], sh) & kmask;
     }
+    // the k-mers at p and p + 1, p even: both come out of the same two packed words
+    static __device__ __forceinline__ void kmer2(const uint32_t *pk, int p, uint32_t kmask, uint32_t &k0, uint32_t &k1) {
+        const int w = p >> 4, sh = (p & 15) * 2;
+        const uint32_t a = pk[w], b = pk[w + 1];
+        k0 = __funnelshift_r(a, b, sh) & kmask;
+        k1 = __funnelshift_r(a, b, sh + 2) & kmask;
+    }
     // position of key / of the first EMPTY in the bucket (-1: none)
     static __device__ __forceinline__ void scan(const uint32_t *base, uint32_t key, int &hit, int &emp) {
         const uint4 kk = lds_v4(base);
         hit = kk.x == key ? 0 : (kk.y == key ? 1 : (kk.z == key ? 2 : (kk.w == key ? 3 : -1)));
         emp = kk.x == EMPTY ? 0 : (kk.y == EMPTY ? 1 : (kk.z == EMPTY ? 2 : (kk.w == EMPTY ? 3 : -1)));
+    }
+    // lookup only: slots fill in order, so the bucket has a free slot iff its last one is free
+    static __device__ __forceinline__ void scan_find(const uint32_t *base, uint32_t key, int &hit, bool &open) {
+        const uint4 kk = lds_v4(base);
+        hit = kk.x == key ? 0 : (kk.y == key ? 1 : (kk.z == key ? 2 : (kk.w == key ? 3 : -1)));
+        open = kk.w == EMPTY;
     }
     static __device__ __forceinline__ uint32_t cas(uint32_t *a, uint32_t v) { return atomicCAS(a, EMPTY, v); }
 };
@@ -100,11 +113,23 @@ template <> struct Bucket<uint64_t> {
         const uint32_t a = pk[w], b = pk[w + 1], c = pk[w + 2];
         return (((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh)) & kmask;
     }
+    static __device__ __forceinline__ void kmer2(const uint32_t *pk, int p, uint64_t kmask, uint64_t &k0, uint64_t &k1) {
+        const int w = p >> 4, sh = (p & 15) * 2;
+        const uint32_t a = pk[w], b = pk[w + 1], c = pk[w + 2];
+        k0 = (((uint64_t)__funnelshift_r(b, c, sh) << 32) | __funnelshift_r(a, b, sh)) & kmask;
+        k1 = (((uint64_t)__funnelshift_r(b, c, sh + 2) << 32) | __funnelshift_r(a, b, sh + 2)) & kmask;
+    }
     static __device__ __forceinline__ void scan(const uint64_t *base, uint64_t key, int &hit, int &emp) {
         const uint4 kk = lds_v4(base);
         const uint64_t k0 = ((uint64_t)kk.y << 32) | kk.x, k1 = ((uint64_t)kk.w << 32) | kk.z;
         hit = k0 == key ? 0 : (k1 == key ? 1 : -1);
         emp = k0 == EMPTY ? 0 : (k1 == EMPTY ? 1 : -1);
+    }
+    static __device__ __forceinline__ void scan_find(const uint64_t *base, uint64_t key, int &hit, bool &open) {
+        const uint4 kk = lds_v4(base);
+        const uint64_t k0 = ((uint64_t)kk.y << 32) | kk.x, k1 = ((uint64_t)kk.w << 32) | kk.z;
+        hit = k0 == key ? 0 : (k1 == key ? 1 : -1);
+        open = k1 == EMPTY;
     }
     static __device__ __forceinline__ uint64_t cas(uint64_t *a, uint64_t v) {
         return (uint64_t)atomicCAS(reinterpret_cast<unsigned long long *>(a), ~0ULL, (unsigned long long)v);
@@ -139,14 +164,16 @@ __device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT
     using B = Bucket<KeyT>;
     uint32_t b = __umulhi(hv, nb);
     for (;;) {
-        int hit, emp;
-        B::scan(keys + b * B::W, key, hit, emp);
+        int hit;
+        bool open;
+        B::scan_find(keys + b * B::W, key, hit, open);
         if (hit >= 0) return b * B::W + hit;
-        if (emp >= 0) return 0xFFFFFFFFu;
+        if (open) return 0xFFFFFFFFu;
         b = b + 1 == nb ? 0 : b + 1;
     }
 }
 
+constexpr uint32_t DUP0 = 0x10000u;      // cnt[]: the k-mer occurs more than once in seq1 (seq-2 counts stay below 2^16)
 struct S12Shared {
     int bad, nS, nE, nA, cycle, big;
     long long bcast[2];
@@ -161,7 +188,7 @@ struct S12Shared {
 template <typename KeyT, bool FULL, int TPB>
 __global__ void __launch_bounds__(TPB, TPB == 256 ? 5 : 1)      // five CTAs per SM for the small-pair case
 stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs,
-                     const int32_t *__restrict__ pair_list, int count, int k, uint32_t cap, int parts,
+                     const int32_t *__restrict__ pair_list, int count, int k, KeyT kmask, uint32_t cap, uint32_t nb, int parts,
                      int words, int maxq, int want_segments, PairOut *__restrict__ pout, Pools pools,
                      Counters *__restrict__ ctr, SlotCfg cfg, uint8_t *__restrict__ nd0, uint8_t *__restrict__ nd1,
                      int32_t *__restrict__ status, int32_t *__restrict__ aof) {
@@ -173,20 +200,18 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     uint32_t *pk1 = pk0 + words;
     KeyT *keys = reinterpret_cast<KeyT *>(pk1 + words);
     uint16_t *pos0 = reinterpret_cast<uint16_t *>(keys + cap);
-    uint16_t *last1 = pos0 + cap;
-    uint8_t *dup0 = reinterpret_cast<uint8_t *>(last1 + cap);
-    uint8_t *dup1 = dup0 + cap;
-    uint16_t *memo = reinterpret_cast<uint16_t *>(dup1 + cap);      // later: aof in shared memory
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(pos0 + cap);       // occurrences in seq2 | DUP0 if repeated in seq1
+    uint16_t *memo = reinterpret_cast<uint16_t *>(cnt + cap);       // later: aof in shared memory
     // aliases valid once the table is dead (after phase B2)
     uint32_t *ska = reinterpret_cast<uint32_t *>(keys);             // unordered run starts (b<<16 | a), cap entries
     uint16_t *ske = pos0;                                           // unordered run ends (b), cap entries
-    uint32_t *srt_s = reinterpret_cast<uint32_t *>(last1);          // rank-sorted starts (4*cap bytes: last1+dup0+dup1)
+    uint32_t *srt_s = cnt;                                          // rank-sorted starts
     uint16_t *srt_e = memo;                                         // rank-sorted ends
     __shared__ S12Shared sh;
 
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t nb = cap / B::W;             // buckets; cap is a multiple of 16, not necessarily a power of two
-    const KeyT kmask = (2 * k >= (int)(8 * sizeof(KeyT))) ? ~(KeyT)0 : (((KeyT)1 << (2 * k)) - 1);
+    // nb = cap / B::W buckets (cap is a multiple of 16, not necessarily a power of two) and
+    // kmask = 4^k - 1 come in as parameters: constant-bank operands instead of registers
     unsigned long long my_cells = 0, my_nseg = 0;
 
     for (int it = blockIdx.x; it < count; it += gridDim.x) {
@@ -211,11 +236,11 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 pk1[w] = r1 > 0 ? pack16_fast(s1 + 16 * w, r1, bad) : 0u;
             }
         }
-        auto init_table = [&]() {       // keys + pos0 + last1 = all ones, dup0 + dup1 = 0
+        auto init_table = [&]() {       // keys + pos0 = all ones, cnt = 0
             uint4 *t4 = reinterpret_cast<uint4 *>(keys);
-            const int n_ff = (int)((cap * (sizeof(KeyT) + 4)) / 16), n_00 = (int)(cap * 2 / 16);
+            const int n_ff = (int)((cap * (sizeof(KeyT) + 2)) / 16), n_00 = (int)(cap * 4 / 16);
             for (int i = tid; i < n_ff; i += T) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-            uint4 *z4 = reinterpret_cast<uint4 *>(dup0);
+            uint4 *z4 = reinterpret_cast<uint4 *>(cnt);
             for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
         };
         init_table();                   // first partition's table, in the same phase as the packing
@@ -231,52 +256,66 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             if (g > 0) { __syncthreads(); init_table(); __syncthreads(); }
             // partition of a k-mer: low 16 bits of its hash (the bucket uses the high bits)
             auto in_part = [&](uint32_t hv) { return !MEDIUM || (int)(((hv & 0xFFFFu) * (uint32_t)parts) >> 16) == g; };
+            // Every thread takes two adjacent positions per round: one pair of packed words
+            // yields both k-mers and the two probes are independent (latency overlap).
             // ---- A: seq1 k-mers
-            for (int p = tid; p < N0; p += T) {
-                const KeyT key = B::kmer(pk0, p, kmask);
+            auto phase_a = [&](KeyT key, int p) {
                 const uint32_t hv = B::mix(key);
-                if (!in_part(hv)) continue;
+                if (!in_part(hv)) return;
                 bool claimed;
                 const uint32_t h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
                 if (claimed) pos0[h] = (uint16_t)p;
-                else dup0[h] = 1;
+                else cnt[h] = DUP0;
+            };
+            for (int p = 2 * tid; p < N0; p += 2 * T) {
+                KeyT k0, k1;
+                B::kmer2(pk0, p, kmask, k0, k1);
+                phase_a(k0, p);
+                if (p + 1 < N0) phase_a(k1, p + 1);
             }
             __syncthreads();
-            // ---- B1: seq2 k-mers
-            for (int q = tid; q < N1; q += T) {
-                const KeyT key = B::kmer(pk1, q, kmask);
+            // ---- B1: seq2 k-mers; memo[q] = slot (or, medium pairs, what an earlier partition left)
+            auto phase_b1 = [&](KeyT key, uint32_t keep) -> uint32_t {
                 const uint32_t hv = B::mix(key);
-                if (!in_part(hv)) continue;
+                if (!in_part(hv)) return keep;
                 uint32_t h;
                 if (FULL) {
                     bool claimed;
                     h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
                 } else {
                     h = bkt_find<KeyT>(keys, nb, key, hv);
-                    if (h != 0xFFFFFFFFu && dup0[h]) h = 0xFFFFFFFFu;
                 }
-                if (h != 0xFFFFFFFFu) last1[h] = (uint16_t)q;
-                memo[q] = h != 0xFFFFFFFFu ? (uint16_t)h : NONE16;
-            }
-            __syncthreads();
-            // ---- B1.5: whoever did not survive in last1 proves a duplicate in seq2
-            for (int q = tid; q < N1; q += T) {
-                if (MEDIUM && !in_part(B::mix(B::kmer(pk1, q, kmask)))) continue;
-                const uint16_t h = memo[q];
-                if (h != NONE16 && last1[h] != (uint16_t)q) dup1[h] = 1;
+                if (h != 0xFFFFFFFFu) atomicAdd(&cnt[h], 1u);      // result unused: a fire-and-forget shared-memory add
+                return h != 0xFFFFFFFFu ? h : (uint32_t)NONE16;
+            };
+            uint32_t *memo2 = reinterpret_cast<uint32_t *>(memo);   // two positions per word
+            for (int q = 2 * tid; q < N1; q += 2 * T) {
+                KeyT k0, k1;
+                B::kmer2(pk1, q, kmask, k0, k1);
+                const uint32_t old = MEDIUM ? memo2[q >> 1] : 0u;
+                const uint32_t m0 = phase_b1(k0, old & 0xFFFFu);
+                const uint32_t m1 = q + 1 < N1 ? phase_b1(k1, old >> 16) : (uint32_t)NONE16;
+                memo2[q >> 1] = m0 | (m1 << 16);
             }
             __syncthreads();
             // ---- B2: anchors; memo[q] becomes aof[q] (position in seq1 or NONE16)
-            for (int q = tid; q < N1; q += T) {
-                if (MEDIUM && !in_part(B::mix(B::kmer(pk1, q, kmask)))) continue;
-                const uint16_t h = memo[q];
-                uint16_t a = NONE16;
+            auto phase_b2 = [&](KeyT key, uint32_t h, int q) -> uint32_t {
+                if (MEDIUM && !in_part(B::mix(key))) return h;
+                uint32_t a = NONE16;
                 if (h != NONE16) {
-                    const bool d = dup0[h] | dup1[h];
+                    const bool d = cnt[h] != 1u;     // repeated in seq1 (DUP0) or seen more than once in seq2
                     if (!d) a = pos0[h];             // NONE16 when the k-mer is private to seq2 (graph mode)
                     if (FULL) nd1[pd.q_base + q] = !d;
                 }
-                memo[q] = a;
+                return a;
+            };
+            for (int q = 2 * tid; q < N1; q += 2 * T) {
+                KeyT k0 = 0, k1 = 0;
+                if (MEDIUM) B::kmer2(pk1, q, kmask, k0, k1);
+                const uint32_t hh = memo2[q >> 1];
+                const uint32_t a0 = phase_b2(k0, hh & 0xFFFFu, q);
+                const uint32_t a1 = q + 1 < N1 ? phase_b2(k1, hh >> 16, q + 1) : (uint32_t)NONE16;
+                memo2[q >> 1] = a0 | (a1 << 16);
             }
             if (FULL) {
                 for (int p = tid; p < N0; p += T) {
@@ -284,7 +323,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                     const uint32_t hv = B::mix(key);
                     if (!in_part(hv)) continue;
                     const uint32_t h = bkt_find<KeyT>(keys, nb, key, hv);
-                    nd0[pd.p_base + p] = !(dup0[h] | dup1[h]);
+                    nd0[pd.p_base + p] = cnt[h] <= 1u;      // not repeated in seq1, at most once in seq2
                 }
             }
         }
@@ -297,14 +336,25 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         __syncthreads();                              // table dead from here on
         // ---- stage 2: run starts / ends (rare) appended unordered
         int cA = 0;
-        for (int q = tid; q < N1; q += T) {
-            const uint16_t a = memo[q];
-            if (a != NONE16) {
-                ++cA;
-                const uint16_t pv = q > 0 ? memo[q - 1] : NONE16;
-                const uint16_t nx = q + 1 < N1 ? memo[q + 1] : NONE16;
-                if (!(pv != NONE16 && (uint16_t)(pv + 1) == a)) ska[atomicAdd(&sh.nS, 1)] = ((uint32_t)q << 16) | a;
-                if (!(nx != NONE16 && nx == (uint16_t)(a + 1))) ske[atomicAdd(&sh.nE, 1)] = (uint16_t)q;
+        {
+            const uint32_t *memo2 = reinterpret_cast<const uint32_t *>(memo);
+            auto is_next = [](uint32_t x, uint32_t y) { return x != NONE16 && y != NONE16 && y == x + 1u; };   // y continues x's run
+            for (int q = 2 * tid; q < N1; q += 2 * T) {
+                const uint32_t w = memo2[q >> 1];             // the odd half past N1 was left NONE16 by B2
+                if (w == 0xFFFFFFFFu) continue;
+                const uint32_t a0 = w & 0xFFFFu, a1 = w >> 16;
+                const uint32_t pv = q > 0 ? memo[q - 1] : NONE16;
+                const uint32_t nx = q + 2 < N1 ? memo[q + 2] : NONE16;
+                if (a0 != NONE16) {
+                    ++cA;
+                    if (!is_next(pv, a0)) ska[atomicAdd(&sh.nS, 1)] = ((uint32_t)q << 16) | a0;
+                    if (!is_next(a0, a1)) ske[atomicAdd(&sh.nE, 1)] = (uint16_t)q;
+                }
+                if (a1 != NONE16) {
+                    ++cA;
+                    if (!is_next(a0, a1)) ska[atomicAdd(&sh.nS, 1)] = ((uint32_t)(q + 1) << 16) | a1;
+                    if (!is_next(a1, nx)) ske[atomicAdd(&sh.nE, 1)] = (uint16_t)(q + 1);
+                }
             }
         }
 #pragma unroll
@@ -449,8 +499,9 @@ static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const in
     if (occ < 1) occ = 1;
     int grid = num_sms * occ;
     if (grid > count) grid = count;
-    kern<<<grid, TPB, smem, st>>>(seqs, pairs, list, count, k, cap, parts, words, maxq, want_segments ? 1 : 0, pout,
-                                  pools, ctr, cfg, nd0, nd1, status, aof);
+    const KeyT kmask = (2 * k >= (int)(8 * sizeof(KeyT))) ? ~(KeyT)0 : (((KeyT)1 << (2 * k)) - 1);
+    kern<<<grid, TPB, smem, st>>>(seqs, pairs, list, count, k, kmask, cap, cap / (uint32_t)Bucket<KeyT>::W, parts, words, maxq,
+                                  want_segments ? 1 : 0, pout, pools, ctr, cfg, nd0, nd1, status, aof);
     return cudaGetLastError();
 }
 
