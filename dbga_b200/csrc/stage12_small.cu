@@ -175,7 +175,7 @@ __device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT
 
 constexpr uint32_t DUP0 = 0x10000u;      // cnt[]: the k-mer occurs more than once in seq1 (seq-2 counts stay below 2^16)
 struct S12Shared {
-    int bad, nS, nE, nA, cycle, big;
+    int nS, nE, nA, big;
     long long bcast[2];
     long long red[32];
 };
@@ -225,7 +225,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             continue;
         }
         __syncthreads();            // previous pair's shared state is no longer in use
-        if (tid == 0) { sh.bad = 0; sh.nS = 0; sh.nE = 0; sh.nA = 0; sh.cycle = 0; sh.big = 0; }
+        if (tid == 0) { sh.nS = 0; sh.nE = 0; sh.nA = 0; sh.big = 0; }
         // ---- pack + table init
         bool bad = false;
         {
@@ -244,10 +244,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
         };
         init_table();                   // first partition's table, in the same phase as the packing
-        __syncthreads();
-        if (bad) sh.bad = 1;
-        __syncthreads();
-        if (sh.bad) {
+        if (__syncthreads_or(bad)) {
             if (tid == 0) { po.status = DBGA_BAD_CHAR; pout[pair] = po; if (MEDIUM) status[pair] = DBGA_BAD_CHAR; }
             continue;
         }
@@ -399,12 +396,17 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             const uint32_t key = S[r];
             a = (int)(key & 0xFFFFu); b = (int)(key >> 16); len = (int)E[r] - b + 1;
         };
-        // ---- colinearity (utils.py:266-291) and the runs pool
+        // ---- colinearity (utils.py:266-291), then room in the runs and slots pools: two
+        //      threads fetch the two counters at once (one global round trip, one barrier)
+        int my_cyc = 0;
         for (int r = tid + 1; r < R; r += T) {
             int a0, b0, l0, a1, b1, l1;
             run(r - 1, a0, b0, l0); run(r, a1, b1, l1);
-            if (a1 <= a0 + l0 - 1) sh.cycle = 1;
+            if (a1 <= a0 + l0 - 1) my_cyc = 1;
         }
+        const bool cyc = __syncthreads_or(my_cyc) != 0;
+        const bool need_slots = !cyc && want_segments;
+        const int n_slots = R == 0 ? 1 : R + 1;
         if (tid == 0) {
             long long base = 0;
             if (R > 0) {
@@ -412,6 +414,11 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 if (base + R > pools.runs_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
             }
             sh.bcast[0] = base;
+        }
+        if (tid == 32 && need_slots) {
+            long long base = (long long)atomicAdd(&ctr->slots_used, (unsigned long long)n_slots);
+            if (base + n_slots > pools.slots_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
+            sh.bcast[1] = base;
         }
         __syncthreads();
         const long long run_base = sh.bcast[0];
@@ -428,7 +435,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             }
         }
         po.n_runs = R; po.run_base = run_base; po.n_anchors = sh.nA;
-        if (sh.cycle) {
+        if (cyc) {
             if (tid == 0) { po.status = DBGA_CYCLE; pout[pair] = po; }
             continue;
         }
@@ -436,13 +443,6 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             if (tid == 0) pout[pair] = po;
             continue;
         }
-        const int n_slots = R == 0 ? 1 : R + 1;
-        if (tid == 0) {
-            long long base = (long long)atomicAdd(&ctr->slots_used, (unsigned long long)n_slots);
-            if (base + n_slots > pools.slots_cap) { atomicExch(&ctr->overflow, 1u); base = -1; }
-            sh.bcast[1] = base;
-        }
-        __syncthreads();
         const long long slot_base = sh.bcast[1];
         if (slot_base < 0) {
             if (tid == 0) { po.status = DBGA_TOO_LARGE; pout[pair] = po; }
