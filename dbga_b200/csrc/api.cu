@@ -495,15 +495,19 @@ int run_pipeline(dbga_ctx *ctx) {
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));
     if (seg) {
-        {   // tiny classes: two launches (small / large shared-memory footprint)
+        {   // tiny classes: one launch per class that fits the register-resident kernel (bound <= 16),
+            // one shared-memory launch for the rest
             TinyBounds tbnd;
             for (int c = 0; c < NUM_TINY; ++c) tbnd.b[c] = ctx->tiny_bound[c];
-            const int split = NUM_TINY / 2;
-            DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, 0, split, tbnd,
-                                             ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
-            ctx->launches += 1;
-            if (tbnd.b[NUM_TINY - 1] > tbnd.b[split - 1]) {
-                DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, split, NUM_TINY,
+            int c = 0;
+            for (; c < NUM_TINY && tbnd.b[c] <= 16; ++c) {
+                if (c > 0 && tbnd.b[c] == tbnd.b[c - 1]) continue;        // empty class
+                DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, c, c + 1, tbnd,
+                                                 ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
+                ctx->launches += 1;
+            }
+            if (c < NUM_TINY && (c == 0 || tbnd.b[NUM_TINY - 1] > tbnd.b[c - 1])) {
+                DBGA_CUDA_CHECK(launch_dp_thread(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, c, NUM_TINY,
                                                  tbnd, ctx->dp, (uint8_t *)ctx->d_str.p, (uint32_t *)ctx->d_tt.p, ctx->num_sms, st));
                 ctx->launches += 1;
             }

@@ -224,9 +224,10 @@ assemble_runs_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         if (po.status != DBGA_OK || meta.x < 0) continue;
         const int n = len - (idx == po.run_base + po.n_runs - 1 ? 1 : 0);
         const PairDesc pd = pairs[pair];
-        const uint8_t *s0 = seqs + pd.off0 + a, *s1 = seqs + pd.off1 + b;
+        const uint8_t *s0 = seqs + pd.off0 + a;
         uint8_t *o0 = aln0 + aln_off[pair] + meta.x, *o1 = aln1 + aln_off[pair] + meta.x;
-        for (int c = gl; c < n; c += ASM_G) { o0[c] = s0[c]; o1[c] = s1[c]; }
+        // inside a run the two sequences are identical (the anchors' k-mers overlap), so one load feeds both rows
+        for (int c = gl; c < n; c += ASM_G) { const uint8_t v = s0[c]; o0[c] = v; o1[c] = v; }
     }
 }
 

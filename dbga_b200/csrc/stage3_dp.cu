@@ -243,6 +243,139 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
   }
 }
 
+// Register-resident variant for the smallest classes (bound <= 4 * NG <= 16 columns): the
+// previous row (T, U) and the per-column score selectors live in registers -- the column
+// loop is fully unrolled, so all indexing is static -- and only the traceback words go to
+// shared memory.  Saves the five shared-memory accesses per cell of the generic kernel.
+template <int NG, bool XY>
+__global__ void __launch_bounds__(TINY_THREADS)
+dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+                     const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
+                     uint8_t *__restrict__ strbuf) {
+    extern __shared__ int smem_i[];
+    constexpr int TH = TINY_THREADS, NB = 4 * NG;
+    const int tid = threadIdx.x;
+    const int gmo = prm.ge - prm.go, ge2 = 2 * prm.ge, tagM = prm.tagM, tagX = prm.tagX, tagY = prm.tagY;
+    const int NEG = NEG_V * SCALE;
+    __shared__ uint32_t s_lut[8];
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { s_lut[c] = prm.lut_lo[c]; s_lut[4 + c] = prm.lut_hi[c]; }
+    }
+    __syncthreads();
+    uint32_t *tbw = reinterpret_cast<uint32_t *>(smem_i) + tid;       // [row][word][thread]
+    const unsigned int count = *count_dev;
+    for (unsigned int base = blockIdx.x * TH; base < count; base += gridDim.x * TH) {
+        const unsigned int item = base + tid;
+        const bool have = item < count;
+        int m = 0, n = 0, sid = 0;
+        const uint8_t *xs = seqs, *ys = seqs;
+        int64_t str_off = 0, row_len = 0;
+        if (have) {
+            sid = list[item];
+            const Slot s = slots[sid];
+            const PairDesc pd = pairs[s.pair];
+            m = s.m; n = s.n;
+            xs = seqs + pd.off0 + s.x0;
+            ys = seqs + pd.off1 + s.y0;
+            str_off = s.str_off;
+            row_len = (pd.off1 - pd.off0) + pd.n1;
+        }
+        uint32_t xcodes = 0;
+        for (int i = 0; i < m; ++i) xcodes |= (uint32_t)base_code(xs[i]) << (2 * i);
+        int T[NB + 1], U[NB + 1];
+        uint32_t sel[NB];
+        T[0] = 0 | tagM;
+        U[0] = gmo | tagM;                                        // X^[1][0] comes from M[0][0]
+        {
+            const int y0 = gmo | tagY;                            // Y^[0][j] = -(go + (j-1) ge) + ge j
+            int u = __viaddmax_s32(NEG | tagM, gmo, NEG | tagX);
+            if (XY) u = max(u, y0 + gmo);
+#pragma unroll
+            for (int j = 1; j <= NB; ++j) {
+                sel[j - 1] = lut_sel(j <= n ? base_code(ys[j - 1]) : 0);
+                T[j] = y0;
+                U[j] = u;
+            }
+        }
+        int mmax = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mmax = max(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+        int eM = 0, eX = 0, eY = 0;
+        const int xi0 = gmo | tagX;                               // X^[i][0] = -(go + (i-1) ge) + ge i
+        uint32_t *tbrow = tbw;
+        for (int i = 1; i <= mmax; ++i) {
+            const int xc = (int)(xcodes >> (2 * (i - 1))) & 3;
+            const uint32_t slo = s_lut[xc], shi = s_lut[4 + xc];
+            int Ml = NEG | tagM, Yl = NEG | tagY, Xl = xi0;
+            int diag = T[0];
+            T[0] = xi0;                                          // max(M, X, Y)[i][0]
+            U[0] = xi0;                                          // X candidate of row i+1, column 0
+            const int ncap = (i == m) ? n : -1;                  // terminal cell: column ncap of this row
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int u4 = 0; u4 < 4; ++u4) {
+                    const int j = 4 * g + u4 + 1;
+                    const int Tj = T[j], Uj = U[j];
+                    const int Mn = strip(diag) + lut_score(slo, shi, sel[j - 1]) + ge2;
+                    const int Xn = strip(Uj) | tagX;
+                    int v = __viaddmax_s32(Ml, gmo, Yl);
+                    if (XY) v = max(v, Xl + gmo);
+                    const int Yn = strip(v) | tagY;
+                    uint32_t d = ((uint32_t)diag & 3u) | ((uint32_t)Uj & ~3u);
+                    d = (d & 15u) | ((uint32_t)v & ~15u);
+                    word |= (d & 0xFFu) << (8 * u4);
+                    int un = __viaddmax_s32(Mn, gmo, Xn);
+                    if (XY) un = max(un, Yn + gmo);
+                    T[j] = __vimax3_s32(Mn, Xn, Yn);
+                    U[j] = un;
+                    if (ncap == j) { eM = Mn; eX = Xn; eY = Yn; }
+                    diag = Tj; Ml = Mn; Yl = Yn; Xl = Xn;
+                }
+                tbrow[g * TH] = word;
+            }
+            tbrow += NG * TH;
+        }
+        if (have) {
+            int st, score;
+            pick_end(eM, eX, eY, prm, st, score);
+            const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
+                                  ((uint32_t)prio_to_state(2, prm) << 4);
+            int i = m, j = n, len = 0;
+            uint8_t *ox = strbuf + str_off, *oy = ox + row_len;
+            while (i > 0 || j > 0) {
+                if (i == 0) st = 2;
+                else if (j == 0) st = 1;
+                uint32_t d = 0;
+                if (i > 0 && j > 0) d = tbw[((i - 1) * NG + ((j - 1) >> 2)) * TH] >> (8 * ((j - 1) & 3));
+                ox[len] = st == 2 ? (uint8_t)'-' : xs[i - 1];
+                oy[len] = st == 1 ? (uint8_t)'-' : ys[j - 1];
+                const uint32_t tag = (d >> (2 * st)) & 3u;
+                i -= (st != 2); j -= (st != 1);
+                st = (int)((pmap >> (2 * tag)) & 3u);
+                ++len;
+            }
+            slots[sid].score = score - prm.ge_raw * (m + n);
+            slots[sid].len = len;
+        }
+    }
+}
+
+template <int NG>
+static void launch_dp_thread_reg_t(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                                   const unsigned int *count_dev, DpParams prm, uint8_t *strbuf, int grid, cudaStream_t st) {
+    const size_t smem = (size_t)(4 * NG) * NG * 4 * TINY_THREADS;
+    if (prm.xy) {
+        cudaFuncSetAttribute(dp_thread_reg_kernel<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dp_thread_reg_kernel<NG, true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
+    } else {
+        cudaFuncSetAttribute(dp_thread_reg_kernel<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dp_thread_reg_kernel<NG, false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
+    }
+}
+
 static size_t dp_thread_smem(int bound, bool tb_in_smem) {
     const int b4 = (bound + 3) & ~3;                   // columns are processed in groups of four
     size_t bytes = (size_t)(2 * (b4 + 1) * 4 + b4 * 2) * TINY_THREADS;
@@ -257,6 +390,13 @@ size_t dp_thread_scratch_bytes(int bound, int num_sms) {
 cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
                              int64_t list_cap, const unsigned int *counts_dev, int c0, int c1, TinyBounds tb,
                              DpParams prm, uint8_t *strbuf, uint32_t *tb_scratch, int num_sms, cudaStream_t st) {
+    if (c1 == c0 + 1 && tb.b[c0] <= 16) {        // one small class: previous row in registers
+        const int grid = dp_thread_grid(num_sms);
+        const int32_t *list = lists + (int64_t)c0 * list_cap;
+        if (tb.b[c0] <= 12) launch_dp_thread_reg_t<3>(seqs, pairs, slots, list, counts_dev + c0, prm, strbuf, grid, st);
+        else launch_dp_thread_reg_t<4>(seqs, pairs, slots, list, counts_dev + c0, prm, strbuf, grid, st);
+        return cudaGetLastError();
+    }
     // traceback in shared memory when that leaves at least four CTAs per SM
     const bool tbs = dp_thread_smem(tb.b[c1 - 1], true) <= 56 * 1024;
     const size_t smem = dp_thread_smem(tb.b[c1 - 1], tbs);
