@@ -76,6 +76,33 @@ __device__ __forceinline__ int prio_to_state(int prio, const DpParams &p) {
     return t == p.tagM ? 0 : (t == p.tagX ? 1 : 2);
 }
 
+// 2-bit codes of the (up to) 16 bases at p, any alignment, code i in bits 2i..2i+1: two aligned
+// 128-bit loads and a branch-free word/byte shift instead of 16 dependent-latency byte loads.
+// The second block is only read when it holds one of the n bases; n == 0 reads nothing.
+__device__ __forceinline__ uint32_t load_codes16(const uint8_t *p, int n) {
+    if (n <= 0) return 0u;
+    const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
+    const uint4 *q = reinterpret_cast<const uint4 *>(p - off);
+    const uint4 a = __ldg(q);
+    uint4 b = make_uint4(0u, 0u, 0u, 0u);
+    if (off + (uint32_t)min(n, 16) > 16u) b = __ldg(q + 1);
+    const uint32_t ws = off >> 2, sh = (off & 3u) * 8u;
+    // words ws .. ws+4 of (a, b)
+    const uint32_t v0 = ws == 0 ? a.x : (ws == 1 ? a.y : (ws == 2 ? a.z : a.w));
+    const uint32_t v1 = ws == 0 ? a.y : (ws == 1 ? a.z : (ws == 2 ? a.w : b.x));
+    const uint32_t v2 = ws == 0 ? a.z : (ws == 1 ? a.w : (ws == 2 ? b.x : b.y));
+    const uint32_t v3 = ws == 0 ? a.w : (ws == 1 ? b.x : (ws == 2 ? b.y : b.z));
+    const uint32_t v4 = ws == 0 ? b.x : (ws == 1 ? b.y : (ws == 2 ? b.z : b.w));
+    auto pack4 = [](uint32_t w) {                                  // 4 ASCII bases -> c0 | c1<<2 | c2<<4 | c3<<6
+        const uint32_t codes = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+        return (codes * 0x01041040u) >> 24;
+    };
+    const uint32_t out = pack4(__funnelshift_r(v0, v1, sh)) | (pack4(__funnelshift_r(v1, v2, sh)) << 8) |
+                         (pack4(__funnelshift_r(v2, v3, sh)) << 16) | (pack4(__funnelshift_r(v3, v4, sh)) << 24);
+    return n >= 16 ? out : (out & ((1u << (2 * n)) - 1u));
+}
+__device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_perm(0x54474341u, 0u, code) & 0xFFu; }   // "ACGT"[code]
+
 // terminal-cell choice under end_order (first wins, strict >)
 __device__ __forceinline__ void pick_end(int Mv, int Xv, int Yv, const DpParams &p, int &state, int &score) {
     const long long cm = (long long)strip(Mv) + p.endM, cx = (long long)strip(Xv) + p.endX, cy = (long long)strip(Yv) + p.endY;
@@ -154,13 +181,13 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
             row_len = (pd.off1 - pd.off0) + pd.n1;
         }
         // seq1 codes of the segment, 2 bits each, loaded back to back (independent loads)
-        unsigned long long xcodes = 0;
-        for (int i = 0; i < m; ++i) xcodes |= (unsigned long long)base_code(xs[i]) << (2 * i);
+        const unsigned long long xcodes = (unsigned long long)load_codes16(xs, m) | ((unsigned long long)load_codes16(xs + 16, m - 16) << 32);
+        const unsigned long long ycodes = (unsigned long long)load_codes16(ys, n) | ((unsigned long long)load_codes16(ys + 16, n - 16) << 32);
         // row 0 and the per-column score selectors
         Tc[0] = 0 | tagM;
         Uc[0] = gmo | tagM;                                       // X^[1][0] comes from M[0][0]
         for (int j = 1; j <= n; ++j) {
-            selc[(j - 1) * TH] = (uint16_t)lut_sel(base_code(ys[j - 1]));
+            selc[(j - 1) * TH] = (uint16_t)lut_sel((int)(ycodes >> (2 * (j - 1))) & 3);
             const int y0 = gmo | tagY;                            // Y^[0][j] = -(go + (j-1) ge) + ge j
             Tc[j * TH] = y0;
             int u = __viaddmax_s32(NEG | tagM, gmo, NEG | tagX);
@@ -229,8 +256,8 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
                 else if (j == 0) st = 1;
                 uint32_t d = 0;
                 if (i > 0 && j > 0) d = tbw[((size_t)(i - 1) * wpr + ((j - 1) >> 2)) * TH] >> (8 * ((j - 1) & 3));
-                ox[len] = st == 2 ? (uint8_t)'-' : xs[i - 1];
-                oy[len] = st == 1 ? (uint8_t)'-' : ys[j - 1];
+                ox[len] = (uint8_t)(st == 2 ? (uint32_t)'-' : code_char((uint32_t)(xcodes >> (2 * (i - 1))) & 3u));
+                oy[len] = (uint8_t)(st == 1 ? (uint32_t)'-' : code_char((uint32_t)(ycodes >> (2 * (j - 1))) & 3u));
                 const uint32_t tag = (d >> (2 * st)) & 3u;
                 i -= (st != 2); j -= (st != 1);
                 st = (int)((pmap >> (2 * tag)) & 3u);
@@ -281,8 +308,7 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             str_off = s.str_off;
             row_len = (pd.off1 - pd.off0) + pd.n1;
         }
-        uint32_t xcodes = 0;
-        for (int i = 0; i < m; ++i) xcodes |= (uint32_t)base_code(xs[i]) << (2 * i);
+        const uint32_t xcodes = load_codes16(xs, m), ycodes = load_codes16(ys, n);
         int T[NB + 1], U[NB + 1];
         uint32_t sel[NB];
         T[0] = 0 | tagM;
@@ -293,7 +319,7 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             if (XY) u = max(u, y0 + gmo);
 #pragma unroll
             for (int j = 1; j <= NB; ++j) {
-                sel[j - 1] = lut_sel(j <= n ? base_code(ys[j - 1]) : 0);
+                sel[j - 1] = lut_sel((int)((ycodes >> (2 * (j - 1))) & 3u));
                 T[j] = y0;
                 U[j] = u;
             }
@@ -350,8 +376,8 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 else if (j == 0) st = 1;
                 uint32_t d = 0;
                 if (i > 0 && j > 0) d = tbw[((i - 1) * NG + ((j - 1) >> 2)) * TH] >> (8 * ((j - 1) & 3));
-                ox[len] = st == 2 ? (uint8_t)'-' : xs[i - 1];
-                oy[len] = st == 1 ? (uint8_t)'-' : ys[j - 1];
+                ox[len] = (uint8_t)(st == 2 ? (uint32_t)'-' : code_char((xcodes >> (2 * (i - 1))) & 3u));
+                oy[len] = (uint8_t)(st == 1 ? (uint32_t)'-' : code_char((ycodes >> (2 * (j - 1))) & 3u));
                 const uint32_t tag = (d >> (2 * st)) & 3u;
                 i -= (st != 2); j -= (st != 1);
                 st = (int)((pmap >> (2 * tag)) & 3u);
