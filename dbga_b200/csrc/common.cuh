@@ -36,12 +36,13 @@ struct Slot {
     int32_t score;        // DP score (0 when one side is empty)
     int32_t len;          // aligned columns produced (before any first-column drop)
     int64_t str_off;      // scratch: reversed rows; row x at [str_off, +m+n), row y after
-    int64_t tb_off;       // scratch: traceback bytes (warp / cta classes)
+    int64_t tb_off;       // warp / cta classes: traceback bytes in the scratch pool; tiny classes: pd.off0
     int32_t pair;
     int32_t cls;          // DP class (CLS_*)
     int32_t out_off;      // assembly: first output column of this slot, relative to the pair
     int32_t skip;         // assembly: 1 = drop the first column (mid segments, debruijn_pairwise.py:499-500)
-    int32_t pad[2];
+    int32_t row_len;      // n0 + n1 of the pair: row y of the scratch sits row_len bytes after row x
+    int32_t n0;           // with tb_off = off0 the tiny kernels find both sequences without reading PairDesc
 };
 static_assert(sizeof(Slot) == 64, "Slot is four 16-byte words");
 

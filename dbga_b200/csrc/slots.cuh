@@ -37,7 +37,8 @@ __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, in
                 }
             }
             s.x0 = x0; s.m = x1 - x0; s.y0 = y0; s.n = y1 - y0;
-            s.score = 0; s.len = 0; s.pair = (int32_t)pair; s.tb_off = 0;
+            s.score = 0; s.len = 0; s.pair = (int32_t)pair; s.tb_off = pd.off0;
+            s.row_len = (int32_t)((pd.off1 - pd.off0) + pd.n1); s.n0 = (int32_t)(pd.off1 - pd.off0);
             s.str_off = str_base + x0 + y0;     // row x; row y at + row_len
             if (s.m > 0 && s.n > 0) {
                 const long long cells = (long long)s.m * s.n;

@@ -173,12 +173,11 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
         if (have) {
             sid = list[item];
             const Slot s = slots[sid];
-            const PairDesc pd = pairs[s.pair];
             m = s.m; n = s.n;
-            xs = seqs + pd.off0 + s.x0;
-            ys = seqs + pd.off1 + s.y0;
+            xs = seqs + s.tb_off + s.x0;                          // tiny classes: tb_off = pd.off0, n0 = pd.off1 - pd.off0
+            ys = seqs + s.tb_off + s.n0 + s.y0;
             str_off = s.str_off;
-            row_len = (pd.off1 - pd.off0) + pd.n1;
+            row_len = s.row_len;
         }
         // seq1 codes of the segment, 2 bits each, loaded back to back (independent loads)
         const unsigned long long xcodes = (unsigned long long)load_codes16(xs, m) | ((unsigned long long)load_codes16(xs + 16, m - 16) << 32);
@@ -301,12 +300,11 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         if (have) {
             sid = list[item];
             const Slot s = slots[sid];
-            const PairDesc pd = pairs[s.pair];
             m = s.m; n = s.n;
-            xs = seqs + pd.off0 + s.x0;
-            ys = seqs + pd.off1 + s.y0;
+            xs = seqs + s.tb_off + s.x0;                          // tiny classes: tb_off = pd.off0, n0 = pd.off1 - pd.off0
+            ys = seqs + s.tb_off + s.n0 + s.y0;
             str_off = s.str_off;
-            row_len = (pd.off1 - pd.off0) + pd.n1;
+            row_len = s.row_len;
         }
         const uint32_t xcodes = load_codes16(xs, m), ycodes = load_codes16(ys, n);
         int T[NB + 1], U[NB + 1];
