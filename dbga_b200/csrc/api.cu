@@ -89,6 +89,12 @@ struct dbga_ctx {
     static constexpr int MAX_SUB = 16;
     cudaStream_t meta_stream = nullptr;   // lanes: upload plan metadata on the shared upload stream
     cudaEvent_t ev_meta = nullptr;
+    // parent only: one download stream for all lanes.  A lane stream that has issued a copy keeps
+    // a foot in the copy engine's queue: the next event / kernel on it was observed to wait behind
+    // OTHER lanes' bulk downloads.  Lane streams therefore carry kernels only.
+    cudaStream_t dl_stream = nullptr;
+    cudaEvent_t ev_dl = nullptr;          // lanes: the chunk's download has left the lane's result buffers
+    bool dl_pending = false;
     cudaStream_t copy_stream = nullptr;   // parent only: one upload stream shared by all lanes (uploads are serial on
                                           // the H2D engine anyway, and every extra stream risks aliasing onto one of the
                                           // CUDA_DEVICE_MAX_CONNECTIONS hardware queues, which creates false dependencies)
@@ -96,6 +102,14 @@ struct dbga_ctx {
     int n_sub = 0;
     int64_t sub_pair_lo[MAX_SUB + 1] = {};
     cudaEvent_t dbg_ev[4] = {};       // DBGA_TRACE: upload begin / end, download begin / end
+    // Pipeline lanes write the per-pair result columns straight into the parent context's
+    // whole-batch device arrays (at the chunk's pair offset), so they travel to the host in
+    // seven copies per batch instead of seven small copies per chunk.
+    struct MetaPtrs {
+        int32_t *status = nullptr; int64_t *score = nullptr, *cells = nullptr; int32_t *nseg = nullptr;
+        int64_t *nanch = nullptr, *aln_off = nullptr, *run_off = nullptr;
+    } ext;
+    bool use_ext = false;
 };
 
 namespace {
@@ -107,7 +121,8 @@ int fail(dbga_ctx *ctx, int code, const char *msg) {
 
 int dev_reserve(dbga_ctx *ctx, DevBuf &b, size_t bytes) {
     if (bytes <= b.cap && b.p) return DBGA_SUCCESS;
-    if (b.p) { DBGA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); DBGA_CUDA_CHECK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    // (rare) growth: a lane's downloads run on the parent's download stream, so wait for the whole device
+    if (b.p) { DBGA_CUDA_CHECK(cudaDeviceSynchronize()); DBGA_CUDA_CHECK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
     size_t want = std::max<size_t>(bytes, 256);
     want = (want + 255) & ~(size_t)255;
     cudaError_t e = cudaMalloc(&b.p, want);
@@ -532,13 +547,18 @@ int run_pipeline(dbga_ctx *ctx) {
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[4], st));
-    DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, (int32_t *)ctx->d_status_out.p, (int32_t *)ctx->d_runs.p,
+    dbga_ctx::MetaPtrs mp = ctx->ext;
+    if (!ctx->use_ext) {
+        mp.status = (int32_t *)ctx->d_status_out.p; mp.score = (int64_t *)ctx->d_score.p; mp.cells = (int64_t *)ctx->d_cells.p;
+        mp.nseg = (int32_t *)ctx->d_nseg.p; mp.nanch = (int64_t *)ctx->d_nanch.p;
+        mp.aln_off = (int64_t *)ctx->d_aln_off.p; mp.run_off = (int64_t *)ctx->d_run_off.p;
+    }
+    DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, mp.status, (int32_t *)ctx->d_runs.p,
                                     ctx->runs_cap, (int2 *)ctx->d_run_meta.p, (Slot *)ctx->d_slots.p, ctx->slots_cap,
-                                    (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p, (int64_t *)ctx->d_aln_off.p,
-                                    (int64_t *)ctx->d_run_cnt.p, (int64_t *)ctx->d_run_off.p, (int64_t *)ctx->d_scan_tmp.p,
+                                    (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p, mp.aln_off,
+                                    (int64_t *)ctx->d_run_cnt.p, mp.run_off, (int64_t *)ctx->d_scan_tmp.p,
                                     (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p, (int32_t *)ctx->d_runs_out.p,
-                                    (int64_t *)ctx->d_score.p, (int64_t *)ctx->d_cells.p, (int32_t *)ctx->d_nseg.p,
-                                    (int64_t *)ctx->d_nanch.p, ctr, seg, ctx->num_sms, st, &ctx->launches));
+                                    mp.score, mp.cells, mp.nseg, mp.nanch, ctr, seg, ctx->num_sms, st, &ctx->launches));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
     return DBGA_SUCCESS;
 }
@@ -587,10 +607,10 @@ int fetch_resolve(dbga_ctx *ctx, bool counters_already_copied) {
 }
 
 // asynchronous device -> host copies of one batch's results (offsets are batch-local)
-int fetch_enqueue(dbga_ctx *ctx, const HostDst &d, int64_t total_aln, int64_t total_runs) {
-    cudaStream_t st = ctx->stream;
+int fetch_enqueue(dbga_ctx *ctx, const HostDst &d, int64_t total_aln, int64_t total_runs, cudaStream_t st) {
     const int64_t P = ctx->P;
     if (!P) return DBGA_SUCCESS;
+    if (!ctx->use_ext) {          // pipeline lanes: the parent fetches these columns once per batch
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.status, ctx->d_status_out.p, 4 * P, cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.score, ctx->d_score.p, 8 * P, cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.cells, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
@@ -598,6 +618,7 @@ int fetch_enqueue(dbga_ctx *ctx, const HostDst &d, int64_t total_aln, int64_t to
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.nanch, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln_off, ctx->d_aln_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.run_off, ctx->d_run_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    }
     if (total_aln) {
         DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln0, ctx->d_aln0.p, total_aln, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln1, ctx->d_aln1.p, total_aln, cudaMemcpyDeviceToHost, st));
@@ -628,7 +649,7 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
               (int64_t *)ctx->h_nanch.p, (int64_t *)ctx->h_aln_off.p, (int64_t *)ctx->h_run_off.p,
               (uint8_t *)ctx->h_aln0.p, (uint8_t *)ctx->h_aln1.p, (int32_t *)ctx->h_runs.p};
     if (P) {
-        rc = fetch_enqueue(ctx, d, total_aln, total_runs);
+        rc = fetch_enqueue(ctx, d, total_aln, total_runs, st);
         if (rc != DBGA_SUCCESS) return rc;
     } else {
         ((int64_t *)ctx->h_aln_off.p)[0] = 0; ((int64_t *)ctx->h_run_off.p)[0] = 0;
@@ -678,18 +699,20 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     const int64_t total_bytes = offsets[2 * P] - offsets[0];
     const bool seg = params->stages == 3;
     constexpr int NL = dbga_ctx::NL;
-    int lag = 0;
     int64_t sub_bytes = 16LL << 20;    // upload piece size
     if (const char *e = getenv("DBGA_SUB_MB")) sub_bytes = (int64_t)std::max(1, atoi(e)) << 20;
     if (!ctx->copy_stream && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(ctx, DBGA_ERR_CUDA, "could not create the upload stream");
+    if (!ctx->dl_stream && cudaStreamCreateWithFlags(&ctx->dl_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(ctx, DBGA_ERR_CUDA, "could not create the download stream");
     for (int i = 0; i < NL; ++i) {
         if (!ctx->lanes[i]) {
             int rc = create_ctx(ctx->device, &ctx->lanes[i]);
             if (rc != DBGA_SUCCESS) return fail(ctx, rc, "could not create a pipeline lane");
             dbga_ctx *l = ctx->lanes[i];
             bool okc = cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
-                       cudaEventCreateWithFlags(&l->ev_meta, cudaEventDisableTiming) == cudaSuccess;
+                       cudaEventCreateWithFlags(&l->ev_meta, cudaEventDisableTiming) == cudaSuccess &&
+                       cudaEventCreateWithFlags(&l->ev_dl, cudaEventDisableTiming) == cudaSuccess;
             l->meta_stream = ctx->copy_stream;
             for (int sb = 0; okc && sb < dbga_ctx::MAX_SUB; ++sb)
                 okc = cudaEventCreateWithFlags(&l->ev_sub[sb], cudaEventDisableTiming) == cudaSuccess;
@@ -725,6 +748,9 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     HRESERVE(h_aln_off, 8 * (P + 2 + nchunks)); HRESERVE(h_run_off, 8 * (P + 2 + nchunks));
     if (seg) { HRESERVE(h_aln0, total_bytes + 16); HRESERVE(h_aln1, total_bytes + 16); }
     HRESERVE(h_runs, std::max<int64_t>((int64_t)ctx->h_runs.cap, total_bytes / 4 + 4096));
+    RESERVE(d_status_out, 4 * (P + 1)); RESERVE(d_score, 8 * (P + 1)); RESERVE(d_cells, 8 * (P + 1));
+    RESERVE(d_nseg, 4 * (P + 1)); RESERVE(d_nanch, 8 * (P + 1));
+    RESERVE(d_aln_off, 8 * (P + 2 + nchunks)); RESERVE(d_run_off, 8 * (P + 2 + nchunks));
     int64_t *aln_off = (int64_t *)ctx->h_aln_off.p, *run_off = (int64_t *)ctx->h_run_off.p;
     std::vector<int64_t> aln_base((size_t)nchunks + 1, 0), run_base((size_t)nchunks + 1, 0);
     float ms[4] = {0, 0, 0, 0};
@@ -732,7 +758,14 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     auto fail_lane = [&](dbga_ctx *l, int rc) { snprintf(ctx->err, sizeof(ctx->err), "%s", l->err); return rc; };
 
     const bool trace = getenv("DBGA_TRACE") != nullptr;
-    if (trace) { cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventSynchronize(ctx->ev[0]); }
+    // DBGA_TRACE: six events per chunk (upload begin / end, kernels begin / end, download begin / end),
+    // read after the batch so that tracing does not serialise the pipeline
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize((size_t)nchunks * 6);
+        for (auto &e : tev) cudaEventCreate(&e);
+        cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventSynchronize(ctx->ev[0]);
+    }
     auto now_ms = [&]() { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
 
     // ---- producer: plan chunk c, queue its upload pieces and its kernels (lane c % NL)
@@ -743,13 +776,19 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         if (cudaSetDevice(ctx->device) != cudaSuccess) return DBGA_ERR_CUDA;
         int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
         if (rc != DBGA_SUCCESS) return rc;
+        // chunk c's offsets land at [a + c, a + c + n + 1) (one extra slot per chunk), fixed up at the end
+        l->use_ext = true;
+        l->ext.status = (int32_t *)ctx->d_status_out.p + a; l->ext.score = (int64_t *)ctx->d_score.p + a;
+        l->ext.cells = (int64_t *)ctx->d_cells.p + a; l->ext.nseg = (int32_t *)ctx->d_nseg.p + a;
+        l->ext.nanch = (int64_t *)ctx->d_nanch.p + a;
+        l->ext.aln_off = (int64_t *)ctx->d_aln_off.p + a + c; l->ext.run_off = (int64_t *)ctx->d_run_off.p + a + c;
         if ((size_t)std::max<int64_t>(l->total_bytes, 16) + 64 > l->d_seqs.cap) cudaStreamSynchronize(ctx->copy_stream);
         rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
         if (rc != DBGA_SUCCESS) return rc;
         // upload in pieces on the shared upload stream (after the lane's previous kernels are done with
         // d_seqs); stage 1+2 of each piece starts as soon as the piece has landed
         if (cudaStreamWaitEvent(ctx->copy_stream, l->ev_ready, 0) != cudaSuccess) return DBGA_ERR_CUDA;
-        if (trace) cudaEventRecord(l->dbg_ev[0], ctx->copy_stream);
+        if (trace) cudaEventRecord(tev[(size_t)c * 6 + 0], ctx->copy_stream);
         const int64_t nb = l->total_bytes, np = b - a;
         int ns = (int)std::max<int64_t>(1, std::min<int64_t>(dbga_ctx::MAX_SUB, (nb + sub_bytes - 1) / sub_bytes));
         if (np < ns) ns = (int)std::max<int64_t>(1, np);
@@ -774,12 +813,15 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
             if (cudaEventRecord(l->ev_sub[sb], ctx->copy_stream) != cudaSuccess) return DBGA_ERR_CUDA;
             prev_off = end_off;
         }
-        if (trace) cudaEventRecord(l->dbg_ev[1], ctx->copy_stream);
+        if (trace) { cudaEventRecord(tev[(size_t)c * 6 + 1], ctx->copy_stream); cudaEventRecord(tev[(size_t)c * 6 + 2], l->stream); }
+        // the lane's previous download must have left its result buffers (committed before this chunk was issued)
+        if (l->dl_pending && cudaStreamWaitEvent(l->stream, l->ev_dl, 0) != cudaSuccess) return DBGA_ERR_CUDA;
         rc = do_run(l, (const uint8_t *)l->d_seqs.p, true);
         if (rc != DBGA_SUCCESS) return rc;
+        if (trace) cudaEventRecord(tev[(size_t)c * 6 + 3], l->stream);
         rc = host_reserve(l, l->h_ctr, sizeof(Counters));
         if (rc != DBGA_SUCCESS) return rc;
-        if (cudaMemcpyAsync(l->h_ctr.p, l->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, l->stream) != cudaSuccess ||
+        if (launch_publish(l->d_ctr.p, l->h_ctr.p, (int)sizeof(Counters), l->stream) != cudaSuccess ||
             cudaEventRecord(l->ev_ready, l->stream) != cudaSuccess)
             return DBGA_ERR_CUDA;
         return DBGA_SUCCESS;
@@ -798,6 +840,7 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
         if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
             for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
+            cudaStreamSynchronize(ctx->dl_stream);
             HostBuf old = ctx->h_runs;
             ctx->h_runs = HostBuf();
             rc = host_reserve(ctx, ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]) * 2);
@@ -815,18 +858,15 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
                   (int32_t *)ctx->h_nseg.p + a, (int64_t *)ctx->h_nanch.p + a, aln_off + a + c, run_off + a + c,
                   (uint8_t *)ctx->h_aln0.p + aln_base[(size_t)c], (uint8_t *)ctx->h_aln1.p + aln_base[(size_t)c],
                   (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c]};
-        if (trace) cudaEventRecord(l->dbg_ev[2], l->stream);
-        rc = fetch_enqueue(l, d, ta, tr);
+        // ev_ready has fired (synchronised above), so the download needs no device-side wait
+        if (trace) cudaEventRecord(tev[(size_t)c * 6 + 4], ctx->dl_stream);
+        rc = fetch_enqueue(l, d, ta, tr, ctx->dl_stream);
         if (rc != DBGA_SUCCESS) return fail_lane(l, rc);
+        if (cudaEventRecord(l->ev_dl, ctx->dl_stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "cudaEventRecord failed");
+        l->dl_pending = true;
         if (trace) {
-            cudaEventRecord(l->dbg_ev[3], l->stream);
-            cudaEventSynchronize(l->dbg_ev[3]);
-            float a0, a1, k0, k1, d0, d1;
-            cudaEventElapsedTime(&a0, ctx->ev[0], l->dbg_ev[0]); cudaEventElapsedTime(&a1, ctx->ev[0], l->dbg_ev[1]);
-            cudaEventElapsedTime(&k0, ctx->ev[0], l->ev[1]); cudaEventElapsedTime(&k1, ctx->ev[0], l->ev[5]);
-            cudaEventElapsedTime(&d0, ctx->ev[0], l->dbg_ev[2]); cudaEventElapsedTime(&d1, ctx->ev[0], l->dbg_ev[3]);
-            fprintf(stderr, "[dbga] chunk %d gpu: h2d %.2f-%.2f kernels %.2f-%.2f (s12 %.2f s3 %.2f asm %.2f) d2h %.2f-%.2f  host now %.2f\n",
-                    c, a0, a1, k0, k1, t1, t3, t4, d0, d1, now_ms());
+            cudaEventRecord(tev[(size_t)c * 6 + 5], ctx->dl_stream);
+            fprintf(stderr, "[dbga] chunk %d committed at host %.2f ms (s12 %.2f s3 %.2f asm %.2f)\n", c, now_ms(), t1, t3, t4);
         }
         return DBGA_SUCCESS;
     };
@@ -836,7 +876,6 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     // is reused only after its previous chunk has been committed).
     std::atomic<int> issued{0}, committed{0}, prod_rc{DBGA_SUCCESS};
     std::atomic<bool> stop{false};
-    (void)lag;
     std::thread producer([&]() {
         for (int c = 0; c < nchunks && !stop.load(); ++c) {
             while (c - committed.load(std::memory_order_acquire) >= NL && !stop.load()) std::this_thread::yield();
@@ -863,10 +902,30 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     if (main_rc != DBGA_SUCCESS) {
         for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
         cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->dl_stream);
         return main_rc;
     }
     for (int i = 0; i < NL; ++i)
         if (cudaStreamSynchronize(ctx->lanes[i]->stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "stream sync failed");
+    {   // the per-pair columns of the whole batch, behind the last chunk's rows
+        cudaStream_t st = ctx->dl_stream;
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status_out.p, 4 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_score.p, ctx->d_score.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cells.p, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nseg.p, ctx->d_nseg.p, 4 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nanch.p, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(aln_off, ctx->d_aln_off.p, 8 * (P + nchunks), cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(run_off, ctx->d_run_off.p, 8 * (P + nchunks), cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    if (trace) {
+        for (int c = 0; c < nchunks; ++c) {
+            float t[6];
+            for (int i = 0; i < 6; ++i) cudaEventElapsedTime(&t[i], ctx->ev[0], tev[(size_t)c * 6 + i]);
+            fprintf(stderr, "[dbga] chunk %d gpu: h2d %.2f-%.2f kernels %.2f-%.2f d2h %.2f-%.2f\n", c, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     // compact the per-chunk offset arrays in place and add the chunk bases
     for (int c = 0; c < nchunks; ++c) {
         const int64_t a = lo[(size_t)c], n = lo[(size_t)c + 1] - a;
@@ -951,7 +1010,9 @@ extern "C" {
 void dbga_destroy(dbga_ctx *ctx) {
     if (!ctx) return;
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); ctx->copy_stream = nullptr; }
+    if (ctx->dl_stream) { cudaStreamSynchronize(ctx->dl_stream); cudaStreamDestroy(ctx->dl_stream); ctx->dl_stream = nullptr; }
     for (auto &l : ctx->lanes) if (l) {
+        if (l->ev_dl) cudaEventDestroy(l->ev_dl);
         if (l->ev_ready) cudaEventDestroy(l->ev_ready);
         if (l->ev_meta) cudaEventDestroy(l->ev_meta);
         for (auto &e : l->ev_sub) if (e) cudaEventDestroy(e);

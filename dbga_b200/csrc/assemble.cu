@@ -246,6 +246,18 @@ cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, cudaStream_t
     return cudaGetLastError();
 }
 
+// Copies a few words to pinned host memory (device-accessible under unified addressing) with
+// plain stores: unlike a cudaMemcpyAsync this does not queue behind the bulk downloads in
+// the copy engine, so the host learns a chunk's counters the moment its kernels are done.
+__global__ void publish_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst_host, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst_host[i] = src[i];
+    __threadfence_system();
+}
+cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStream_t st) {
+    publish_kernel<<<1, 64, 0, st>>>(reinterpret_cast<const uint32_t *>(src), reinterpret_cast<uint32_t *>(dst_host), bytes / 4);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
                             const int32_t *status, const int32_t *runs, int64_t runs_cap, int2 *run_meta, Slot *slots,
                             int64_t slots_cap, const uint8_t *strbuf, int64_t *aln_len, int64_t *aln_off,

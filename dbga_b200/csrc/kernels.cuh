@@ -78,6 +78,7 @@ cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t 
                             int32_t *runs_out, int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
                             Counters *ctr, bool want_rows, int num_sms, cudaStream_t st, int *launches);
 
+cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStream_t st);
 cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, cudaStream_t st);
 
 // ---- integer-pipe microbenchmark
