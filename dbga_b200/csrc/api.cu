@@ -198,6 +198,37 @@ int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
         d.lut_hi[a] = v[2] | (v[3] << 16);
     }
     ctx->max_abs_score = mx;
+    // packed 16-bit form (stage3_dp16.cu).  Constants: valid values V = H + ge (i + j) are
+    // >= -(|smin| + 4 go) >= -300 under the limits below; stored = 4 (V - off) + priority;
+    // "minus infinity" sits at -30968 and drifts by less than 1200 either way, which stays
+    // below the valid floor 4 (-300 - off) = -29400 less one gap open and above -32768.
+    Dp16 &h = d.h;
+    h = Dp16{};
+    int smax = 0, lo = 0, hi = 0;
+    for (int i = 0; i < 16; ++i) {
+        smax = std::max(smax, p.score[i]);
+        lo = std::min(lo, p.score[i] + 2 * d.ge_raw);
+        hi = std::max(hi, p.score[i] + 2 * d.ge_raw);
+    }
+    h.ok = d.go_raw <= 40 && d.ge_raw <= d.go_raw && lo >= -32 && hi <= 31 && getenv("DBGA_NO_WF16") == nullptr;
+    if (h.ok) {
+        auto dup = [](int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; };
+        h.off = 7050;
+        h.G = dup(4 * (d.ge_raw - d.go_raw));
+        h.tagM = dup(ORDER_PRIO[p.pred_order][0]);
+        h.tagX = dup(ORDER_PRIO[p.pred_order][1]);
+        h.tagY = dup(ORDER_PRIO[p.pred_order][2]);
+        for (int a = 0; a < 4; ++a) {
+            uint32_t w = 0;
+            for (int c = 0; c < 4; ++c) w |= ((uint32_t)(4 * (p.score[a * 4 + c] + 2 * d.ge_raw)) & 0xFFu) << (8 * c);
+            h.lut[a] = w;
+        }
+        h.q0 = 4 * (0 - h.off);
+        h.qneg = -30968;
+        h.qy0 = 4 * (d.ge_raw - d.go_raw - h.off);
+        h.per_step = std::max(0, smax) + 2 * d.ge_raw;
+        h.ulimit = 8191 + h.off - 41;
+    }
     return DBGA_SUCCESS;
 }
 
@@ -530,6 +561,16 @@ int run_pipeline(dbga_ctx *ctx) {
         if (ctx->grid_warp) {
             for (int cls = CLS_WARP2; cls <= CLS_WARP16; ++cls) {
                 const int g = ctx->seen_work[cls] ? ctx->grid_warp : std::min(ctx->grid_warp, ctx->num_sms);
+                // segments the packed 16-bit form can hold go to dp_wf16_kernel, the rest of the
+                // list to the 32-bit kernel; a class whose every member fits launches only the former
+                const int rows16 = 32 * wf_rows_per_lane(cls);
+                if (ctx->dp.h.ok) {
+                    DBGA_CUDA_CHECK(launch_dp_wavefront16(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
+                                                          &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                          (uint8_t *)ctx->d_tb.p, st));
+                    ctx->launches += 1;
+                    if (cls != CLS_WARP16 && wf16_ok(ctx->dp.h, rows16, 1 << 30, wf_rows_per_lane(cls) / 2)) continue;
+                }
                 DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
                                                     &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,
                                                     (uint8_t *)ctx->d_tb.p, (int4 *)ctx->d_bnd_w.p, ctx->bnd_stride_warp, st));

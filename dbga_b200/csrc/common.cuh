@@ -81,6 +81,20 @@ constexpr int TAGMUL = 21;
 constexpr int32_t NEG_V = -(1 << 24);          // "minus infinity" in score units
 constexpr int64_t MAX_ABS_SCORE = (1 << 24) - (1 << 20);
 
+// Packed 16-bit wavefront (dp_wf16_kernel): two cells per 32-bit register, scores as
+// 4 * (V - off) + priority in each int16 half.  Built by make_dp_params; ok = 0 when the
+// scoring parameters do not fit the packed form (the 32-bit kernels then take everything).
+struct Dp16 {
+    uint32_t G;               // 4 * (ge - go) in both halves
+    uint32_t tagM, tagX, tagY; // priority (0..2) in both halves
+    uint32_t lut[4];          // per seq1 base: int8 4 * (S + 2 ge) for seq2 base A, C, G, T
+    int32_t q0, qneg, qy0;    // 16-bit encodings (no tag) of M[0][0], "minus infinity", Y^[0][c]
+    int32_t off;              // V offset: stored = 4 * (V - off) + priority
+    int32_t per_step;         // max(0, largest substitution score) + 2 ge: growth of H^ per diagonal step
+    int32_t ulimit;           // largest H^ the encoding can hold
+    int32_t ok;
+};
+
 struct DpParams {
     int32_t go, ge;           // SCALE * gap open (first gap char), SCALE * extend
     int32_t tagM, tagX, tagY; // TAGMUL * priority (0..2); higher priority wins ties
@@ -89,13 +103,27 @@ struct DpParams {
     uint32_t lut_lo[4];       // per seq1 base: int16 (SCALE*S + tagM) for seq2 base A,C
     uint32_t lut_hi[4];       //                                             ...  G,T
     int32_t go_raw, ge_raw;
+    Dp16 h;                   // packed 16-bit form of the same parameters
 };
 
-// traceback bytes of one wavefront segment: one block of (n + 32) step rows x 32*R columns per
-// 32*R matrix rows, whatever number of warps shares the segment
+// Does segment (m, n) go to the packed 16-bit wavefront with R16 matrix rows per half-lane?
+// One pass of 64 half-lanes covers 64 * R16 rows; rows are padded to whole lanes and one
+// column past n is computed, and every such cell must stay below the encoding's ceiling.
+__host__ __device__ inline bool wf16_ok(const Dp16 &h, int m, int n, int R16) {
+    if (!h.ok) return false;
+    const int mp = ((m + 2 * R16 - 1) / (2 * R16)) * (2 * R16);
+    if (mp > 64 * R16) return false;
+    const long long lim = mp < n + 1 ? mp : n + 1;
+    return (long long)h.per_step * lim + 64 <= (long long)h.ulimit;
+}
+
+// traceback bytes of one wavefront segment: one block of step rows x 32*R columns per 32*R
+// matrix rows, whatever number of warps shares the segment.  The 32-bit kernels use n + 32
+// step rows per block, the packed 16-bit kernel (same row width, 64 half-lanes) n + WF16_TB_PAD.
+constexpr int WF16_TB_PAD = 66;
 __host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int rows_per_lane) {
     const int64_t rows_per_warp = 32 * rows_per_lane;
-    return ((m + rows_per_warp - 1) / rows_per_warp) * (n + 32) * rows_per_warp;
+    return ((m + rows_per_warp - 1) / rows_per_warp) * (n + WF16_TB_PAD) * rows_per_warp;
 }
 
 // ------------------------------------------------------------------ small device utils

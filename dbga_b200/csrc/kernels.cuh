@@ -66,6 +66,10 @@ cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *s
 cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                 const unsigned int *count_dev, int grid, int cls, DpParams prm,
                                 uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);
+// packed 16-bit wavefront over the same class list (takes the segments wf16_ok accepts)
+cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                                  const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
+                                  uint8_t *tb, cudaStream_t st);
 cudaError_t launch_dp_long(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                            const unsigned int *count_dev, int grid_clusters, int grid_ctas, unsigned int few, DpParams prm,
                            uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);

@@ -34,6 +34,7 @@
 #include <cstdlib>
 
 #include "kernels.cuh"
+#include "dp_walk.cuh"
 #include <cooperative_groups.h>
 
 namespace dbga {
@@ -69,39 +70,6 @@ __device__ __forceinline__ int lut_score(uint32_t lo, uint32_t hi, uint32_t sel)
     return r;
 }
 __device__ __forceinline__ uint32_t lut_sel(int ycode) { return 0x9910u + 0x2222u * (uint32_t)ycode; }
-
-__device__ __forceinline__ int prio_to_state(int prio, const DpParams &p) {
-    // 0 = M, 1 = X, 2 = Y
-    const int t = prio * TAGMUL;
-    return t == p.tagM ? 0 : (t == p.tagX ? 1 : 2);
-}
-
-// 2-bit codes of the (up to) 16 bases at p, any alignment, code i in bits 2i..2i+1: two aligned
-// 128-bit loads and a branch-free word/byte shift instead of 16 dependent-latency byte loads.
-// The second block is only read when it holds one of the n bases; n == 0 reads nothing.
-__device__ __forceinline__ uint32_t load_codes16(const uint8_t *p, int n) {
-    if (n <= 0) return 0u;
-    const uint32_t off = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 15);
-    const uint4 *q = reinterpret_cast<const uint4 *>(p - off);
-    const uint4 a = __ldg(q);
-    uint4 b = make_uint4(0u, 0u, 0u, 0u);
-    if (off + (uint32_t)min(n, 16) > 16u) b = __ldg(q + 1);
-    const uint32_t ws = off >> 2, sh = (off & 3u) * 8u;
-    // words ws .. ws+4 of (a, b)
-    const uint32_t v0 = ws == 0 ? a.x : (ws == 1 ? a.y : (ws == 2 ? a.z : a.w));
-    const uint32_t v1 = ws == 0 ? a.y : (ws == 1 ? a.z : (ws == 2 ? a.w : b.x));
-    const uint32_t v2 = ws == 0 ? a.z : (ws == 1 ? a.w : (ws == 2 ? b.x : b.y));
-    const uint32_t v3 = ws == 0 ? a.w : (ws == 1 ? b.x : (ws == 2 ? b.y : b.z));
-    const uint32_t v4 = ws == 0 ? b.x : (ws == 1 ? b.y : (ws == 2 ? b.z : b.w));
-    auto pack4 = [](uint32_t w) {                                  // 4 ASCII bases -> c0 | c1<<2 | c2<<4 | c3<<6
-        const uint32_t codes = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
-        return (codes * 0x01041040u) >> 24;
-    };
-    const uint32_t out = pack4(__funnelshift_r(v0, v1, sh)) | (pack4(__funnelshift_r(v1, v2, sh)) << 8) |
-                         (pack4(__funnelshift_r(v2, v3, sh)) << 16) | (pack4(__funnelshift_r(v3, v4, sh)) << 24);
-    return n >= 16 ? out : (out & ((1u << (2 * n)) - 1u));
-}
-__device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_perm(0x54474341u, 0u, code) & 0xFFu; }   // "ACGT"[code]
 
 // terminal-cell choice under end_order (first wins, strict >)
 __device__ __forceinline__ void pick_end(int Mv, int Xv, int Yv, const DpParams &p, int &state, int &score) {
@@ -449,7 +417,6 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     constexpr int D = WF_D, C = WF_C, RING = WF_RING;
     constexpr int GW = W * CL;                                // warps working on one segment
     constexpr int ROWS_PASS = GW * 32 * R;
-    constexpr int WIN_W = (32 * R >= 64) ? 64 : 32 * R;       // traceback window width in bytes
     __shared__ int4 ring[W + 1][RING];
     __shared__ WfShared sh;
     __shared__ __align__(16) uint8_t win[32][64];      // traceback window
@@ -487,6 +454,9 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
         const Slot s = slots[sid];
         const PairDesc pd = pairs[s.pair];
         const int m = s.m, n = s.n;
+        if constexpr (W == 1 && CL == 1) {
+            if (wf16_ok(prm.h, m, n, R / 2)) continue;       // the packed 16-bit kernel of this class takes it
+        }
         const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
         uint8_t *tb = tb_pool + s.tb_off;
         const int passes = (m + ROWS_PASS - 1) / ROWS_PASS;
@@ -608,87 +578,12 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             } else {
                 pick_end(sh.endM, sh.endX, sh.endY, prm, st, score);
             }
-            int i = m, j = n, len = 0;
             const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
             uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
             // state reached through a traceback tag: packed table prio -> state (0 = M, 1 = X, 2 = Y)
             const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
                                   ((uint32_t)prio_to_state(2, prm) << 4);
-            // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
-            // runs the same walk (uniform control flow).  Only the kind of each step is kept, as
-            // two bit masks per group of 32 steps (bit t of mY: step t consumes a seq-1 base, of
-            // mX: a seq-2 base); a full group is turned into the two rows' characters by all 32
-            // lanes at once, so the sequence loads stay off the walk's dependency chain.
-            // In state M the 32 lanes probe the next 32 cells of the diagonal together and the
-            // walk jumps over the whole run of M -> M steps (most of the path between similar
-            // sequences); everything else goes one cell at a time.
-            int win_blk = -1, win_row_hi = 0, win_col_lo = 0;
-            uint32_t mY = 0, mX = 0;
-            int pos = 0, gbase = 0;
-            int ib = m, jb = n;                              // (i, j) before the first step of the group
-            const uint32_t lt = (1u << lane) - 1u;
-            auto flush = [&](int cnt) {
-                if (lane < cnt) {
-                    const int it = ib - __popc(mY & lt), jt = jb - __popc(mX & lt);
-                    ox[gbase + lane] = ((mY >> lane) & 1u) ? xs[it - 1] : (uint8_t)'-';
-                    oy[gbase + lane] = ((mX >> lane) & 1u) ? ys[jt - 1] : (uint8_t)'-';
-                }
-                ib -= __popc(mY); jb -= __popc(mX);
-                gbase += cnt; mY = 0; mX = 0; pos = 0;
-            };
-            auto emit = [&](int state, int count) {
-                len += count;
-                while (count > 0) {
-                    const int take = min(count, 32 - pos);
-                    const uint32_t bits = (take == 32 ? 0xffffffffu : ((1u << take) - 1u)) << pos;
-                    if (state != 2) mY |= bits;
-                    if (state != 1) mX |= bits;
-                    pos += take; count -= take;
-                    if (pos == 32) flush(32);
-                }
-            };
-            while (i > 0 || j > 0) {
-                if (i == 0) { emit(2, j); break; }           // first row / column: one long gap
-                if (j == 0) { emit(1, i); break; }
-                const int i0 = i - 1;
-                const int blk = i0 / (32 * R), cb = i0 % (32 * R);      // (pass * GW + warp), l * R + r
-                const int row = j + cb / R;
-                if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= (unsigned)WIN_W) {
-                    __syncwarp();
-                    win_blk = blk; win_row_hi = row;
-                    win_col_lo = (WIN_W == 64) ? max(0, (cb & ~31) - 32) : 0;
-                    const int rr = row - lane;
-                    uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
-                    if (rr >= 1) {
-                        const uint4 *p = reinterpret_cast<const uint4 *>(tb + ((int64_t)blk * tb_rows + rr) * (int64_t)(32 * R) + win_col_lo);
-                        a = p[0]; b = p[1];
-                        if constexpr (WIN_W == 64) { c4 = p[2]; d4 = p[3]; }
-                    }
-                    uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
-                    dst[0] = a; dst[1] = b;
-                    if constexpr (WIN_W == 64) { dst[2] = c4; dst[3] = d4; }
-                    __syncwarp();
-                }
-                if (st == 0) {
-                    const int il = i0 - lane, jl = j - lane;
-                    bool ok = false;
-                    if (il >= 0 && jl >= 1) {
-                        const int bl = il / (32 * R), cl = il % (32 * R);
-                        const unsigned dr = (unsigned)(win_row_hi - (jl + cl / R)), dc = (unsigned)(cl - win_col_lo);
-                        if (bl == win_blk && dr < 32u && dc < (unsigned)WIN_W)
-                            ok = ((pmap >> (2 * (win[dr][dc] & 3u))) & 3u) == 0u;
-                    }
-                    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-                    const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
-                    if (c > 0) { emit(0, c); i -= c; j -= c; continue; }
-                }
-                const uint32_t d = win[win_row_hi - row][cb - win_col_lo];
-                emit(st, 1);
-                const uint32_t tag = (d >> (2 * st)) & 3u;
-                i -= (st != 2); j -= (st != 1);
-                st = (int)((pmap >> (2 * tag)) & 3u);
-            }
-            if (pos) flush(pos);
+            const int len = wf_traceback<32 * R, R>(win, tb, tb_rows, xs, ys, m, n, st, pmap, ox, oy, lane);
             if (lane == 0) { slots[sid].score = score - prm.ge_raw * (m + n); slots[sid].len = len; }
         }
         __syncthreads();

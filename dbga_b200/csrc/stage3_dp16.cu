@@ -1,0 +1,201 @@
+// Stage 3, packed 16-bit wavefront: the same affine-gap (Gotoh) global alignment as
+// stage3_dp.cu (replaces cogent3.align.global_pairwise as called from dna_global_aln,
+// reference src/dbga/utils.py:157-192, call site :185), two cells per 32-bit register.
+//
+// A warp is 64 half-lanes: lane l owns 2R consecutive matrix rows, the first R in the low
+// int16 halves of its registers, the next R in the high halves.  At step t the low half is
+// at column t - 2l and the high half one column behind it (t - 2l - 1), so the high half's
+// row above is the low half's last row one step earlier (same thread, no shuffle) and the
+// low half's row above is the previous lane's high half one step earlier (one shuffle +
+// PRMT per state).  All arithmetic is the sm_100a packed forms: VIMNMX3.S16x2,
+// VIADDMNMX.S16x2, VIADD.16x2.
+//
+// Encoding per half: 4 * (V - off) + priority(state), V = H + ge * (i + j) (gap extension is
+// free, as in the 32-bit kernels); the integer max breaks ties in the configured first-wins
+// order and leaves the winner's tag in the low two bits, which become the traceback byte
+// (bits 0-1: predecessor of M, 2-3: of X, 4-5: of Y).  Substitution scores are int8 LUT
+// bytes picked and sign-extended for both halves by one PRMT.  `off` places the valid range
+// asymmetrically: valid values are >= about -(|s| + 4 go), "minus infinity" sits in a band
+// below that which a few additions cannot leave, and the rest of the int16 range is head
+// room for per_step * min(m, n) (wf16_ok decides per segment; the 32-bit kernels take the
+// rest).  Column 0 and the column before it are computed like any other from minus-infinity
+// registers, which yields exactly X^[i][0] = ge - go and minus infinity for M and Y, so a
+// half-lane needs no start-up masking.  One pass only (m <= 64 R); traceback bytes use the
+// 32-bit kernels' step-major layout (row = step, 64 R bytes per row) and the shared walker.
+#include "dp_walk.cuh"
+#include "kernels.cuh"
+
+namespace dbga {
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+__device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
+
+template <int R, bool XY>
+__global__ void __launch_bounds__(32)
+dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+               const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
+               uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool) {
+    __shared__ __align__(16) uint8_t win[32][64];      // traceback window
+    __shared__ uint32_t s_lut[4];
+    const int lane = threadIdx.x;
+    const Dp16 &h = prm.h;
+    if (lane < 4) s_lut[lane] = h.lut[lane];
+    __syncwarp();
+    constexpr uint32_t KS = 0xFFFCFFFCu, K3 = 0x00030003u, K15 = 0x000F000Fu, FULL = 0xffffffffu;
+    constexpr int ROWW = 64 * R;
+    const uint32_t G = h.G, tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
+    const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
+    // row 0 as seen by lane 0's low half (arrives where the shuffle would put it: high half)
+    const uint32_t r0M0 = (dup16(h.q0) | tagM) << 16, r0Mn = negM << 16, r0X = negX << 16,
+                   r0Y = (dup16(h.qy0) | tagY) << 16, r0Yn = negY << 16;
+    const unsigned int count = *count_dev;
+
+    for (unsigned int item = blockIdx.x; item < count; item += gridDim.x) {
+        const int sid = list[item];
+        const Slot s = slots[sid];
+        const int m = s.m, n = s.n;
+        if (!wf16_ok(h, m, n, R)) continue;                  // the 32-bit kernel of this class takes it
+        const PairDesc pd = pairs[s.pair];
+        const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
+        uint8_t *tb = tb_pool + s.tb_off;
+        const int nl = (m + 2 * R - 1) / (2 * R);            // lanes with rows
+        const bool lane_on = lane < nl;
+        uint32_t lutA[R], lutB[R], Mr[R], Xr[R], Yr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int iA = lane * 2 * R + r, iB = iA + R;    // 0-based matrix rows
+            lutA[r] = s_lut[iA < m ? base_code(xs[iA]) : 0];
+            lutB[r] = s_lut[iB < m ? base_code(xs[iB]) : 0];
+            Mr[r] = negM; Xr[r] = negX; Yr[r] = negY;
+        }
+        uint32_t dgM = negM, dgX = negX, dgY = negY;
+        // the terminal cell: half-lane ve, row re of it, reached at step te
+        const int ve = (m - 1) / R, re = (m - 1) % R, te = n + ve, le = ve >> 1;
+        uint32_t eM = 0, eX = 0, eY = 0;
+        // seq2 codes for lane 0, sixteen per word, the next word in flight
+        uint32_t wy = load_codes16(ys, n), wy_next = load_codes16(ys + 16, n - 16);
+        uint32_t yprev = 0, sel_cur = 0xC480u, sel_prev = 0xC480u;
+        uint8_t *tbw = tb + lane * 2 * R;
+        const int T = n + 2 * nl;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            // lane 0: selector for columns (t, t - 1); lane l gets lane l-1's selector of two steps ago
+            uint32_t ycur = 0;
+            if (t >= 1) {
+                const int idx = t - 1;
+                if ((idx & 15) == 0 && idx > 0) { wy = wy_next; wy_next = load_codes16(ys + idx + 16, n - idx - 16); }
+                ycur = (wy >> (2 * (idx & 15))) & 3u;
+            }
+            const uint32_t sel0 = 0xC480u + 0x11u * ycur + 0x1100u * yprev;
+            yprev = ycur;
+            const uint32_t sel_in = __shfl_up_sync(FULL, sel_prev, 1);
+            sel_prev = sel_cur;
+            sel_cur = lane == 0 ? sel0 : sel_in;
+            // the row above: low half <- previous lane's high half, high half <- own low half
+            uint32_t sM = __shfl_up_sync(FULL, Mr[R - 1], 1);
+            uint32_t sX = __shfl_up_sync(FULL, Xr[R - 1], 1);
+            uint32_t sY = __shfl_up_sync(FULL, Yr[R - 1], 1);
+            if (lane == 0) { sM = t == 0 ? r0M0 : r0Mn; sX = r0X; sY = t >= 1 ? r0Y : r0Yn; }
+            const uint32_t uM = prmt(sM, Mr[R - 1], 0x5432u), uX = prmt(sX, Xr[R - 1], 0x5432u),
+                           uY = prmt(sY, Yr[R - 1], 0x5432u);
+            const int jl = t - 2 * lane;
+            if (lane_on && jl >= 0 && jl <= n + 1) {
+                uint32_t dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
+                uint32_t D[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t oM = Mr[r], oX = Xr[r], oY = Yr[r];
+                    const uint32_t tt = __vimax3_s16x2(dM, dX, dY);
+                    uint32_t u = __viaddmax_s16x2(aM, G, aX);
+                    uint32_t v = __viaddmax_s16x2(oM, G, oY);
+                    if (XY) {
+                        u = __viaddmax_s16x2(aY, G, u);
+                        v = __viaddmax_s16x2(oX, G, v);
+                    }
+                    const uint32_t sc = prmt(lutA[r], lutB[r], sel_cur);
+                    Mr[r] = (__vadd2(tt, sc) & KS) | tagM;
+                    Xr[r] = (u & KS) | tagX;
+                    Yr[r] = (v & KS) | tagY;
+                    uint32_t d = (tt & K3) | ((u << 2) & ~K3);
+                    d = (d & K15) | ((v << 4) & ~K15);
+                    D[r] = d;
+                    dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
+                }
+                // bytes: low-half rows 0..R-1, then high-half rows 0..R-1 (= matrix row order)
+                uint8_t *tbp = tbw + (int64_t)t * ROWW;
+                if constexpr (R == 1) {
+                    *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)prmt(D[0], 0u, 0x4420u);
+                } else if constexpr (R == 2) {
+                    *reinterpret_cast<uint32_t *>(tbp) = prmt(D[0], D[1], 0x6240u);
+                } else {
+                    uint32_t lo[R / 4], hi[R / 4];
+#pragma unroll
+                    for (int g = 0; g < R / 4; ++g) {
+                        const uint32_t E = prmt(D[4 * g], D[4 * g + 1], 0x6240u), F = prmt(D[4 * g + 2], D[4 * g + 3], 0x6240u);
+                        lo[g] = prmt(E, F, 0x5410u);
+                        hi[g] = prmt(E, F, 0x7632u);
+                    }
+                    if constexpr (R == 4) {
+                        *reinterpret_cast<uint2 *>(tbp) = make_uint2(lo[0], hi[0]);
+                    } else if constexpr (R == 8) {
+                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(lo[0], lo[1], hi[0], hi[1]);
+                    } else {
+                        static_assert(R == 16, "R must be 1, 2, 4, 8 or 16");
+                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4 *>(tbp + 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    }
+                }
+                if (t == te && lane == le) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r == re) { eM = Mr[r]; eX = Xr[r]; eY = Yr[r]; }
+                }
+                dgM = uM; dgX = uX; dgY = uY;
+            }
+        }
+        // ------------------------------------------------------------------ terminal cell
+        eM = __shfl_sync(FULL, eM, le); eX = __shfl_sync(FULL, eX, le); eY = __shfl_sync(FULL, eY, le);
+        const int sh = (ve & 1) ? 16 : 0;
+        const int vM = (int)(int16_t)(eM >> sh), vX = (int)(int16_t)(eX >> sh), vY = (int)(int16_t)(eY >> sh);
+        // end_order: first wins, strict > (oracle/dbga_oracle.py pick of the terminal state)
+        const int cm = (vM & ~3) + prm.endM, cx = (vX & ~3) + prm.endX, cy = (vY & ~3) + prm.endY;
+        int best = cm, st = 0;
+        if (cx > best) { best = cx; st = 1; }
+        if (cy > best) { best = cy; st = 2; }
+        const int score = (best >> 2) + h.off - prm.ge_raw * (m + n);
+        const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
+        uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
+        const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
+                              ((uint32_t)prio_to_state(2, prm) << 4);
+        __syncwarp();
+        const int len = wf_traceback<ROWW, R>(win, tb, (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap, ox, oy, lane);
+        if (lane == 0) { slots[sid].score = score; slots[sid].len = len; }
+        __syncwarp();
+    }
+}
+
+template <int R>
+static void launch_wf16_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                          const unsigned int *count_dev, const DpParams &prm, uint8_t *strbuf, uint8_t *tb, cudaStream_t st) {
+    if (prm.xy) dp_wf16_kernel<R, true><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
+    else dp_wf16_kernel<R, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
+}
+
+// cls: CLS_WARP2 / 4 / 8 / 16; the packed kernel runs half as many rows per half-lane as the
+// class's 32-bit kernel runs per lane (same 32 * R-byte traceback rows)
+cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                                  const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
+                                  uint8_t *tb, cudaStream_t st) {
+    if (grid <= 0 || !prm.h.ok) return cudaSuccess;
+    if (cls == CLS_WARP2) launch_wf16_t<1>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    else if (cls == CLS_WARP4) launch_wf16_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    else if (cls == CLS_WARP8) launch_wf16_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    else launch_wf16_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    return cudaGetLastError();
+}
+
+}  // namespace dbga

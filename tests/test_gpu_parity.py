@@ -310,3 +310,50 @@ def test_graph_flags_in_a_batch(aligner):
         nd0, nd1 = res.graph_flags(i)
         assert np.array_equal(nd0, ref.nondup0) and np.array_equal(nd1, ref.nondup1)
         assert [tuple(x) for x in res.anchors(i).tolist()] == [tuple(x) for x in ref.anchors.tolist()]
+
+
+def test_packed16_wavefront(aligner):
+    """The packed 16-bit wavefront (two cells per register, dp_wf16_kernel) against the oracle:
+    every warp class (1 / 2 / 4 / 8 rows per half-lane), partial lanes, segments on both sides
+    of the encoding's ceiling (per_step * min(m, n) vs ulimit: above it the 32-bit kernel runs),
+    every tie-breaking convention, and scoring tables at and beyond the int8 LUT limits."""
+    rng = random.Random(41)
+    shapes = [(33, 33), (64, 64), (65, 40), (64, 500), (63, 64), (100, 90), (128, 128), (127, 129), (129, 300),
+              (200, 35), (256, 256), (255, 257), (257, 300), (300, 2), (2, 300), (500, 512), (512, 512), (511, 37),
+              (512, 2000), (40, 3000), (300, 9000), (513, 513), (1000, 1000), (1080, 1090), (1090, 1100),
+              (1024, 60), (60, 1024), (33, 1), (1, 33), (450, 450)]
+    pairs = []
+    for m, n in shapes:
+        x = rand_seq(rng, m)
+        r = rng.random()
+        if r < 0.6:
+            y = (mutate(rng, x, 0.1, 0.05) + rand_seq(rng, n))[:n]
+        elif r < 0.8:
+            y = rand_seq(rng, n)
+        else:                                   # shifted copy: long terminal gaps
+            y = (rand_seq(rng, n // 3) + x)[:n]
+        pairs.append((x, y))
+
+    def run(conv=O.DEFAULT, sub=None, **score):
+        res = aligner.global_align_pairs(sub or pairs, gap_len_mode=conv.gap_len_mode, xy_allowed=conv.xy_allowed,
+                                         pred_order=conv.pred_order, end_order=conv.end_order, **score)
+        for i, (x, y) in enumerate(sub or pairs):
+            sc, ax, ay = CO.gotoh(x, y, conv=conv, **score)
+            assert res.status[i] == O.OK
+            assert res.score[i] == sc, (i, len(x), len(y), conv, score)
+            assert res.alignment(i) == (ax, ay), (i, len(x), len(y), conv, score)
+
+    run()
+    # with >= 592 pairs in the batch the big shapes stay in the warp classes instead of the CTA class
+    filler = [(rand_seq(rng, 40), rand_seq(rng, 45)) for _ in range(600)]
+    run(sub=pairs + filler)
+    small = [p for p in pairs if len(p[0]) * len(p[1]) <= 70000]
+    for g, xy, po, eo in itertools.product((0, 1), (False, True), O.ORDERS, ("XMY", "MYX", "YMX")):
+        run(O.Convention(g, xy, po, eo), sub=small)
+    run(O.Convention(1, True, "YXM", "MYX"))
+    run(match=15, transition=-4, transversion=-48, d=40, e=8)      # s + 2e in [-32, 31], go = 40: the limits
+    run(match=16, transition=-4, transversion=-8, d=40, e=8)       # one past the LUT limit: 32-bit kernels
+    run(match=5, transition=-4, transversion=-4, d=41, e=1)        # gap open past the limit: 32-bit kernels
+    run(match=1, transition=0, transversion=-1, d=0, e=0)
+    run(match=31, transition=-30, transversion=-32, d=3, e=0)      # steep: ceiling reached at ~490 rows
+    run(match=-3, transition=2, transversion=5, d=7, e=3)          # mismatches score higher than matches
