@@ -220,9 +220,12 @@ int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
         h.tagY = dup(ORDER_PRIO[p.pred_order][2]);
         for (int a = 0; a < 4; ++a) {
             uint32_t w = 0;
-            for (int c = 0; c < 4; ++c) w |= ((uint32_t)(4 * (p.score[a * 4 + c] + 2 * d.ge_raw)) & 0xFFu) << (8 * c);
+            for (int c = 0; c < 4; ++c)
+                w |= ((uint32_t)(4 * (p.score[a * 4 + c] + 2 * d.ge_raw) + ORDER_PRIO[p.pred_order][0]) & 0xFFu) << (8 * c);
             h.lut[a] = w;
         }
+        h.mul[0] = 0xFFFFFFFFu; h.mul[1] = 4; h.mul[2] = 16; h.mul[3] = 256;
+        h.tbk = 4 * ORDER_PRIO[p.pred_order][1] + 16 * ORDER_PRIO[p.pred_order][2];
         h.q0 = 4 * (0 - h.off);
         h.qneg = -30968;
         h.qy0 = 4 * (d.ge_raw - d.go_raw - h.off);
@@ -568,7 +571,7 @@ int run_pipeline(dbga_ctx *ctx) {
                     DBGA_CUDA_CHECK(launch_dp_wavefront16(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
                                                           &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,
                                                           (uint8_t *)ctx->d_tb.p, st));
-                    ctx->launches += 1;
+                    ctx->launches += cls == CLS_WARP16 ? 2 : 1;
                     if (cls != CLS_WARP16 && wf16_ok(ctx->dp.h, rows16, 1 << 30, wf_rows_per_lane(cls) / 2)) continue;
                 }
                 DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,

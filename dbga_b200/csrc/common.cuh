@@ -87,7 +87,9 @@ constexpr int64_t MAX_ABS_SCORE = (1 << 24) - (1 << 20);
 struct Dp16 {
     uint32_t G;               // 4 * (ge - go) in both halves
     uint32_t tagM, tagX, tagY; // priority (0..2) in both halves
-    uint32_t lut[4];          // per seq1 base: int8 4 * (S + 2 ge) for seq2 base A, C, G, T
+    uint32_t lut[4];          // per seq1 base: int8 4 * (S + 2 ge) + priority(M) for seq2 base A, C, G, T
+    uint32_t mul[4];          // -1, 4, 16, 256: IMAD multipliers kept in registers
+    uint32_t tbk;             // 4 * priority(X) + 16 * priority(Y): bias of a raw traceback byte
     int32_t q0, qneg, qy0;    // 16-bit encodings (no tag) of M[0][0], "minus infinity", Y^[0][c]
     int32_t off;              // V offset: stored = 4 * (V - off) + priority
     int32_t per_step;         // max(0, largest substitution score) + 2 ge: growth of H^ per diagonal step
@@ -116,11 +118,17 @@ __host__ __device__ inline bool wf16_ok(const Dp16 &h, int m, int n, int R16) {
     const long long lim = mp < n + 1 ? mp : n + 1;
     return (long long)h.per_step * lim + 64 <= (long long)h.ulimit;
 }
+// Rows per half-lane of the packed kernel that takes segment (m, n) of warp class cls, 0 = none
+// (the class's 32-bit kernel runs it).  The open-ended class splits at 512 rows.
+__host__ __device__ inline int wf16_pick(const Dp16 &h, int cls, int m, int n) {
+    const int r16 = cls == CLS_WARP2 ? 1 : (cls == CLS_WARP4 ? 2 : (cls == CLS_WARP8 ? 4 : (m <= 512 ? 8 : 16)));
+    return wf16_ok(h, m, n, r16) ? r16 : 0;
+}
 
 // traceback bytes of one wavefront segment: one block of step rows x 32*R columns per 32*R
 // matrix rows, whatever number of warps shares the segment.  The 32-bit kernels use n + 32
 // step rows per block, the packed 16-bit kernel (same row width, 64 half-lanes) n + WF16_TB_PAD.
-constexpr int WF16_TB_PAD = 66;
+constexpr int WF16_TB_PAD = 82;       // 64 half-lanes of skew + whole chunks of 16 steps
 __host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int rows_per_lane) {
     const int64_t rows_per_warp = 32 * rows_per_lane;
     return ((m + rows_per_warp - 1) / rows_per_warp) * (n + WF16_TB_PAD) * rows_per_warp;

@@ -47,10 +47,22 @@ __device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_per
 // shared memory owned by the warp.  st: state chosen at the terminal cell.  pmap: packed table
 // tag -> state (0 = M, 1 = X, 2 = Y).  Rows are written reversed at ox / oy; returns the
 // number of alignment columns.
-template <int ROWW, int RDIV>
+// PR > 0: the packed kernel's byte order inside a lane's 2 * PR bytes (pairs of rows (r, r+1) of the
+// low and high half-lanes: [low r, low r+1, high r, high r+1]); PR = 0: bytes in matrix-row order.
+template <int PR>
+__device__ __forceinline__ int wf_col(int c) {
+    if constexpr (PR == 0) return c;
+    else {
+        const int q = c % (2 * PR), hh = q / PR, r = q % PR;
+        return c - q + 4 * (r >> 1) + 2 * hh + (r & 1);
+    }
+}
+
+template <int ROWW, int RDIV, int PR = 0>
 __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *__restrict__ tb, int64_t tb_rows,
                                             const uint8_t *__restrict__ xs, const uint8_t *__restrict__ ys, int m, int n,
-                                            int st, uint32_t pmap, uint8_t *__restrict__ ox, uint8_t *__restrict__ oy, int lane) {
+                                            int st, uint32_t pmap, uint8_t *__restrict__ ox, uint8_t *__restrict__ oy, int lane,
+                                            uint32_t bias4 = 0u) {
     constexpr int WIN_W = (ROWW >= 64) ? 64 : ROWW;       // traceback window width in bytes
     int i = m, j = n, len = 0;
     // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
@@ -86,6 +98,12 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
             if (pos == 32) flush(32);
         }
     };
+    // PR > 0: the packed kernel stores each group of four bytes as one word less bias4 (exact
+    // 32-bit arithmetic, see stage3_dp16.cu); bytes are read through their word
+    auto tb_byte = [&](int r, int c) -> uint32_t {
+        if constexpr (PR == 0) return win[r][c];
+        else return ((*reinterpret_cast<const uint32_t *>(&win[r][c & ~3]) + bias4) >> (8 * (c & 3))) & 0xFFu;
+    };
     while (i > 0 || j > 0) {
         if (i == 0) { emit(2, j); break; }           // first row / column: one long gap
         if (j == 0) { emit(1, i); break; }
@@ -115,13 +133,13 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
                 const int bl = il / (ROWW), cl = il % (ROWW);
                 const unsigned dr = (unsigned)(win_row_hi - (jl + cl / RDIV)), dc = (unsigned)(cl - win_col_lo);
                 if (bl == win_blk && dr < 32u && dc < (unsigned)WIN_W)
-                    ok = ((pmap >> (2 * (win[dr][dc] & 3u))) & 3u) == 0u;
+                    ok = ((pmap >> (2 * (tb_byte(dr, wf_col<PR>(cl) - win_col_lo) & 3u))) & 3u) == 0u;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, ok);
             const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
             if (c > 0) { emit(0, c); i -= c; j -= c; continue; }
         }
-        const uint32_t d = win[win_row_hi - row][cb - win_col_lo];
+        const uint32_t d = tb_byte(win_row_hi - row, wf_col<PR>(cb) - win_col_lo);
         emit(st, 1);
         const uint32_t tag = (d >> (2 * st)) & 3u;
         i -= (st != 2); j -= (st != 1);

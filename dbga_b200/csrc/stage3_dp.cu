@@ -455,7 +455,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
         const PairDesc pd = pairs[s.pair];
         const int m = s.m, n = s.n;
         if constexpr (W == 1 && CL == 1) {
-            if (wf16_ok(prm.h, m, n, R / 2)) continue;       // the packed 16-bit kernel of this class takes it
+            if (wf16_pick(prm.h, s.cls, m, n)) continue;     // a packed 16-bit kernel of this class takes it
         }
         const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
         uint8_t *tb = tb_pool + s.tb_off;

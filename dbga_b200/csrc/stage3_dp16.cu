@@ -32,6 +32,11 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 
 template <int R, bool XY>
@@ -45,7 +50,10 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
     const Dp16 &h = prm.h;
     if (lane < 4) s_lut[lane] = h.lut[lane];
     __syncwarp();
-    constexpr uint32_t KS = 0xFFFCFFFCu, K3 = 0x00030003u, K15 = 0x000F000Fu, FULL = 0xffffffffu;
+    constexpr uint32_t KS = 0xFFFCFFFCu, FULL = 0xffffffffu;
+    // multipliers the compiler cannot see through: a literal * 4 would become LEA / SHL on the ALU pipe
+    const uint32_t cm1 = h.mul[0], c4 = h.mul[1], c16 = h.mul[2], c256 = h.mul[3];
+    const uint32_t K1 = h.tbk * 0x00010001u;
     constexpr int ROWW = 64 * R;
     const uint32_t G = h.G, tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
     const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
@@ -58,12 +66,11 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         const int sid = list[item];
         const Slot s = slots[sid];
         const int m = s.m, n = s.n;
-        if (!wf16_ok(h, m, n, R)) continue;                  // the 32-bit kernel of this class takes it
+        if (wf16_pick(h, s.cls, m, n) != R) continue;        // another kernel of this class takes it
         const PairDesc pd = pairs[s.pair];
         const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
         uint8_t *tb = tb_pool + s.tb_off;
         const int nl = (m + 2 * R - 1) / (2 * R);            // lanes with rows
-        const bool lane_on = lane < nl;
         uint32_t lutA[R], lutB[R], Mr[R], Xr[R], Yr[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -76,34 +83,36 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         // the terminal cell: half-lane ve, row re of it, reached at step te
         const int ve = (m - 1) / R, re = (m - 1) % R, te = n + ve, le = ve >> 1;
         uint32_t eM = 0, eX = 0, eY = 0;
-        // seq2 codes for lane 0, sixteen per word, the next word in flight
-        uint32_t wy = load_codes16(ys, n), wy_next = load_codes16(ys + 16, n - 16);
         uint32_t yprev = 0, sel_cur = 0xC480u, sel_prev = 0xC480u;
         uint8_t *tbw = tb + lane * 2 * R;
+        // Steps run in whole chunks of 16 (one word of seq2 codes for lane 0: the code of column t
+        // is bits 2s of the word loaded at ys - 1 + t0, the next word in flight).  No lane is
+        // masked: a lane computes garbage before its first column (and after its last), into its
+        // own registers and its own traceback bytes, and is put back to minus infinity at the end
+        // of step 2 * lane - 1, just before its low half reaches column 0.
         const int T = n + 2 * nl;
-#pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-            // lane 0: selector for columns (t, t - 1); lane l gets lane l-1's selector of two steps ago
-            uint32_t ycur = 0;
-            if (t >= 1) {
-                const int idx = t - 1;
-                if ((idx & 15) == 0 && idx > 0) { wy = wy_next; wy_next = load_codes16(ys + idx + 16, n - idx - 16); }
-                ycur = (wy >> (2 * (idx & 15))) & 3u;
-            }
-            const uint32_t sel0 = 0xC480u + 0x11u * ycur + 0x1100u * yprev;
-            yprev = ycur;
-            const uint32_t sel_in = __shfl_up_sync(FULL, sel_prev, 1);
-            sel_prev = sel_cur;
-            sel_cur = lane == 0 ? sel0 : sel_in;
-            // the row above: low half <- previous lane's high half, high half <- own low half
-            uint32_t sM = __shfl_up_sync(FULL, Mr[R - 1], 1);
-            uint32_t sX = __shfl_up_sync(FULL, Xr[R - 1], 1);
-            uint32_t sY = __shfl_up_sync(FULL, Yr[R - 1], 1);
-            if (lane == 0) { sM = t == 0 ? r0M0 : r0Mn; sX = r0X; sY = t >= 1 ? r0Y : r0Yn; }
-            const uint32_t uM = prmt(sM, Mr[R - 1], 0x5432u), uX = prmt(sX, Xr[R - 1], 0x5432u),
-                           uY = prmt(sY, Yr[R - 1], 0x5432u);
-            const int jl = t - 2 * lane;
-            if (lane_on && jl >= 0 && jl <= n + 1) {
+        const int reset_at = 2 * lane - 1;
+        uint32_t wy_next = load_codes16(ys - 1, n + 1);
+        for (int t0 = 0; t0 < T; t0 += 16) {
+            const uint32_t wy = wy_next;
+            wy_next = load_codes16(ys + 15 + t0, n - 15 - t0);
+#pragma unroll 2
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                const int t = t0 + sidx;
+                // lane 0: selector for columns (t, t - 1); lane l gets lane l-1's selector of two steps ago
+                const uint32_t ycur = (wy >> (2 * sidx)) & 3u;
+                const uint32_t sel0 = 0xC480u + 0x11u * ycur + 0x1100u * yprev;
+                yprev = ycur;
+                const uint32_t sel_in = __shfl_up_sync(FULL, sel_prev, 1);
+                sel_prev = sel_cur;
+                sel_cur = lane == 0 ? sel0 : sel_in;
+                // the row above: low half <- previous lane's high half, high half <- own low half
+                uint32_t sM = __shfl_up_sync(FULL, Mr[R - 1], 1);
+                uint32_t sX = __shfl_up_sync(FULL, Xr[R - 1], 1);
+                uint32_t sY = __shfl_up_sync(FULL, Yr[R - 1], 1);
+                if (lane == 0) { sM = t == 0 ? r0M0 : r0Mn; sX = r0X; sY = t >= 1 ? r0Y : r0Yn; }
+                const uint32_t uM = prmt(sM, Mr[R - 1], 0x5432u), uX = prmt(sX, Xr[R - 1], 0x5432u),
+                               uY = prmt(sY, Yr[R - 1], 0x5432u);
                 uint32_t dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
                 uint32_t D[R];
 #pragma unroll
@@ -116,37 +125,36 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                         u = __viaddmax_s16x2(aY, G, u);
                         v = __viaddmax_s16x2(oX, G, v);
                     }
-                    const uint32_t sc = prmt(lutA[r], lutB[r], sel_cur);
-                    Mr[r] = (__vadd2(tt, sc) & KS) | tagM;
+                    // ALU pipe (the bottleneck: half issue rate): three maxes, three bit strips,
+                    // the score PRMT and the packed add.  Everything else is IMAD on the FMA pipe.
+                    const uint32_t ts = tt & KS;
                     Xr[r] = (u & KS) | tagX;
                     Yr[r] = (v & KS) | tagY;
-                    uint32_t d = (tt & K3) | ((u << 2) & ~K3);
-                    d = (d & K15) | ((v << 4) & ~K15);
-                    D[r] = d;
+                    Mr[r] = __vadd2(ts, prmt(lutA[r], lutB[r], sel_cur));       // LUT bytes carry M's tag
+                    // winner tags as exact integer differences (tt & 3, (u & 3) - pX, (v & 3) - pY per half;
+                    // borrows between the fields cancel when the walker adds tbk to every byte of the word)
+                    const uint32_t et = imad(ts, cm1, tt), eu = imad(Xr[r], cm1, u), ev = imad(Yr[r], cm1, v);
+                    D[r] = imad(ev, c16, imad(eu, c4, et));
                     dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
                 }
-                // bytes: low-half rows 0..R-1, then high-half rows 0..R-1 (= matrix row order)
+                // traceback bytes of the lane, per pair of rows (r, r+1): [low r, low r+1, high r, high r+1]
                 uint8_t *tbp = tbw + (int64_t)t * ROWW;
                 if constexpr (R == 1) {
-                    *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)prmt(D[0], 0u, 0x4420u);
-                } else if constexpr (R == 2) {
-                    *reinterpret_cast<uint32_t *>(tbp) = prmt(D[0], D[1], 0x6240u);
+                    *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)prmt(D[0] + K1, 0u, 0x4420u);
                 } else {
-                    uint32_t lo[R / 4], hi[R / 4];
+                    uint32_t E[R / 2];
 #pragma unroll
-                    for (int g = 0; g < R / 4; ++g) {
-                        const uint32_t E = prmt(D[4 * g], D[4 * g + 1], 0x6240u), F = prmt(D[4 * g + 2], D[4 * g + 3], 0x6240u);
-                        lo[g] = prmt(E, F, 0x5410u);
-                        hi[g] = prmt(E, F, 0x7632u);
-                    }
-                    if constexpr (R == 4) {
-                        *reinterpret_cast<uint2 *>(tbp) = make_uint2(lo[0], hi[0]);
+                    for (int g = 0; g < R / 2; ++g) E[g] = imad(D[2 * g + 1], c256, D[2 * g]);   // the walker adds the bias
+                    if constexpr (R == 2) {
+                        *reinterpret_cast<uint32_t *>(tbp) = E[0];
+                    } else if constexpr (R == 4) {
+                        *reinterpret_cast<uint2 *>(tbp) = make_uint2(E[0], E[1]);
                     } else if constexpr (R == 8) {
-                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(lo[0], lo[1], hi[0], hi[1]);
+                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(E[0], E[1], E[2], E[3]);
                     } else {
                         static_assert(R == 16, "R must be 1, 2, 4, 8 or 16");
-                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                        *reinterpret_cast<uint4 *>(tbp + 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(E[0], E[1], E[2], E[3]);
+                        *reinterpret_cast<uint4 *>(tbp + 16) = make_uint4(E[4], E[5], E[6], E[7]);
                     }
                 }
                 if (t == te && lane == le) {
@@ -155,6 +163,11 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                         if (r == re) { eM = Mr[r]; eX = Xr[r]; eY = Yr[r]; }
                 }
                 dgM = uM; dgX = uX; dgY = uY;
+                if (t == reset_at) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) { Mr[r] = negM; Xr[r] = negX; Yr[r] = negY; }
+                    dgM = negM; dgX = negX; dgY = negY;
+                }
             }
         }
         // ------------------------------------------------------------------ terminal cell
@@ -172,7 +185,8 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
                               ((uint32_t)prio_to_state(2, prm) << 4);
         __syncwarp();
-        const int len = wf_traceback<ROWW, R>(win, tb, (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap, ox, oy, lane);
+        const int len = wf_traceback<ROWW, R, (R >= 2 ? R : 0)>(win, tb, (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap, ox, oy, lane,
+                                                               R >= 2 ? h.tbk * 0x01010101u : 0u);
         if (lane == 0) { slots[sid].score = score; slots[sid].len = len; }
         __syncwarp();
     }
@@ -194,7 +208,10 @@ cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Sl
     if (cls == CLS_WARP2) launch_wf16_t<1>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
     else if (cls == CLS_WARP4) launch_wf16_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
     else if (cls == CLS_WARP8) launch_wf16_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
-    else launch_wf16_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    else {
+        launch_wf16_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+        launch_wf16_t<16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    }
     return cudaGetLastError();
 }
 
