@@ -580,6 +580,14 @@ int run_pipeline(dbga_ctx *ctx) {
                 ctx->launches += 1;
             }
         }
+        if (ctx->grid_warp && ctx->dp.h.ok) {
+            bool seen = false;
+            for (int cls = CLS_WARP2; cls <= CLS_WARP16; ++cls) seen = seen || ctx->seen_work[cls];
+            DBGA_CUDA_CHECK(launch_dp_traceback16(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls,
+                                                  seen ? ctx->num_sms * 16 : ctx->num_sms, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                                  (const uint8_t *)ctx->d_tb.p, st));
+            ctx->launches += 1;
+        }
         if (ctx->grid_cta) {
             const bool seen = ctx->seen_work[CLS_CTA];
             DBGA_CUDA_CHECK(launch_dp_long(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,

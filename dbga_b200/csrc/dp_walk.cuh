@@ -47,29 +47,42 @@ __device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_per
 // shared memory owned by the warp.  st: state chosen at the terminal cell.  pmap: packed table
 // tag -> state (0 = M, 1 = X, 2 = Y).  Rows are written reversed at ox / oy; returns the
 // number of alignment columns.
-// PR > 0: the packed kernel's byte order inside a lane's 2 * PR bytes (pairs of rows (r, r+1) of the
-// low and high half-lanes: [low r, low r+1, high r, high r+1]); PR = 0: bytes in matrix-row order.
-template <int PR>
-__device__ __forceinline__ int wf_col(int c) {
-    if constexpr (PR == 0) return c;
-    else {
-        const int q = c % (2 * PR), hh = q / PR, r = q % PR;
-        return c - q + 4 * (r >> 1) + 2 * hh + (r & 1);
-    }
+// Table geometry.  roww_sh: log2 of the bytes per step row (= matrix rows per block); rdiv_sh:
+// log2 of the matrix rows per wavefront lane (half-lane for the packed kernel); pr_sh >= 1: the
+// packed kernel's byte order inside a lane's 2 * PR bytes, PR = 1 << pr_sh (pairs of rows
+// (r, r+1) of the low and high half-lanes: [low r, low r+1, high r, high r+1]), each group of
+// four bytes stored as one word less bias4 (exact 32-bit arithmetic, see stage3_dp16.cu);
+// pr_sh < 0: bytes in matrix-row order, no bias.  The 32-bit kernels pass constants, which
+// fold away after inlining.
+struct WalkGeom {
+    int roww_sh, rdiv_sh, pr_sh;
+    uint32_t bias4;
+};
+
+__device__ __forceinline__ int wf_col(int c, int pr_sh) {
+    if (pr_sh < 0) return c;
+    const int pr = 1 << pr_sh;
+    const int q = c & (2 * pr - 1), hh = q >> pr_sh, r = q & (pr - 1);
+    return c - q + 4 * (r >> 1) + 2 * hh + (r & 1);
 }
 
-template <int ROWW, int RDIV, int PR = 0>
+// One warp walks; every lane runs the same walk (uniform control flow).  win: 32 x 64 bytes of
+// shared memory owned by the warp.  st: state chosen at the terminal cell.  pmap: packed table
+// tag -> state (0 = M, 1 = X, 2 = Y).  Rows are written reversed at ox / oy; returns the
+// number of alignment columns.
 __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *__restrict__ tb, int64_t tb_rows,
                                             const uint8_t *__restrict__ xs, const uint8_t *__restrict__ ys, int m, int n,
                                             int st, uint32_t pmap, uint8_t *__restrict__ ox, uint8_t *__restrict__ oy, int lane,
-                                            uint32_t bias4 = 0u) {
-    constexpr int WIN_W = (ROWW >= 64) ? 64 : ROWW;       // traceback window width in bytes
+                                            const WalkGeom g) {
+    constexpr int WIN_W = 64;                        // traceback window width in bytes (every row is >= 64 bytes)
+    const int roww_mask = (1 << g.roww_sh) - 1;
     int i = m, j = n, len = 0;
     // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
     // runs the same walk (uniform control flow).  Only the kind of each step is kept, as
     // two bit masks per group of 32 steps (bit t of mY: step t consumes a seq-1 base, of
     // mX: a seq-2 base); a full group is turned into the two rows' characters by all 32
-    // lanes at once, so the sequence loads stay off the walk's dependency chain.
+    // lanes at once, so the sequence loads stay off the walk's dependency chain: a group's
+    // characters are loaded when it is full and stored when the next one is (or at the end).
     // In state M the 32 lanes probe the next 32 cells of the diagonal together and the
     // walk jumps over the whole run of M -> M steps (most of the path between similar
     // sequences); everything else goes one cell at a time.
@@ -78,11 +91,19 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
     int pos = 0, gbase = 0;
     int ib = m, jb = n;                              // (i, j) before the first step of the group
     const uint32_t lt = (1u << lane) - 1u;
+    uint8_t pend_x = 0, pend_y = 0;                  // characters of the previous group, not stored yet
+    int pend_at = -1;
+    auto drain = [&]() {
+        if (pend_at >= 0) { ox[pend_at] = pend_x; oy[pend_at] = pend_y; }
+        pend_at = -1;
+    };
     auto flush = [&](int cnt) {
+        drain();
         if (lane < cnt) {
             const int it = ib - __popc(mY & lt), jt = jb - __popc(mX & lt);
-            ox[gbase + lane] = ((mY >> lane) & 1u) ? xs[it - 1] : (uint8_t)'-';
-            oy[gbase + lane] = ((mX >> lane) & 1u) ? ys[jt - 1] : (uint8_t)'-';
+            pend_x = ((mY >> lane) & 1u) ? xs[it - 1] : (uint8_t)'-';
+            pend_y = ((mX >> lane) & 1u) ? ys[jt - 1] : (uint8_t)'-';
+            pend_at = gbase + lane;
         }
         ib -= __popc(mY); jb -= __popc(mX);
         gbase += cnt; mY = 0; mX = 0; pos = 0;
@@ -98,54 +119,51 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
             if (pos == 32) flush(32);
         }
     };
-    // PR > 0: the packed kernel stores each group of four bytes as one word less bias4 (exact
-    // 32-bit arithmetic, see stage3_dp16.cu); bytes are read through their word
     auto tb_byte = [&](int r, int c) -> uint32_t {
-        if constexpr (PR == 0) return win[r][c];
-        else return ((*reinterpret_cast<const uint32_t *>(&win[r][c & ~3]) + bias4) >> (8 * (c & 3))) & 0xFFu;
+        if (g.pr_sh < 0) return win[r][c];
+        return ((*reinterpret_cast<const uint32_t *>(&win[r][c & ~3]) + g.bias4) >> (8 * (c & 3))) & 0xFFu;
     };
     while (i > 0 || j > 0) {
         if (i == 0) { emit(2, j); break; }           // first row / column: one long gap
         if (j == 0) { emit(1, i); break; }
         const int i0 = i - 1;
-        const int blk = i0 / (ROWW), cb = i0 % (ROWW);      // (pass * GW + warp), l * R + r
-        const int row = j + cb / RDIV;
+        const int blk = i0 >> g.roww_sh, cb = i0 & roww_mask;      // (pass * GW + warp), l * R + r
+        const int row = j + (cb >> g.rdiv_sh);
         if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= (unsigned)WIN_W) {
             __syncwarp();
             win_blk = blk; win_row_hi = row;
-            win_col_lo = (WIN_W == 64) ? max(0, (cb & ~31) - 32) : 0;
+            win_col_lo = max(0, (cb & ~31) - 32);
             const int rr = row - lane;
             uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
             if (rr >= 1) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(tb + ((int64_t)blk * tb_rows + rr) * (int64_t)(ROWW) + win_col_lo);
-                a = p[0]; b = p[1];
-                if constexpr (WIN_W == 64) { c4 = p[2]; d4 = p[3]; }
+                const uint4 *p = reinterpret_cast<const uint4 *>(tb + (((int64_t)blk * tb_rows + rr) << g.roww_sh) + win_col_lo);
+                a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
             }
             uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
-            dst[0] = a; dst[1] = b;
-            if constexpr (WIN_W == 64) { dst[2] = c4; dst[3] = d4; }
+            dst[0] = a; dst[1] = b; dst[2] = c4; dst[3] = d4;
             __syncwarp();
         }
         if (st == 0) {
             const int il = i0 - lane, jl = j - lane;
             bool ok = false;
             if (il >= 0 && jl >= 1) {
-                const int bl = il / (ROWW), cl = il % (ROWW);
-                const unsigned dr = (unsigned)(win_row_hi - (jl + cl / RDIV)), dc = (unsigned)(cl - win_col_lo);
+                const int bl = il >> g.roww_sh, cl = il & roww_mask;
+                const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh))), dc = (unsigned)(cl - win_col_lo);
                 if (bl == win_blk && dr < 32u && dc < (unsigned)WIN_W)
-                    ok = ((pmap >> (2 * (tb_byte(dr, wf_col<PR>(cl) - win_col_lo) & 3u))) & 3u) == 0u;
+                    ok = ((pmap >> (2 * (tb_byte(dr, wf_col(cl, g.pr_sh) - win_col_lo) & 3u))) & 3u) == 0u;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, ok);
             const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
             if (c > 0) { emit(0, c); i -= c; j -= c; continue; }
         }
-        const uint32_t d = tb_byte(win_row_hi - row, wf_col<PR>(cb) - win_col_lo);
+        const uint32_t d = tb_byte(win_row_hi - row, wf_col(cb, g.pr_sh) - win_col_lo);
         emit(st, 1);
         const uint32_t tag = (d >> (2 * st)) & 3u;
         i -= (st != 2); j -= (st != 1);
         st = (int)((pmap >> (2 * tag)) & 3u);
     }
     if (pos) flush(pos);
+    drain();
     return len;
 }
 

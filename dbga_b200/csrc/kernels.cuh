@@ -70,6 +70,10 @@ cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot
 cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                   const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
                                   uint8_t *tb, cudaStream_t st);
+// traceback of everything the packed kernels processed, all four warp classes in one launch
+cudaError_t launch_dp_traceback16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
+                                  int64_t list_cap, const unsigned int *counts_dev, int grid, DpParams prm,
+                                  uint8_t *strbuf, const uint8_t *tb, cudaStream_t st);
 cudaError_t launch_dp_long(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                            const unsigned int *count_dev, int grid_clusters, int grid_ctas, unsigned int few, DpParams prm,
                            uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);

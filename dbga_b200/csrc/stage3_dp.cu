@@ -583,7 +583,9 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
             // state reached through a traceback tag: packed table prio -> state (0 = M, 1 = X, 2 = Y)
             const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
                                   ((uint32_t)prio_to_state(2, prm) << 4);
-            const int len = wf_traceback<32 * R, R>(win, tb, tb_rows, xs, ys, m, n, st, pmap, ox, oy, lane);
+            constexpr int RSH = R == 2 ? 1 : (R == 4 ? 2 : (R == 8 ? 3 : 4));
+            static_assert((1 << RSH) == R, "rows per lane must be 2, 4, 8 or 16");
+            const int len = wf_traceback(win, tb, tb_rows, xs, ys, m, n, st, pmap, ox, oy, lane, WalkGeom{5 + RSH, RSH, -1, 0u});
             if (lane == 0) { slots[sid].score = score - prm.ge_raw * (m + n); slots[sid].len = len; }
         }
         __syncthreads();

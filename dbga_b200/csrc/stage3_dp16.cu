@@ -40,11 +40,10 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 __device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 
 template <int R, bool XY>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, R == 16 ? 12 : 24)
 dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
                uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool) {
-    __shared__ __align__(16) uint8_t win[32][64];      // traceback window
     __shared__ uint32_t s_lut[4];
     const int lane = threadIdx.x;
     const Dp16 &h = prm.h;
@@ -180,21 +179,53 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         if (cx > best) { best = cx; st = 1; }
         if (cy > best) { best = cy; st = 2; }
         const int score = (best >> 2) + h.off - prm.ge_raw * (m + n);
-        const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
-        uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
-        const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
-                              ((uint32_t)prio_to_state(2, prm) << 4);
-        __syncwarp();
-        const int len = wf_traceback<ROWW, R, (R >= 2 ? R : 0)>(win, tb, (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap, ox, oy, lane,
-                                                               R >= 2 ? h.tbk * 0x01010101u : 0u);
-        if (lane == 0) { slots[sid].score = score; slots[sid].len = len; }
-        __syncwarp();
+        // the traceback runs in dp_tb16_kernel; the terminal state travels in slot.len
+        if (lane == 0) { slots[sid].score = score; slots[sid].len = st; }
+    }
+}
+
+// Traceback of every segment the packed forward kernels processed: one warp per segment over
+// the four warp-class lists.  Kept out of the forward kernels because the walk is a chain of
+// memory latencies (window loads, character loads): inside them it held a third of the warps
+// of an SM sub-partition off the ALU pipe; here 64 warps per SM overlap their latencies.
+constexpr int TB16_WARPS = 4;
+__global__ void __launch_bounds__(TB16_WARPS * 32)
+dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+               const int32_t *__restrict__ lists, int64_t list_cap, const unsigned int *__restrict__ counts_dev,
+               DpParams prm, uint8_t *__restrict__ strbuf, const uint8_t *__restrict__ tb_pool) {
+    __shared__ __align__(16) uint8_t win[TB16_WARPS][32][64];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned int gw = blockIdx.x * TB16_WARPS + w, nw = gridDim.x * TB16_WARPS;
+    const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
+                          ((uint32_t)prio_to_state(2, prm) << 4);
+    for (int cls = CLS_WARP2; cls <= CLS_WARP16; ++cls) {
+        const unsigned int count = counts_dev[cls];
+        const int32_t *list = lists + (int64_t)cls * list_cap;
+        for (unsigned int item = gw; item < count; item += nw) {
+            const int sid = list[item];
+            const Slot s = slots[sid];
+            const int m = s.m, n = s.n;
+            const int R = wf16_pick(prm.h, cls, m, n);
+            if (!R) continue;                                // a 32-bit kernel did forward pass and traceback
+            const PairDesc pd = pairs[s.pair];
+            const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
+            const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
+            uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
+            const int rsh = 31 - __clz(R);
+            const WalkGeom g{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u};
+            const int len = wf_traceback(win[w], tb_pool + s.tb_off, (int64_t)n + WF16_TB_PAD, xs, ys, m, n, s.len, pmap,
+                                         ox, oy, lane, g);
+            if (lane == 0) slots[sid].len = len;
+            __syncwarp();
+        }
     }
 }
 
 template <int R>
 static void launch_wf16_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                           const unsigned int *count_dev, const DpParams &prm, uint8_t *strbuf, uint8_t *tb, cudaStream_t st) {
+    // grid comes sized for 16 warps per SM; these kernels fit 24 (R <= 8) or 12 (R = 16)
+    grid = grid * (R == 16 ? 12 : 24) / 16;
     if (prm.xy) dp_wf16_kernel<R, true><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
     else dp_wf16_kernel<R, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
 }
@@ -212,6 +243,14 @@ cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Sl
         launch_wf16_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
         launch_wf16_t<16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dp_traceback16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
+                                  int64_t list_cap, const unsigned int *counts_dev, int grid, DpParams prm,
+                                  uint8_t *strbuf, const uint8_t *tb, cudaStream_t st) {
+    if (grid <= 0 || !prm.h.ok) return cudaSuccess;
+    dp_tb16_kernel<<<grid, TB16_WARPS * 32, 0, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, prm, strbuf, tb);
     return cudaGetLastError();
 }
 
