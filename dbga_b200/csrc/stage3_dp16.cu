@@ -40,7 +40,7 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 __device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 
 template <int R, bool XY>
-__global__ void __launch_bounds__(32, R == 16 ? 12 : 24)
+__global__ void __launch_bounds__(32, R == 16 ? 12 : 20)
 dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
                uint8_t *__restrict__ strbuf, uint8_t *__restrict__ tb_pool) {
@@ -69,7 +69,6 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         const PairDesc pd = pairs[s.pair];
         const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
         uint8_t *tb = tb_pool + s.tb_off;
-        const int nl = (m + 2 * R - 1) / (2 * R);            // lanes with rows
         uint32_t lutA[R], lutB[R], Mr[R], Xr[R], Yr[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -81,18 +80,20 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         uint32_t dgM = negM, dgX = negX, dgY = negY;
         // the terminal cell: half-lane ve, row re of it, reached at step te
         const int ve = (m - 1) / R, re = (m - 1) % R, te = n + ve, le = ve >> 1;
-        uint32_t eM = 0, eX = 0, eY = 0;
-        uint32_t yprev = 0, sel_cur = 0xC480u, sel_prev = 0xC480u;
-        uint8_t *tbw = tb + lane * 2 * R;
-        // Steps run in whole chunks of 16 (one word of seq2 codes for lane 0: the code of column t
-        // is bits 2s of the word loaded at ys - 1 + t0, the next word in flight).  No lane is
-        // masked: a lane computes garbage before its first column (and after its last), into its
-        // own registers and its own traceback bytes, and is put back to minus infinity at the end
-        // of step 2 * lane - 1, just before its low half reaches column 0.
-        const int T = n + 2 * nl;
-        const int reset_at = 2 * lane - 1;
-        uint32_t wy_next = load_codes16(ys - 1, n + 1);
-        for (int t0 = 0; t0 < T; t0 += 16) {
+        // Steps run in whole chunks of 16 (one word of seq2 codes for lane 0) that end exactly at
+        // step te, so the terminal cell is still in its registers after the loop; the first chunk
+        // may start at a negative step.  No lane is masked.  Before its low half reaches column 0 a
+        // lane sees the initial selector 0x8888 (score 0 or -1: the sign of a LUT byte), and
+        // minus infinity in, minus infinity out: its registers only drift down by at most 4 per
+        // step.  After its last column it computes garbage nobody reads.  Traceback rows are
+        // offset by 16 so that negative steps have somewhere to write.
+        const int nch = (te + 16) >> 4, t_start = te + 1 - 16 * nch;
+        uint32_t yprev = 0, sel_cur = 0x8888u, sel_prev = 0x8888u;
+        uint8_t *tbw = tb + 16 * ROWW + lane * 2 * R;
+        // code of column t = bits 2 (t - t0) of the chunk's word; t0 <= 0 only in the first chunk,
+        // whose word is built from ys[0..15] so that nothing before ys is read
+        uint32_t wy_next = (uint32_t)((unsigned long long)load_codes16(ys, n) << (2 * (1 - t_start)));
+        for (int t0 = t_start; t0 <= te; t0 += 16) {
             const uint32_t wy = wy_next;
             wy_next = load_codes16(ys + 15 + t0, n - 15 - t0);
 #pragma unroll 2
@@ -100,7 +101,7 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                 const int t = t0 + sidx;
                 // lane 0: selector for columns (t, t - 1); lane l gets lane l-1's selector of two steps ago
                 const uint32_t ycur = (wy >> (2 * sidx)) & 3u;
-                const uint32_t sel0 = 0xC480u + 0x11u * ycur + 0x1100u * yprev;
+                const uint32_t sel0 = t < 0 ? 0x8888u : 0xC480u + 0x11u * ycur + 0x1100u * yprev;   // t < 0: lane 0 is not running yet either
                 yprev = ycur;
                 const uint32_t sel_in = __shfl_up_sync(FULL, sel_prev, 1);
                 sel_prev = sel_cur;
@@ -156,20 +157,14 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                         *reinterpret_cast<uint4 *>(tbp + 16) = make_uint4(E[4], E[5], E[6], E[7]);
                     }
                 }
-                if (t == te && lane == le) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r)
-                        if (r == re) { eM = Mr[r]; eX = Xr[r]; eY = Yr[r]; }
-                }
                 dgM = uM; dgX = uX; dgY = uY;
-                if (t == reset_at) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) { Mr[r] = negM; Xr[r] = negX; Yr[r] = negY; }
-                    dgM = negM; dgX = negX; dgY = negY;
-                }
             }
         }
         // ------------------------------------------------------------------ terminal cell
+        uint32_t eM = 0, eX = 0, eY = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == re) { eM = Mr[r]; eX = Xr[r]; eY = Yr[r]; }
         eM = __shfl_sync(FULL, eM, le); eX = __shfl_sync(FULL, eX, le); eY = __shfl_sync(FULL, eY, le);
         const int sh = (ve & 1) ? 16 : 0;
         const int vM = (int)(int16_t)(eM >> sh), vX = (int)(int16_t)(eX >> sh), vY = (int)(int16_t)(eY >> sh);
@@ -213,7 +208,7 @@ dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
             uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
             const int rsh = 31 - __clz(R);
             const WalkGeom g{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u};
-            const int len = wf_traceback(win[w], tb_pool + s.tb_off, (int64_t)n + WF16_TB_PAD, xs, ys, m, n, s.len, pmap,
+            const int len = wf_traceback(win[w], tb_pool + s.tb_off + (16 << g.roww_sh), (int64_t)n + WF16_TB_PAD, xs, ys, m, n, s.len, pmap,
                                          ox, oy, lane, g);
             if (lane == 0) slots[sid].len = len;
             __syncwarp();
@@ -224,8 +219,8 @@ dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
 template <int R>
 static void launch_wf16_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                           const unsigned int *count_dev, const DpParams &prm, uint8_t *strbuf, uint8_t *tb, cudaStream_t st) {
-    // grid comes sized for 16 warps per SM; these kernels fit 24 (R <= 8) or 12 (R = 16)
-    grid = grid * (R == 16 ? 12 : 24) / 16;
+    // grid comes sized for 16 warps per SM; these kernels fit 20 (R <= 8) or 12 (R = 16)
+    grid = grid * (R == 16 ? 12 : 20) / 16;
     if (prm.xy) dp_wf16_kernel<R, true><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
     else dp_wf16_kernel<R, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
 }
