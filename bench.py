@@ -12,7 +12,8 @@ path; time = max over ranks.
 
 JSON keys beyond the base contract: `roofline` (dominant kernel vs measured HBM peak),
 `cpu_baseline` (oracle C port on the host cores), `dp` (stage-3 GCUPS vs the measured
-integer-pipe rate), `stages_ms`, `cycle_frac`.
+integer-pipe rate on the workload, and `dp.microbench`: the same on 1024 x 1024 segments),
+`stages_ms`, `cycle_frac`.
 """
 from __future__ import annotations
 
@@ -286,6 +287,29 @@ def run_ours(args):
           "roofline = measured int32 5add:4max mix rate / 9 ops per cell; cfg3 segments are ~10x10 so this "
           "stage is latency/launch bound here (see DESIGN.md DP microbenchmark)"}
 
+    # ---------------- DP microbenchmark (the integer roofline is only testable on long
+    # segments): 3814 uniform 1024 x 1024 global alignments, device-resident, stage-3 time from the
+    # library's CUDA events on the launching stream (forward kernels + traceback kernel)
+    if not args.no_dp_micro:
+        L, Pm = 1024, 3814
+        mb, mo = synth_batch(Pm, L, 0.05, 0.01, seed=L)
+        d_m = torch.from_numpy(np.concatenate([mb, np.zeros(64, np.uint8)])).to(dev)
+        torch.cuda.synchronize()
+        alm = Aligner(local)
+        alm.plan(mo, alm.params(1), global_only=True)
+        t3 = []
+        for it in range(6):
+            alm.run(d_m.data_ptr())
+            rm = alm.fetch(unpack=False)
+            if it >= 3:
+                t3.append(rm.ms_stage3)
+        mcells = int(rm.dp_cells_total)
+        mg = mcells / (min(t3) * 1e-3) / 1e9
+        dp["microbench"] = {"workload": f"{Pm} global alignments of {L} x {L} (5 % substitutions, 1 % indels)",
+                            "cells": mcells, "stage3_ms": min(t3), "gcups": mg, "frac": mg / roof_gcups,
+                            "kernel": "dp_wf16_kernel<16> (packed int16x2 wavefront) + dp_tb16_kernel"}
+        alm.close()
+
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -335,6 +359,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=50_000, help="pairs per CPU-baseline pass")
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dp-micro", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

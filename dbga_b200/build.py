@@ -54,6 +54,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(l)
     if jobs or force or _stale(LIB, objs):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lpthread"])
+    # issue-rate microbenchmark of the DP cell's instructions (tools/pipe_rates.cu), a standalone binary
+    tool_src = os.path.join(os.path.dirname(HERE), "tools", "pipe_rates.cu")
+    tool_bin = os.path.join(os.path.dirname(HERE), "tools", "bin", "pipe_rates")
+    if os.path.exists(tool_src) and (force or _stale(tool_bin, [tool_src])):
+        os.makedirs(os.path.dirname(tool_bin), exist_ok=True)
+        run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", tool_bin, tool_src])
     return LIB
 
 
