@@ -214,6 +214,7 @@ int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
     if (h.ok) {
         auto dup = [](int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; };
         h.off = 7050;
+        h.pair = getenv("DBGA_WF16_NOPAIR") == nullptr;
         h.G = dup(4 * (d.ge_raw - d.go_raw));
         h.tagM = dup(ORDER_PRIO[p.pred_order][0]);
         h.tagX = dup(ORDER_PRIO[p.pred_order][1]);
@@ -572,7 +573,7 @@ int run_pipeline(dbga_ctx *ctx) {
                                                           &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,
                                                           (uint8_t *)ctx->d_tb.p, st));
                     ctx->launches += cls == CLS_WARP16 ? 2 : 1;
-                    if (cls != CLS_WARP16 && wf16_ok(ctx->dp.h, rows16, 1 << 30, wf_rows_per_lane(cls) / 2)) continue;
+                    if (cls != CLS_WARP16 && wf16_pick(ctx->dp.h, cls, rows16, 1 << 30)) continue;
                 }
                 DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
                                                     &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,

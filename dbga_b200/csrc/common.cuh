@@ -95,6 +95,7 @@ struct Dp16 {
     int32_t per_step;         // max(0, largest substitution score) + 2 ge: growth of H^ per diagonal step
     int32_t ulimit;           // largest H^ the encoding can hold
     int32_t ok;
+    int32_t pair;             // two segments per warp (dp_wf16p_kernel) for segments of up to 512 rows
 };
 
 struct DpParams {
@@ -118,9 +119,19 @@ __host__ __device__ inline bool wf16_ok(const Dp16 &h, int m, int n, int R16) {
     const long long lim = mp < n + 1 ? mp : n + 1;
     return (long long)h.per_step * lim + 64 <= (long long)h.ulimit;
 }
-// Rows per half-lane of the packed kernel that takes segment (m, n) of warp class cls, 0 = none
-// (the class's 32-bit kernel runs it).  The open-ended class splits at 512 rows.
+// Which packed kernel takes segment (m, n) of warp class cls: 0 = none (the class's 32-bit kernel
+// runs it); R = the half-lane kernel with R rows per half-lane; WF16_PAIR + R = the two-segments-
+// per-warp kernel with R rows per lane (h.pair: every segment of up to 32 R rows of the class,
+// all of whose cells -- padding rows and the partner's extra columns included -- stay below
+// the ceiling).  The open-ended class splits at 512 rows.
+constexpr int WF16_PAIR = 64;
 __host__ __device__ inline int wf16_pick(const Dp16 &h, int cls, int m, int n) {
+    if (!h.ok) return 0;
+    if (h.pair) {
+        const int R = wf_rows_per_lane(cls);
+        // (not in the open-ended class: 16 rows per lane for two segments cost more registers than they save)
+        if (cls != CLS_WARP16 && m <= 32 * R && (long long)h.per_step * (32 * R) + 64 <= (long long)h.ulimit) return WF16_PAIR + R;
+    }
     const int r16 = cls == CLS_WARP2 ? 1 : (cls == CLS_WARP4 ? 2 : (cls == CLS_WARP8 ? 4 : (m <= 512 ? 8 : 16)));
     return wf16_ok(h, m, n, r16) ? r16 : 0;
 }

@@ -39,6 +39,45 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
 }
 __device__ __forceinline__ uint32_t dup16(int v) { return ((uint32_t)v & 0xFFFFu) * 0x10001u; }
 
+// The per-lane constants of the packed cell.
+struct Wf16Consts {
+    uint32_t G, tagX, tagY, cm1, c4, c16;
+};
+
+// One step of one lane: R packed rows at the lane's current column(s).  (dM,dX,dY): the row above
+// at the previous column, (aM,aX,aY): the row above at this column; Mr/Xr/Yr: the lane's rows at
+// the previous column in, at this column out.  D[r]: raw traceback fields of row r's two cells
+// (tt & 3, (u & 3) - pX, (v & 3) - pY per half as et + 4 eu + 16 ev, exact 32-bit arithmetic:
+// the borrows between fields cancel once tbk is added to every byte).
+// ALU pipe (the bottleneck: half issue rate): three maxes, three bit strips, the score PRMT and
+// the packed add per row.  Everything else is IMAD on the FMA pipe, with multipliers the
+// compiler cannot see through (a literal * 4 would become LEA / SHL on the ALU pipe).
+template <int R, bool XY>
+__device__ __forceinline__ void wf16_rows(uint32_t (&Mr)[R], uint32_t (&Xr)[R], uint32_t (&Yr)[R], uint32_t (&D)[R],
+                                          const uint32_t (&lutA)[R], const uint32_t (&lutB)[R], uint32_t sel,
+                                          uint32_t dM, uint32_t dX, uint32_t dY, uint32_t aM, uint32_t aX, uint32_t aY,
+                                          const Wf16Consts &c) {
+    constexpr uint32_t KS = 0xFFFCFFFCu;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t oM = Mr[r], oX = Xr[r], oY = Yr[r];
+        const uint32_t tt = __vimax3_s16x2(dM, dX, dY);
+        uint32_t u = __viaddmax_s16x2(aM, c.G, aX);
+        uint32_t v = __viaddmax_s16x2(oM, c.G, oY);
+        if (XY) {
+            u = __viaddmax_s16x2(aY, c.G, u);
+            v = __viaddmax_s16x2(oX, c.G, v);
+        }
+        const uint32_t ts = tt & KS;
+        Xr[r] = (u & KS) | c.tagX;
+        Yr[r] = (v & KS) | c.tagY;
+        Mr[r] = __vadd2(ts, prmt(lutA[r], lutB[r], sel));       // LUT bytes carry M's tag
+        const uint32_t et = imad(ts, c.cm1, tt), eu = imad(Xr[r], c.cm1, u), ev = imad(Yr[r], c.cm1, v);
+        D[r] = imad(ev, c.c16, imad(eu, c.c4, et));
+        dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
+    }
+}
+
 template <int R, bool XY>
 __global__ void __launch_bounds__(32, R == 16 ? 12 : 20)
 dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
@@ -49,12 +88,12 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
     const Dp16 &h = prm.h;
     if (lane < 4) s_lut[lane] = h.lut[lane];
     __syncwarp();
-    constexpr uint32_t KS = 0xFFFCFFFCu, FULL = 0xffffffffu;
-    // multipliers the compiler cannot see through: a literal * 4 would become LEA / SHL on the ALU pipe
-    const uint32_t cm1 = h.mul[0], c4 = h.mul[1], c16 = h.mul[2], c256 = h.mul[3];
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t c256 = h.mul[3];
+    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], h.mul[1], h.mul[2]};
     const uint32_t K1 = h.tbk * 0x00010001u;
     constexpr int ROWW = 64 * R;
-    const uint32_t G = h.G, tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
+    const uint32_t tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
     const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
     // row 0 as seen by lane 0's low half (arrives where the shuffle would put it: high half)
     const uint32_t r0M0 = (dup16(h.q0) | tagM) << 16, r0Mn = negM << 16, r0X = negX << 16,
@@ -113,30 +152,8 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                 if (lane == 0) { sM = t == 0 ? r0M0 : r0Mn; sX = r0X; sY = t >= 1 ? r0Y : r0Yn; }
                 const uint32_t uM = prmt(sM, Mr[R - 1], 0x5432u), uX = prmt(sX, Xr[R - 1], 0x5432u),
                                uY = prmt(sY, Yr[R - 1], 0x5432u);
-                uint32_t dM = dgM, dX = dgX, dY = dgY, aM = uM, aX = uX, aY = uY;
                 uint32_t D[R];
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const uint32_t oM = Mr[r], oX = Xr[r], oY = Yr[r];
-                    const uint32_t tt = __vimax3_s16x2(dM, dX, dY);
-                    uint32_t u = __viaddmax_s16x2(aM, G, aX);
-                    uint32_t v = __viaddmax_s16x2(oM, G, oY);
-                    if (XY) {
-                        u = __viaddmax_s16x2(aY, G, u);
-                        v = __viaddmax_s16x2(oX, G, v);
-                    }
-                    // ALU pipe (the bottleneck: half issue rate): three maxes, three bit strips,
-                    // the score PRMT and the packed add.  Everything else is IMAD on the FMA pipe.
-                    const uint32_t ts = tt & KS;
-                    Xr[r] = (u & KS) | tagX;
-                    Yr[r] = (v & KS) | tagY;
-                    Mr[r] = __vadd2(ts, prmt(lutA[r], lutB[r], sel_cur));       // LUT bytes carry M's tag
-                    // winner tags as exact integer differences (tt & 3, (u & 3) - pX, (v & 3) - pY per half;
-                    // borrows between the fields cancel when the walker adds tbk to every byte of the word)
-                    const uint32_t et = imad(ts, cm1, tt), eu = imad(Xr[r], cm1, u), ev = imad(Yr[r], cm1, v);
-                    D[r] = imad(ev, c16, imad(eu, c4, et));
-                    dM = oM; dX = oX; dY = oY; aM = Mr[r]; aX = Xr[r]; aY = Yr[r];
-                }
+                wf16_rows<R, XY>(Mr, Xr, Yr, D, lutA, lutB, sel_cur, dgM, dgX, dgY, uM, uX, uY, cc);
                 // traceback bytes of the lane, per pair of rows (r, r+1): [low r, low r+1, high r, high r+1]
                 uint8_t *tbp = tbw + (int64_t)t * ROWW;
                 if constexpr (R == 1) {
@@ -179,6 +196,144 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
     }
 }
 
+// ---------------------------------------------------------------------- two segments per warp
+// Throughput form for segments of up to 32 R rows: the low halves of a warp's registers carry one
+// segment (A), the high halves another (B, the next entry of the class list), both at column
+// t - lane.  Same cell, same encoding; no half-lane skew (32 lanes of skew instead of 64, plain
+// shuffles for the row above), and the per-step overhead is shared by two segments.  Rows and
+// columns run to the larger of the two segments; the smaller one computes cells nobody reads
+// (seq2 codes past its end are 0, rows past its end use base code 0: all below the ceiling
+// wf16_pick checks for 32 R rows).  Each segment has its own traceback table, in the 32-bit
+// kernels' layout (row = step + 16, byte = matrix row).
+template <int R, bool XY>
+__global__ void __launch_bounds__(32, R == 16 ? 12 : 20)
+dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+                const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
+                uint8_t *__restrict__ tb_pool) {
+    __shared__ uint32_t s_lut[4];
+    const int lane = threadIdx.x;
+    const Dp16 &h = prm.h;
+    if (lane < 4) s_lut[lane] = h.lut[lane];
+    __syncwarp();
+    constexpr uint32_t FULL = 0xffffffffu;
+    constexpr int ROWW = 32 * R;
+    const uint32_t c256 = h.mul[3], K4 = h.tbk * 0x01010101u;
+    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], h.mul[1], h.mul[2]};
+    const uint32_t tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
+    const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
+    const uint32_t r0M0 = dup16(h.q0) | tagM, r0Y = dup16(h.qy0) | tagY;
+    const unsigned int count = *count_dev;
+
+    for (unsigned int g = blockIdx.x; 2 * g < count; g += gridDim.x) {
+        // the two list entries of this warp; an entry another kernel takes leaves its half idle
+        int sid[2], m[2], n[2];
+        const uint8_t *xs[2], *ys[2];
+        uint8_t *tb[2];
+        bool have[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const unsigned int item = 2 * g + e;
+            have[e] = false; sid[e] = 0; m[e] = 0; n[e] = 0; xs[e] = seqs; ys[e] = seqs; tb[e] = tb_pool;
+            if (item < count) {
+                sid[e] = list[item];
+                const Slot s = slots[sid[e]];
+                if (wf16_pick(h, s.cls, s.m, s.n) == WF16_PAIR + R) {
+                    const PairDesc pd = pairs[s.pair];
+                    have[e] = true; m[e] = s.m; n[e] = s.n;
+                    xs[e] = seqs + pd.off0 + s.x0; ys[e] = seqs + pd.off1 + s.y0;
+                    tb[e] = tb_pool + s.tb_off + 16 * ROWW + lane * R;
+                }
+            }
+        }
+        if (!have[0] && !have[1]) continue;
+        uint32_t lutA[R], lutB[R], Mr[R], Xr[R], Yr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = lane * R + r;                       // 0-based matrix row
+            lutA[r] = s_lut[i < m[0] ? base_code(xs[0][i]) : 0];
+            lutB[r] = s_lut[i < m[1] ? base_code(xs[1][i]) : 0];
+            Mr[r] = negM; Xr[r] = negX; Yr[r] = negY;
+        }
+        uint32_t dgM = negM, dgX = negX, dgY = negY;
+        // a segment's terminal cell is reached at step te = n + (lane of row m)
+        int te[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) te[e] = have[e] ? n[e] + (m[e] - 1) / R : -1;
+        const int t_end = max(te[0], te[1]);
+        const int nch = (t_end + 16) >> 4, t_start = t_end + 1 - 16 * nch;      // whole chunks of 16 steps ending at t_end
+        uint32_t sel_cur = 0x8888u;                           // idle lanes: score 0 or -1, minus infinity stays put
+        uint32_t wnA = (uint32_t)((unsigned long long)load_codes16(ys[0], n[0]) << (2 * (1 - t_start)));
+        uint32_t wnB = (uint32_t)((unsigned long long)load_codes16(ys[1], n[1]) << (2 * (1 - t_start)));
+        for (int t0 = t_start; t0 <= t_end; t0 += 16) {
+            const uint32_t wA = wnA, wB = wnB;
+            wnA = load_codes16(ys[0] + 15 + t0, n[0] - 15 - t0);
+            wnB = load_codes16(ys[1] + 15 + t0, n[1] - 15 - t0);
+#pragma unroll 2
+            for (int sidx = 0; sidx < 16; ++sidx) {
+                const int t = t0 + sidx;
+                // lane 0: selector for column t of both segments; lane l gets lane l-1's of one step ago
+                const uint32_t yA = (wA >> (2 * sidx)) & 3u, yB = (wB >> (2 * sidx)) & 3u;
+                const uint32_t sel0 = t < 0 ? 0x8888u : 0xC480u + 0x11u * yA + 0x1100u * yB;
+                const uint32_t sel_in = __shfl_up_sync(FULL, sel_cur, 1);
+                sel_cur = lane == 0 ? sel0 : sel_in;
+                uint32_t uM = __shfl_up_sync(FULL, Mr[R - 1], 1);
+                uint32_t uX = __shfl_up_sync(FULL, Xr[R - 1], 1);
+                uint32_t uY = __shfl_up_sync(FULL, Yr[R - 1], 1);
+                if (lane == 0) { uM = t == 0 ? r0M0 : negM; uX = negX; uY = t >= 1 ? r0Y : negY; }
+                uint32_t D[R];
+                wf16_rows<R, XY>(Mr, Xr, Yr, D, lutA, lutB, sel_cur, dgM, dgX, dgY, uM, uX, uY, cc);
+                dgM = uM; dgX = uX; dgY = uY;
+                // traceback bytes: pairs of rows as one word [A r, A r+1, B r, B r+1] plus the bias, then split
+                // steps past a segment's own last one (its partner is still running) all land in one spare row
+                uint8_t *pa = tb[0] + (int64_t)min(t, te[0] + 1) * ROWW, *pb = tb[1] + (int64_t)min(t, te[1] + 1) * ROWW;
+                uint32_t E[R / 2];
+#pragma unroll
+                for (int q = 0; q < R / 2; ++q) E[q] = imad(D[2 * q + 1], c256, D[2 * q]) + K4;
+                if constexpr (R == 2) {
+                    if (have[0]) *reinterpret_cast<uint16_t *>(pa) = (uint16_t)E[0];
+                    if (have[1]) *reinterpret_cast<uint16_t *>(pb) = (uint16_t)(E[0] >> 16);
+                } else {
+                    uint32_t wa[R / 4], wb[R / 4];
+#pragma unroll
+                    for (int q = 0; q < R / 4; ++q) {
+                        wa[q] = prmt(E[2 * q], E[2 * q + 1], 0x5410u);
+                        wb[q] = prmt(E[2 * q], E[2 * q + 1], 0x7632u);
+                    }
+                    if constexpr (R == 4) {
+                        if (have[0]) *reinterpret_cast<uint32_t *>(pa) = wa[0];
+                        if (have[1]) *reinterpret_cast<uint32_t *>(pb) = wb[0];
+                    } else if constexpr (R == 8) {
+                        if (have[0]) *reinterpret_cast<uint2 *>(pa) = make_uint2(wa[0], wa[1]);
+                        if (have[1]) *reinterpret_cast<uint2 *>(pb) = make_uint2(wb[0], wb[1]);
+                    } else {
+                        static_assert(R == 16, "R must be 2, 4, 8 or 16");
+                        if (have[0]) *reinterpret_cast<uint4 *>(pa) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                        if (have[1]) *reinterpret_cast<uint4 *>(pb) = make_uint4(wb[0], wb[1], wb[2], wb[3]);
+                    }
+                }
+                // a lane that has just finished a segment's last column leaves its rows' three states in the
+                // first rows of that segment's table (free by then: only steps < 0 ever wrote there); the
+                // traceback kernel picks the terminal cell out of them
+                const int jcol = t - lane;
+                if (jcol == n[0] && have[0]) {
+                    uint16_t *eb = reinterpret_cast<uint16_t *>(tb[0] - (int64_t)16 * ROWW - lane * R) + lane * R;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        eb[r] = (uint16_t)Mr[r]; eb[ROWW + r] = (uint16_t)Xr[r]; eb[2 * ROWW + r] = (uint16_t)Yr[r];
+                    }
+                }
+                if (jcol == n[1] && have[1]) {
+                    uint16_t *eb = reinterpret_cast<uint16_t *>(tb[1] - (int64_t)16 * ROWW - lane * R) + lane * R;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        eb[r] = (uint16_t)(Mr[r] >> 16); eb[ROWW + r] = (uint16_t)(Xr[r] >> 16); eb[2 * ROWW + r] = (uint16_t)(Yr[r] >> 16);
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Traceback of every segment the packed forward kernels processed: one warp per segment over
 // the four warp-class lists.  Kept out of the forward kernels because the walk is a chain of
 // memory latencies (window loads, character loads): inside them it held a third of the warps
@@ -187,7 +342,7 @@ constexpr int TB16_WARPS = 4;
 __global__ void __launch_bounds__(TB16_WARPS * 32)
 dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                const int32_t *__restrict__ lists, int64_t list_cap, const unsigned int *__restrict__ counts_dev,
-               DpParams prm, uint8_t *__restrict__ strbuf, const uint8_t *__restrict__ tb_pool) {
+               DpParams prm, uint8_t *__restrict__ strbuf, const uint8_t *tb_pool) {
     __shared__ __align__(16) uint8_t win[TB16_WARPS][32][64];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned int gw = blockIdx.x * TB16_WARPS + w, nw = gridDim.x * TB16_WARPS;
@@ -200,15 +355,31 @@ dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
             const int sid = list[item];
             const Slot s = slots[sid];
             const int m = s.m, n = s.n;
-            const int R = wf16_pick(prm.h, cls, m, n);
-            if (!R) continue;                                // a 32-bit kernel did forward pass and traceback
+            const int pick = wf16_pick(prm.h, cls, m, n);
+            if (!pick) continue;                             // a 32-bit kernel did forward pass and traceback
+            const bool paired = pick >= WF16_PAIR;
+            const int R = paired ? pick - WF16_PAIR : pick;
             const PairDesc pd = pairs[s.pair];
             const uint8_t *xs = seqs + pd.off0 + s.x0, *ys = seqs + pd.off1 + s.y0;
             const int64_t row_len = (pd.off1 - pd.off0) + pd.n1;
             uint8_t *ox = strbuf + s.str_off, *oy = ox + row_len;
             const int rsh = 31 - __clz(R);
-            const WalkGeom g{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u};
-            const int len = wf_traceback(win[w], tb_pool + s.tb_off + (16 << g.roww_sh), (int64_t)n + WF16_TB_PAD, xs, ys, m, n, s.len, pmap,
+            // paired kernel: the 32-bit kernels' table (32 R bytes per row, matrix-row order, true bytes);
+            // half-lane kernel: 64 R bytes per row, row pairs interleaved, biased words
+            const WalkGeom g = paired ? WalkGeom{5 + rsh, rsh, -1, 0u}
+                                      : WalkGeom{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u};
+            int st = s.len;                                  // half-lane kernel: the terminal state travels in slot.len
+            if (paired) {                                    // paired kernel: last-column states at the head of the table
+                const uint16_t *eb = reinterpret_cast<const uint16_t *>(tb_pool + s.tb_off);
+                const int roww = 32 * R;
+                const int vM = (int)(int16_t)eb[m - 1], vX = (int)(int16_t)eb[roww + m - 1], vY = (int)(int16_t)eb[2 * roww + m - 1];
+                const int cm = (vM & ~3) + prm.endM, cx = (vX & ~3) + prm.endX, cy = (vY & ~3) + prm.endY;
+                int best = cm; st = 0;
+                if (cx > best) { best = cx; st = 1; }
+                if (cy > best) { best = cy; st = 2; }
+                if (lane == 0) slots[sid].score = (best >> 2) + prm.h.off - prm.ge_raw * (m + n);
+            }
+            const int len = wf_traceback(win[w], tb_pool + s.tb_off + (16 << g.roww_sh), (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap,
                                          ox, oy, lane, g);
             if (lane == 0) slots[sid].len = len;
             __syncwarp();
@@ -225,12 +396,31 @@ static void launch_wf16_t(int grid, const uint8_t *seqs, const PairDesc *pairs, 
     else dp_wf16_kernel<R, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf, tb);
 }
 
+template <int R>
+static void launch_wf16p_t(int grid, const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                           const unsigned int *count_dev, const DpParams &prm, uint8_t *tb, cudaStream_t st) {
+    grid = grid * 20 / 16;
+    if (prm.xy) dp_wf16p_kernel<R, true><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, tb);
+    else dp_wf16p_kernel<R, false><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, prm, tb);
+}
+
 // cls: CLS_WARP2 / 4 / 8 / 16; the packed kernel runs half as many rows per half-lane as the
 // class's 32-bit kernel runs per lane (same 32 * R-byte traceback rows)
 cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                   const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
                                   uint8_t *tb, cudaStream_t st) {
     if (grid <= 0 || !prm.h.ok) return cudaSuccess;
+    const int rpl = wf_rows_per_lane(cls);
+    bool all_paired = false;       // every member of the class goes to the two-segments-per-warp kernel
+    if (prm.h.pair) {
+        if (cls == CLS_WARP2) launch_wf16p_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st);
+        else if (cls == CLS_WARP4) launch_wf16p_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st);
+        else if (cls == CLS_WARP8) launch_wf16p_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st);
+        all_paired = wf16_pick(prm.h, cls, 32 * rpl, 1 << 30) == WF16_PAIR + rpl;
+    }
+    if (all_paired) return cudaGetLastError();
+    // half-lane kernels: the whole class without pairing; with it, what the paired kernel cannot take
+    // (the open-ended class's segments of more than 512 rows, or scoring too steep for 32 R rows)
     if (cls == CLS_WARP2) launch_wf16_t<1>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
     else if (cls == CLS_WARP4) launch_wf16_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
     else if (cls == CLS_WARP8) launch_wf16_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);

@@ -23,3 +23,19 @@ def chunked(k=10):
         with torch.cuda.stream(s1): d[i*c:(i+1)*c].copy_(h[i*c:(i+1)*c], non_blocking=True)
         with torch.cuda.stream(s2): h2[i*c:(i+1)*c].copy_(d2[i*c:(i+1)*c], non_blocking=True)
 print("chunked concurrent ms", t(chunked))
+print("chunked x20 concurrent ms", t(lambda: chunked(20)))
+print("chunked x40 concurrent ms", t(lambda: chunked(40)))
+# the same with an SM-heavy kernel running next to the copies
+s3 = torch.cuda.Stream()
+a = torch.randn(8192, 8192, device="cuda")
+def both_busy():
+    with torch.cuda.stream(s3):
+        for _ in range(6): torch.mm(a, a)
+    both()
+print("concurrent + GEMMs ms", t(both_busy))
+x = torch.empty(1 << 28, dtype=torch.float32, device="cuda")
+def both_membound():
+    with torch.cuda.stream(s3):
+        for _ in range(12): x.mul_(1.0001)
+    both()
+print("concurrent + HBM-bound kernels ms", t(both_membound))
