@@ -20,6 +20,8 @@ from __future__ import annotations
 import argparse
 import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: one hardware queue per stream
+if _os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":    # NCCL's banner goes to stdout, which carries the one JSON line
+    _os.environ["NCCL_DEBUG"] = "WARN"
 import json
 import os
 import sys
