@@ -357,3 +357,46 @@ def test_packed16_wavefront(aligner):
     run(match=1, transition=0, transversion=-1, d=0, e=0)
     run(match=31, transition=-30, transversion=-32, d=3, e=0)      # steep: ceiling reached at ~490 rows
     run(match=-3, transition=2, transversion=5, d=7, e=3)          # mismatches score higher than matches
+    # gap extension so large that 32 R rows of a lane pair pass the ceiling (growth 80 per diagonal step):
+    # the two-segments-per-warp kernels hand their classes to the half-lane kernels (up to ~189 rows) and
+    # those hand the rest to the 32-bit kernels
+    run(match=-50, transition=-60, transversion=-70, d=40, e=40)
+
+
+def test_packed16_full_size_properties(aligner):
+    """The DP microbenchmark's shapes at size (thousands of segments per packed kernel, lists long
+    enough that every warp pairs many different neighbours): degapped rows == inputs, the affine
+    score recomputed from the returned rows == the reported score (an independent restatement of
+    the objective, not of the kernel), and every 50th pair bit-exact against the oracle."""
+    def affine_score(a, b, match=10, transition=-1, transversion=-8, d=10, e=2):
+        pur = {"A", "G"}
+        sc, gx, gy = 0, False, False          # inside a gap in row a / row b
+        for x, y in zip(a, b):
+            if x == "-":
+                sc -= e if gx else d
+                gx, gy = True, False
+            elif y == "-":
+                sc -= e if gy else d
+                gx, gy = False, True
+            else:
+                sc += match if x == y else (transition if (x in pur) == (y in pur) else transversion)
+                gx = gy = False
+        return sc
+
+    rng = random.Random(77)
+    pairs = []
+    for lo, hi, cnt in ((33, 64, 1500), (65, 128, 900), (129, 256, 600), (257, 512, 300), (513, 1024, 120)):
+        for _ in range(cnt):
+            m = rng.randint(lo, hi)
+            x = rand_seq(rng, m)
+            y = mutate(rng, x, 0.05, 0.01) if rng.random() < 0.8 else rand_seq(rng, rng.randint(lo, hi))
+            pairs.append((x, y or "A"))
+    res = aligner.global_align_pairs(pairs)
+    assert (res.status == O.OK).all()
+    for i, (x, y) in enumerate(pairs):
+        ax, ay = res.alignment(i)
+        assert len(ax) == len(ay) and ax.replace("-", "") == x and ay.replace("-", "") == y, i
+        assert affine_score(ax, ay) == res.score[i], (i, len(x), len(y))
+        if i % 50 == 0:
+            sc, ox, oy = CO.gotoh(x, y)
+            assert (res.score[i], ax, ay) == (sc, ox, oy), (i, len(x), len(y))
