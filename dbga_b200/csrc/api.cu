@@ -571,8 +571,7 @@ int run_pipeline(dbga_ctx *ctx) {
                 if (ctx->dp.h.ok) {
                     DBGA_CUDA_CHECK(launch_dp_wavefront16(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,
                                                           &ctr->n_cls[cls], g, cls, ctx->dp, (uint8_t *)ctx->d_str.p,
-                                                          (uint8_t *)ctx->d_tb.p, st));
-                    ctx->launches += cls == CLS_WARP16 ? 2 : 1;
+                                                          (uint8_t *)ctx->d_tb.p, st, &ctx->launches));
                     if (cls != CLS_WARP16 && wf16_pick(ctx->dp.h, cls, rows16, 1 << 30)) continue;
                 }
                 DBGA_CUDA_CHECK(launch_dp_wavefront(seqs, pairs, pools.slots, pools.lists + (int64_t)cls * pools.list_cap,

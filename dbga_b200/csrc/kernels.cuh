@@ -69,7 +69,7 @@ cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot
 // packed 16-bit wavefront over the same class list (takes the segments wf16_ok accepts)
 cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                   const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
-                                  uint8_t *tb, cudaStream_t st);
+                                  uint8_t *tb, cudaStream_t st, int *launches);
 // traceback of everything the packed kernels processed, all four warp classes in one launch
 cudaError_t launch_dp_traceback16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
                                   int64_t list_cap, const unsigned int *counts_dev, int grid, DpParams prm,

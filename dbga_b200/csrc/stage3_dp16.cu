@@ -408,25 +408,25 @@ static void launch_wf16p_t(int grid, const uint8_t *seqs, const PairDesc *pairs,
 // class's 32-bit kernel runs per lane (same 32 * R-byte traceback rows)
 cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                   const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
-                                  uint8_t *tb, cudaStream_t st) {
+                                  uint8_t *tb, cudaStream_t st, int *launches) {
     if (grid <= 0 || !prm.h.ok) return cudaSuccess;
     const int rpl = wf_rows_per_lane(cls);
     bool all_paired = false;       // every member of the class goes to the two-segments-per-warp kernel
     if (prm.h.pair) {
-        if (cls == CLS_WARP2) launch_wf16p_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st);
-        else if (cls == CLS_WARP4) launch_wf16p_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st);
-        else if (cls == CLS_WARP8) launch_wf16p_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st);
+        if (cls == CLS_WARP2) { launch_wf16p_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st); *launches += 1; }
+        else if (cls == CLS_WARP4) { launch_wf16p_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st); *launches += 1; }
+        else if (cls == CLS_WARP8) { launch_wf16p_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, tb, st); *launches += 1; }
         all_paired = wf16_pick(prm.h, cls, 32 * rpl, 1 << 30) == WF16_PAIR + rpl;
     }
     if (all_paired) return cudaGetLastError();
     // half-lane kernels: the whole class without pairing; with it, what the paired kernel cannot take
     // (the open-ended class's segments of more than 512 rows, or scoring too steep for 32 R rows)
-    if (cls == CLS_WARP2) launch_wf16_t<1>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
-    else if (cls == CLS_WARP4) launch_wf16_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
-    else if (cls == CLS_WARP8) launch_wf16_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+    if (cls == CLS_WARP2) { launch_wf16_t<1>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st); *launches += 1; }
+    else if (cls == CLS_WARP4) { launch_wf16_t<2>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st); *launches += 1; }
+    else if (cls == CLS_WARP8) { launch_wf16_t<4>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st); *launches += 1; }
     else {
-        launch_wf16_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
-        launch_wf16_t<16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st);
+        { launch_wf16_t<8>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st); *launches += 1; }
+        { launch_wf16_t<16>(grid, seqs, pairs, slots, list, count_dev, prm, strbuf, tb, st); *launches += 1; }
     }
     return cudaGetLastError();
 }
