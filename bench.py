@@ -320,11 +320,14 @@ def run_ours(args):
         sample = min(P, args.ref_sample)
         sb, so = buf[:int(offs[2 * sample])], offs[:2 * sample + 1]
         CO.align_batch(sb[:int(so[min(2 * 512, 2 * sample)])], so[:min(2 * 512, 2 * sample) + 1], k, threads=cores)
-        t0 = time.perf_counter()
-        CO.align_batch(sb, so, k, threads=cores)
-        cdt = time.perf_counter() - t0
-        cpu = {"value": sample / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
-               "sample": f"first {sample} pairs of the same batch, one pass, {cdt:.2f} s; C restatement "
+        passes, cdt = 0, 0.0
+        while cdt < args.cpu_seconds:                 # whole passes over the sample until the budget is spent
+            t0 = time.perf_counter()
+            CO.align_batch(sb, so, k, threads=cores)
+            cdt += time.perf_counter() - t0
+            passes += 1
+        cpu = {"value": sample * passes / cdt, "unit": "pairs/s", "cores": cores, "kind": "port",
+               "sample": f"first {sample} pairs of the same batch, {passes} passes, {cdt:.1f} s of CPU time; C restatement "
                          "(oracle/dbga_oracle.c) of the reference path, pthreads over all host cores"}
 
     line = {
@@ -361,6 +364,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=50_000, help="pairs per CPU-baseline pass")
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time spent on the cpu_baseline leg")
     ap.add_argument("--no-dp-micro", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
