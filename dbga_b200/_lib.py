@@ -22,7 +22,7 @@ EXPORTS = (
     "dbga_create", "dbga_destroy", "dbga_last_error", "dbga_set_stream", "dbga_set_scratch_limit",
     "dbga_host_alloc", "dbga_host_free", "dbga_align_batch", "dbga_plan", "dbga_plan_global",
     "dbga_plan_run", "dbga_plan_fetch", "dbga_measure_int_peak", "dbga_global_align_batch",
-    "dbga_version",
+    "dbga_kmer_stats", "dbga_version",
 )
 
 
@@ -92,6 +92,9 @@ def load():
     lib.dbga_plan_fetch.restype = C.c_int
     lib.dbga_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     lib.dbga_measure_int_peak.restype = C.c_int
+    lib.dbga_kmer_stats.argtypes = [vp, vp, C.POINTER(C.c_int64), C.c_int64, C.c_int32, C.POINTER(C.c_int32),
+                                    C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.dbga_kmer_stats.restype = C.c_int
     lib.dbga_version.restype = C.c_int
     _lib = lib
     return lib

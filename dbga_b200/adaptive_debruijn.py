@@ -13,22 +13,8 @@ from typing import Any, List, Sequence, Tuple
 
 from .batch import make_dna_scoring_dict
 from .debruijn_pairwise import DeBruijnPairwise
-from .utils import NodeType, dna_global_aln, get_closest_odd, get_kmers, load_sequences
-
-
-def predict_p(seqs, k: int) -> float:
-    """Similarity estimate from the Jaccard index of the two k-mer sets (utils.py:372-395)."""
-    a = set(get_kmers(str(seqs.seqs[0]), k))
-    b = set(get_kmers(str(seqs.seqs[1]), k))
-    return (len(a & b) / len(a | b)) ** (1 / k)
-
-
-def predict_final_p(seqs) -> float:
-    """Minimum of predict_p over the candidate k range (utils.py:398-413)."""
-    shortest = min(len(s) for s in seqs.seqs)
-    lo = math.ceil(math.log(shortest, 4))
-    hi = math.ceil(math.log2(shortest)) + 10
-    return min(predict_p(seqs, k) for k in range(lo, hi))
+from .kmersize import predict_final_p, predict_p  # noqa: F401  (GPU k-mer set statistics, utils.py:371-413)
+from .utils import NodeType, dna_global_aln, get_closest_odd, load_sequences
 
 
 def get_seqs_entropy(seqs) -> float:

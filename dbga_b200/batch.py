@@ -192,6 +192,21 @@ class Aligner:
         self.last_raw = res
         return self._unpack(res, self._plan_graph) if unpack else res
 
+    def kmer_stats(self, pairs: Sequence[Tuple[str, str]], k: int):
+        """|K0|, |K1|, |K0 & K1| of the k-mer sets of every pair (what predict_p and the k-size
+        heuristics are computed from, utils.py:371-413, kmersize.py:10-14).
+        Returns (status, distinct0, distinct1, shared) as numpy arrays."""
+        buf, offs = pack_pairs(pairs)
+        P = len(pairs)
+        status = np.zeros(P, np.int32)
+        d0, d1, sh = np.zeros(P, np.int64), np.zeros(P, np.int64), np.zeros(P, np.int64)
+        i64 = C.POINTER(C.c_int64)
+        rc = self.lib.dbga_kmer_stats(self.h, C.c_void_p(buf.ctypes.data), offs.ctypes.data_as(i64), P, int(k),
+                                      status.ctypes.data_as(C.POINTER(C.c_int32)), d0.ctypes.data_as(i64),
+                                      d1.ctypes.data_as(i64), sh.ctypes.data_as(i64))
+        self._check(rc, "dbga_kmer_stats")
+        return status, d0, d1, sh
+
     def set_stream(self, stream_ptr: int):
         self._check(self.lib.dbga_set_stream(self.h, C.c_void_p(int(stream_ptr))), "dbga_set_stream")
 

@@ -1148,6 +1148,78 @@ int dbga_plan_fetch(dbga_ctx *ctx, dbga_result *out) {
     return do_fetch(ctx, out);
 }
 
+int dbga_kmer_stats(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P, int32_t k,
+                    int32_t *status, int64_t *distinct0, int64_t *distinct1, int64_t *shared) {
+    if (!ctx) return DBGA_ERR_ARG;
+    if (P < 0 || (P > 0 && (!seqs || !offsets || !status || !distinct0 || !distinct1 || !shared)))
+        return fail(ctx, DBGA_ERR_ARG, "null argument");
+    if (k < 1 || k > 31) return fail(ctx, DBGA_ERR_ARG, "k must be in 1..31");
+    if (P == 0) return DBGA_SUCCESS;
+    if (P > 0x7fffff00LL) return fail(ctx, DBGA_ERR_ARG, "too many pairs in one batch");
+    DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int64_t base = offsets[0], total = offsets[2 * P] - base;
+    // pairs whose table fits shared memory share one launch (sized for the largest of them);
+    // the others are counted one at a time in a global-memory table
+    const int key_bytes = k <= 15 ? 4 : 8;
+    auto cap_of = [](int64_t keys) { return ((uint64_t)keys * 3 / 2 + 64 + 15) / 16 * 16; };
+    auto words_of = [](int64_t n) { return (int)((((n + 15) / 16 + 3) + 1) & ~1LL); };
+    int64_t max_keys = 0, max_n = 0;
+    std::vector<int64_t> large;
+    for (int64_t i = 0; i < P; ++i) {
+        const int64_t n0 = offsets[2 * i + 1] - offsets[2 * i], n1 = offsets[2 * i + 2] - offsets[2 * i + 1];
+        if (n0 < 0 || n1 < 0) return fail(ctx, DBGA_ERR_ARG, "offsets must be non-decreasing");
+        if (n0 < k || n1 < k) continue;            // K_INVALID, decided on the device
+        const int64_t keys = (n0 - k + 1) + (n1 - k + 1), nmax = std::max(n0, n1);
+        if (kmer_stats_smem(key_bytes, (uint32_t)std::min<uint64_t>(cap_of(keys), 1u << 30), words_of(nmax)) > SMEM_LIMIT - 1024) {
+            large.push_back(i);
+            continue;
+        }
+        max_keys = std::max(max_keys, keys); max_n = std::max(max_n, nmax);
+    }
+    cudaStream_t st = ctx->stream;
+    RESERVE(d_seqs, (size_t)total + 64);
+    RESERVE(d_aln_off, 8 * (2 * P + 1));           // offsets
+    RESERVE(d_status, 4 * P);
+    RESERVE(d_nseg, 12 * P);                        // three counts per pair
+    HRESERVE(h_nseg, 12 * P); HRESERVE(h_status, 4 * P);
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_seqs.p, seqs + base, (size_t)total, cudaMemcpyHostToDevice, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_aln_off.p, offsets, 8 * (size_t)(2 * P + 1), cudaMemcpyHostToDevice, st));
+    if (large.size() < (size_t)P) {
+        DBGA_CUDA_CHECK(launch_kmer_stats((const uint8_t *)ctx->d_seqs.p, (const int64_t *)ctx->d_aln_off.p, base, P, k,
+                                          (uint32_t)cap_of(max_keys), words_of(max_n), max_keys, max_n,
+                                          (int32_t *)ctx->d_status.p, (int32_t *)ctx->d_nseg.p, ctx->num_sms, st));
+    }
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nseg.p, ctx->d_nseg.p, 12 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status.p, 4 * (size_t)P, cudaMemcpyDeviceToHost, st));
+    DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+    const int32_t *c = (const int32_t *)ctx->h_nseg.p, *hs = (const int32_t *)ctx->h_status.p;
+    for (int64_t i = 0; i < P; ++i) {
+        const int64_t n0 = offsets[2 * i + 1] - offsets[2 * i], n1 = offsets[2 * i + 2] - offsets[2 * i + 1];
+        if (n0 < k || n1 < k) {                    // utils.py:129-130 (such a pair may be outside the launch's size class)
+            status[i] = DBGA_K_INVALID; distinct0[i] = distinct1[i] = shared[i] = 0;
+            continue;
+        }
+        status[i] = hs[i]; distinct0[i] = c[3 * i]; distinct1[i] = c[3 * i + 1]; shared[i] = c[3 * i + 2];
+    }
+    for (int64_t i : large) {
+        const int64_t o0 = offsets[2 * i] - base, o1 = offsets[2 * i + 1] - base, o2 = offsets[2 * i + 2] - base;
+        const uint64_t lcap = cap_of((o1 - o0 - k + 1) + (o2 - o1 - k + 1));
+        RESERVE(d_table, lcap * 12 + 64);
+        unsigned long long *keys = (unsigned long long *)ctx->d_table.p;
+        uint32_t *flag = (uint32_t *)(keys + lcap);
+        unsigned int *counts = (unsigned int *)ctx->d_status.p;      // the small pairs' results are on the host already
+        DBGA_CUDA_CHECK(launch_kmer_stats_large((const uint8_t *)ctx->d_seqs.p + o0, o1 - o0, (const uint8_t *)ctx->d_seqs.p + o1,
+                                                o2 - o1, k, keys, flag, lcap, counts, ctx->num_sms, st));
+        unsigned int hc[4];
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(hc, counts, sizeof(hc), cudaMemcpyDeviceToHost, st));
+        DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+        status[i] = hc[3] ? DBGA_BAD_CHAR : DBGA_OK;
+        distinct0[i] = hc[3] ? 0 : hc[0]; distinct1[i] = hc[3] ? 0 : hc[1]; shared[i] = hc[3] ? 0 : hc[2];
+    }
+    ctx->planned = false;          // the plan's device buffers were reused
+    return DBGA_SUCCESS;
+}
+
 int dbga_measure_int_peak(dbga_ctx *ctx, double out[3]) {
     if (!ctx || !out) return DBGA_ERR_ARG;
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));

@@ -89,6 +89,16 @@ cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t 
 cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStream_t st);
 cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, cudaStream_t st);
 
+// ---- k-mer set statistics (|K0|, |K1|, |K0 & K1| per pair), small pairs only
+size_t kmer_stats_smem(int key_bytes, uint32_t cap, int words);
+cudaError_t launch_kmer_stats(const uint8_t *seqs, const int64_t *offsets, int64_t off_base, int64_t count, int k,
+                              uint32_t cap, int words, int64_t max_keys, int64_t max_n, int32_t *status, int32_t *out,
+                              int num_sms, cudaStream_t st);
+
+cudaError_t launch_kmer_stats_large(const uint8_t *seq0, int64_t n0, const uint8_t *seq1, int64_t n1, int k,
+                                    unsigned long long *keys, uint32_t *flag, uint64_t cap, unsigned int *counts,
+                                    int num_sms, cudaStream_t st);
+
 // ---- integer-pipe microbenchmark
 cudaError_t launch_int_peak(int which, int iters, int *sink, int num_sms, cudaStream_t st);
 

@@ -122,6 +122,17 @@ int dbga_measure_int_peak(dbga_ctx *ctx, double out[3]);
 int dbga_global_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets,
                             int64_t num_pairs, const dbga_params *params, dbga_result *out);
 
+/* k-mer set statistics of P pairs (host buffers, same offsets convention, synchronous):
+ * distinct0[i] = |K0|, distinct1[i] = |K1|, shared[i] = |K0 & K1| for the k-mer sets of pair i.
+ * What the reference's k heuristics are computed from: predict_p / predict_final_p
+ * (src/dbga/utils.py:371-413: (shared / (distinct0 + distinct1 - shared)) ** (1 / k)) and
+ * kmers_larger_than_threshold (src/dbga/kmersize.py:10-14: (N - distinct) / N).
+ * status[i]: DBGA_OK, DBGA_K_INVALID (k > a length), DBGA_BAD_CHAR.  Pairs whose k-mers fit a
+ * shared-memory table (about 9 kb per sequence at k <= 15) share one launch; longer pairs are
+ * counted one at a time, the whole GPU on a global-memory table. */
+int dbga_kmer_stats(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t num_pairs, int32_t k,
+                    int32_t *status, int64_t *distinct0, int64_t *distinct1, int64_t *shared);
+
 int dbga_version(void);
 
 #ifdef __cplusplus

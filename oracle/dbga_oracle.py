@@ -374,3 +374,34 @@ def synth_pair(n: int, p_sub: float, p_indel: float, seed: int):
     s0 = lut[a].tobytes().decode()
     s1 = lut[np.asarray(out, dtype=np.int64)].tobytes().decode() if out else ""
     return s0, s1
+
+
+# ---------------------------------------------------------------- k-size heuristics
+def kmer_stats(s0: str, s1: str, k: int) -> Tuple[int, int, int]:
+    """(|K0|, |K1|, |K0 & K1|) for the k-mer sets of the two sequences: the set arithmetic of
+    predict_p (reference src/dbga/utils.py:387-391) on get_kmers (utils.py:108-131)."""
+    if k < 0 or k > len(s0) or k > len(s1):
+        raise ValueError("Invalid k size for kmers")          # utils.py:129-130
+    a = {s0[i:i + k] for i in range(len(s0) - k + 1)}
+    b = {s1[i:i + k] for i in range(len(s1) - k + 1)}
+    return len(a), len(b), len(a & b)
+
+
+def predict_p(s0: str, s1: str, k: int) -> float:
+    """utils.py:371-395: (|K0 & K1| / |K0 | K1|) ** (1 / k)."""
+    d0, d1, sh = kmer_stats(s0, s1, k)
+    return (sh / (d0 + d1 - sh)) ** (1 / k)
+
+
+def predict_final_p(s0: str, s1: str) -> float:
+    """utils.py:398-413: the minimum of predict_p over k in [ceil(log4 L), ceil(log2 L) + 10)."""
+    import math
+    shortest = min(len(s0), len(s1))
+    return min(predict_p(s0, s1, k) for k in range(math.ceil(math.log(shortest, 4)), math.ceil(math.log2(shortest)) + 10))
+
+
+def kmers_larger_than_threshold(seq: str, k: int, threshold: float) -> bool:
+    """src/dbga/kmersize.py:10-14: repeated k-mer occurrences / all occurrences > threshold."""
+    n = len(seq) - k + 1
+    distinct = len({seq[i:i + k] for i in range(n)})
+    return (n - distinct) / n > threshold

@@ -400,3 +400,46 @@ def test_packed16_full_size_properties(aligner):
         if i % 50 == 0:
             sc, ox, oy = CO.gotoh(x, y)
             assert (res.score[i], ax, ay) == (sc, ox, oy), (i, len(x), len(y))
+
+
+def test_kmer_stats_and_k_heuristics(aligner):
+    """dbga_kmer_stats (|K0|, |K1|, |K0 & K1| on the device) against the oracle's set arithmetic
+    for k in 1..31 (32- and 64-bit keys), both table paths (shared memory; one long pair in the
+    global-memory table), error statuses; and predict_p / predict_final_p /
+    kmers_larger_than_threshold built on it against values recorded from the reference's own
+    functions (tests/golden/ref_kmer_heuristics.json)."""
+    import json
+    import os
+    from dbga_b200 import kmersize as KS
+    rng = random.Random(91)
+    pairs = [O.synth_pair(n, ps, pi, 7000 + i) for i, (n, ps, pi) in enumerate(
+        [(40, 0.05, 0.02), (300, 0.1, 0.02), (1500, 0.018, 0.002), (1500, 0.3, 0.05), (5000, 0.01, 0.001)] * 3)]
+    pairs += [("A" * 200, "A" * 150), ("ACGT" * 60, "TGCA" * 50), (rand_seq(rng, 64), rand_seq(rng, 900))]
+    for k in (1, 2, 3, 5, 9, 12, 15, 16, 17, 24, 31):
+        use = [(a, b) for a, b in pairs if len(a) >= k and len(b) >= k]
+        st, d0, d1, sh = aligner.kmer_stats(use, k)
+        assert (st == O.OK).all()
+        for i, (a, b) in enumerate(use):
+            assert (int(d0[i]), int(d1[i]), int(sh[i])) == O.kmer_stats(a, b, k), (i, k, len(a), len(b))
+    # a pair far beyond the shared-memory table next to small ones, and the error statuses
+    big = O.synth_pair(60000, 0.01, 0.002, 5)
+    mixed = [pairs[0], big, ("ACG", "ACGTACGT" * 4), ("ACGTNCGT" * 4, "ACGTACGT" * 4), pairs[2]]
+    for k in (5, 11, 20):
+        st, d0, d1, sh = aligner.kmer_stats(mixed, k)
+        assert st.tolist() == [O.OK, O.OK, O.K_INVALID, O.BAD_CHAR, O.OK]
+        for i in (0, 1, 4):
+            assert (int(d0[i]), int(d1[i]), int(sh[i])) == O.kmer_stats(*mixed[i], k), (i, k)
+    st, *_ = aligner.kmer_stats([(big[0], big[1][:30000] + "N" + big[1][30000:])], 11)
+    assert st.tolist() == [O.BAD_CHAR]
+    # the reference's heuristics, bit for bit (same float expression on the same integers)
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_kmer_heuristics.json")))
+    for c in g["cases"]:
+        for k, p in c["predict_p"].items():
+            assert KS.predict_p_batch([(c["s0"], c["s1"])], int(k))[0] == p
+        for key, v in c["dup_prop_gt"].items():
+            k, th = key.split(":")
+            assert KS.kmers_larger_than_threshold(c["s0"], int(k), float(th)) == v
+    finals = KS.predict_final_p_batch([(c["s0"], c["s1"]) for c in g["cases"]])
+    assert finals.tolist() == [c["predict_final_p"] for c in g["cases"]]
+    with pytest.raises(ValueError, match="Invalid k size"):
+        KS.predict_p_batch([("ACGT", "ACG")], 4)

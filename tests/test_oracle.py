@@ -152,3 +152,21 @@ def test_batch_oracle_matches_single():
         if r.status == O.OK:
             assert out["score"][i] == r.score and out["aln_len"][i] == len(r.aln0)
             assert out["dp_cells"][i] == r.dp_cells
+
+
+def test_kmer_heuristics_vs_reference_goldens():
+    """predict_p / predict_final_p / kmers_larger_than_threshold: the oracle's restatement against
+    values recorded from the reference's own functions (oracle/make_golden_kmer.py)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_kmer_heuristics.json")))
+    assert len(g["cases"]) >= 20
+    for c in g["cases"]:
+        for k, p in c["predict_p"].items():
+            assert O.predict_p(c["s0"], c["s1"], int(k)) == p
+        assert O.predict_final_p(c["s0"], c["s1"]) == c["predict_final_p"]
+        for key, v in c["dup_prop_gt"].items():
+            k, th = key.split(":")
+            assert O.kmers_larger_than_threshold(c["s0"], int(k), float(th)) == v
+    with pytest.raises(ValueError, match="Invalid k size"):
+        O.kmer_stats("ACGT", "ACG", 4)
