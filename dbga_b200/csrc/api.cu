@@ -313,7 +313,8 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                         uint32_t gr = 256;
                         while ((uint64_t)gr * 16 < w) gr <<= 1;
                         const uint32_t c = (uint32_t)((w + gr - 1) / gr * gr);
-                        if (c <= 32768 && stage12_small_smem(key_bytes, c, words0, (int)N1) <= 200 * 1024) { parts = g; pcap = c; }
+                        // (medium pairs keep memo[] in global memory: no per-position shared memory)
+                        if (c <= 32768 && stage12_small_smem(key_bytes, c, words0, 0) <= 216 * 1024) { parts = g; pcap = c; }
                     }
                 }
                 if (parts) by_cap[{parts, pcap}].push_back((int32_t)i);
@@ -333,7 +334,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                 ctx->h_list.push_back(i);
             }
             c.words = (((nmax + 15) / 16 + 3) + 1) & ~1;
-            c.maxq = qmax;
+            c.maxq = c.parts > 1 ? 0 : qmax;
             if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq) > SMEM_LIMIT) {
                 // mixed extremes inside one class: fall back to the large path for this class
                 ctx->h_list.resize((size_t)c.begin);

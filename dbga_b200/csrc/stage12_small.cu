@@ -98,6 +98,13 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             continue;
         }
         const int N0 = pd.n0 - k + 1, N1 = pd.n1 - k + 1;
+        if (MEDIUM) {
+            // medium pairs keep memo[] in global memory (L2), in the tail of the pair's own aof[] region:
+            // the last 2 * N1e bytes of its 4 * N1 (N1e = N1 rounded up to even; 4-byte aligned either
+            // way).  That leaves the whole shared memory to the table: fewer partitions, fewer re-scans.
+            const int N1e = (N1 + 1) & ~1;
+            memo = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(aof + pd.q_base) + 4 * (int64_t)N1 - 2 * (int64_t)N1e);
+        }
         for (int g = 0; g < parts; ++g) {
             if (g > 0) { __syncthreads(); init_table(); __syncthreads(); }
             // partition of a k-mer: low 16 bits of its hash (the bucket uses the high bits)
@@ -175,8 +182,15 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         }
         if (MEDIUM) {                                 // medium pair: hand aof[] to the generic stage 2
             __syncthreads();
+            // expand in place, lowest positions first: the int32 written at q lands on the 16-bit entries
+            // 2q - N1 (+2) <= q, all read in this or an earlier round (read, barrier, write)
             int32_t *ga = aof + pd.q_base;
-            for (int q = tid; q < N1; q += T) { const uint16_t a = memo[q]; ga[q] = a == NONE16 ? -1 : (int32_t)a; }
+            for (int q0 = 0; q0 < N1; q0 += T) {
+                const int q = q0 + tid;
+                const uint16_t a = q < N1 ? memo[q] : NONE16;
+                __syncthreads();
+                if (q < N1) ga[q] = a == NONE16 ? -1 : (int32_t)a;
+            }
             continue;
         }
         __syncthreads();                              // table dead from here on
