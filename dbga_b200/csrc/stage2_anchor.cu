@@ -59,25 +59,40 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
         //      run starts, run ends and anchors (no block barrier inside the scan loops)
         const int chunk = (((N1 + nw - 1) / nw) + 31) & ~31;
         const int q_lo = min(N1, wid * chunk), q_hi = min(N1, q_lo + chunk);
-        auto classify = [&](int q, int &a, bool &isS, bool &isE) {
-            a = -1; isS = false; isE = false;
-            if (q < q_hi) {
-                a = a_of[q];
-                if (a >= 0) {
-                    const int pv = q > 0 ? a_of[q - 1] : -1;
-                    const int nx = q + 1 < N1 ? a_of[q + 1] : -1;
-                    isS = !(pv >= 0 && pv + 1 == a);
-                    isE = !(nx >= 0 && nx == a + 1);
-                }
+        // A block of U x 32 consecutive positions per iteration: every lane loads its U values back to back
+        // (independent loads: one memory round trip per block instead of one per 32 positions) and gets
+        // its neighbours' values by shuffle; only the block's two edge neighbours are extra loads.
+        constexpr int U = 4;
+        auto load_block = [&](int base, int (&a)[U], bool (&isS)[U], bool (&isE)[U]) {
+            int edge_lo = -1, edge_hi = -1;
+            if (lane == 0 && base > 0) edge_lo = a_of[base - 1];
+            if (lane == 31 && base + 32 * U < N1) edge_hi = a_of[base + 32 * U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + 32 * u + lane;
+                a[u] = q < N1 ? a_of[q] : -1;          // values past the warp's own range (q >= q_hi) are neighbours only
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + 32 * u + lane;
+                int pv = __shfl_up_sync(0xffffffffu, a[u], 1), nx = __shfl_down_sync(0xffffffffu, a[u], 1);
+                const int pv0 = u > 0 ? __shfl_sync(0xffffffffu, a[u > 0 ? u - 1 : 0], 31) : edge_lo;
+                const int nx31 = u + 1 < U ? __shfl_sync(0xffffffffu, a[u + 1 < U ? u + 1 : U - 1], 0) : edge_hi;
+                if (lane == 0) pv = pv0;
+                if (lane == 31) nx = nx31;
+                const bool own = q < q_hi && a[u] >= 0;
+                isS[u] = own && !(pv >= 0 && pv + 1 == a[u]);
+                isE[u] = own && !(nx >= 0 && nx == a[u] + 1);
+                if (q >= q_hi) a[u] = -1;
             }
         };
         int cS = 0, cE = 0;
         long long cA = 0;
-#pragma unroll 4
-        for (int q = q_lo + lane; q < q_hi; q += 32) {
-            int a; bool isS, isE;
-            classify(q, a, isS, isE);
-            cA += a >= 0; cS += isS; cE += isE;
+        for (int base = q_lo; base < q_hi; base += 32 * U) {
+            int a[U]; bool isS[U], isE[U];
+            load_block(base, a, isS, isE);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { cA += a[u] >= 0; cS += isS[u]; cE += isE[u]; }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { cS += __shfl_xor_sync(0xffffffffu, cS, o); cE += __shfl_xor_sync(0xffffffffu, cE, o); }
@@ -109,19 +124,22 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
         }
         int32_t *runs = pools.runs + 3 * run_base;
         // ---- pass 2: ordered compaction of run starts (a, b) and run ends (b), per warp chunk
-        for (int base = q_lo; base < q_hi; base += 32) {
-            const int q = base + lane;
-            int a; bool isS, isE;
-            classify(q, a, isS, isE);
-            const unsigned bS = __ballot_sync(0xffffffffu, isS), bE = __ballot_sync(0xffffffffu, isE);
+        for (int base = q_lo; base < q_hi; base += 32 * U) {
+            int a[U]; bool isS[U], isE[U];
+            load_block(base, a, isS, isE);
             const unsigned lt = (1u << lane) - 1u;
-            if (isS) {
-                const int idx = offS + __popc(bS & lt);
-                runs[3 * (int64_t)idx] = a;
-                runs[3 * (int64_t)idx + 1] = q;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = base + 32 * u + lane;
+                const unsigned bS = __ballot_sync(0xffffffffu, isS[u]), bE = __ballot_sync(0xffffffffu, isE[u]);
+                if (isS[u]) {
+                    const int idx = offS + __popc(bS & lt);
+                    runs[3 * (int64_t)idx] = a[u];
+                    runs[3 * (int64_t)idx + 1] = q;
+                }
+                if (isE[u]) runs[3 * (int64_t)(offE + __popc(bE & lt)) + 2] = q;   // end b, turned into len below
+                offS += __popc(bS); offE += __popc(bE);
             }
-            if (isE) runs[3 * (int64_t)(offE + __popc(bE & lt)) + 2] = q;   // end b, turned into len below
-            offS += __popc(bS); offE += __popc(bE);
         }
         __syncthreads();
         // ---- run lengths, then the colinearity check (utils.py:266-291): seq-1 positions of
