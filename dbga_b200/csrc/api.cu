@@ -300,7 +300,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             const int nmax = std::max(pd.n0, pd.n1);
             const int words = (((nmax + 15) / 16 + 3) + 1) & ~1;
             const bool fits = cap <= 32768 && N0 < 65000 && N1 < 65000 &&   // 16-bit positions in shared memory
-                              stage12_small_smem(key_bytes, cap, words, (int)N1) <= SMEM_LIMIT;
+                              stage12_small_smem(key_bytes, cap, words, (int)N1, false) <= SMEM_LIMIT;
             if (fits) {
                 by_cap[{1, cap}].push_back((int32_t)i);
             } else {
@@ -311,10 +311,11 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                     for (int g = 2; g <= 8 && !parts; ++g) {
                         uint64_t w = keys * 170 / 100 / g + 64;       // 1.7 x the expected keys per partition
                         uint32_t gr = 256;
-                        while ((uint64_t)gr * 16 < w) gr <<= 1;
+                        while ((uint64_t)gr * 64 < w) gr <<= 1;        // fine granule: every slot counts against the partition count
                         const uint32_t c = (uint32_t)((w + gr - 1) / gr * gr);
-                        // (medium pairs keep memo[] in global memory: no per-position shared memory)
-                        if (c <= 32768 && stage12_small_smem(key_bytes, c, words0, 0) <= 216 * 1024) { parts = g; pcap = c; }
+                        // (medium pairs keep memo[] in global memory and fold position and counters into one word:
+                        //  shared memory holds the packed sequences and 8- or 12-byte slots, nothing else)
+                        if (c <= 32768 && stage12_small_smem(key_bytes, c, words0, 0, true) <= 224 * 1024) { parts = g; pcap = c; }
                     }
                 }
                 if (parts) by_cap[{parts, pcap}].push_back((int32_t)i);
@@ -335,7 +336,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             }
             c.words = (((nmax + 15) / 16 + 3) + 1) & ~1;
             c.maxq = c.parts > 1 ? 0 : qmax;
-            if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq) > SMEM_LIMIT) {
+            if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq, c.parts > 1) > SMEM_LIMIT) {
                 // mixed extremes inside one class: fall back to the large path for this class
                 ctx->h_list.resize((size_t)c.begin);
                 for (int32_t i : members) large.push_back(i);

@@ -36,7 +36,7 @@ struct Pools {
 };
 
 // ---- stages 1+2 fused (pairs whose table fits in shared memory)
-size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq);
+size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq, bool medium);
 cudaError_t launch_stage12_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
                                  uint32_t cap, int parts, int words, int maxq, bool full, bool want_segments,
                                  PairOut *pout, Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,

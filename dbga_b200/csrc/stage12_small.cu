@@ -22,6 +22,7 @@
 
 namespace dbga {
 
+constexpr uint32_t MDUP0 = 0x80000000u;  // medium pairs' merged word: repeated in seq1
 constexpr uint32_t DUP0 = 0x10000u;      // cnt[]: the k-mer occurs more than once in seq1 (seq-2 counts stay below 2^16)
 struct S12Shared {
     int nS, nE, nA, big;
@@ -48,8 +49,13 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     uint32_t *pk0 = reinterpret_cast<uint32_t *>(smem);
     uint32_t *pk1 = pk0 + words;
     KeyT *keys = reinterpret_cast<KeyT *>(pk1 + words);
+    // small pairs: a 16-bit seq-1 position and one 32-bit word per slot (occurrences in seq2 | DUP0 if
+    // repeated in seq1).  Medium pairs fold both into the word (8 bytes per slot with 32-bit keys,
+    // fewer table partitions): bits 0-15 seq-1 position + 1 (0: none), bits 16-31 occurrences in seq2
+    // with MDUP0 = bit 31 for "repeated in seq1"; every update is an atomic OR / ADD, so the claimer's
+    // position and a later finder's flag commute.
     uint16_t *pos0 = reinterpret_cast<uint16_t *>(keys + cap);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(pos0 + cap);       // occurrences in seq2 | DUP0 if repeated in seq1
+    uint32_t *cnt = MEDIUM ? reinterpret_cast<uint32_t *>(keys + cap) : reinterpret_cast<uint32_t *>(pos0 + cap);
     uint16_t *memo = reinterpret_cast<uint16_t *>(cnt + cap);       // later: aof in shared memory
     // aliases valid once the table is dead (after phase B2)
     uint32_t *ska = reinterpret_cast<uint32_t *>(keys);             // unordered run starts (b<<16 | a), cap entries
@@ -87,7 +93,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         }
         auto init_table = [&]() {       // keys + pos0 = all ones, cnt = 0
             uint4 *t4 = reinterpret_cast<uint4 *>(keys);
-            const int n_ff = (int)((cap * (sizeof(KeyT) + 2)) / 16), n_00 = (int)(cap * 4 / 16);
+            const int n_ff = (int)((cap * (sizeof(KeyT) + (MEDIUM ? 0 : 2))) / 16), n_00 = (int)(cap * 4 / 16);
             for (int i = tid; i < n_ff; i += T) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
             uint4 *z4 = reinterpret_cast<uint4 *>(cnt);
             for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -117,7 +123,8 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 if (!in_part(hv)) return;
                 bool claimed;
                 const uint32_t h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
-                if (claimed) pos0[h] = (uint16_t)p;
+                if (MEDIUM) atomicOr(&cnt[h], claimed ? (uint32_t)p + 1u : MDUP0);
+                else if (claimed) pos0[h] = (uint16_t)p;
                 else cnt[h] = DUP0;
             };
             for (int p = 2 * tid; p < N0; p += 2 * T) {
@@ -138,7 +145,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 } else {
                     h = bkt_find<KeyT>(keys, nb, key, hv);
                 }
-                if (h != 0xFFFFFFFFu) atomicAdd(&cnt[h], 1u);      // result unused: a fire-and-forget shared-memory add
+                if (h != 0xFFFFFFFFu) atomicAdd(&cnt[h], MEDIUM ? 0x10000u : 1u);      // result unused: a fire-and-forget shared-memory add
                 return h != 0xFFFFFFFFu ? h : (uint32_t)NONE16;
             };
             uint32_t *memo2 = reinterpret_cast<uint32_t *>(memo);   // two positions per word
@@ -156,8 +163,9 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 if (MEDIUM && !in_part(B::mix(key))) return h;
                 uint32_t a = NONE16;
                 if (h != NONE16) {
-                    const bool d = cnt[h] != 1u;     // repeated in seq1 (DUP0) or seen more than once in seq2
-                    if (!d) a = pos0[h];             // NONE16 when the k-mer is private to seq2 (graph mode)
+                    const uint32_t w = cnt[h];
+                    const bool d = MEDIUM ? (w >> 16) != 1u : w != 1u;     // repeated in seq1 (DUP0) or seen more than once in seq2
+                    if (!d) a = MEDIUM ? ((w & 0xFFFFu) - 1u) & 0xFFFFu : pos0[h];   // NONE16 when the k-mer is private to seq2 (graph mode)
                     if (FULL) nd1[pd.q_base + q] = !d;
                 }
                 return a;
@@ -176,7 +184,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                     const uint32_t hv = B::mix(key);
                     if (!in_part(hv)) continue;
                     const uint32_t h = bkt_find<KeyT>(keys, nb, key, hv);
-                    nd0[pd.p_base + p] = cnt[h] <= 1u;      // not repeated in seq1, at most once in seq2
+                    nd0[pd.p_base + p] = (MEDIUM ? cnt[h] >> 16 : cnt[h]) <= 1u;      // not repeated in seq1, at most once in seq2
                 }
             }
         }
@@ -343,8 +351,9 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     }
 }
 
-size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq) {
-    return (size_t)words * 8 + (size_t)cap * (key_bytes + 6) + (size_t)((maxq + 7) / 8 * 8) * 2 + 16;
+// medium: the partitioned-table instantiation (no 16-bit position array, no shared-memory memo[])
+size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq, bool medium) {
+    return (size_t)words * 8 + (size_t)cap * (key_bytes + (medium ? 4 : 6)) + (size_t)((maxq + 7) / 8 * 8) * 2 + 16;
 }
 
 template <typename KeyT, bool FULL, int TPB>
@@ -352,7 +361,7 @@ static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const in
                             uint32_t cap, int parts, int words, int maxq, bool want_segments, PairOut *pout,
                             Pools pools, Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int32_t *status,
                             int32_t *aof, int num_sms, cudaStream_t st) {
-    const size_t smem = stage12_small_smem(sizeof(KeyT), cap, words, maxq);
+    const size_t smem = stage12_small_smem(sizeof(KeyT), cap, words, maxq, TPB > 256);
     auto kern = stage12_small_kernel<KeyT, FULL, TPB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
