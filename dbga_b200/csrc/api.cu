@@ -63,6 +63,7 @@ struct dbga_ctx {
     int large_begin = 0;
     int stage2_begin = 0;      // first list entry that needs the generic stage-2 kernel (medium + large pairs)
     int stage2_threads = 128;
+    int64_t n_long_pairs = 0;  // pairs whose stage 2 runs on a thread-block cluster (more than S2_CLUSTER_ABOVE seq-2 positions)
     int64_t runs_cap = 0, slots_cap = 0, tb_cap = 0;
     int64_t bnd_stride_warp = 0, bnd_stride_cta = 0;
     int grid_warp = 0, grid_cta = 0, grid_cluster = 0;
@@ -420,7 +421,15 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     ctx->runs_cap = std::max<int64_t>(ctx->runs_cap, std::min<int64_t>(worst_runs, ctx->sumN1 / 16 + 4 * P + 1024));
     ctx->slots_cap = std::max<int64_t>(ctx->slots_cap, ctx->runs_cap + P + 16);
     ctx->tb_cap = std::max<int64_t>(ctx->tb_cap, std::min<int64_t>(ctx->scratch_limit, 64LL << 20));
-    ctx->stage2_threads = mx1 <= 4096 ? 128 : (mx1 <= 65536 ? 256 : 1024);
+    ctx->n_long_pairs = 0;
+    for (int64_t i = 0; i < P; ++i) ctx->n_long_pairs += (ctx->h_pairs[(size_t)i].n1 - k + 1) > S2_CLUSTER_ABOVE;
+    // the very long pairs go to the cluster kernel; the CTA kernel is sized for the rest
+    int mx1_cta = 0;
+    for (int64_t i = 0; i < P; ++i) {
+        const int n1 = ctx->h_pairs[(size_t)i].n1;
+        if (no_anchors || n1 - k + 1 <= S2_CLUSTER_ABOVE) mx1_cta = std::max(mx1_cta, n1);
+    }
+    ctx->stage2_threads = mx1_cta <= 4096 ? 128 : (mx1_cta <= 65536 ? 256 : 1024);
     {   // tiny DP classes: a substitution bubble is (k+1) x (k+1), so bucket around multiples of it
         const int b0 = std::min(TINY_MAX, no_anchors ? 8 : k + 1);
         ctx->tiny_bound[0] = b0;
@@ -541,8 +550,8 @@ int run_pipeline(dbga_ctx *ctx) {
             DBGA_CUDA_CHECK(launch_stage2(pairs, lst, cnt, ctx->no_anchors ? 1 : ctx->prm.k, ctx->no_anchors, seg,
                                           (int32_t *)ctx->d_aof.p, (int32_t *)ctx->d_status.p, pout, pools, ctr,
                                           ctx->stage2_threads, ctx->num_sms, ctx->max_abs_score, ctx->dp.go_raw,
-                                          ctx->dp.ge_raw, st));
-            ctx->launches += 1;
+                                          ctx->dp.ge_raw, ctx->no_anchors ? 0 : ctx->n_long_pairs, st));
+            ctx->launches += (!ctx->no_anchors && ctx->n_long_pairs > 0) ? 2 : 1;
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));

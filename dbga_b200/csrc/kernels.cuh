@@ -52,7 +52,9 @@ cudaError_t launch_stage1_large(const uint8_t *seqs, const PairDesc *pairs, cons
 // pair_list == nullptr: all pairs 0..num_pairs-1
 cudaError_t launch_stage2(const PairDesc *pairs, const int32_t *pair_list, int64_t num_pairs, int k, bool no_anchors, bool want_segments,
                           const int32_t *aof, int32_t *status, PairOut *out, Pools pools, Counters *ctr,
-                          int threads, int num_sms, int max_abs_score, int go_raw, int ge_raw, cudaStream_t st);
+                          int threads, int num_sms, int max_abs_score, int go_raw, int ge_raw, int64_t cluster_pairs,
+                          cudaStream_t st);
+constexpr int S2_CLUSTER_ABOVE = 65536;   // seq-2 positions beyond which a pair's stage 2 runs on a thread-block cluster
 
 // ---- stage 3
 // count_dev: device pointer to the number of list entries (no host round trip needed)

@@ -12,11 +12,14 @@ struct SlotCfg {
 };
 
 // run(r, a, b, len) returns run r (ascending b).  flag_big: shared int, set on TOO_LARGE.
+// tid / T: this thread's index among, and the number of, the threads that share the pair (a CTA, or all
+// CTAs of a thread-block cluster); whole warps only.
 template <class RunFn>
 __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, int R, RunFn run, int64_t slot_base,
                                             const Pools &pools, Counters *ctr, SlotCfg cfg, int *flag_big,
-                                            unsigned long long &my_cells, unsigned long long &my_nseg) {
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31;
+                                            unsigned long long &my_cells, unsigned long long &my_nseg,
+                                            int tid = (int)threadIdx.x, int T = (int)blockDim.x) {
+    const int lane = tid & 31;
     const int n_slots = R == 0 ? 1 : R + 1;
     const int64_t str_base = 2 * pd.off0;
     for (int base = 0; base < n_slots; base += T) {

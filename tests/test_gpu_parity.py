@@ -443,3 +443,13 @@ def test_kmer_stats_and_k_heuristics(aligner):
     assert finals.tolist() == [c["predict_final_p"] for c in g["cases"]]
     with pytest.raises(ValueError, match="Invalid k size"):
         KS.predict_p_batch([("ACGT", "ACG")], 4)
+
+
+def test_very_long_pairs_take_the_cluster_stage2(aligner):
+    """Pairs with more than 65 536 seq-2 positions run stage 2 on a thread-block cluster
+    (stage2_cluster_kernel): anchors, status and alignment against the oracle, next to shorter
+    pairs in the same batch (CTA stage 2), with and without a cycle."""
+    pairs = [O.synth_pair(90000, 0.004, 0.001, 411), O.synth_pair(1500, 0.018, 0.002, 7), O.synth_pair(30000, 0.004, 0.001, 12),
+             O.synth_pair(70000, 0.01, 0.002, 413)]
+    for k in (15, 11):
+        check_batch(aligner, pairs, k)
