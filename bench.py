@@ -20,8 +20,14 @@ from __future__ import annotations
 import argparse
 import os as _os
 _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before CUDA initialises: one hardware queue per stream
-if _os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":    # NCCL's banner goes to stdout, which carries the one JSON line
-    _os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version
+# banner at the first communicator, for one) is sent to stderr; emit() writes to the real stdout
+_REAL_STDOUT = _os.dup(1)
+_os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 import json
 import os
 import sys
@@ -152,7 +158,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cycle_frac": float((out["status"] == 1).mean()),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------ our arm
@@ -348,7 +354,7 @@ def run_ours(args):
         "cycle_frac": float((status == 1).mean()),
         "ok_frac": float(ok.mean()),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
