@@ -7,13 +7,18 @@ One "step" = one pass of the whole hot path (stage 1 k-mer hashing, stage 2 anch
 stage 3 DP, assembly) over one batch of synthetic pairs.  Workload (N=1): BASELINE config
 [2], "100k synthetic 1.5 kb pairs at 2 % divergence, k=9" (config [1], a single 10 kb pair at
 k=7, is parity-correctly a "Cycles detected" error for every seed and is covered in tests).
-N>1: every rank gets its own 100k-pair batch (weak scaling), no collective on the data
-path; time = max over ranks.
+N>1: every rank gets its own 100k-pair batch (weak scaling; `--scaling strong`: the workload's
+pairs are sharded over the ranks instead, BASELINE config [2] "sharded by pair across 1/2/4/8
+GPUs"), no collective on the data path; time = max over ranks.
 
 JSON keys beyond the base contract: `roofline` (dominant kernel vs measured HBM peak),
 `cpu_baseline` (oracle C port on the host cores), `dp` (stage-3 GCUPS vs the measured
 integer-pipe rate on the workload, and `dp.microbench`: the same on 1024 x 1024 segments),
-`stages_ms`, `cycle_frac`.
+`stages_ms`, `cycle_frac`, `plan_ms` (host planning, outside `value`'s timed region, inside
+`e2e`'s), `parity` (the timed batch diffed against the oracle: status, score, DP cells, anchors
+and the full gapped rows of every checked pair; any mismatch makes the run exit non-zero) and
+`e2e_variants` (the same end-to-end call with other wire formats: anchor runs returned too,
+compact rows, compact rows + host expansion, 2-bit packed input).
 """
 from __future__ import annotations
 
@@ -128,7 +133,8 @@ def ncu_traffic():
 def run_reference(args):
     """The reference's CPU implementation of the path.  The reference is pure Python +
     cogent3 (absent here and on the GPU box) and cannot travel, so this arm times its C
-    restatement (oracle/dbga_oracle.c, kind "port") with all host threads."""
+    restatement (oracle/dbga_oracle.c, kind "port") with all host threads, on the same batch
+    as our arm (same generator, seed and size)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -139,7 +145,7 @@ def run_reference(args):
     P = min(args.pairs or P_full, args.ref_sample)
     buf, offs = synth_batch(P, n, ps, pi, seed=args.seed)
     cores = os.cpu_count() or 1
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, min(args.warmup, 2))):
         CO.align_batch(buf, offs, k, threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -149,9 +155,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": workload_desc(name, P_full), "sample": f"{P} pairs per step"},
+        "config": {"workload": workload_desc(name, P_full), "pairs_per_gpu": P_full,
+                   "sample": f"{P} pairs per step (rank 0's batch, the whole batch)" if P == P_full else f"{P} pairs per step"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{P} pairs of the workload per step, {args.steps} steps; C restatement of the "
                                    "reference path (reference = Python + cogent3, not runnable here)"},
@@ -162,11 +169,22 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------ our arm
+def result_bytes(raw, P, flags):
+    """bytes one dbga_align_batch call brings back (counted from the arrays the result points to)"""
+    n_aln = int(np.ctypeslib.as_array(raw.aln_off, shape=(P + 1,))[-1])
+    n_runs = int(np.ctypeslib.as_array(raw.run_off, shape=(P + 1,))[-1])
+    d2h = 2 * n_aln + 12 * n_runs + P * (4 + 8 + 8 + 4 + 8 + 16) + 16 * (P + 1)
+    if flags & 2:
+        d2h += 4 * (n_runs + P)
+    return d2h, n_aln, n_runs
+
+
 def run_ours(args):
     import ctypes as C
     import torch
-    from dbga_b200 import Aligner, _lib
-    from dbga_b200.synth import synth_batch, pairs_from_buffers
+    from dbga_b200 import Aligner, _lib, pack_ascii
+    from dbga_b200.sharding import shard_range
+    from dbga_b200.synth import synth_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -180,15 +198,31 @@ def run_ours(args):
 
     name = args.workload
     P_full, n, ps, pi, k = WORKLOADS[name]
-    P = args.pairs or P_full
+    P_job = args.pairs or P_full
+    strong = args.scaling == "strong"
     al = Aligner(local)
     lib = al.lib
-    # pinned host input (the e2e leg copies from here every step)
-    cap = P * (2 * n + 64)
-    hptr = lib.dbga_host_alloc(cap)
-    hbuf = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_uint8)), shape=(cap,))
-    buf, offs = synth_batch(P, n, ps, pi, seed=args.seed + 7919 * rank, out=hbuf)
+    if strong:
+        # the job is ONE batch of P_job pairs (same seed on every rank), rank r takes its contiguous shard
+        lo_p, hi_p = shard_range(P_job, rank, world)
+        P = hi_p - lo_p
+        full_buf, full_offs = synth_batch(P_job, n, ps, pi, seed=args.seed)
+        b0, b1 = int(full_offs[2 * lo_p]), int(full_offs[2 * hi_p])
+        cap = b1 - b0 + 64
+        hptr = lib.dbga_host_alloc(cap)
+        hbuf = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_uint8)), shape=(cap,))
+        hbuf[:b1 - b0] = full_buf[b0:b1]
+        buf, offs = hbuf, (full_offs[2 * lo_p:2 * hi_p + 1] - b0).copy()
+        del full_buf
+    else:
+        P = P_job
+        # pinned host input (the e2e leg copies from here every step)
+        cap = P * (2 * n + 64)
+        hptr = lib.dbga_host_alloc(cap)
+        hbuf = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_uint8)), shape=(cap,))
+        buf, offs = synth_batch(P, n, ps, pi, seed=args.seed + 7919 * rank, out=hbuf)
     total_bytes = int(offs[-1])
+    total_pairs = P_job if strong else world * P
     prm = al.params(k)
 
     stream = torch.cuda.Stream(device=dev)      # the library launches on this stream; events too
@@ -203,12 +237,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---------------- device-resident leg (`value`): plan once, K x kernels only
     al.plan(offs, prm)
     for _ in range(max(3, args.warmup)):
         al.run(d_seqs.data_ptr())
         res = al.fetch(unpack=False)      # also sizes the pools (re-runs stage 2.. on overflow)
     launches_per_step = int(res.kernel_launches)
+    plan_ms = float(res.ms_plan)
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -219,13 +261,9 @@ def run_ours(args):
     e1.record(stream)
     torch.cuda.synchronize()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     barrier()
-    value = world * P * args.steps / (ms * 1e-3)
+    value = total_pairs * args.steps / (ms * 1e-3)
 
     # ---------------- per-stage device times (CUDA events inside the library, same stream)
     st_acc = np.zeros(4)
@@ -238,42 +276,114 @@ def run_ours(args):
     status = full.status
     ok = status == 0
     cells = int(full.timing["dp_cells"])
-    M_total = int(full.n_anchors[ok | (status == 1)].sum())
-    # sanity on the timed workload (size-independent properties; the oracle is not used here)
-    rs = np.random.default_rng(1)
-    for i in rs.choice(P, size=min(P, 64), replace=False):
-        if status[i] != 0:
-            continue
-        a0, a1 = full.alignment(int(i))
-        s0, s1 = pairs_from_buffers(buf, offs, [int(i)])[0]
-        assert len(a0) == len(a1) and a0.replace("-", "") == s0 and a1.replace("-", "") == s1, "degap check failed"
+    n_aln = int(full.aln_off[-1])
 
-    # ---------------- end-to-end leg: pinned host in -> C ABI -> pinned host out
-    al2 = Aligner(local)          # own streams: dbga_align_batch pipelines chunks over three lanes
-    for _ in range(2):
-        raw = al2.align_buffers(hptr, offs, prm, unpack=False)
-    barrier()
+    # ---------------- end-to-end leg: pinned host in -> C ABI -> pinned host out.  The headline form
+    # returns what DeBruijnPairwise.alignment() returns (the gapped rows + per-pair columns; the anchor
+    # runs stay on the device: DBGA_FLAG_NO_RUNS); the other wire formats are timed the same way.
+    al2 = Aligner(local)          # own streams: dbga_align_batch pipelines chunks over four lanes
+
+    def time_e2e(flags, packed=None, expand=False, steps=None):
+        steps = steps or args.steps
+        p2 = al2.params(k, flags=flags)
+        src = packed if packed is not None else hptr
+        rows = None
+        if expand:
+            cap2 = total_bytes + 16
+            r0 = np.ctypeslib.as_array(C.cast(lib.dbga_host_alloc(cap2), C.POINTER(C.c_uint8)), shape=(cap2,))
+            r1 = np.ctypeslib.as_array(C.cast(lib.dbga_host_alloc(cap2), C.POINTER(C.c_uint8)), shape=(cap2,))
+            eoff = np.zeros(P + 1, np.int64)
+            i64 = C.POINTER(C.c_int64)
+            o64 = np.ascontiguousarray(offs, np.int64)
+
+        def once():
+            raw = al2.align_buffers(src, offs, p2, unpack=False, packed=packed is not None)
+            if expand:
+                rc = lib.dbga_expand_rows(C.c_void_p(hptr), o64.ctypes.data_as(i64), C.byref(raw), C.c_void_p(r0.ctypes.data),
+                                          C.c_void_p(r1.ctypes.data), cap2, eoff.ctypes.data_as(i64), 0)
+                assert rc == 0
+            return raw
+        for _ in range(2):
+            raw = once()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            raw = once()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        d2h, _, _ = result_bytes(raw, P, flags)
+        if expand:
+            rows = (eoff.copy(), r0, r1)
+        h2d = (4 * (int(offs[-1]) // 16 + 2 * P + 1) if packed is not None else total_bytes) + 44 * P
+        return {"value": total_pairs * steps / dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": dt / steps * 1e3}, raw, rows
+
+    e2e, raw_e2e, _ = time_e2e(_lib.FLAG_NO_RUNS)
+    e2e_rows_equal = bool(np.array_equal(np.ctypeslib.as_array(raw_e2e.aln_off, shape=(P + 1,)), full.aln_off) and
+                          np.array_equal(np.ctypeslib.as_array(raw_e2e.aln0, shape=(max(n_aln, 1),))[:n_aln], full.aln0) and
+                          np.array_equal(np.ctypeslib.as_array(raw_e2e.aln1, shape=(max(n_aln, 1),))[:n_aln], full.aln1) and
+                          np.array_equal(np.ctypeslib.as_array(raw_e2e.status, shape=(P,)), status))
+    variants = {}
+    if not args.no_variants:
+        vsteps = max(3, args.steps // 2)
+        variants["rows+anchor_runs (flags=0, the round-1 form)"], _, _ = time_e2e(0, steps=vsteps)
+        variants["compact_rows (segment columns + runs; flags=COMPACT_ROWS)"], _, _ = time_e2e(_lib.FLAG_COMPACT_ROWS, steps=vsteps)
+        variants["compact_rows + dbga_expand_rows on the host (full rows in host memory)"], _, rows = \
+            time_e2e(_lib.FLAG_COMPACT_ROWS, expand=True, steps=vsteps)
+        exp_equal = bool(np.array_equal(rows[0], full.aln_off) and np.array_equal(rows[1][:n_aln], full.aln0) and
+                         np.array_equal(rows[2][:n_aln], full.aln1))
+        words = pack_ascii(buf[:total_bytes], offs)
+        wptr = lib.dbga_host_alloc(words.nbytes)
+        wpin = np.ctypeslib.as_array(C.cast(wptr, C.POINTER(C.c_uint32)), shape=(len(words),))
+        wpin[:] = words
+        variants["2-bit packed input (dbga_align_batch_packed), rows out (flags=NO_RUNS)"], raw_pk, _ = \
+            time_e2e(_lib.FLAG_NO_RUNS, packed=wptr, steps=vsteps)
+        pk_equal = bool(np.array_equal(np.ctypeslib.as_array(raw_pk.aln0, shape=(max(n_aln, 1),))[:n_aln], full.aln0))
+        variants["2-bit packed input + compact_rows"], _, _ = time_e2e(_lib.FLAG_COMPACT_ROWS, packed=wptr, steps=vsteps)
+        variants["all forms byte-identical to the device-resident result"] = exp_equal and pk_equal
+
+    # ---------------- parity gate: the timed batch against the oracle (the CPU leg's own pass)
+    from oracle import c_oracle as CO
+    cores = os.cpu_count() or 1
+    if world == 1:
+        sample = min(P, args.ref_sample)
+    else:
+        sample = min(P, 4000)                 # every rank checks the head of its own batch
+    sb, so = buf[:int(offs[2 * sample])], offs[:2 * sample + 1]
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        raw = al2.align_buffers(hptr, offs, prm, unpack=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    ref = CO.check_batch(sb, so, k, full.aln_off[:sample + 1], full.aln0, full.aln1, full.run_off[:sample + 1],
+                         full.runs.reshape(-1), threads=cores if world == 1 else max(1, cores // world))
+    first_pass = time.perf_counter() - t0
+    okr = ref["status"] == 0
+    rep = okr | (ref["status"] == 1)
+    mism = int((full.status[:sample] != ref["status"]).sum())
+    mism += int((full.score[:sample][okr] != ref["score"][okr]).sum())
+    mism += int((full.dp_cells[:sample][okr] != ref["dp_cells"][okr]).sum())
+    mism += int((np.diff(full.aln_off[:sample + 1])[okr] != ref["aln_len"][okr]).sum())
+    mism += int((full.n_anchors[:sample][rep] != ref["n_anchors"][rep]).sum())
+    mism += int((ref["diff"] != 0).sum())
+    mism += 0 if e2e_rows_equal else 1
+    if variants and not variants["all forms byte-identical to the device-resident result"]:
+        mism += 1
     if dist is not None:
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_value = world * P * args.steps / dt
-    n_aln = int(np.ctypeslib.as_array(raw.aln_off, shape=(P + 1,))[-1])
-    n_runs = int(np.ctypeslib.as_array(raw.run_off, shape=(P + 1,))[-1])
-    h2d = total_bytes + 40 * P + 4 * P
-    d2h = 2 * n_aln + 12 * n_runs + P * (4 + 8 + 8 + 4 + 8) + 16 * (P + 1)
+        t = torch.tensor([mism], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        mism = int(t.item())
+    parity = {"checked_pairs": sample * world, "rows_diffed": int(okr.sum()) * (world if world > 1 else 1), "mismatches": mism,
+              "what": "status, score, dp_cells, aligned length, n_anchors, every anchor and both full gapped rows of "
+                      "every checked pair of the timed batch vs oracle/dbga_oracle.c; the end-to-end result (and every "
+                      "wire variant) byte-identical to the device-resident one",
+              "e2e_rows_equal_device_rows": e2e_rows_equal}
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
+        if mism:
+            sys.exit(1)
         return
 
-    # ---------------- roofline of the dominant kernel (stage 1) and DP GCUPS
+    # ---------------- roofline of the dominant kernel and DP GCUPS
     peaks, peak_src = measured_peaks()
     stage_names = ["stage12_kmer_anchor", "stage2_large_pairs", "stage3_dp", "assemble"]
     dom = int(np.argmax(st_ms))
@@ -287,6 +397,11 @@ def run_ours(args):
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic.get(stage_names[dom]),
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": float(st_ms[dom])}
+    asm_bytes = total_bytes // 2 + 2 * n_aln + 16 * n_runs_total
+    roofline["assemble"] = {"achieved": asm_bytes / (st_ms[3] * 1e-3) / 1e9, "frac": asm_bytes / (st_ms[3] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                            "algorithmic_bytes_per_launch": asm_bytes, "launch_ms": float(st_ms[3]),
+                            "traffic": traffic.get("assemble"),
+                            "note": "seq1 bytes + both rows + runs / item offsets; layout + copy kernels"}
     intpk = al.int_peak()
     gcups = cells / (st_ms[2] * 1e-3) / 1e9 if st_ms[2] > 0 else 0.0
     roof_gcups = intpk["mix_ops_per_s"] / 9 / 1e9
@@ -296,37 +411,35 @@ def run_ours(args):
           "stage is latency/launch bound here (see DESIGN.md DP microbenchmark)"}
 
     # ---------------- DP microbenchmark (the integer roofline is only testable on long
-    # segments): 3814 uniform 1024 x 1024 global alignments, device-resident, stage-3 time from the
+    # segments): uniform L x L global alignments, device-resident, stage-3 time from the
     # library's CUDA events on the launching stream (forward kernels + traceback kernel)
     if not args.no_dp_micro:
-        L, Pm = 1024, 3814
-        mb, mo = synth_batch(Pm, L, 0.05, 0.01, seed=L)
-        d_m = torch.from_numpy(np.concatenate([mb, np.zeros(64, np.uint8)])).to(dev)
-        torch.cuda.synchronize()
-        alm = Aligner(local)
-        alm.plan(mo, alm.params(1), global_only=True)
-        t3 = []
-        for it in range(6):
-            alm.run(d_m.data_ptr())
-            rm = alm.fetch(unpack=False)
-            if it >= 3:
-                t3.append(rm.ms_stage3)
-        mcells = int(rm.dp_cells_total)
-        mg = mcells / (min(t3) * 1e-3) / 1e9
-        dp["microbench"] = {"workload": f"{Pm} global alignments of {L} x {L} (5 % substitutions, 1 % indels)",
-                            "cells": mcells, "stage3_ms": min(t3), "gcups": mg, "frac": mg / roof_gcups,
-                            "kernel": "dp_wf16_kernel<16> (packed int16x2 wavefront) + dp_tb16_kernel"}
-        alm.close()
+        micro = []
+        for L, Pm in ((1024, 3814), (4096, 238)):
+            mb, mo = synth_batch(Pm, L, 0.05, 0.01, seed=L)
+            d_m = torch.from_numpy(np.concatenate([mb, np.zeros(64, np.uint8)])).to(dev)
+            torch.cuda.synchronize()
+            alm = Aligner(local)
+            alm.plan(mo, alm.params(1), global_only=True)
+            t3 = []
+            for it in range(6):
+                alm.run(d_m.data_ptr())
+                rm = alm.fetch(unpack=False)
+                if it >= 3:
+                    t3.append(rm.ms_stage3)
+            mcells = int(rm.dp_cells_total)
+            mg = mcells / (min(t3) * 1e-3) / 1e9
+            micro.append({"workload": f"{Pm} global alignments of {L} x {L} (5 % substitutions, 1 % indels)",
+                          "cells": mcells, "stage3_ms": min(t3), "gcups": mg, "frac": mg / roof_gcups})
+            alm.close()
+            del d_m
+        dp["microbench"] = micro[0]
+        dp["microbench_4096"] = micro[1]
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
-        from oracle import c_oracle as CO
-        cores = os.cpu_count() or 1
-        sample = min(P, args.ref_sample)
-        sb, so = buf[:int(offs[2 * sample])], offs[:2 * sample + 1]
-        CO.align_batch(sb[:int(so[min(2 * 512, 2 * sample)])], so[:min(2 * 512, 2 * sample) + 1], k, threads=cores)
-        passes, cdt = 0, 0.0
+        passes, cdt = 1, first_pass            # the parity pass above was the first one (it also compares rows)
         while cdt < args.cpu_seconds:                 # whole passes over the sample until the budget is spent
             t0 = time.perf_counter()
             CO.align_batch(sb, so, k, threads=cores)
@@ -339,16 +452,20 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": workload_desc(name, P), "pairs_per_gpu": P,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": workload_desc(name, P_job), "pairs_per_gpu": P if not strong else f"{P_job} / {world}",
                    "l2": f"inputs {total_bytes / 1e6:.0f} MB + outputs {2 * n_aln / 1e6:.0f} MB per step exceed the 126 MB L2",
-                   "parallelism": f"pairs sharded by index over {world} GPU(s), no collective"},
+                   "parallelism": f"pairs sharded by index over {world} GPU(s), no collective",
+                   "value_is": "kernels only on a device-resident, pre-planned batch (plan_ms of host work per batch is outside it; "
+                               "e2e includes it)"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": dt / args.steps * 1e3},
+        "e2e": e2e,
+        "e2e_variants": variants,
+        "plan_ms": plan_ms,
         "gpu_launches": launches_per_step * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "dp": dp,
         "stages_ms": dict(zip(stage_names, [float(x) for x in st_ms])),
         "cycle_frac": float((status == 1).mean()),
@@ -357,6 +474,9 @@ def run_ours(args):
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
+    if mism:
+        sys.stderr.write(f"PARITY FAILURE: {mism} mismatches against the oracle\n")
+        sys.exit(1)
 
 
 def main():
@@ -366,12 +486,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the workload's)")
-    ap.add_argument("--ref-sample", type=int, default=50_000, help="pairs per CPU-baseline pass")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets the workload's pairs; strong: the workload's pairs are sharded over the GPUs")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (strong: in the job); default: the workload's")
+    ap.add_argument("--ref-sample", type=int, default=100_000, help="pairs per CPU-baseline pass / parity check")
     ap.add_argument("--seed", type=int, default=20261019)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU time spent on the cpu_baseline leg")
     ap.add_argument("--no-dp-micro", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the other wire formats of the end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdbga_b200.so")
 
 OK, CYCLE, K_INVALID, BAD_CHAR, TOO_LARGE = 0, 1, 2, 3, 4
+FLAG_NO_RUNS, FLAG_COMPACT_ROWS = 1, 2
 ORDERS = ("XMY", "XYM", "MXY", "MYX", "YXM", "YMX")
 
 # every symbol include/dbga_b200.h declares
@@ -23,14 +24,17 @@ EXPORTS = (
     "dbga_host_alloc", "dbga_host_free", "dbga_align_batch", "dbga_plan", "dbga_plan_global",
     "dbga_plan_run", "dbga_plan_fetch", "dbga_measure_int_peak", "dbga_global_align_batch",
     "dbga_kmer_stats", "dbga_version",
+    "dbga_align_batch_packed", "dbga_packed_words", "dbga_pack_ascii", "dbga_expand_rows",
+    "dbga_multi_create", "dbga_multi_destroy", "dbga_multi_last_error", "dbga_align_batch_multi",
 )
+MAX_SHARDS = 16
 
 
 class Params(C.Structure):
     _fields_ = [("k", C.c_int32), ("score", C.c_int32 * 16), ("gap_open", C.c_int32),
                 ("gap_extend", C.c_int32), ("gap_len_mode", C.c_int32), ("xy_allowed", C.c_int32),
                 ("pred_order", C.c_int32), ("end_order", C.c_int32), ("stages", C.c_int32),
-                ("want_graph", C.c_int32)]
+                ("want_graph", C.c_int32), ("flags", C.c_int32)]
 
 
 class Result(C.Structure):
@@ -45,7 +49,13 @@ class Result(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_stage1", C.c_float), ("ms_stage2", C.c_float),
                 ("ms_stage3", C.c_float), ("ms_assemble", C.c_float), ("ms_d2h", C.c_float),
                 ("ms_total", C.c_float), ("dp_cells_total", C.c_int64),
-                ("dp_segments_total", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("dp_segments_total", C.c_int64), ("kernel_launches", C.c_int64),
+                ("sop", C.POINTER(C.c_int32)), ("seg_cols", C.POINTER(C.c_int32)), ("ms_plan", C.c_float)]
+
+
+class MultiResult(C.Structure):
+    _fields_ = [("num_shards", C.c_int32), ("pad", C.c_int32), ("pair_lo", C.c_int64 * (MAX_SHARDS + 1)),
+                ("shard", Result * MAX_SHARDS), ("ms_total", C.c_float)]
 
 
 _lib = None
@@ -96,12 +106,29 @@ def load():
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.dbga_kmer_stats.restype = C.c_int
     lib.dbga_version.restype = C.c_int
+    i64p, u32p = C.POINTER(C.c_int64), C.POINTER(C.c_uint32)
+    lib.dbga_align_batch_packed.argtypes = [vp, vp, i64p, C.c_int64, C.POINTER(Params), C.POINTER(Result)]
+    lib.dbga_align_batch_packed.restype = C.c_int
+    lib.dbga_packed_words.argtypes = [i64p, C.c_int64]
+    lib.dbga_packed_words.restype = C.c_int64
+    lib.dbga_pack_ascii.argtypes = [vp, i64p, C.c_int64, vp, C.c_int]
+    lib.dbga_pack_ascii.restype = C.c_int64
+    lib.dbga_expand_rows.argtypes = [vp, i64p, C.POINTER(Result), vp, vp, C.c_int64, i64p, C.c_int]
+    lib.dbga_expand_rows.restype = C.c_int
+    lib.dbga_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.dbga_multi_create.restype = C.c_int
+    lib.dbga_multi_destroy.argtypes = [vp]
+    lib.dbga_multi_destroy.restype = None
+    lib.dbga_multi_last_error.argtypes = [vp]
+    lib.dbga_multi_last_error.restype = C.c_char_p
+    lib.dbga_align_batch_multi.argtypes = [vp, vp, vp, i64p, C.c_int64, C.POINTER(Params), C.POINTER(MultiResult)]
+    lib.dbga_align_batch_multi.restype = C.c_int
     _lib = lib
     return lib
 
 
 def make_params(k, score16, d=10, e=2, gap_len_mode=0, xy_allowed=False, pred_order="XMY",
-                end_order="XMY", stages=3, want_graph=False) -> Params:
+                end_order="XMY", stages=3, want_graph=False, flags=0) -> Params:
     p = Params()
     p.k = int(k)
     for i, v in enumerate(score16):
@@ -111,6 +138,7 @@ def make_params(k, score16, d=10, e=2, gap_len_mode=0, xy_allowed=False, pred_or
     p.pred_order = ORDERS.index(pred_order) if isinstance(pred_order, str) else int(pred_order)
     p.end_order = ORDERS.index(end_order) if isinstance(end_order, str) else int(end_order)
     p.stages, p.want_graph = int(stages), int(bool(want_graph))
+    p.flags = int(flags)
     return p
 
 

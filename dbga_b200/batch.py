@@ -63,6 +63,8 @@ class BatchResult:
     nondup0: Optional[np.ndarray] = None
     q_off: Optional[np.ndarray] = None
     nondup1: Optional[np.ndarray] = None
+    sop: Optional[np.ndarray] = None       # [P, 4] match, mismatch, gap_open, gap_extend (utils.py:440-504)
+    seg_cols: Optional[np.ndarray] = None  # FLAG_COMPACT_ROWS: columns per segment
     timing: dict = field(default_factory=dict)
 
     def __len__(self):
@@ -135,8 +137,12 @@ class Aligner:
             status=aa(res.status, P, np.int32), score=aa(res.score, P, np.int64),
             dp_cells=aa(res.dp_cells, P, np.int64), dp_segments=aa(res.dp_segments, P, np.int32),
             n_anchors=aa(res.n_anchors, P, np.int64), run_off=run_off,
-            runs=aa(res.runs, 3 * nr, np.int32).reshape(nr, 3), aln_off=aln_off,
+            runs=aa(res.runs, 3 * nr if res.runs else 0, np.int32).reshape(-1, 3), aln_off=aln_off,
             aln0=aa(res.aln0, na, np.uint8), aln1=aa(res.aln1, na, np.uint8))
+        if res.sop:
+            out.sop = aa(res.sop, 4 * P, np.int32).reshape(P, 4)
+        if res.seg_cols:
+            out.seg_cols = aa(res.seg_cols, nr + P, np.int32)
         if want_graph:
             out.p_off = aa(res.p_off, P + 1, np.int64)
             out.q_off = aa(res.q_off, P + 1, np.int64)
@@ -144,22 +150,40 @@ class Aligner:
             out.nondup1 = aa(res.nondup1, int(out.q_off[-1]) if P else 0, np.uint8)
         out.timing = dict(ms_h2d=res.ms_h2d, ms_stage1=res.ms_stage1, ms_stage2=res.ms_stage2,
                           ms_stage3=res.ms_stage3, ms_assemble=res.ms_assemble, ms_d2h=res.ms_d2h,
-                          ms_total=res.ms_total, dp_cells=int(res.dp_cells_total),
+                          ms_total=res.ms_total, ms_plan=res.ms_plan, dp_cells=int(res.dp_cells_total),
                           dp_segments=int(res.dp_segments_total), launches=int(res.kernel_launches))
         return out
 
-    def align_buffers(self, seqs: np.ndarray, offsets: np.ndarray, prm: _lib.Params,
-                      global_only: bool = False, unpack: bool = True):
-        """seqs: uint8 host buffer (numpy or pinned), offsets int64[2P+1]."""
+    def align_buffers(self, seqs, offsets: np.ndarray, prm: _lib.Params,
+                      global_only: bool = False, unpack: bool = True, packed: bool = False):
+        """seqs: uint8 host buffer (numpy or pinned; or its address), offsets int64[2P+1].
+        packed=True: `seqs` is the 2-bit packed form of the batch (pack_ascii), a uint32 buffer."""
         offsets = np.ascontiguousarray(offsets, np.int64)
         P = (len(offsets) - 1) // 2
         res = _lib.Result()
-        fn = self.lib.dbga_global_align_batch if global_only else self.lib.dbga_align_batch
+        fn = (self.lib.dbga_align_batch_packed if packed else
+              self.lib.dbga_global_align_batch if global_only else self.lib.dbga_align_batch)
         ptr = seqs if isinstance(seqs, int) else seqs.ctypes.data
         rc = fn(self.h, C.c_void_p(ptr), offsets.ctypes.data_as(C.POINTER(C.c_int64)), P, C.byref(prm), C.byref(res))
         self._check(rc, fn.__name__)
         self.last_raw = res
-        return self._unpack(res, bool(prm.want_graph) and not global_only) if unpack else res
+        return self._unpack(res, bool(prm.want_graph) and not global_only and not packed) if unpack else res
+
+    def expand_rows(self, seqs, offsets: np.ndarray, raw: "_lib.Result", threads: int = 0):
+        """Full gapped rows of a FLAG_COMPACT_ROWS result (dbga_expand_rows): -> (aln_off, row0, row1)."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        P = int(raw.num_pairs)
+        cap = int(offsets[-1] - offsets[0]) + 16
+        row0, row1 = np.empty(cap, np.uint8), np.empty(cap, np.uint8)
+        off = np.zeros(P + 1, np.int64)
+        ptr = seqs if isinstance(seqs, int) else seqs.ctypes.data
+        rc = self.lib.dbga_expand_rows(C.c_void_p(ptr), offsets.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(raw),
+                                       C.c_void_p(row0.ctypes.data), C.c_void_p(row1.ctypes.data), cap,
+                                       off.ctypes.data_as(C.POINTER(C.c_int64)), int(threads))
+        if rc != 0:
+            raise RuntimeError(f"dbga_expand_rows failed (rc={rc})")
+        n = int(off[-1])
+        return off, row0[:n], row1[:n]
 
     def align_pairs(self, pairs: Sequence[Tuple[str, str]], k: int, match=10, transition=-1,
                     transversion=-8, d=10, e=2, s=None, stages=3, want_graph=False, **conv) -> BatchResult:
@@ -217,6 +241,65 @@ class Aligner:
         out = (C.c_double * 3)()
         self._check(self.lib.dbga_measure_int_peak(self.h, out), "dbga_measure_int_peak")
         return dict(add_ops_per_s=out[0], max_ops_per_s=out[1], mix_ops_per_s=out[2])
+
+
+def pack_ascii(buf: np.ndarray, offsets: np.ndarray, threads: int = 0) -> np.ndarray:
+    """2-bit packed form of a batch in the C ABI's canonical layout (dbga_pack_ascii): sequence j
+    starts at word (offsets[j] >> 4) + j.  Raises ValueError on a character outside ACGT."""
+    lib = _lib.load()
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    nseq = len(offsets) - 1
+    i64 = C.POINTER(C.c_int64)
+    words = int(lib.dbga_packed_words(offsets.ctypes.data_as(i64), nseq))
+    out = np.zeros(words, np.uint32)
+    buf = np.ascontiguousarray(buf, np.uint8)
+    bad = lib.dbga_pack_ascii(C.c_void_p(buf.ctypes.data), offsets.ctypes.data_as(i64), nseq, C.c_void_p(out.ctypes.data), int(threads))
+    if bad != 0:
+        raise ValueError(f"{bad} sequence(s) hold characters outside ACGT")
+    return out
+
+
+class MultiAligner:
+    """One host process, several GPUs (dbga_align_batch_multi): the batch is cut into contiguous
+    shards of equal bytes, one per device, each driven by its own host thread; no collective."""
+
+    def __init__(self, devices: Sequence[int]):
+        self.lib = _lib.load()
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = self.lib.dbga_multi_create(arr, len(self.devices), C.byref(h))
+        if rc != 0 or not h:
+            raise RuntimeError(f"dbga_multi_create({self.devices}) failed (rc={rc}); dbga_b200 has no CPU fallback")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dbga_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align_buffers(self, seqs, offsets: np.ndarray, prm: _lib.Params, packed=None, unpack: bool = True):
+        """-> list of (pair_lo, BatchResult) per shard (unpack=False: the raw MultiResult)."""
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        P = (len(offsets) - 1) // 2
+        res = _lib.MultiResult()
+        sp = None if seqs is None else (seqs if isinstance(seqs, int) else seqs.ctypes.data)
+        pp = None if packed is None else (packed if isinstance(packed, int) else packed.ctypes.data)
+        rc = self.lib.dbga_align_batch_multi(self.h, C.c_void_p(sp), C.c_void_p(pp), offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                             P, C.byref(prm), C.byref(res))
+        if rc != 0:
+            raise RuntimeError(f"dbga_align_batch_multi failed (rc={rc}): {self.lib.dbga_multi_last_error(self.h).decode()}")
+        self.last_raw = res
+        if not unpack:
+            return res
+        un = Aligner._unpack
+        return [(int(res.pair_lo[d]), un(None, res.shard[d], False)) for d in range(res.num_shards)]
 
 
 _default: dict = {}

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include <cstdlib>
 #include <cstring>
@@ -74,13 +76,14 @@ struct dbga_ctx {
     const uint8_t *d_seqs_run = nullptr;
 
     // ---- device buffers (grow only)
-    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_run_meta, d_slots, d_lists,
-        d_tt, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_len, d_aln_off, d_run_cnt,
-        d_run_off, d_scan_tmp, d_aln0, d_aln1, d_runs_out, d_score, d_cells, d_nseg, d_nanch, d_status_out,
-        d_sink;
+    DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_item_off, d_slots, d_lists,
+        d_tt, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_off, d_tile_off,
+        d_run_off, d_scan, d_aln0, d_aln1, d_runs_out, d_score, d_cells, d_nseg, d_nanch, d_status_out,
+        d_sop, d_segcols, d_pk_in, d_sink;
     // ---- pinned host result buffers
     HostBuf h_status, h_score, h_cells, h_nseg, h_nanch, h_aln_off, h_run_off, h_aln0, h_aln1, h_runs, h_nd0,
-        h_nd1, h_poff, h_qoff, h_ctr, h_meta;
+        h_nd1, h_poff, h_qoff, h_ctr, h_meta, h_sop, h_segcols;
+    float ms_plan = 0.f;
     // ---- pipelined dbga_align_batch: child contexts (own stream + workspaces) used round-robin
     static constexpr int NL = 4;
     dbga_ctx *lanes[NL] = {nullptr, nullptr, nullptr, nullptr};
@@ -108,9 +111,15 @@ struct dbga_ctx {
     // seven copies per batch instead of seven small copies per chunk.
     struct MetaPtrs {
         int32_t *status = nullptr; int64_t *score = nullptr, *cells = nullptr; int32_t *nseg = nullptr;
-        int64_t *nanch = nullptr, *aln_off = nullptr, *run_off = nullptr;
+        int64_t *nanch = nullptr, *aln_off = nullptr, *run_off = nullptr; int32_t *sop = nullptr;
     } ext;
     bool use_ext = false;
+    int multi_peers = 1;      // contexts driven side by side by one dbga_align_batch_multi call
+    // Host waits.  Spinning (CUDA's default on an idle box) answers fastest, but every rank of an
+    // 8-GPU job keeps two threads spinning; with fewer than four host cores per GPU the waits
+    // sleep instead (cudaEventBlockingSync events, condition variable between producer and consumer).
+    bool spin = true;
+    cudaEvent_t ev_block = nullptr;
 };
 
 namespace {
@@ -118,6 +127,22 @@ namespace {
 int fail(dbga_ctx *ctx, int code, const char *msg) {
     snprintf(ctx->err, sizeof(ctx->err), "%s", msg);
     return code;
+}
+
+bool decide_spin(int peers) {
+    if (const char *e = getenv("DBGA_SPIN")) return atoi(e) != 0;
+    int local = 1;
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
+    const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
+    return cores / std::max(peers, local) >= 4;
+}
+
+// waits for everything queued on st so far
+cudaError_t wait_stream(dbga_ctx *ctx, cudaStream_t st) {
+    if (ctx->spin || !ctx->ev_block) return cudaStreamSynchronize(st);
+    cudaError_t e = cudaEventRecord(ctx->ev_block, st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ctx->ev_block);
 }
 
 int dev_reserve(dbga_ctx *ctx, DevBuf &b, size_t bytes) {
@@ -243,6 +268,7 @@ constexpr size_t L2_TABLE_BUDGET = 64u << 20;
 int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params *params, bool no_anchors,
             int64_t off_base = 0) {
     ctx->planned = false; ctx->ran = false;
+    const auto t_plan0 = std::chrono::steady_clock::now();
     if (!offsets || !params || P < 0) return fail(ctx, DBGA_ERR_ARG, "null argument");
     if (P > 0x7fffff00LL) return fail(ctx, DBGA_ERR_ARG, "too many pairs in one batch");
     if (!no_anchors && (params->k < 1 || params->k > 31)) return fail(ctx, DBGA_ERR_ARG, "k must be in 1..31");
@@ -460,21 +486,22 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         RESERVE(d_aln0, std::max<int64_t>(ctx->total_bytes, 1));
         RESERVE(d_aln1, std::max<int64_t>(ctx->total_bytes, 1));
     }
-    RESERVE(d_aln_len, 8 * (P + 1)); RESERVE(d_aln_off, 8 * (P + 2));
-    RESERVE(d_run_cnt, 8 * (P + 1)); RESERVE(d_run_off, 8 * (P + 2));
-    RESERVE(d_scan_tmp, 8 * (P / 2048 + 2));
+    RESERVE(d_aln_off, 8 * (P + 2)); RESERVE(d_run_off, 8 * (P + 2)); RESERVE(d_tile_off, 8 * (P + 2));
+    RESERVE(d_scan, sizeof(AsmScanRec) * (asm_scan_blocks(P) + 1));
     RESERVE(d_score, 8 * (P + 1)); RESERVE(d_cells, 8 * (P + 1)); RESERVE(d_nseg, 4 * (P + 1));
-    RESERVE(d_nanch, 8 * (P + 1));
+    RESERVE(d_nanch, 8 * (P + 1)); RESERVE(d_sop, 16 * (P + 1));
+    ctx->ms_plan = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
     ctx->planned = true;
     return DBGA_SUCCESS;
 }
 
 int reserve_pools(dbga_ctx *ctx) {
     RESERVE(d_runs, 12 * ctx->runs_cap);
-    RESERVE(d_run_meta, 8 * ctx->runs_cap);
     RESERVE(d_runs_out, 12 * ctx->runs_cap);
+    if (ctx->prm.flags & DBGA_FLAG_COMPACT_ROWS) RESERVE(d_segcols, 4 * (ctx->runs_cap + ctx->P + 1));
     if (ctx->prm.stages == 3) {
         RESERVE(d_slots, sizeof(Slot) * ctx->slots_cap);
+        RESERVE(d_item_off, 8 * ctx->slots_cap);
         RESERVE(d_lists, 4 * ctx->slots_cap * NUM_CLS);
         RESERVE(d_tt, dp_thread_scratch_bytes(TINY_MAX, ctx->num_sms));
         if (ctx->grid_warp || ctx->grid_cta) RESERVE(d_tb, ctx->tb_cap);
@@ -493,7 +520,8 @@ int run_pipeline(dbga_ctx *ctx) {
     if (rc != DBGA_SUCCESS) return rc;
     ctx->launches = 0;
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[1], st));
-    DBGA_CUDA_CHECK(launch_clear((Counters *)ctx->d_ctr.p, (int32_t *)ctx->d_status.p, P, st));
+    DBGA_CUDA_CHECK(launch_clear((Counters *)ctx->d_ctr.p, (int32_t *)ctx->d_status.p, P, (AsmScanRec *)ctx->d_scan.p,
+                                 asm_scan_blocks(P), st));
     ctx->launches += 1;
     Pools pools;
     pools.runs = (int32_t *)ctx->d_runs.p; pools.runs_cap = ctx->runs_cap;
@@ -614,14 +642,14 @@ int run_pipeline(dbga_ctx *ctx) {
     if (!ctx->use_ext) {
         mp.status = (int32_t *)ctx->d_status_out.p; mp.score = (int64_t *)ctx->d_score.p; mp.cells = (int64_t *)ctx->d_cells.p;
         mp.nseg = (int32_t *)ctx->d_nseg.p; mp.nanch = (int64_t *)ctx->d_nanch.p;
-        mp.aln_off = (int64_t *)ctx->d_aln_off.p; mp.run_off = (int64_t *)ctx->d_run_off.p;
+        mp.aln_off = (int64_t *)ctx->d_aln_off.p; mp.run_off = (int64_t *)ctx->d_run_off.p; mp.sop = (int32_t *)ctx->d_sop.p;
     }
-    DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, mp.status, (int32_t *)ctx->d_runs.p,
-                                    ctx->runs_cap, (int2 *)ctx->d_run_meta.p, (Slot *)ctx->d_slots.p, ctx->slots_cap,
-                                    (uint8_t *)ctx->d_str.p, (int64_t *)ctx->d_aln_len.p, mp.aln_off,
-                                    (int64_t *)ctx->d_run_cnt.p, mp.run_off, (int64_t *)ctx->d_scan_tmp.p,
-                                    (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p, (int32_t *)ctx->d_runs_out.p,
-                                    mp.score, mp.cells, mp.nseg, mp.nanch, ctr, seg, ctx->num_sms, st, &ctx->launches));
+    const AsmOut ao{mp.status, mp.score, mp.cells, mp.nseg, mp.nanch, mp.aln_off, mp.run_off, seg ? mp.sop : nullptr};
+    DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, (int32_t *)ctx->d_runs.p, (Slot *)ctx->d_slots.p,
+                                    (uint8_t *)ctx->d_str.p, (int32_t *)ctx->d_item_off.p, (AsmScanRec *)ctx->d_scan.p,
+                                    (int64_t *)ctx->d_tile_off.p, ao, (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p,
+                                    (int32_t *)ctx->d_runs_out.p, (int32_t *)ctx->d_segcols.p, ctr, ctx->prm.flags,
+                                    ctx->num_sms, st, &ctx->launches));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
     return DBGA_SUCCESS;
 }
@@ -639,7 +667,7 @@ int do_run(dbga_ctx *ctx, const uint8_t *d_seqs, bool keep_sub = false) {
 
 struct HostDst {
     int32_t *status; int64_t *score; int64_t *cells; int32_t *nseg; int64_t *nanch;
-    int64_t *aln_off; int64_t *run_off; uint8_t *aln0; uint8_t *aln1; int32_t *runs;
+    int64_t *aln_off; int64_t *run_off; uint8_t *aln0; uint8_t *aln1; int32_t *runs; int32_t *sop; int32_t *segcols;
 };
 
 // counters -> host; on pool overflow grow to the measured need and re-run the pipeline
@@ -681,12 +709,15 @@ int fetch_enqueue(dbga_ctx *ctx, const HostDst &d, int64_t total_aln, int64_t to
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.nanch, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln_off, ctx->d_aln_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.run_off, ctx->d_run_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
+    if (ctx->prm.stages == 3) DBGA_CUDA_CHECK(cudaMemcpyAsync(d.sop, ctx->d_sop.p, 16 * P, cudaMemcpyDeviceToHost, st));
     }
     if (total_aln) {
         DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln0, ctx->d_aln0.p, total_aln, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln1, ctx->d_aln1.p, total_aln, cudaMemcpyDeviceToHost, st));
     }
     if (total_runs) DBGA_CUDA_CHECK(cudaMemcpyAsync(d.runs, ctx->d_runs_out.p, 12 * total_runs, cudaMemcpyDeviceToHost, st));
+    if ((ctx->prm.flags & DBGA_FLAG_COMPACT_ROWS) && ctx->prm.stages == 3)
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(d.segcols, ctx->d_segcols.p, 4 * (total_runs + P), cudaMemcpyDeviceToHost, st));
     return DBGA_SUCCESS;
 }
 
@@ -708,9 +739,13 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     const int64_t total_aln = seg ? (int64_t)hc->total_aln : 0, total_runs = (int64_t)hc->total_runs;
     HRESERVE(h_aln0, std::max<int64_t>(total_aln, 1)); HRESERVE(h_aln1, std::max<int64_t>(total_aln, 1));
     HRESERVE(h_runs, 12 * std::max<int64_t>(total_runs, 1));
+    HRESERVE(h_sop, 16 * (P + 1));
+    const bool compact = seg && (ctx->prm.flags & DBGA_FLAG_COMPACT_ROWS);
+    if (compact) HRESERVE(h_segcols, 4 * (total_runs + P + 1));
     HostDst d{(int32_t *)ctx->h_status.p, (int64_t *)ctx->h_score.p, (int64_t *)ctx->h_cells.p, (int32_t *)ctx->h_nseg.p,
               (int64_t *)ctx->h_nanch.p, (int64_t *)ctx->h_aln_off.p, (int64_t *)ctx->h_run_off.p,
-              (uint8_t *)ctx->h_aln0.p, (uint8_t *)ctx->h_aln1.p, (int32_t *)ctx->h_runs.p};
+              (uint8_t *)ctx->h_aln0.p, (uint8_t *)ctx->h_aln1.p, (int32_t *)ctx->h_runs.p, (int32_t *)ctx->h_sop.p,
+              (int32_t *)ctx->h_segcols.p};
     if (P) {
         rc = fetch_enqueue(ctx, d, total_aln, total_runs, st);
         if (rc != DBGA_SUCCESS) return rc;
@@ -733,6 +768,8 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     out->status = d.status; out->score = d.score; out->dp_cells = d.cells; out->dp_segments = d.nseg;
     out->n_anchors = d.nanch; out->run_off = d.run_off; out->runs = d.runs; out->aln_off = d.aln_off;
     out->aln0 = d.aln0; out->aln1 = d.aln1;
+    out->sop = seg ? d.sop : nullptr; out->seg_cols = compact ? d.segcols : nullptr;
+    out->ms_plan = ctx->ms_plan;
     if (!seg && P) { for (int64_t i = 0; i <= P; ++i) d.aln_off[i] = 0; }
     if (full) {
         out->p_off = (int64_t *)ctx->h_poff.p; out->nondup0 = (uint8_t *)ctx->h_nd0.p;
@@ -756,7 +793,7 @@ int create_ctx(int device, dbga_ctx **out);
 // contexts (lanes).  Each lane's stream carries H2D -> kernels -> D2H of its chunk in order,
 // so at any time one lane uploads, one computes and one downloads.  The host never waits
 // for anything but the small counters of the previous chunk (needed to size its D2H).
-int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P,
+int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, int64_t seq0, const int64_t *offsets, int64_t P,
                     const dbga_params *params, dbga_result *out, bool no_anchors, int64_t chunk_bytes) {
     const auto t_begin = std::chrono::steady_clock::now();
     const int64_t total_bytes = offsets[2 * P] - offsets[0];
@@ -768,12 +805,13 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         return fail(ctx, DBGA_ERR_CUDA, "could not create the upload stream");
     if (!ctx->dl_stream && cudaStreamCreateWithFlags(&ctx->dl_stream, cudaStreamNonBlocking) != cudaSuccess)
         return fail(ctx, DBGA_ERR_CUDA, "could not create the download stream");
+    const bool spin = ctx->spin = decide_spin(ctx->multi_peers);
     for (int i = 0; i < NL; ++i) {
         if (!ctx->lanes[i]) {
             int rc = create_ctx(ctx->device, &ctx->lanes[i]);
             if (rc != DBGA_SUCCESS) return fail(ctx, rc, "could not create a pipeline lane");
             dbga_ctx *l = ctx->lanes[i];
-            bool okc = cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming) == cudaSuccess &&
+            bool okc = cudaEventCreateWithFlags(&l->ev_ready, cudaEventDisableTiming | (spin ? 0 : cudaEventBlockingSync)) == cudaSuccess &&
                        cudaEventCreateWithFlags(&l->ev_meta, cudaEventDisableTiming) == cudaSuccess &&
                        cudaEventCreateWithFlags(&l->ev_dl, cudaEventDisableTiming) == cudaSuccess;
             l->meta_stream = ctx->copy_stream;
@@ -791,18 +829,32 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     std::vector<int64_t> lo;
     lo.push_back(0);
     {
+        // sizes in bytes: 8, 16, 32, ... up to chunk_bytes, and back down to 8 MB at the end -- the last
+        // chunk's kernels and download are the tail nothing can overlap with
         int64_t first_mb = 8;
         if (const char *e = getenv("DBGA_FIRST_MB")) first_mb = std::max(1, atoi(e));
-        int64_t want = std::min<int64_t>(first_mb << 20, chunk_bytes), next_cut = want;
-        for (int64_t i = 1; i < P; ++i) {
-            if (offsets[2 * i] - offsets[0] >= next_cut) {
+        chunk_bytes = std::min<int64_t>(chunk_bytes, std::max<int64_t>(4LL << 20, total_bytes / 4));      // small batches still pipeline
+        const int64_t small = std::min<int64_t>(std::min<int64_t>(first_mb << 20, chunk_bytes), std::max<int64_t>(2LL << 20, total_bytes / 8));
+        std::vector<int64_t> head, tail;
+        int64_t used = 0;
+        for (int64_t w = small; w < chunk_bytes && used + 2 * w < total_bytes / 2; w *= 2) { head.push_back(w); tail.push_back(w); used += 2 * w; }
+        const int64_t rest = total_bytes - used;
+        const int64_t nmid = std::max<int64_t>(1, (rest + chunk_bytes - 1) / chunk_bytes);
+        std::vector<int64_t> sizes = head;
+        for (int64_t i = 0; i < nmid; ++i) sizes.push_back(rest / nmid + 1);
+        for (size_t i = tail.size(); i-- > 0;) sizes.push_back(tail[i]);
+        int64_t cut = 0;
+        size_t si = 0;
+        cut = sizes[0];
+        for (int64_t i = 1; i < P && si + 1 < sizes.size(); ++i) {
+            if (offsets[2 * i] - offsets[0] >= cut) {
                 lo.push_back(i);
-                want = std::min<int64_t>(want * 2, chunk_bytes);
-                next_cut = (offsets[2 * i] - offsets[0]) + want;
+                ++si;
+                cut = (offsets[2 * i] - offsets[0]) + sizes[si];
             }
         }
         // a tiny tail chunk is merged into its predecessor
-        if (lo.size() > 1 && total_bytes - (offsets[2 * lo.back()] - offsets[0]) < (4LL << 20)) lo.pop_back();
+        if (lo.size() > 1 && total_bytes - (offsets[2 * lo.back()] - offsets[0]) < (2LL << 20)) lo.pop_back();
         lo.push_back(P);
     }
     const int nchunks = (int)lo.size() - 1;
@@ -810,13 +862,17 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     HRESERVE(h_nseg, 4 * (P + 1)); HRESERVE(h_nanch, 8 * (P + 1));
     HRESERVE(h_aln_off, 8 * (P + 2 + nchunks)); HRESERVE(h_run_off, 8 * (P + 2 + nchunks));
     if (seg) { HRESERVE(h_aln0, total_bytes + 16); HRESERVE(h_aln1, total_bytes + 16); }
-    HRESERVE(h_runs, std::max<int64_t>((int64_t)ctx->h_runs.cap, total_bytes / 4 + 4096));
+    const bool compact = seg && (params->flags & DBGA_FLAG_COMPACT_ROWS);
+    const bool no_runs = (params->flags & DBGA_FLAG_NO_RUNS) && !compact;
+    if (!no_runs) HRESERVE(h_runs, std::max<int64_t>((int64_t)ctx->h_runs.cap, total_bytes / 4 + 4096));
+    if (compact) HRESERVE(h_segcols, std::max<int64_t>((int64_t)ctx->h_segcols.cap, total_bytes / 12 + 4 * P + 4096));
+    HRESERVE(h_sop, 16 * (P + 1));
     RESERVE(d_status_out, 4 * (P + 1)); RESERVE(d_score, 8 * (P + 1)); RESERVE(d_cells, 8 * (P + 1));
-    RESERVE(d_nseg, 4 * (P + 1)); RESERVE(d_nanch, 8 * (P + 1));
+    RESERVE(d_nseg, 4 * (P + 1)); RESERVE(d_nanch, 8 * (P + 1)); RESERVE(d_sop, 16 * (P + 1));
     RESERVE(d_aln_off, 8 * (P + 2 + nchunks)); RESERVE(d_run_off, 8 * (P + 2 + nchunks));
     int64_t *aln_off = (int64_t *)ctx->h_aln_off.p, *run_off = (int64_t *)ctx->h_run_off.p;
     std::vector<int64_t> aln_base((size_t)nchunks + 1, 0), run_base((size_t)nchunks + 1, 0);
-    float ms[4] = {0, 0, 0, 0};
+    float ms[4] = {0, 0, 0, 0}, plan_ms_total = 0.f;
     int64_t cells = 0, nsegs = 0, launches = 0;
     auto fail_lane = [&](dbga_ctx *l, int rc) { snprintf(ctx->err, sizeof(ctx->err), "%s", l->err); return rc; };
 
@@ -839,11 +895,12 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         if (cudaSetDevice(ctx->device) != cudaSuccess) return DBGA_ERR_CUDA;
         int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
         if (rc != DBGA_SUCCESS) return rc;
+        plan_ms_total += l->ms_plan;
         // chunk c's offsets land at [a + c, a + c + n + 1) (one extra slot per chunk), fixed up at the end
         l->use_ext = true;
         l->ext.status = (int32_t *)ctx->d_status_out.p + a; l->ext.score = (int64_t *)ctx->d_score.p + a;
         l->ext.cells = (int64_t *)ctx->d_cells.p + a; l->ext.nseg = (int32_t *)ctx->d_nseg.p + a;
-        l->ext.nanch = (int64_t *)ctx->d_nanch.p + a;
+        l->ext.nanch = (int64_t *)ctx->d_nanch.p + a; l->ext.sop = (int32_t *)ctx->d_sop.p + 4 * a;
         l->ext.aln_off = (int64_t *)ctx->d_aln_off.p + a + c; l->ext.run_off = (int64_t *)ctx->d_run_off.p + a + c;
         if ((size_t)std::max<int64_t>(l->total_bytes, 16) + 64 > l->d_seqs.cap) cudaStreamSynchronize(ctx->copy_stream);
         rc = dev_reserve(l, l->d_seqs, (size_t)std::max<int64_t>(l->total_bytes, 16) + 64);
@@ -853,6 +910,33 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         if (cudaStreamWaitEvent(ctx->copy_stream, l->ev_ready, 0) != cudaSuccess) return DBGA_ERR_CUDA;
         if (trace) cudaEventRecord(tev[(size_t)c * 6 + 0], ctx->copy_stream);
         const int64_t nb = l->total_bytes, np = b - a;
+        if (packed) {
+            // 2-bit input: the chunk's words go up in one piece and are expanded on the device
+            const int64_t w_lo = (offsets[2 * a] >> 4) + seq0 + 2 * a, w_hi = (offsets[2 * b] >> 4) + seq0 + 2 * b;
+            if ((size_t)(4 * (w_hi - w_lo) + 64) > l->d_pk_in.cap) cudaStreamSynchronize(ctx->copy_stream);
+            rc = dev_reserve(l, l->d_pk_in, (size_t)(4 * (w_hi - w_lo) + 64));
+            if (rc != DBGA_SUCCESS) return rc;
+            if (w_hi > w_lo && cudaMemcpyAsync(l->d_pk_in.p, packed + w_lo, (size_t)(4 * (w_hi - w_lo)), cudaMemcpyHostToDevice,
+                                               ctx->copy_stream) != cudaSuccess)
+                return DBGA_ERR_CUDA;
+            if (cudaEventRecord(l->ev_sub[0], ctx->copy_stream) != cudaSuccess) return DBGA_ERR_CUDA;
+            if (trace) { cudaEventRecord(tev[(size_t)c * 6 + 1], ctx->copy_stream); cudaEventRecord(tev[(size_t)c * 6 + 2], l->stream); }
+            if (l->dl_pending && cudaStreamWaitEvent(l->stream, l->ev_dl, 0) != cudaSuccess) return DBGA_ERR_CUDA;
+            if (cudaStreamWaitEvent(l->stream, l->ev_sub[0], 0) != cudaSuccess) return DBGA_ERR_CUDA;
+            if (launch_unpack((const uint32_t *)l->d_pk_in.p, (const PairDesc *)l->d_pairs.p, np, base, seq0 + 2 * a, w_lo,
+                              (uint8_t *)l->d_seqs.p, l->num_sms, l->stream) != cudaSuccess)
+                return DBGA_ERR_CUDA;
+            rc = do_run(l, (const uint8_t *)l->d_seqs.p, false);
+            if (rc != DBGA_SUCCESS) return rc;
+            l->launches += 1;
+            if (trace) cudaEventRecord(tev[(size_t)c * 6 + 3], l->stream);
+            rc = host_reserve(l, l->h_ctr, sizeof(Counters));
+            if (rc != DBGA_SUCCESS) return rc;
+            if (launch_publish(l->d_ctr.p, l->h_ctr.p, (int)sizeof(Counters), l->stream) != cudaSuccess ||
+                cudaEventRecord(l->ev_ready, l->stream) != cudaSuccess)
+                return DBGA_ERR_CUDA;
+            return DBGA_SUCCESS;
+        }
         int ns = (int)std::max<int64_t>(1, std::min<int64_t>(dbga_ctx::MAX_SUB, (nb + sub_bytes - 1) / sub_bytes));
         if (np < ns) ns = (int)std::max<int64_t>(1, np);
         l->n_sub = ns;
@@ -901,15 +985,23 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         int64_t ta = seg ? (int64_t)hc->total_aln : 0, tr = (int64_t)hc->total_runs;
         aln_base[(size_t)c + 1] = aln_base[(size_t)c] + ta;
         run_base[(size_t)c + 1] = run_base[(size_t)c] + tr;
-        if ((size_t)(12 * run_base[(size_t)c + 1]) > ctx->h_runs.cap) {     // rare: grow the pinned runs buffer
+        auto grow_keep = [&](HostBuf &hb, size_t need, size_t used) -> int {       // rare: grow a pinned result buffer
+            if (need <= hb.cap) return DBGA_SUCCESS;
             for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
             cudaStreamSynchronize(ctx->dl_stream);
-            HostBuf old = ctx->h_runs;
-            ctx->h_runs = HostBuf();
-            rc = host_reserve(ctx, ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]) * 2);
-            if (rc != DBGA_SUCCESS) return rc;
-            memcpy(ctx->h_runs.p, old.p, (size_t)(12 * run_base[(size_t)c]));
+            HostBuf old = hb;
+            hb = HostBuf();
+            const int r = host_reserve(ctx, hb, need * 2);
+            if (r != DBGA_SUCCESS) return r;
+            if (used) memcpy(hb.p, old.p, used);
             cudaFreeHost(old.p);
+            return DBGA_SUCCESS;
+        };
+        rc = grow_keep(ctx->h_runs, (size_t)(12 * run_base[(size_t)c + 1]), (size_t)(12 * run_base[(size_t)c]));
+        if (rc != DBGA_SUCCESS) return rc;
+        if (compact) {
+            rc = grow_keep(ctx->h_segcols, (size_t)(4 * (run_base[(size_t)c + 1] + lo[(size_t)c + 1])), (size_t)(4 * (run_base[(size_t)c] + a)));
+            if (rc != DBGA_SUCCESS) return rc;
         }
         float t1 = 0, t2 = 0, t3 = 0, t4 = 0;
         cudaEventElapsedTime(&t1, l->ev[1], l->ev[2]); cudaEventElapsedTime(&t2, l->ev[2], l->ev[3]);
@@ -920,7 +1012,8 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         HostDst d{(int32_t *)ctx->h_status.p + a, (int64_t *)ctx->h_score.p + a, (int64_t *)ctx->h_cells.p + a,
                   (int32_t *)ctx->h_nseg.p + a, (int64_t *)ctx->h_nanch.p + a, aln_off + a + c, run_off + a + c,
                   (uint8_t *)ctx->h_aln0.p + aln_base[(size_t)c], (uint8_t *)ctx->h_aln1.p + aln_base[(size_t)c],
-                  (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c]};
+                  (int32_t *)ctx->h_runs.p + 3 * run_base[(size_t)c], (int32_t *)ctx->h_sop.p + 4 * a,
+                  compact ? (int32_t *)ctx->h_segcols.p + run_base[(size_t)c] + a : nullptr};
         // ev_ready has fired (synchronised above), so the download needs no device-side wait
         if (trace) cudaEventRecord(tev[(size_t)c * 6 + 4], ctx->dl_stream);
         rc = fetch_enqueue(l, d, ta, tr, ctx->dl_stream);
@@ -939,28 +1032,42 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     // is reused only after its previous chunk has been committed).
     std::atomic<int> issued{0}, committed{0}, prod_rc{DBGA_SUCCESS};
     std::atomic<bool> stop{false};
+    std::mutex mu;
+    std::condition_variable cv;
+    // spin: poll the atomics (fastest hand-over); otherwise sleep on the condition variable
+    auto wait_until = [&](auto pred) {
+        if (spin) { while (!pred()) std::this_thread::yield(); return; }
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, pred);
+    };
+    auto publish = [&](std::atomic<int> &var, int v) {
+        if (spin) { var.store(v, std::memory_order_release); return; }
+        { std::lock_guard<std::mutex> lk(mu); var.store(v, std::memory_order_release); }
+        cv.notify_all();
+    };
     std::thread producer([&]() {
         for (int c = 0; c < nchunks && !stop.load(); ++c) {
-            while (c - committed.load(std::memory_order_acquire) >= NL && !stop.load()) std::this_thread::yield();
+            wait_until([&]() { return c - committed.load(std::memory_order_acquire) < NL || stop.load(); });
             if (stop.load()) break;
             const int rc = issue(c);
             if (rc != DBGA_SUCCESS) {
-                snprintf(ctx->err, sizeof(ctx->err), "pipeline producer: %s", ctx->lanes[c % NL]->err);
-                prod_rc.store(rc);
+                snprintf(ctx->err, sizeof(ctx->err), "pipeline producer: %.400s", ctx->lanes[c % NL]->err);
+                publish(prod_rc, rc);
                 break;
             }
-            issued.store(c + 1, std::memory_order_release);
+            publish(issued, c + 1);
         }
     });
     int main_rc = DBGA_SUCCESS;
     for (int c = 0; c < nchunks; ++c) {
-        while (issued.load(std::memory_order_acquire) <= c && prod_rc.load() == DBGA_SUCCESS) std::this_thread::yield();
+        wait_until([&]() { return issued.load(std::memory_order_acquire) > c || prod_rc.load() != DBGA_SUCCESS; });
         if (issued.load(std::memory_order_acquire) <= c) { main_rc = prod_rc.load(); break; }
         main_rc = commit(c);
         if (main_rc != DBGA_SUCCESS) break;
-        committed.store(c + 1, std::memory_order_release);
+        publish(committed, c + 1);
     }
-    stop.store(true);
+    if (spin) stop.store(true);
+    else { { std::lock_guard<std::mutex> lk(mu); stop.store(true); } cv.notify_all(); }
     producer.join();
     if (main_rc != DBGA_SUCCESS) {
         for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
@@ -968,8 +1075,7 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         cudaStreamSynchronize(ctx->dl_stream);
         return main_rc;
     }
-    for (int i = 0; i < NL; ++i)
-        if (cudaStreamSynchronize(ctx->lanes[i]->stream) != cudaSuccess) return fail(ctx, DBGA_ERR_CUDA, "stream sync failed");
+    // (every lane's last chunk was committed after its ev_ready fired: the lane streams are idle)
     {   // the per-pair columns of the whole batch, behind the last chunk's rows
         cudaStream_t st = ctx->dl_stream;
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_status.p, ctx->d_status_out.p, 4 * P, cudaMemcpyDeviceToHost, st));
@@ -977,9 +1083,10 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cells.p, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nseg.p, ctx->d_nseg.p, 4 * P, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nanch.p, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
+        if (seg) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_sop.p, ctx->d_sop.p, 16 * P, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(aln_off, ctx->d_aln_off.p, 8 * (P + nchunks), cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(run_off, ctx->d_run_off.p, 8 * (P + nchunks), cudaMemcpyDeviceToHost, st));
-        DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
+        DBGA_CUDA_CHECK(wait_stream(ctx, st));
     }
     if (trace) {
         for (int c = 0; c < nchunks; ++c) {
@@ -1005,34 +1112,50 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     out->dp_cells = (int64_t *)ctx->h_cells.p; out->dp_segments = (int32_t *)ctx->h_nseg.p;
     out->n_anchors = (int64_t *)ctx->h_nanch.p; out->run_off = run_off; out->runs = (int32_t *)ctx->h_runs.p;
     out->aln_off = aln_off; out->aln0 = (uint8_t *)ctx->h_aln0.p; out->aln1 = (uint8_t *)ctx->h_aln1.p;
+    out->sop = seg ? (int32_t *)ctx->h_sop.p : nullptr; out->seg_cols = compact ? (int32_t *)ctx->h_segcols.p : nullptr;
+    out->ms_plan = plan_ms_total;
+    if (no_runs) out->runs = nullptr;
     out->ms_stage1 = ms[0]; out->ms_stage2 = ms[1]; out->ms_stage3 = ms[2]; out->ms_assemble = ms[3];
     out->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     out->dp_cells_total = cells; out->dp_segments_total = nsegs; out->kernel_launches = launches;
     return DBGA_SUCCESS;
 }
 
-int align_common(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t P, const dbga_params *params,
-                 dbga_result *out, bool no_anchors) {
-    if (!ctx || !out || !offsets || !params || (!seqs && P > 0)) return DBGA_ERR_ARG;
+// packed != nullptr: 2-bit input in the canonical layout; sequence j of this call is sequence seq0 + j of
+// that layout (a shard of a larger batch keeps the batch's word positions)
+int align_common(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, const int64_t *offsets, int64_t P,
+                 const dbga_params *params, dbga_result *out, bool no_anchors, int64_t seq0 = 0) {
+    if (!ctx || !out || !offsets || !params || (!seqs && !packed && P > 0)) return DBGA_ERR_ARG;
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
     if (P >= 64 && !params->want_graph && ctx->own_stream) {
         const int64_t total = offsets[2 * P] - offsets[0];
         if (total >= (16LL << 20)) {
             int64_t chunk_mb = 32;
             if (const char *e = getenv("DBGA_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
-            return align_pipelined(ctx, seqs, offsets, P, params, out, no_anchors, std::max<int64_t>(chunk_mb << 20, total / 200));
+            return align_pipelined(ctx, seqs, packed, seq0, offsets, P, params, out, no_anchors, std::max<int64_t>(chunk_mb << 20, total / 200));
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[0], ctx->stream));
-    int rc = do_plan(ctx, offsets, P, params, no_anchors);
+    const int64_t base = P > 0 ? offsets[0] : 0;
+    int rc = do_plan(ctx, offsets, P, params, no_anchors, base);
     if (rc != DBGA_SUCCESS) return rc;
     RESERVE(d_seqs, std::max<int64_t>(ctx->total_bytes, 16) + 16);
-    if (ctx->total_bytes)
-        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_seqs.p, seqs, (size_t)ctx->total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int extra_launches = 0;
+    if (packed && P > 0) {
+        const int64_t w_lo = (offsets[0] >> 4) + seq0, w_hi = (offsets[2 * P] >> 4) + seq0 + 2 * P;
+        RESERVE(d_pk_in, 4 * (w_hi - w_lo) + 64);
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_pk_in.p, packed + w_lo, (size_t)(4 * (w_hi - w_lo)), cudaMemcpyHostToDevice, ctx->stream));
+        DBGA_CUDA_CHECK(launch_unpack((const uint32_t *)ctx->d_pk_in.p, (const PairDesc *)ctx->d_pairs.p, P, base, seq0, w_lo,
+                                      (uint8_t *)ctx->d_seqs.p, ctx->num_sms, ctx->stream));
+        extra_launches = 1;
+    } else if (ctx->total_bytes) {
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_seqs.p, seqs + base, (size_t)ctx->total_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     rc = do_run(ctx, (const uint8_t *)ctx->d_seqs.p);
     if (rc != DBGA_SUCCESS) return rc;
     rc = do_fetch(ctx, out);
     if (rc != DBGA_SUCCESS) return rc;
+    out->kernel_launches += extra_launches;
     cudaEventElapsedTime(&out->ms_h2d, ctx->ev[0], ctx->ev[1]);
     cudaEventElapsedTime(&out->ms_total, ctx->ev[0], ctx->ev[7]);
     return DBGA_SUCCESS;
@@ -1063,6 +1186,7 @@ int create_ctx(int device, dbga_ctx **out) {
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
     *out = ctx;
     return DBGA_SUCCESS;
 }
@@ -1086,17 +1210,18 @@ void dbga_destroy(dbga_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf *dbs[] = {&ctx->d_seqs, &ctx->d_pairs, &ctx->d_list, &ctx->d_large, &ctx->d_status, &ctx->d_aof, &ctx->d_nd0,
-                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_run_meta, &ctx->d_slots, &ctx->d_lists, &ctx->d_tt, &ctx->d_ctr,
-                     &ctx->d_tb, &ctx->d_bnd_w, &ctx->d_bnd_c, &ctx->d_str, &ctx->d_packed, &ctx->d_table, &ctx->d_aln_len,
-                     &ctx->d_aln_off, &ctx->d_run_cnt, &ctx->d_run_off, &ctx->d_scan_tmp, &ctx->d_aln0, &ctx->d_aln1,
+                     &ctx->d_nd1, &ctx->d_pout, &ctx->d_runs, &ctx->d_item_off, &ctx->d_slots, &ctx->d_lists, &ctx->d_tt, &ctx->d_ctr,
+                     &ctx->d_tb, &ctx->d_bnd_w, &ctx->d_bnd_c, &ctx->d_str, &ctx->d_packed, &ctx->d_table, &ctx->d_tile_off,
+                     &ctx->d_aln_off, &ctx->d_run_off, &ctx->d_scan, &ctx->d_aln0, &ctx->d_aln1,
                      &ctx->d_runs_out, &ctx->d_score, &ctx->d_cells, &ctx->d_nseg, &ctx->d_nanch, &ctx->d_status_out,
-                     &ctx->d_sink};
+                     &ctx->d_sop, &ctx->d_segcols, &ctx->d_pk_in, &ctx->d_sink};
     for (DevBuf *b : dbs) if (b->p) cudaFree(b->p);
     HostBuf *hbs[] = {&ctx->h_status, &ctx->h_score, &ctx->h_cells, &ctx->h_nseg, &ctx->h_nanch, &ctx->h_aln_off,
                       &ctx->h_run_off, &ctx->h_aln0, &ctx->h_aln1, &ctx->h_runs, &ctx->h_nd0, &ctx->h_nd1, &ctx->h_poff,
-                      &ctx->h_qoff, &ctx->h_ctr, &ctx->h_meta};
+                      &ctx->h_qoff, &ctx->h_ctr, &ctx->h_meta, &ctx->h_sop, &ctx->h_segcols};
     for (HostBuf *b : hbs) if (b->p) cudaFreeHost(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1129,7 +1254,13 @@ void dbga_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int dbga_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t num_pairs,
                      const dbga_params *params, dbga_result *out) {
-    return align_common(ctx, seqs, offsets, num_pairs, params, out, false);
+    return align_common(ctx, seqs, nullptr, offsets, num_pairs, params, out, false);
+}
+
+int dbga_align_batch_packed(dbga_ctx *ctx, const uint32_t *packed, const int64_t *offsets, int64_t num_pairs,
+                            const dbga_params *params, dbga_result *out) {
+    if (!packed && num_pairs > 0) return DBGA_ERR_ARG;
+    return align_common(ctx, nullptr, packed, offsets, num_pairs, params, out, false);
 }
 
 int dbga_global_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, int64_t num_pairs,
@@ -1137,7 +1268,7 @@ int dbga_global_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *o
     if (!params) return DBGA_ERR_ARG;
     dbga_params p = *params;
     p.stages = 3; p.want_graph = 0;
-    return align_common(ctx, seqs, offsets, num_pairs, &p, out, true);
+    return align_common(ctx, seqs, nullptr, offsets, num_pairs, &p, out, true);
 }
 
 int dbga_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t num_pairs, const dbga_params *params) {
@@ -1227,7 +1358,7 @@ int dbga_kmer_stats(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         status[i] = hc[3] ? DBGA_BAD_CHAR : DBGA_OK;
         distinct0[i] = hc[3] ? 0 : hc[0]; distinct1[i] = hc[3] ? 0 : hc[1]; shared[i] = hc[3] ? 0 : hc[2];
     }
-    ctx->planned = false;          // the plan's device buffers were reused
+    ctx->planned = false; ctx->ran = false;          // the plan's device buffers were reused: no stale fetch
     return DBGA_SUCCESS;
 }
 
@@ -1250,6 +1381,164 @@ int dbga_measure_int_peak(dbga_ctx *ctx, double out[3]) {
         const double ops = (double)ctx->num_sms * 8 * 256 * (double)iters * 16 * 9;
         out[which] = ops / (best * 1e-3);
     }
+    return DBGA_SUCCESS;
+}
+
+
+// ---------------------------------------------------------------- host helpers (no GPU work)
+int64_t dbga_packed_words(const int64_t *offsets, int64_t num_seqs) {
+    if (!offsets || num_seqs < 0) return -1;
+    return (offsets[num_seqs] >> 4) + num_seqs + 1;
+}
+
+}  // extern "C"
+
+namespace {
+template <class Fn> void parallel_ranges(int64_t n, int threads, Fn fn) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, n / 256));
+    if (threads <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back([=]() { fn(n * t / threads, n * (t + 1) / threads); });
+    for (auto &x : th) x.join();
+}
+}  // namespace
+
+extern "C" {
+
+int64_t dbga_pack_ascii(const uint8_t *seqs, const int64_t *offsets, int64_t num_seqs, uint32_t *packed, int threads) {
+    if (!seqs || !offsets || !packed || num_seqs < 0) return -1;
+    std::atomic<int64_t> bad{0};
+    parallel_ranges(num_seqs, threads, [&](int64_t lo, int64_t hi) {
+        int64_t nbad = 0;
+        for (int64_t j = lo; j < hi; ++j) {
+            const uint8_t *src = seqs + offsets[j];
+            const int64_t len = offsets[j + 1] - offsets[j];
+            uint32_t *dst = packed + (offsets[j] >> 4) + j;
+            bool b = false;
+            for (int64_t w = 0; w * 16 < len; ++w) {
+                const int64_t nv = std::min<int64_t>(16, len - 16 * w);
+                uint32_t word = 0;
+                for (int64_t i = 0; i < nv; ++i) {
+                    const uint8_t c = src[16 * w + i];
+                    const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
+                    b |= "ACGT"[code] != (char)c;
+                    word |= code << (2 * i);
+                }
+                dst[w] = word;
+            }
+            nbad += b;
+        }
+        bad += nbad;
+    });
+    return bad.load();
+}
+
+int dbga_expand_rows(const uint8_t *seqs, const int64_t *offsets, const dbga_result *res, uint8_t *row0, uint8_t *row1,
+                     int64_t cap, int64_t *aln_off_full, int threads) {
+    if (!seqs || !offsets || !res || !row0 || !row1 || !aln_off_full) return DBGA_ERR_ARG;
+    const int64_t P = res->num_pairs;
+    if (P > 0 && (!res->seg_cols || !res->runs || !res->run_off || !res->aln_off || !res->status)) return DBGA_ERR_ARG;
+    // full length of every pair: its segment columns + the run bodies (the last merge node belongs to the tail)
+    parallel_ranges(P, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            int64_t len = 0;
+            if (res->status[i] == DBGA_OK) {
+                const int64_t r0 = res->run_off[i], R = res->run_off[i + 1] - r0;
+                len = res->aln_off[i + 1] - res->aln_off[i];
+                for (int64_t r = 0; r < R; ++r) len += res->runs[3 * (r0 + r) + 2];
+                if (R > 0) len -= 1;
+            }
+            aln_off_full[i + 1] = len;
+        }
+    });
+    aln_off_full[0] = 0;
+    for (int64_t i = 0; i < P; ++i) aln_off_full[i + 1] += aln_off_full[i];
+    if (aln_off_full[P] > cap) return DBGA_ERR_ARG;
+    parallel_ranges(P, threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            if (res->status[i] != DBGA_OK) continue;
+            const int64_t r0 = res->run_off[i], R = res->run_off[i + 1] - r0;
+            const int32_t *sc = res->seg_cols + r0 + i;
+            const uint8_t *c0 = res->aln0 + res->aln_off[i], *c1 = res->aln1 + res->aln_off[i];
+            const uint8_t *s0 = seqs + offsets[2 * i];
+            uint8_t *o0 = row0 + aln_off_full[i], *o1 = row1 + aln_off_full[i];
+            for (int64_t t = 0; t <= R; ++t) {
+                const int32_t cols = sc[t];
+                memcpy(o0, c0, (size_t)cols); memcpy(o1, c1, (size_t)cols);
+                o0 += cols; o1 += cols; c0 += cols; c1 += cols;
+                if (t < R) {          // inside a run both rows are the input bytes (debruijn_pairwise.py:384-388, 508-509)
+                    const int32_t a = res->runs[3 * (r0 + t)], len = res->runs[3 * (r0 + t) + 2] - (t == R - 1 ? 1 : 0);
+                    memcpy(o0, s0 + a, (size_t)len); memcpy(o1, s0 + a, (size_t)len);
+                    o0 += len; o1 += len;
+                }
+            }
+        }
+    });
+    return DBGA_SUCCESS;
+}
+
+// ---------------------------------------------------------------- one call, several GPUs
+struct dbga_multi {
+    int n = 0;
+    dbga_ctx *ctx[DBGA_MAX_SHARDS] = {};
+    char err[512] = {0};
+};
+
+int dbga_multi_create(const int *devices, int num_devices, dbga_multi **out) {
+    if (!out || !devices || num_devices < 1 || num_devices > DBGA_MAX_SHARDS) return DBGA_ERR_ARG;
+    *out = nullptr;
+    dbga_multi *m = new dbga_multi();
+    for (int d = 0; d < num_devices; ++d) {
+        const int rc = create_ctx(devices[d], &m->ctx[d]);
+        if (rc != DBGA_SUCCESS) { for (int e = 0; e < d; ++e) dbga_destroy(m->ctx[e]); delete m; return rc; }
+        m->ctx[d]->multi_peers = num_devices;
+        ++m->n;
+    }
+    *out = m;
+    return DBGA_SUCCESS;
+}
+
+void dbga_multi_destroy(dbga_multi *m) {
+    if (!m) return;
+    for (int d = 0; d < m->n; ++d) dbga_destroy(m->ctx[d]);
+    delete m;
+}
+
+const char *dbga_multi_last_error(dbga_multi *m) { return m ? m->err : "null handle"; }
+
+int dbga_align_batch_multi(dbga_multi *m, const uint8_t *seqs, const uint32_t *packed, const int64_t *offsets,
+                           int64_t num_pairs, const dbga_params *params, dbga_multi_result *out) {
+    if (!m || !out || !offsets || !params || num_pairs < 0 || (!seqs && !packed && num_pairs > 0)) return DBGA_ERR_ARG;
+    const auto t0 = std::chrono::steady_clock::now();
+    memset(out, 0, sizeof(*out));
+    const int n = m->n;
+    out->num_shards = n;
+    // contiguous shards of (nearly) equal bytes: pair p goes to the shard its first byte falls into
+    const int64_t b0 = offsets[0], total = num_pairs > 0 ? offsets[2 * num_pairs] - b0 : 0;
+    out->pair_lo[0] = 0;
+    for (int d = 1; d < n; ++d) {
+        const int64_t target = b0 + total * d / n;
+        int64_t lo = out->pair_lo[d - 1], hi = num_pairs;
+        while (lo < hi) { const int64_t mid = (lo + hi) / 2; if (offsets[2 * mid] < target) lo = mid + 1; else hi = mid; }
+        out->pair_lo[d] = lo;
+    }
+    out->pair_lo[n] = num_pairs;
+    int rcs[DBGA_MAX_SHARDS] = {};
+    std::vector<std::thread> th;
+    for (int d = 0; d < n; ++d) {
+        th.emplace_back([&, d]() {
+            const int64_t lo = out->pair_lo[d], cnt = out->pair_lo[d + 1] - lo;
+            rcs[d] = align_common(m->ctx[d], seqs, packed, offsets + 2 * lo, cnt, params, &out->shard[d], false, 2 * lo);
+        });
+    }
+    for (auto &x : th) x.join();
+    for (int d = 0; d < n; ++d)
+        if (rcs[d] != DBGA_SUCCESS) {
+            snprintf(m->err, sizeof(m->err), "shard %d (device %d): %.400s", d, m->ctx[d]->device, m->ctx[d]->err);
+            return rcs[d];
+        }
+    out->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return DBGA_SUCCESS;
 }
 

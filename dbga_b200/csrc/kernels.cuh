@@ -23,6 +23,9 @@ struct Counters {
     unsigned long long nseg;           // DP segments
     unsigned long long total_runs;
     unsigned long long total_aln;
+    unsigned long long total_tiles;    // copy tiles of the assembler
+    unsigned int scan_ticket;          // assembler's layout pass: next block of pairs
+    unsigned int pad;
 };
 
 struct Pools {
@@ -81,15 +84,22 @@ cudaError_t launch_dp_long(const uint8_t *seqs, const PairDesc *pairs, Slot *slo
                            uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);
 
 // ---- assembly
+// per-pair result columns (the context's own arrays, or a pipeline lane's window into its parent's)
+struct AsmOut {
+    int32_t *status; int64_t *score, *cells; int32_t *nseg; int64_t *nanch, *aln_off, *run_off; int32_t *sop;
+};
+// one record per block of pairs of the layout pass: block aggregate / inclusive prefix of
+// (aligned columns, reported runs, copy tiles) + flag (0 none, 1 aggregate, 2 prefix)
+struct AsmScanRec { unsigned long long agg[3]; unsigned long long pre[3]; unsigned int flag; unsigned int pad[3]; };
+inline int64_t asm_scan_blocks(int64_t num_pairs) { return (num_pairs + 63) / 64; }
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
-                            const int32_t *status, const int32_t *runs, int64_t runs_cap, int2 *run_meta, Slot *slots,
-                            int64_t slots_cap, const uint8_t *strbuf, int64_t *aln_len, int64_t *aln_off,
-                            int64_t *run_cnt, int64_t *run_off, int64_t *scan_tmp, uint8_t *aln0, uint8_t *aln1,
-                            int32_t *runs_out, int64_t *score, int64_t *cells, int32_t *nseg, int64_t *n_anchors,
-                            Counters *ctr, bool want_rows, int num_sms, cudaStream_t st, int *launches);
+                            const int32_t *runs, const Slot *slots, const uint8_t *strbuf, int32_t *item_off,
+                            AsmScanRec *scan, int64_t *tile_off, AsmOut out, uint8_t *aln0, uint8_t *aln1,
+                            int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags, int num_sms,
+                            cudaStream_t st, int *launches);
 
 cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStream_t st);
-cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, cudaStream_t st);
+cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, AsmScanRec *scan, int64_t nscan, cudaStream_t st);
 
 // ---- k-mer set statistics (|K0|, |K1|, |K0 & K1| per pair), small pairs only
 size_t kmer_stats_smem(int key_bytes, uint32_t cap, int words);
@@ -100,6 +110,10 @@ cudaError_t launch_kmer_stats(const uint8_t *seqs, const int64_t *offsets, int64
 cudaError_t launch_kmer_stats_large(const uint8_t *seq0, int64_t n0, const uint8_t *seq1, int64_t n1, int k,
                                     unsigned long long *keys, uint32_t *flag, uint64_t cap, unsigned int *counts,
                                     int num_sms, cudaStream_t st);
+
+// ---- 2-bit packed input -> the ASCII layout the kernels read (pack.cu)
+cudaError_t launch_unpack(const uint32_t *packed, const PairDesc *pairs, int64_t num_pairs, int64_t base,
+                          int64_t first_seq, int64_t word_base, uint8_t *seqs, int num_sms, cudaStream_t st);
 
 // ---- integer-pipe microbenchmark
 cudaError_t launch_int_peak(int which, int iters, int *sink, int num_sms, cudaStream_t st);

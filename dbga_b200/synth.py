@@ -69,3 +69,50 @@ def pairs_from_buffers(buf: np.ndarray, offsets: np.ndarray, idx):
         a, b, c = int(offsets[2 * i]), int(offsets[2 * i + 1]), int(offsets[2 * i + 2])
         out.append((buf[a:b].tobytes().decode(), buf[b:c].tobytes().decode()))
     return out
+
+
+def synth_long_pair(n: int = 1_000_000, n_bubbles: int = 10, seed: int = 1, background: float = 0.0003,
+                    bubble_sub: float = 0.30, bubble_indel: float = 0.04, bubble_len=(2000, 5000)):
+    """BASELINE config [4] ("single 1 Mb pair with long indel-rich bubbles (multi-kb segments)",
+    SURVEY 8d): s0 uniform; s1 = s0 with a very low background substitution rate plus `n_bubbles`
+    planted windows of 2-5 kb in which s1 is a heavily diverged copy of s0's window -- per base
+    `bubble_sub` substitutions and `bubble_indel` indel events (half insertions of uniform random
+    bases, half deletions, length ~ Geometric(mean 3)) -- so that no k=15 anchor survives inside a
+    window and both sides of the bubble are multi-kb and of different lengths.
+    -> (buf uint8, offsets int64[3]).  Seeds for which the reference raises "Cycles detected" exist
+    (SURVEY 8d); callers search for the first seed the oracle accepts."""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 4, n, dtype=np.uint8)
+    b = a.copy()
+    m = rng.random(n) < background
+    b[m] = (b[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
+    lo_l, hi_l = bubble_len
+    stride = max(hi_l + 1000, (n - 2 * hi_l) // max(1, n_bubbles))
+    cand = np.arange(hi_l, n - 2 * hi_l, stride)
+    pos = np.sort(rng.choice(cand, min(n_bubbles, len(cand)), replace=False))
+    parts, cur = [], 0
+    for p in pos:
+        L = int(rng.integers(lo_l, hi_l))
+        parts.append(b[cur:p])
+        win = a[p:p + L]
+        out, i = [], 0
+        sub = rng.random(L) < bubble_sub
+        ev = rng.random(L) < bubble_indel
+        ins = rng.random(L) < 0.5
+        ln = rng.geometric(1.0 / 3.0, size=L)
+        newb = rng.integers(1, 4, L, dtype=np.uint8)
+        while i < L:
+            if ev[i]:
+                if ins[i]:
+                    out.append(rng.integers(0, 4, int(ln[i]), dtype=np.uint8))
+                else:
+                    i += int(ln[i])
+                    continue
+            out.append(np.array([(win[i] + newb[i]) & 3 if sub[i] else win[i]], np.uint8))
+            i += 1
+        parts.append(np.concatenate(out) if out else np.zeros(0, np.uint8))
+        cur = p + L
+    parts.append(b[cur:])
+    b2 = np.concatenate(parts)
+    buf = np.concatenate([_LUT[a], _LUT[b2]])
+    return buf, np.array([0, n, n + len(b2)], np.int64)

@@ -52,7 +52,18 @@ typedef struct dbga_params {
     int32_t end_order;    /* default 0 = X,M,Y                                          */
     int32_t stages;       /* 2: stop after stages 1-2 (constructor)   3: full alignment */
     int32_t want_graph;   /* 1: also return per-k-mer "non-duplicate" flags (node ids)  */
+    int32_t flags;        /* DBGA_FLAG_* below, 0 = everything (round-1 behaviour)      */
 } dbga_params;
+
+/* dbga_params.flags: what travels back to the host (the end-to-end path is bound by the host link).
+ * NO_RUNS       the anchor-run list is not returned (run_off all zero, runs NULL); n_anchors still is.
+ *               DeBruijnPairwise.alignment() itself never returns anchors (debruijn_pairwise.py:543).
+ * COMPACT_ROWS  aln0 / aln1 carry only the columns the DP (or an empty-side segment) produced; the
+ *               columns inside a run of anchors are the caller's own input bytes and are not sent.
+ *               seg_cols tells how many columns each segment has; dbga_expand_rows rebuilds the
+ *               full gapped rows on the host.  Implies runs; sop is not computed. */
+#define DBGA_FLAG_NO_RUNS 1
+#define DBGA_FLAG_COMPACT_ROWS 2
 
 typedef struct dbga_ctx dbga_ctx;
 
@@ -83,6 +94,14 @@ typedef struct dbga_result {
     int64_t dp_cells_total;
     int64_t dp_segments_total;
     int64_t kernel_launches;    /* kernels of this library launched for the batch         */
+    /* [4P] match, mismatch, gap_open, gap_extend of every aligned pair: the reference's
+       pairwise_alignment_score (src/dbga/utils.py:440-504), counted on the device while the rows
+       are written (zero for pairs that are not DBGA_OK; not computed with COMPACT_ROWS)          */
+    const int32_t *sop;
+    /* COMPACT_ROWS only: [run_off[P] + P] columns of segment t of pair i at seg_cols[run_off[i] + i + t],
+       t = 0 .. (number of runs of pair i)                                                        */
+    const int32_t *seg_cols;
+    float ms_plan;              /* host time spent planning (classing, metadata), milliseconds    */
 } dbga_result;
 
 /* Context: one CUDA device, one stream, grow-only workspaces. */
@@ -103,6 +122,46 @@ void dbga_host_free(void *p);
  * offsets : [2P+1]; sequence j of pair i is seqs[offsets[2i+j] : offsets[2i+j+1]] */
 int dbga_align_batch(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets,
                      int64_t num_pairs, const dbga_params *params, dbga_result *out);
+
+/* 2-bit packed input: a quarter of the bytes on the host link.  Canonical layout of a batch of
+ * num_seqs = 2P sequences described by the same offsets[] (in bases) as the ASCII entry: sequence j
+ * starts at 32-bit word (offsets[j] >> 4) + j of `packed`; base i of it occupies bits 2 (i & 15) and up
+ * of word i >> 4; A, C, G, T = 0, 1, 2, 3 (non-ACGT input cannot be represented: dbga_pack_ascii
+ * reports it).  dbga_packed_words(offsets, 2P) is the size of the buffer in words.  Results are the
+ * same ASCII gapped rows as dbga_align_batch. */
+int64_t dbga_packed_words(const int64_t *offsets, int64_t num_seqs);
+/* ASCII -> packed on the host (threads <= 0: all cores); returns the number of sequences that held a
+ * character outside ACGT (packed as A), or -1 on a null argument. */
+int64_t dbga_pack_ascii(const uint8_t *seqs, const int64_t *offsets, int64_t num_seqs, uint32_t *packed, int threads);
+int dbga_align_batch_packed(dbga_ctx *ctx, const uint32_t *packed, const int64_t *offsets, int64_t num_pairs,
+                            const dbga_params *params, dbga_result *out);
+
+/* One call, several GPUs of one box (pairs shard by index, no collective, results
+ * gathered on the host): the batch is cut into num_devices contiguous shards of equal bytes, every
+ * shard runs dbga_align_batch on its own context / GPU from its own host thread, and the shards'
+ * results come back side by side (shard d holds pairs pair_lo[d] .. pair_lo[d+1]-1; offsets inside a
+ * shard's result are shard-local).  packed != NULL: 2-bit input (seqs may then be NULL). */
+#define DBGA_MAX_SHARDS 16
+typedef struct dbga_multi dbga_multi;
+typedef struct dbga_multi_result {
+    int32_t num_shards;
+    int32_t pad;
+    int64_t pair_lo[DBGA_MAX_SHARDS + 1];
+    dbga_result shard[DBGA_MAX_SHARDS];
+    float ms_total;             /* host wall clock of the whole call */
+} dbga_multi_result;
+int dbga_multi_create(const int *devices, int num_devices, dbga_multi **out);
+void dbga_multi_destroy(dbga_multi *m);
+const char *dbga_multi_last_error(dbga_multi *m);
+int dbga_align_batch_multi(dbga_multi *m, const uint8_t *seqs, const uint32_t *packed, const int64_t *offsets,
+                           int64_t num_pairs, const dbga_params *params, dbga_multi_result *out);
+
+/* Host-side expansion of a COMPACT_ROWS result into the full gapped rows (what the call returns
+ * without the flag): row0 / row1 receive aln_off_full[P] bytes each, aln_off_full [P+1] the offsets.
+ * seqs / offsets: the batch's input.  threads <= 0: all host cores.  Returns DBGA_SUCCESS, or
+ * DBGA_ERR_ARG if a row would exceed cap bytes. */
+int dbga_expand_rows(const uint8_t *seqs, const int64_t *offsets, const dbga_result *res, uint8_t *row0,
+                     uint8_t *row1, int64_t cap, int64_t *aln_off_full, int threads);
 
 /* Split form: plan (host-side sizing + metadata upload), run on device-resident
  * sequences (kernels only, nothing copied), fetch (device -> host). */

@@ -54,6 +54,7 @@ def lib():
         _lib.oracle_free_pair.argtypes = [C.POINTER(Pair)]
         _lib.oracle_gotoh.restype = C.c_int32
         _lib.oracle_align_batch.restype = None
+        _lib.oracle_check_batch.restype = None
     return _lib
 
 
@@ -144,4 +145,41 @@ def align_batch(seqs: np.ndarray, offsets: np.ndarray, k: int, match=10, transit
                          C.byref(cv), C.c_int32(threads), p(status, C.c_int32), p(score, C.c_int64), p(alen, C.c_int64),
                          p(cells, C.c_int64), p(nanch, C.c_int64))
     return dict(status=status, score=score, aln_len=alen, dp_cells=cells, n_anchors=nanch,
+                threads=threads)
+
+
+def check_batch(seqs: np.ndarray, offsets: np.ndarray, k: int, aln_off=None, aln0=None, aln1=None,
+                run_off=None, runs=None, match=10, transition=-1, transversion=-8, d=10, e=2,
+                conv: pyo.Convention = pyo.DEFAULT, s=None, threads: int = 0):
+    """align_batch plus a pair-by-pair comparison, in C, of the gapped rows (aln_off / aln0 / aln1)
+    and of the anchors (run_off / runs as (a, b, len) triples) that another implementation produced.
+    Returns align_batch's columns and `diff` (bit 0: rows differ, bit 1: anchors differ)."""
+    L = lib()
+    P = (len(offsets) - 1) // 2
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    status = np.zeros(P, np.int32)
+    score = np.zeros(P, np.int64)
+    alen = np.zeros(P, np.int64)
+    cells = np.zeros(P, np.int64)
+    nanch = np.zeros(P, np.int64)
+    diff = np.zeros(P, np.int32)
+    cv = conv_struct(conv)
+    threads = threads or (os.cpu_count() or 1)
+    keep = []
+
+    def p(a, t, dt):
+        if a is None:
+            return C.cast(None, C.POINTER(t))
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(t))
+
+    L.oracle_check_batch(p(seqs, C.c_uint8, np.uint8), p(offsets, C.c_int64, np.int64), C.c_int64(P), C.c_int32(k),
+                         score_array(match, transition, transversion, s), C.c_int32(d), C.c_int32(e),
+                         C.byref(cv), C.c_int32(threads), p(status, C.c_int32, np.int32), p(score, C.c_int64, np.int64),
+                         p(alen, C.c_int64, np.int64), p(cells, C.c_int64, np.int64), p(nanch, C.c_int64, np.int64),
+                         p(aln_off, C.c_int64, np.int64), p(aln0, C.c_uint8, np.uint8), p(aln1, C.c_uint8, np.uint8),
+                         p(run_off, C.c_int64, np.int64), p(runs, C.c_int32, np.int32), p(diff, C.c_int32, np.int32))
+    return dict(status=status, score=score, aln_len=alen, dp_cells=cells, n_anchors=nanch, diff=diff,
                 threads=threads)

@@ -305,6 +305,11 @@ typedef struct {
     const uint8_t *seqs; const int64_t *offsets; int64_t P; int32_t k; const int32_t *score;
     int32_t d, e; const oracle_conv *cv;
     int32_t *status; int64_t *scores, *aln_len, *dp_cells, *n_anchors;
+    /* optional: rows / anchor runs produced by the implementation under test, compared here
+     * pair by pair (diff[i] bit 0: gapped rows differ, bit 1: anchors differ) */
+    const int64_t *chk_aln_off; const uint8_t *chk_aln0, *chk_aln1;
+    const int64_t *chk_run_off; const int32_t *chk_runs;
+    int32_t *diff;
     atomic_long next;
 } batch_job;
 
@@ -321,24 +326,63 @@ static void *batch_worker(void *arg) {
                               j->e, j->cv, 0, 3, &r);
             j->status[i] = r.status; j->scores[i] = r.score; j->aln_len[i] = r.aln_len;
             j->dp_cells[i] = r.dp_cells; j->n_anchors[i] = r.n_anchors;
+            if (j->diff) {
+                int32_t df = 0;
+                if (j->chk_aln_off && r.status == ST_OK) {
+                    const int64_t a = j->chk_aln_off[i], len = j->chk_aln_off[i + 1] - a;
+                    if (len != r.aln_len || memcmp(j->chk_aln0 + a, r.aln0, (size_t)len) != 0 ||
+                        memcmp(j->chk_aln1 + a, r.aln1, (size_t)len) != 0)
+                        df |= 1;
+                }
+                if (j->chk_run_off && (r.status == ST_OK || r.status == ST_CYCLE)) {
+                    /* runs (a, b, len) expand to anchors (a+u, b+u), u < len, ascending b */
+                    int64_t t = 0;
+                    int bad = 0;
+                    for (int64_t q = j->chk_run_off[i]; q < j->chk_run_off[i + 1] && !bad; ++q) {
+                        const int32_t a = j->chk_runs[3 * q], b = j->chk_runs[3 * q + 1], len = j->chk_runs[3 * q + 2];
+                        for (int32_t u = 0; u < len; ++u, ++t)
+                            if (t >= r.n_anchors || r.anchors[2 * t] != a + u || r.anchors[2 * t + 1] != b + u) { bad = 1; break; }
+                    }
+                    if (bad || t != r.n_anchors) df |= 2;
+                }
+                j->diff[i] = df;
+            }
             oracle_free_pair(&r);
         }
     }
     return NULL;
 }
 
-void oracle_align_batch(const uint8_t *seqs, const int64_t *offsets, int64_t P, int32_t k,
-                        const int32_t score[16], int32_t d, int32_t e, const oracle_conv *cv,
-                        int32_t threads, int32_t *status, int64_t *scores, int64_t *aln_len,
-                        int64_t *dp_cells, int64_t *n_anchors) {
-    batch_job job = {seqs, offsets, P, k, score, d, e, cv, status, scores, aln_len, dp_cells, n_anchors, 0};
+static void run_batch(batch_job *job, int32_t threads) {
     if (threads < 1) threads = 1;
     if (threads > 1024) threads = 1024;
     pthread_t *tid = malloc(sizeof(pthread_t) * (size_t)threads);
     int started = 0;
     for (int t = 0; t < threads - 1; ++t)
-        if (pthread_create(&tid[started], NULL, batch_worker, &job) == 0) ++started;
-    batch_worker(&job);
+        if (pthread_create(&tid[started], NULL, batch_worker, job) == 0) ++started;
+    batch_worker(job);
     for (int t = 0; t < started; ++t) pthread_join(tid[t], NULL);
     free(tid);
+}
+
+void oracle_align_batch(const uint8_t *seqs, const int64_t *offsets, int64_t P, int32_t k,
+                        const int32_t score[16], int32_t d, int32_t e, const oracle_conv *cv,
+                        int32_t threads, int32_t *status, int64_t *scores, int64_t *aln_len,
+                        int64_t *dp_cells, int64_t *n_anchors) {
+    batch_job job = {seqs, offsets, P, k, score, d, e, cv, status, scores, aln_len, dp_cells, n_anchors,
+                     NULL, NULL, NULL, NULL, NULL, NULL, 0};
+    run_batch(&job, threads);
+}
+
+/* Same batch, and every pair's gapped rows / anchors are compared with the ones another
+ * implementation produced (any of the chk_* groups may be NULL).  diff[P] receives the flags. */
+void oracle_check_batch(const uint8_t *seqs, const int64_t *offsets, int64_t P, int32_t k,
+                        const int32_t score[16], int32_t d, int32_t e, const oracle_conv *cv,
+                        int32_t threads, int32_t *status, int64_t *scores, int64_t *aln_len,
+                        int64_t *dp_cells, int64_t *n_anchors, const int64_t *chk_aln_off,
+                        const uint8_t *chk_aln0, const uint8_t *chk_aln1, const int64_t *chk_run_off,
+                        const int32_t *chk_runs, int32_t *diff) {
+    batch_job job = {seqs, offsets, P, k, score, d, e, cv, status, scores, aln_len, dp_cells, n_anchors,
+                     chk_aln_off, chk_aln0, chk_aln1, chk_run_off, chk_runs, diff, 0};
+    run_batch(&job, threads);
 }

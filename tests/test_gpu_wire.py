@@ -1,0 +1,144 @@
+"""What travels over the host link: the NO_RUNS / COMPACT_ROWS result forms, the
+2-bit packed input entry, the one-call multi-GPU entry, and the alignment-quality counts
+(pairwise_alignment_score, reference src/dbga/utils.py:440-504) the assembler emits.  Every form
+must reproduce, byte for byte, what the plain dbga_align_batch call returns.  Needs a B200."""
+import numpy as np
+import pytest
+
+from oracle import dbga_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def aligner():
+    from dbga_b200 import Aligner
+    a = Aligner(0)
+    yield a
+    a.close()
+
+
+@pytest.fixture(scope="module")
+def batch():
+    """~24 MB: large enough for the chunked pipeline, mixed with a few odd pairs."""
+    from dbga_b200.batch import pack_pairs
+    pairs = [O.synth_pair(1500, 0.018, 0.002, 31000 + s) for s in range(8000)]
+    pairs[17] = ("ACGTACGTAC", "ACGTACGTAC")
+    pairs[18] = (pairs[18][0], pairs[18][0][:40])               # very unbalanced
+    pairs[4000] = O.synth_pair(9000, 0.01, 0.002, 5)
+    buf, offs = pack_pairs(pairs)
+    return pairs, buf, offs
+
+
+def _same_rows(a, b):
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.score, b.score)
+    assert np.array_equal(a.aln_off, b.aln_off) and np.array_equal(a.aln0, b.aln0) and np.array_equal(a.aln1, b.aln1)
+    assert np.array_equal(a.dp_cells, b.dp_cells) and np.array_equal(a.n_anchors, b.n_anchors)
+
+
+def test_sop_counts_reference_goldens(aligner, ref_fixtures):
+    """reference tests/test_utils.py:158-215 (sop) on alignments produced by the device: the counts
+    of the rows the assembler wrote equal the host restatement (dbga_b200.quality) of the
+    reference's loop; the reference's own sop goldens are checked against that restatement in
+    tests/test_host_api.py."""
+    from dbga_b200 import quality
+    pairs = [O.synth_pair(400, 0.05, 0.03, 100 + s) for s in range(300)] + [tuple(fx["seqs"]) for fx in ref_fixtures["e2e"]]
+    for k in (3, 7):
+        res = aligner.align_pairs(pairs, k)
+        assert res.sop is not None and res.sop.shape == (len(pairs), 4)
+        n = 0
+        for i in range(len(pairs)):
+            if res.status[i] != O.OK:
+                assert not res.sop[i].any()
+                continue
+            lo, hi = int(res.aln_off[i]), int(res.aln_off[i + 1])
+            want = quality.score_rows(res.aln0[lo:hi], res.aln1[lo:hi])
+            assert res.sop[i].tolist() == [want["match"], want["mismatch"], want["gap_open"], want["gap_extend"]], (k, i)
+            n += 1
+        assert n > 50
+
+
+def test_sop_counts_in_a_pipelined_batch(aligner, batch):
+    from dbga_b200 import quality
+    pairs, buf, offs = batch
+    res = aligner.align_buffers(buf, offs, aligner.params(9))
+    assert res.timing["launches"] > 40                            # several chunks
+    for i in list(range(0, len(pairs), 211)) + [17, 18, 4000]:
+        if res.status[i] != O.OK:
+            continue
+        lo, hi = int(res.aln_off[i]), int(res.aln_off[i + 1])
+        want = quality.score_rows(res.aln0[lo:hi], res.aln1[lo:hi])
+        assert res.sop[i].tolist() == list(want.values()), i
+    # whole-batch identity: every column is exactly one of the four kinds
+    ok = res.status == O.OK
+    assert np.array_equal(res.sop[ok].sum(axis=1), np.diff(res.aln_off)[ok])
+
+
+def test_no_runs_flag(aligner, batch):
+    from dbga_b200 import _lib
+    pairs, buf, offs = batch
+    full = aligner.align_buffers(buf, offs, aligner.params(9))
+    lean = aligner.align_buffers(buf, offs, aligner.params(9, flags=_lib.FLAG_NO_RUNS))
+    _same_rows(full, lean)
+    assert len(lean.runs) == 0 and not lean.run_off.any() and len(full.runs) > 0
+    small = pairs[:50]
+    a = aligner.align_pairs(small, 9)
+    b = aligner.align_pairs(small, 9, flags=_lib.FLAG_NO_RUNS)          # direct (unchunked) path
+    _same_rows(a, b)
+    assert len(b.runs) == 0
+
+
+@pytest.mark.parametrize("count", [60, 8000])
+def test_compact_rows_expand_to_the_full_rows(aligner, batch, count):
+    from dbga_b200 import _lib
+    from dbga_b200.batch import pack_pairs
+    pairs, buf, offs = batch
+    buf, offs = pack_pairs(pairs[:count]) if count < len(pairs) else (buf, offs)
+    full = aligner.align_buffers(buf, offs, aligner.params(9))
+    raw = aligner.align_buffers(buf, offs, aligner.params(9, flags=_lib.FLAG_COMPACT_ROWS), unpack=False)
+    comp = aligner._unpack(raw, False)
+    assert np.array_equal(comp.status, full.status) and np.array_equal(comp.score, full.score)
+    assert np.array_equal(comp.runs, full.runs) and np.array_equal(comp.run_off, full.run_off)
+    assert comp.aln_off[-1] < full.aln_off[-1] // 2                       # far fewer bytes came back
+    off, r0, r1 = aligner.expand_rows(buf, offs, raw)
+    assert np.array_equal(off, full.aln_off) and np.array_equal(r0, full.aln0) and np.array_equal(r1, full.aln1)
+
+
+@pytest.mark.parametrize("count", [60, 8000])
+def test_packed_input_equals_ascii_input(aligner, batch, count):
+    from dbga_b200 import pack_ascii
+    from dbga_b200.batch import pack_pairs
+    pairs, buf, offs = batch
+    buf, offs = pack_pairs(pairs[:count]) if count < len(pairs) else (buf, offs)
+    full = aligner.align_buffers(buf, offs, aligner.params(9))
+    words = pack_ascii(buf, offs)
+    res = aligner.align_buffers(words, offs, aligner.params(9), packed=True)
+    _same_rows(full, res)
+    assert np.array_equal(full.runs, res.runs)
+    with pytest.raises(ValueError):
+        pack_ascii(np.frombuffer(b"ACGTNACGT", np.uint8), np.array([0, 5, 9], np.int64))
+
+
+def test_multi_entry_two_contexts(aligner, batch):
+    """dbga_align_batch_multi with two shards (two contexts on the devices present: on a one-GPU box
+    both on device 0): shard results side by side equal the single call, ASCII and packed input."""
+    import torch
+    from dbga_b200 import MultiAligner, pack_ascii
+    pairs, buf, offs = batch
+    full = aligner.align_buffers(buf, offs, aligner.params(9))
+    devs = [0, 1] if torch.cuda.device_count() > 1 else [0, 0]
+    m = MultiAligner(devs)
+    try:
+        for packed in (None, pack_ascii(buf, offs)):
+            shards = m.align_buffers(buf if packed is None else None, offs, aligner.params(9), packed=packed)
+            assert len(shards) == 2 and shards[0][0] == 0 and 0 < shards[1][0] < len(pairs)
+            status = np.concatenate([r.status for _, r in shards])
+            assert np.array_equal(status, full.status)
+            assert np.array_equal(np.concatenate([r.score for _, r in shards]), full.score)
+            assert np.array_equal(np.concatenate([r.aln0 for _, r in shards]), full.aln0)
+            assert np.array_equal(np.concatenate([r.aln1 for _, r in shards]), full.aln1)
+            assert np.array_equal(np.concatenate([r.runs for _, r in shards]), full.runs)
+            lo1, r1 = shards[1]
+            assert r1.alignment(5) == full.alignment(lo1 + 5)
+    finally:
+        m.close()

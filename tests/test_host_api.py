@@ -30,11 +30,25 @@ def test_library_exports_every_declared_symbol(built):
     assert lib.dbga_version() >= 100
 
 
-def test_struct_layouts_match_header(built):
+def test_struct_layouts_match_header(built, tmp_path):
+    """sizeof / offsetof of the header's structs as gcc sees them == the ctypes mirrors."""
+    import subprocess
     from dbga_b200 import _lib
-    assert ctypes.sizeof(_lib.Params) == 4 * (1 + 16 + 2 + 4 + 2)
-    # 15 pointers/int64 + 7 floats (+pad) + 3 int64
-    assert ctypes.sizeof(_lib.Result) == 8 * 15 + 4 * 8 + 8 * 3
+    fields = {"dbga_params": _lib.Params, "dbga_result": _lib.Result, "dbga_multi_result": _lib.MultiResult}
+    lines = []
+    for cname, ct in fields.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dbga_b200.h"\nint main(void){' + "".join(lines) + "return 0;}")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in fields.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for f, _ in ct._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(ct, f).offset, (cname, f)
 
 
 def test_no_cpu_fallback_without_gpu(built):
