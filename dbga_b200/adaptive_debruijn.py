@@ -95,4 +95,16 @@ def adpt_dbg_alignment(data: Any, moltype: str, match: int = 10, transition: int
         aln = dna_global_aln(strings[0], strings[1], s, d, e)
     else:
         aln = adpt_dbg_alignment_recursive(strings, 0, k_choice, s, d, e)
-    return "".join(f">{name}\n{row}\n" for name, row in zip(sc.names, aln))
+    return alignment_to_fasta(dict(zip(sc.names, aln)))
+
+
+def alignment_to_fasta(alignment_dict, block_size: int = 60) -> str:
+    """cogent3.format.fasta.alignment_to_fasta as the reference calls it (adaptive_debruijn.py:86-88,
+    default block_size=60): ">label", then the row in blocks of 60 columns, one per line."""
+    out = []
+    for name, row in alignment_dict.items():
+        out.append(f">{name}\n")
+        row = str(row)
+        for i in range(0, len(row), block_size):
+            out.append(row[i:i + block_size] + "\n")
+    return "".join(out)

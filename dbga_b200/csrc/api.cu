@@ -79,7 +79,7 @@ struct dbga_ctx {
     DevBuf d_seqs, d_pairs, d_list, d_large, d_status, d_aof, d_nd0, d_nd1, d_pout, d_runs, d_item_off, d_slots, d_lists,
         d_tt, d_ctr, d_tb, d_bnd_w, d_bnd_c, d_str, d_packed, d_table, d_aln_off, d_tile_off,
         d_run_off, d_scan, d_aln0, d_aln1, d_runs_out, d_score, d_cells, d_nseg, d_nanch, d_status_out,
-        d_sop, d_segcols, d_pk_in, d_sink;
+        d_sop, d_segcols, d_pk_in, d_item_src, d_tile_pair, d_sink;
     // ---- pinned host result buffers
     HostBuf h_status, h_score, h_cells, h_nseg, h_nanch, h_aln_off, h_run_off, h_aln0, h_aln1, h_runs, h_nd0,
         h_nd1, h_poff, h_qoff, h_ctr, h_meta, h_sop, h_segcols;
@@ -271,7 +271,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     const auto t_plan0 = std::chrono::steady_clock::now();
     if (!offsets || !params || P < 0) return fail(ctx, DBGA_ERR_ARG, "null argument");
     if (P > 0x7fffff00LL) return fail(ctx, DBGA_ERR_ARG, "too many pairs in one batch");
-    if (!no_anchors && (params->k < 1 || params->k > 31)) return fail(ctx, DBGA_ERR_ARG, "k must be in 1..31");
+    if (!no_anchors && params->k < 1) return fail(ctx, DBGA_ERR_ARG, "k must be >= 1");
     if (params->stages != 2 && params->stages != 3) return fail(ctx, DBGA_ERR_ARG, "stages must be 2 or 3");
     ctx->prm = *params;
     ctx->no_anchors = no_anchors;
@@ -326,7 +326,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                                                 ? want / gran * gran : (want + gran - 1) / gran * gran);
             const int nmax = std::max(pd.n0, pd.n1);
             const int words = (((nmax + 15) / 16 + 3) + 1) & ~1;
-            const bool fits = cap <= 32768 && N0 < 65000 && N1 < 65000 &&   // 16-bit positions in shared memory
+            const bool fits = k <= 31 && cap <= 32768 && N0 < 65000 && N1 < 65000 &&   // 16-bit positions in shared memory; k >= 32: by-reference keys, global table
                               stage12_small_smem(key_bytes, cap, words, (int)N1, false) <= SMEM_LIMIT;
             if (fits) {
                 by_cap[{1, cap}].push_back((int32_t)i);
@@ -334,7 +334,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                 // medium: split the keys over 2..8 table partitions that take turns in shared memory
                 int parts = 0;
                 uint32_t pcap = 0;
-                if (N0 < 65000 && N1 < 65000) {
+                if (k <= 31 && N0 < 65000 && N1 < 65000) {
                     for (int g = 2; g <= 8 && !parts; ++g) {
                         uint64_t w = keys * 170 / 100 / g + 64;       // 1.7 x the expected keys per partition
                         uint32_t gr = 256;
@@ -488,6 +488,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     }
     RESERVE(d_aln_off, 8 * (P + 2)); RESERVE(d_run_off, 8 * (P + 2)); RESERVE(d_tile_off, 8 * (P + 2));
     RESERVE(d_scan, sizeof(AsmScanRec) * (asm_scan_blocks(P) + 1));
+    RESERVE(d_tile_pair, sizeof(AsmTile) * (ctx->total_bytes / ASM_TILE_COLS + P + 2));
     RESERVE(d_score, 8 * (P + 1)); RESERVE(d_cells, 8 * (P + 1)); RESERVE(d_nseg, 4 * (P + 1));
     RESERVE(d_nanch, 8 * (P + 1)); RESERVE(d_sop, 16 * (P + 1));
     ctx->ms_plan = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_plan0).count();
@@ -502,6 +503,7 @@ int reserve_pools(dbga_ctx *ctx) {
     if (ctx->prm.stages == 3) {
         RESERVE(d_slots, sizeof(Slot) * ctx->slots_cap);
         RESERVE(d_item_off, 8 * ctx->slots_cap);
+        RESERVE(d_item_src, 16 * ctx->slots_cap);
         RESERVE(d_lists, 4 * ctx->slots_cap * NUM_CLS);
         RESERVE(d_tt, dp_thread_scratch_bytes(TINY_MAX, ctx->num_sms));
         if (ctx->grid_warp || ctx->grid_cta) RESERVE(d_tb, ctx->tb_cap);
@@ -646,8 +648,9 @@ int run_pipeline(dbga_ctx *ctx) {
     }
     const AsmOut ao{mp.status, mp.score, mp.cells, mp.nseg, mp.nanch, mp.aln_off, mp.run_off, seg ? mp.sop : nullptr};
     DBGA_CUDA_CHECK(launch_assemble(seqs, pairs, P, pout, (int32_t *)ctx->d_runs.p, (Slot *)ctx->d_slots.p,
-                                    (uint8_t *)ctx->d_str.p, (int32_t *)ctx->d_item_off.p, (AsmScanRec *)ctx->d_scan.p,
-                                    (int64_t *)ctx->d_tile_off.p, ao, (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p,
+                                    (uint8_t *)ctx->d_str.p, (int32_t *)ctx->d_item_off.p, (long long *)ctx->d_item_src.p,
+                                    (AsmScanRec *)ctx->d_scan.p, (AsmTile *)ctx->d_tile_pair.p, ao,
+                                    (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p,
                                     (int32_t *)ctx->d_runs_out.p, (int32_t *)ctx->d_segcols.p, ctr, ctx->prm.flags,
                                     ctx->num_sms, st, &ctx->launches));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
@@ -1214,7 +1217,7 @@ void dbga_destroy(dbga_ctx *ctx) {
                      &ctx->d_tb, &ctx->d_bnd_w, &ctx->d_bnd_c, &ctx->d_str, &ctx->d_packed, &ctx->d_table, &ctx->d_tile_off,
                      &ctx->d_aln_off, &ctx->d_run_off, &ctx->d_scan, &ctx->d_aln0, &ctx->d_aln1,
                      &ctx->d_runs_out, &ctx->d_score, &ctx->d_cells, &ctx->d_nseg, &ctx->d_nanch, &ctx->d_status_out,
-                     &ctx->d_sop, &ctx->d_segcols, &ctx->d_pk_in, &ctx->d_sink};
+                     &ctx->d_sop, &ctx->d_segcols, &ctx->d_pk_in, &ctx->d_item_src, &ctx->d_tile_pair, &ctx->d_sink};
     for (DevBuf *b : dbs) if (b->p) cudaFree(b->p);
     HostBuf *hbs[] = {&ctx->h_status, &ctx->h_score, &ctx->h_cells, &ctx->h_nseg, &ctx->h_nanch, &ctx->h_aln_off,
                       &ctx->h_run_off, &ctx->h_aln0, &ctx->h_aln1, &ctx->h_runs, &ctx->h_nd0, &ctx->h_nd1, &ctx->h_poff,
@@ -1295,7 +1298,7 @@ int dbga_kmer_stats(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
     if (!ctx) return DBGA_ERR_ARG;
     if (P < 0 || (P > 0 && (!seqs || !offsets || !status || !distinct0 || !distinct1 || !shared)))
         return fail(ctx, DBGA_ERR_ARG, "null argument");
-    if (k < 1 || k > 31) return fail(ctx, DBGA_ERR_ARG, "k must be in 1..31");
+    if (k < 1) return fail(ctx, DBGA_ERR_ARG, "k must be >= 1");
     if (P == 0) return DBGA_SUCCESS;
     if (P > 0x7fffff00LL) return fail(ctx, DBGA_ERR_ARG, "too many pairs in one batch");
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -1312,7 +1315,7 @@ int dbga_kmer_stats(dbga_ctx *ctx, const uint8_t *seqs, const int64_t *offsets, 
         if (n0 < 0 || n1 < 0) return fail(ctx, DBGA_ERR_ARG, "offsets must be non-decreasing");
         if (n0 < k || n1 < k) continue;            // K_INVALID, decided on the device
         const int64_t keys = (n0 - k + 1) + (n1 - k + 1), nmax = std::max(n0, n1);
-        if (kmer_stats_smem(key_bytes, (uint32_t)std::min<uint64_t>(cap_of(keys), 1u << 30), words_of(nmax)) > SMEM_LIMIT - 1024) {
+        if (k > 31 || kmer_stats_smem(key_bytes, (uint32_t)std::min<uint64_t>(cap_of(keys), 1u << 30), words_of(nmax)) > SMEM_LIMIT - 1024) {
             large.push_back(i);
             continue;
         }

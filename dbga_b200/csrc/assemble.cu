@@ -24,61 +24,116 @@ constexpr int ASM_THREADS = 128;
 constexpr int LAY_PAIRS = 64;
 constexpr int LAY_THREADS = 256;
 
-__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int *p) {
-    return *reinterpret_cast<const volatile unsigned int *>(p);
+struct LayMeta { long long run_base, slot_base, n_anchors, off0, off1; int status, R, n_slots, row_len; };
+
+// flag hand-over of the look-back: release store / acquire load at GPU scope (the record's
+// payload is written before the flag and read after it)
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
-__global__ void __launch_bounds__(LAY_THREADS)
-asm_layout_kernel(const PairOut *__restrict__ pout, int64_t num_pairs, const Slot *__restrict__ slots,
-                  const int32_t *__restrict__ runs, int32_t *__restrict__ item_off, AsmScanRec *__restrict__ scan,
-                  Counters *__restrict__ ctr, AsmOut out, int64_t *__restrict__ tile_off, int flags) {
+__global__ void __launch_bounds__(LAY_THREADS, 5)
+asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__ pairs, int64_t num_pairs,
+                  const Slot *__restrict__ slots, const int32_t *__restrict__ runs, int32_t *__restrict__ item_off,
+                  long long *__restrict__ item_src, AsmScanRec *__restrict__ scan, Counters *__restrict__ ctr, AsmOut out,
+                  AsmTile *__restrict__ tiles, int flags) {
     __shared__ long long s_v[3][LAY_PAIRS];
-    __shared__ long long s_excl[3];
+    __shared__ LayMeta s_meta[LAY_PAIRS];
+    __shared__ long long s_excl[3], s_tot[3];
     __shared__ unsigned int s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool compact = (flags & DBGA_FLAG_COMPACT_ROWS) != 0, no_runs = (flags & DBGA_FLAG_NO_RUNS) != 0 && !compact;
     if (tid == 0) s_ticket = atomicAdd(&ctr->scan_ticket, 1u);
     __syncthreads();
     const int64_t blk = s_ticket, pair0 = blk * LAY_PAIRS;
-    for (int w = wid; w < LAY_PAIRS; w += LAY_THREADS / 32) {
+    // metadata of the block's pairs: one round trip for all of them (thread t fetches pair t), then
+    // every warp reads its pairs' records from shared memory
+    constexpr int PER_WARP = LAY_PAIRS / (LAY_THREADS / 32);
+    if (tid < LAY_PAIRS) {
+        LayMeta mt;
+        mt.status = DBGA_K_INVALID; mt.R = 0; mt.n_slots = 0; mt.run_base = 0; mt.slot_base = 0; mt.n_anchors = 0; mt.off0 = 0; mt.off1 = 0; mt.row_len = 0;
+        if (pair0 + tid < num_pairs) {
+            const PairOut po = pout[pair0 + tid];
+            mt.status = po.status; mt.R = po.n_runs; mt.n_slots = po.n_slots; mt.run_base = po.run_base; mt.slot_base = po.slot_base;
+            mt.n_anchors = po.n_anchors;
+            mt.off0 = pairs[pair0 + tid].off0; mt.off1 = pairs[pair0 + tid].off1;
+            mt.row_len = (int)(mt.off1 - mt.off0) + pairs[pair0 + tid].n1;
+        }
+        s_meta[tid] = mt;
+    }
+    __syncthreads();
+    for (int j = 0; j < PER_WARP; ++j) {
+        const int w = wid + (LAY_THREADS / 32) * j;
         const int64_t pair = pair0 + w;
-        long long carry = 0, sc = 0, ce = 0, nrep = 0;
-        int ns = 0, ntile = 0, st = DBGA_OK;
+        long long sc = 0, ce = 0, nrep = 0;
+        unsigned int carry = 0;
+        int ns = 0, ntile = 0;
+        int st = s_meta[w].status;
         if (pair < num_pairs) {
-            const PairOut po = pout[pair];
-            st = po.status;
+            const int R = s_meta[w].R, n_slots = s_meta[w].n_slots;
+            const long long run_base = s_meta[w].run_base, slot_base = s_meta[w].slot_base;
+            const long long off0 = s_meta[w].off0, off1 = s_meta[w].off1;
+            const long long n_anchors = s_meta[w].n_anchors;
             bool ok = st == DBGA_OK;
             const bool report = ok || st == DBGA_CYCLE;
-            const int R = po.n_runs;
-            if (ok && po.n_slots > 0) {
-                const int n_items = po.n_slots + R;
-                int32_t *io = item_off + 2 * po.slot_base;
-                for (int ib = 0; ib < n_items; ib += 32) {
-                    const int it = ib + lane;
-                    long long len = 0;
-                    if (it < n_items) {
-                        const int t = it >> 1;
-                        if (R == 0 || (it & 1) == 0) {
-                            const Slot *sp = slots + po.slot_base + t;
-                            const int2 sl = *reinterpret_cast<const int2 *>(&sp->score);     // (score, len)
-                            const int2 mn = make_int2(sp->m, sp->n);
-                            const bool mid = R > 0 && t > 0 && t < po.n_slots - 1;
-                            len = sl.y - ((mid && sl.y > 0) ? 1 : 0);                        // debruijn_pairwise.py:499-500
-                            if (mn.x > 0 && mn.y > 0) { sc += sl.x; ce += (long long)mn.x * mn.y; ++ns; }
-                        } else if (!compact) {
-                            len = runs[3 * (po.run_base + t) + 2] - (t == R - 1 ? 1 : 0);   // last merge node is left to the tail
+            if (ok && n_slots > 0) {
+                int32_t *io = item_off + 2 * slot_base;
+                long long *is = item_src + 2 * slot_base;
+                bool big = false;
+                // lane handles slot t and the run that follows it (items 2t, 2t + 1)
+                for (int tb = 0; tb < n_slots; tb += 32) {
+                    const int t = tb + lane;
+                    unsigned int len_s = 0, len_r = 0;
+                    long long src_s = 0, src_r = 0;
+                    if (t < n_slots) {
+                        const Slot *sp = slots + slot_base + t;
+                        const int4 xy = *reinterpret_cast<const int4 *>(sp);             // (x0, m, y0, n)
+                        const int2 sl = *reinterpret_cast<const int2 *>(&sp->score);     // (score, len)
+                        int3 rn = make_int3(0, 0, 0);
+                        if (t < R) { const int32_t *rp = runs + 3 * (run_base + t); rn = make_int3(rp[0], rp[1], rp[2]); }
+                        const bool mid = R > 0 && t > 0 && t < n_slots - 1;
+                        const int skip = (mid && sl.y > 0) ? 1 : 0;                      // debruijn_pairwise.py:499-500
+                        len_s = (unsigned int)(sl.y - skip);
+                        if (xy.y > 0 && xy.w > 0) {
+                            sc += sl.x; ce += (long long)xy.y * xy.w; ++ns;
+                            src_s = ((2 * off0 + xy.x + xy.z + (sl.y - 1 - skip)) << 2) | 0;      // reversed rows in the scratch
+                        } else if (xy.y > 0) {
+                            src_s = ((off0 + xy.x + skip) << 2) | 1;                     // utils.py:187-188
+                        } else {
+                            src_s = ((off1 + xy.z + skip) << 2) | 2;                     // utils.py:189-190
+                        }
+                        if (t < R) {
+                            if (!compact) len_r = (unsigned int)(rn.z - (t == R - 1 ? 1 : 0));      // last merge node is left to the tail
+                            src_r = ((off0 + rn.x) << 2) | 3;
                         }
                     }
-                    long long inc = len;
+                    const unsigned int len = len_s + len_r;
+                    unsigned int inc = len;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) {
-                        const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+                        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
                         if (lane >= o) inc += v;
                     }
-                    if (it < n_items) io[it] = (int32_t)(carry + inc - len);
-                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                    const unsigned int ex = carry + inc - len;
+                    if (t < n_slots) {
+                        if (R > 0 && t < R) {
+                            *reinterpret_cast<int2 *>(io + 2 * t) = make_int2((int)ex, (int)(ex + len_s));
+                            *reinterpret_cast<longlong2 *>(is + 2 * t) = make_longlong2(src_s, src_r);
+                        } else {
+                            io[R > 0 ? 2 * t : 0] = (int)ex;
+                            is[R > 0 ? 2 * t : 0] = src_s;
+                        }
+                    }
+                    const unsigned int add = __shfl_sync(0xffffffffu, inc, 31);
+                    big = big || carry + add < carry || carry + add > 0x7fffffffu;      // 32-bit item offsets
+                    carry += add;
                 }
-                if (carry > 0x7fffffffLL) { ok = false; st = DBGA_TOO_LARGE; carry = 0; }      // 32-bit item offsets
+                if (big) { ok = false; st = DBGA_TOO_LARGE; }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -89,217 +144,262 @@ asm_layout_kernel(const PairOut *__restrict__ pout, int64_t num_pairs, const Slo
             if (!ok) { carry = 0; sc = 0; ce = 0; ns = 0; }
             nrep = (report && !no_runs && st != DBGA_TOO_LARGE) ? R : 0;     // cycle pairs still report the anchors that cycle
             ntile = (int)((carry + ASM_TILE - 1) / ASM_TILE);
-            if (ntile == 0 && (nrep > 0 || (compact && ok && po.n_slots > 0))) ntile = 1;   // runs / segment widths are copied by the pair's first tile
+            if (ntile == 0 && (nrep > 0 || (compact && ok && n_slots > 0))) ntile = 1;   // runs / segment widths are copied by the pair's first tile
             if (lane == 0) {
                 out.score[pair] = sc; out.cells[pair] = ce; out.nseg[pair] = ns;
-                out.nanch[pair] = (ok || st == DBGA_CYCLE) ? po.n_anchors : 0;
+                out.nanch[pair] = (ok || st == DBGA_CYCLE) ? n_anchors : 0;
                 out.status[pair] = st;
                 if (out.sop) *reinterpret_cast<int4 *>(out.sop + 4 * pair) = make_int4(0, 0, 0, 0);
             }
         }
-        if (lane == 0) { s_v[0][w] = carry; s_v[1][w] = nrep; s_v[2][w] = ntile; }
+        if (lane == 0) { s_v[0][w] = carry; s_v[1][w] = nrep; s_v[2][w] = ntile; s_meta[w].status = st; }
     }
     __syncthreads();
     if (wid == 0) {
-        long long a[3][2], inc[3], tot[3];
-#pragma unroll
+        // block-local exclusive prefixes (in place) and block totals of the three quantities
+#pragma unroll 1
         for (int q = 0; q < 3; ++q) {
-            a[q][0] = s_v[q][2 * lane]; a[q][1] = s_v[q][2 * lane + 1];
-            inc[q] = a[q][0] + a[q][1];
+            const long long a0 = s_v[q][2 * lane], a1 = s_v[q][2 * lane + 1];
+            long long inc = a0 + a1;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const long long v = __shfl_up_sync(0xffffffffu, inc[q], o);
-                if (lane >= o) inc[q] += v;
+                const long long v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
             }
-            tot[q] = __shfl_sync(0xffffffffu, inc[q], 31);
+            s_v[q][2 * lane] = inc - a0 - a1;
+            s_v[q][2 * lane + 1] = inc - a1;
+            if (lane == 31) s_tot[q] = inc;
         }
+        __syncwarp();
         if (lane == 0) {
             AsmScanRec *me = scan + blk;
-            long long ex[3] = {0, 0, 0};
+            long long ex0 = 0, ex1 = 0, ex2 = 0;
             if (blk > 0) {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) me->agg[q] = (unsigned long long)tot[q];
-                __threadfence();
-                atomicExch(&me->flag, 1u);
+                me->agg[0] = (unsigned long long)s_tot[0]; me->agg[1] = (unsigned long long)s_tot[1]; me->agg[2] = (unsigned long long)s_tot[2];
+                st_release_u32(&me->flag, 1u);
                 for (int64_t j = blk - 1; j >= 0; --j) {        // decoupled look-back
                     const AsmScanRec *r = scan + j;
                     unsigned int f;
-                    do { f = ld_volatile_u32(&r->flag); } while (f == 0u);
-                    __threadfence();
+                    do { f = ld_acquire_u32(&r->flag); } while (f == 0u);
                     const volatile unsigned long long *src = f == 2u ? r->pre : r->agg;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) ex[q] += (long long)src[q];
+                    ex0 += (long long)src[0]; ex1 += (long long)src[1]; ex2 += (long long)src[2];
                     if (f == 2u) break;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < 3; ++q) me->pre[q] = (unsigned long long)(ex[q] + tot[q]);
-            __threadfence();
-            atomicExch(&me->flag, 2u);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) s_excl[q] = ex[q];
+            me->pre[0] = (unsigned long long)(ex0 + s_tot[0]); me->pre[1] = (unsigned long long)(ex1 + s_tot[1]);
+            me->pre[2] = (unsigned long long)(ex2 + s_tot[2]);
+            st_release_u32(&me->flag, 2u);
+            s_excl[0] = ex0; s_excl[1] = ex1; s_excl[2] = ex2;
         }
         __syncwarp();
-        int64_t *dst[3] = {out.aln_off, out.run_off, tile_off};
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-            const long long e0 = s_excl[q] + inc[q] - a[q][0] - a[q][1];
-            const int64_t p0 = pair0 + 2 * lane;
-            if (p0 < num_pairs) dst[q][p0] = e0;
-            if (p0 + 1 < num_pairs) dst[q][p0 + 1] = e0 + a[q][0];
-            if (lane == 31 && pair0 + LAY_PAIRS >= num_pairs) {          // last block: grand totals
-                const long long g = s_excl[q] + tot[q];
-                dst[q][num_pairs] = g;
-                if (q == 0) ctr->total_aln = (unsigned long long)g;
-                else if (q == 1) ctr->total_runs = (unsigned long long)g;
-                else ctr->total_tiles = (unsigned long long)g;
-            }
+        const bool last_blk = pair0 + LAY_PAIRS >= num_pairs;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {                                    // the lane's two pairs
+            const int w = 2 * lane + h;
+            const int64_t p = pair0 + w;
+            if (p >= num_pairs) break;
+            const long long a_off = s_excl[0] + s_v[0][w], r_off = s_excl[1] + s_v[1][w], t_off = s_excl[2] + s_v[2][w];
+            out.aln_off[p] = a_off; out.run_off[p] = r_off;
+            const long long aln_len = (w + 1 < LAY_PAIRS ? s_v[0][w + 1] : s_tot[0]) - s_v[0][w];
+            const long long ntile = (w + 1 < LAY_PAIRS ? s_v[2][w + 1] : s_tot[2]) - s_v[2][w];
+            const LayMeta &mt = s_meta[w];
+            AsmTile tr;
+            tr.a_off = a_off; tr.item_base = 2 * mt.slot_base; tr.run_base = mt.run_base; tr.run_off = r_off;
+            tr.aln_len = (int)aln_len; tr.row_len = mt.row_len; tr.pair = (int)p; tr.R = mt.R; tr.n_slots = mt.n_slots;
+            tr.ok = mt.status == DBGA_OK && mt.n_slots > 0;
+            tr.n_items = tr.ok ? mt.n_slots + mt.R : 0;
+            for (long long t = 0; t < ntile; ++t) { tr.tp = (int)t; tiles[t_off + t] = tr; }     // one record per copy tile
+        }
+        if (lane == 0 && last_blk) {                                     // last block: grand totals
+            out.aln_off[num_pairs] = s_excl[0] + s_tot[0]; out.run_off[num_pairs] = s_excl[1] + s_tot[1];
+            ctr->total_aln = (unsigned long long)(s_excl[0] + s_tot[0]);
+            ctr->total_runs = (unsigned long long)(s_excl[1] + s_tot[1]);
+            ctr->total_tiles = (unsigned long long)(s_excl[2] + s_tot[2]);
         }
     }
 }
 
-// ---------------------------------------------------------------- output-centric copy
-// Where the bytes of one item come from: column d of the item is p0[d * st0] / p1[d * st1].
-// Inside a run both rows are the same sequence bytes; a DP segment's rows sit reversed in the
-// scratch (stage 3 writes them while walking back); a one-sided segment is sequence bytes against
-// a constant '-' (stride 0).
+// ---------------------------------------------------------------- copy
+// Where the bytes of an item come from is resolved once, by the layout pass (item_src: byte offset
+// << 2 | kind).  kind 0: DP segment, rows reversed in the scratch (stage 3 writes them walking
+// back; row 2 sits row_len bytes after row 1), offset = scratch position of the item's first
+// emitted column, step -1.  kind 1 / 2: one side empty (utils.py:187-190): sequence bytes of seq1 /
+// seq2 against '-'.  kind 3: a run of anchors, both rows are the same seq1 bytes.
+//
+// asm_copy_kernel: a CTA takes one tile of ASM_TILE output columns of one pair (tile_pair[] names
+// the pair).  Phase 1 is item-centric (8 lanes per item, no divergence inside a group) and stages
+// the two rows in shared memory at the alignment of their final addresses; phase 2 is
+// output-centric: a thread owns a 16-byte aligned chunk of both rows (128-bit stores) and
+// classifies its 16 columns for pairwise_alignment_score (reference src/dbga/utils.py:440-504:
+// match / mismatch / gap_open / gap_extend; a gap column extends iff the previous column is a gap
+// in the same row only) with byte-SIMD compares -- the column before the tile is staged too.
 __device__ const uint8_t g_dash[16] = {'-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-'};
+constexpr int ASM_G = 8;                      // lanes per item in phase 1
+constexpr int ASM_SBUF = ASM_TILE + 48;       // 16 bytes of slack before (previous column at 15) + tile + alignment slack
+constexpr int ASM_WIN = 256;                  // items whose offsets / sources are staged at a time
 
-struct AsmSrc { const uint8_t *p0, *p1; int st0, st1; };
-
-__device__ __forceinline__ AsmSrc asm_resolve(int i, int d, int outlen, int R, int n_slots, const PairDesc &pd,
-                                              const int32_t *__restrict__ gr, const uint8_t *__restrict__ seqs,
-                                              const uint8_t *__restrict__ strbuf) {
-    AsmSrc s;
-    const int t = i >> 1;
-    if (R > 0 && (i & 1)) {                         // run t: anchors (a + u, b + u)
-        s.p0 = s.p1 = seqs + pd.off0 + __ldg(gr + 3 * t) + d;
-        s.st0 = s.st1 = 1;
-        return s;
-    }
-    int x0 = 0, x1 = pd.n0, y0 = 0, y1 = pd.n1;
-    if (R > 0) {
-        if (t > 0) { const int len = __ldg(gr + 3 * t - 1); x0 = __ldg(gr + 3 * t - 3) + len - 1; y0 = __ldg(gr + 3 * t - 2) + len - 1; }
-        if (t < R) { x1 = __ldg(gr + 3 * t); y1 = __ldg(gr + 3 * t + 1); }
-    }
-    const int m = x1 - x0, n = y1 - y0;
-    const int skip = (R > 0 && t > 0 && t < n_slots - 1) ? 1 : 0;          // (an item of this kind with len == 0 is never resolved)
-    if (m > 0 && n > 0) {                           // reversed rows: column c of the segment is at [L - 1 - c]
-        const int L = outlen + skip;
-        s.p0 = strbuf + 2 * pd.off0 + x0 + y0 + (L - 1 - skip - d);
-        s.p1 = s.p0 + ((pd.off1 - pd.off0) + pd.n1);
-        s.st0 = s.st1 = -1;
-    } else if (m > 0) {                             // utils.py:187-188
-        s.p0 = seqs + pd.off0 + x0 + skip + d; s.st0 = 1;
-        s.p1 = g_dash; s.st1 = 0;
-    } else {                                        // utils.py:189-190
-        s.p0 = g_dash; s.st0 = 0;
-        s.p1 = seqs + pd.off1 + y0 + skip + d; s.st1 = 1;
-    }
-    return s;
-}
-
-// A CTA takes one tile of ASM_TILE output columns of one pair; a thread owns a 16-byte aligned
-// chunk of the two output rows, finds the item its first column falls into (binary search over the
-// pair's item offsets) and walks the items from there.  The four alignment-quality counts of
-// pairwise_alignment_score (reference src/dbga/utils.py:440-504) fall out of the same walk: every
-// column is classified (match / mismatch / gap in row 1 / gap in row 2) and a gap column extends
-// iff the previous column is of the same kind.
-__global__ void __launch_bounds__(ASM_THREADS)
-asm_copy_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, int64_t num_pairs,
-                const PairOut *__restrict__ pout, const int32_t *__restrict__ runs, const int32_t *__restrict__ item_off,
-                const Counters *__restrict__ ctr, const uint8_t *__restrict__ strbuf, AsmOut out,
-                const int64_t *__restrict__ tile_off, uint8_t *__restrict__ aln0, uint8_t *__restrict__ aln1,
-                int32_t *__restrict__ runs_out, int32_t *__restrict__ seg_cols, int flags) {
-    __shared__ long long s_pair;
+__global__ void __launch_bounds__(ASM_THREADS, 10)
+asm_copy_kernel(const uint8_t *__restrict__ seqs, const int32_t *__restrict__ runs, const int32_t *__restrict__ item_off,
+                const long long *__restrict__ item_src, const Counters *__restrict__ ctr,
+                const uint8_t *__restrict__ strbuf, int32_t *__restrict__ sop, const AsmTile *__restrict__ tiles,
+                uint8_t *__restrict__ aln0, uint8_t *__restrict__ aln1, int32_t *__restrict__ runs_out,
+                int32_t *__restrict__ seg_cols, int flags) {
+    __shared__ __align__(16) uint8_t sbuf[2][ASM_SBUF];
+    __shared__ int s_io[ASM_WIN + 1];
+    __shared__ long long s_is[ASM_WIN];
     __shared__ int s_cnt[4];
+    __shared__ int s_ilo;
     const int tid = threadIdx.x, lane = tid & 31;
     const bool compact = (flags & DBGA_FLAG_COMPACT_ROWS) != 0, no_runs = (flags & DBGA_FLAG_NO_RUNS) != 0 && !compact;
+    const bool want_sop = sop != nullptr && !compact;
     const long long total_tiles = (long long)ctr->total_tiles;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        __syncthreads();
-        if (tid == 0) {                 // the pair that owns this tile: last p with tile_off[p] <= tile
-            long long lo = 0, hi = num_pairs;               // invariant: tile_off[lo] <= tile < tile_off[hi]
-            while (hi - lo > 1) {
-                const long long mid = (lo + hi) >> 1;
-                if (tile_off[mid] <= tile) lo = mid; else hi = mid;
-            }
-            s_pair = lo;
-            s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
+        AsmTile tr;
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(tiles + tile);
+            uint4 *d = reinterpret_cast<uint4 *>(&tr);
+            d[0] = __ldg(q); d[1] = __ldg(q + 1); d[2] = __ldg(q + 2); d[3] = __ldg(q + 3);
         }
-        __syncthreads();
-        const int64_t pair = s_pair;
-        const PairOut po = pout[pair];
-        const PairDesc pd = pairs[pair];
-        const int tp = (int)(tile - tile_off[pair]);
-        const int64_t a_off = out.aln_off[pair];
-        const int aln_len = (int)(out.aln_off[pair + 1] - a_off);
-        const int R = po.n_runs;
-        const int32_t *gr = runs + 3 * po.run_base;
-        const bool ok = po.status == DBGA_OK && po.n_slots > 0;
-        const int n_items = ok ? po.n_slots + R : 0;
-        const int32_t *io = item_off + 2 * po.slot_base;
-        if (tp == 0) {
-            const int64_t r_off = out.run_off[pair];
-            if (!no_runs && R > 0) for (int r = tid; r < 3 * R; r += ASM_THREADS) runs_out[3 * r_off + r] = __ldg(gr + r);
-            if (compact && ok)           // columns of every segment, in output order (what dbga_expand_rows reads)
-                for (int t = tid; t < po.n_slots; t += ASM_THREADS) {
+        const int aln_len = tr.aln_len, R = tr.R, n_items = tr.n_items;
+        const int32_t *io = item_off + tr.item_base;
+        const long long *is = item_src + tr.item_base;
+        if (tr.tp == 0) {
+            const int32_t *gr = runs + 3 * tr.run_base;
+            if (!no_runs && R > 0) for (int r = tid; r < 3 * R; r += ASM_THREADS) runs_out[3 * tr.run_off + r] = __ldg(gr + r);
+            if (compact && tr.ok)        // columns of every segment, in output order (what dbga_expand_rows reads)
+                for (int t = tid; t < tr.n_slots; t += ASM_THREADS) {
                     const int i = R > 0 ? 2 * t : 0;
-                    seg_cols[r_off + pair + t] = (i + 1 < n_items ? __ldg(io + i + 1) : aln_len) - __ldg(io + i);
+                    seg_cols[tr.run_off + tr.pair + t] = (i + 1 < n_items ? __ldg(io + i + 1) : aln_len) - __ldg(io + i);
                 }
         }
-        const int c_lo = tp * ASM_TILE, c_hi = min(c_lo + ASM_TILE, aln_len);
+        const int c_lo = tr.tp * ASM_TILE, c_hi = min(c_lo + ASM_TILE, aln_len);
         if (c_hi <= c_lo) continue;
-        const int64_t g_lo = a_off + c_lo, g_hi = a_off + c_hi;
+        const int c_lo1 = c_lo > 0 ? c_lo - 1 : 0;          // one column early: the previous column's kind
+        const int64_t g_lo = tr.a_off + c_lo, g_hi = tr.a_off + c_hi;
         const int64_t base0 = g_lo & ~(int64_t)15;
-        int cnt_m = 0, cnt_x = 0, cnt_o = 0, cnt_e = 0;
-        for (int64_t cb = base0 + 16 * (int64_t)tid; cb < g_hi; cb += 16 * ASM_THREADS) {
-            const int64_t b0 = cb < g_lo ? g_lo : cb, b1 = cb + 16 < g_hi ? cb + 16 : g_hi;
-            const int nb = (int)(b1 - b0);
-            const int c_first = (int)(b0 - a_off);
-            int c = c_first > 0 ? c_first - 1 : 0;       // one column early: the previous column's kind
-            bool warm = c_first > 0;
-            int lo = 0, hi = n_items;                   // last item with start <= c
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(io + mid) <= c) lo = mid; else hi = mid;
-            }
-            int i = lo;
-            int start = __ldg(io + i);
-            int end = i + 1 < n_items ? __ldg(io + i + 1) : aln_len;
-            AsmSrc s = asm_resolve(i, c - start, end - start, R, po.n_slots, pd, gr, seqs, strbuf);
-            unsigned long long w0l = 0, w0h = 0, w1l = 0, w1h = 0;
-            int prev = 0, k = 0;
-            const int c_end = c_first + nb;
-            for (; c < c_end; ++c) {
-                if (c == end) {
-                    do { ++i; start = end; end = i + 1 < n_items ? __ldg(io + i + 1) : aln_len; } while (end == start);
-                    s = asm_resolve(i, 0, end - start, R, po.n_slots, pd, gr, seqs, strbuf);
+        __syncthreads();                                    // the previous tile's phase 2 is done with sbuf
+        if (aln_len > ASM_TILE) {
+            // first item of the tile: last item whose start is <= c_lo1 (warp 0, 32 probes per round)
+            if (tid < 32) {
+                int lo = 0, hi = n_items;                   // start[lo] <= c_lo1 < start[hi]
+                while (hi - lo > 1) {
+                    const int step = (hi - lo + 31) >> 5;
+                    const int idx = lo + (lane + 1) * step;
+                    const bool le = idx < hi && __ldg(io + idx) <= c_lo1;
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, le));
+                    const int nlo = lo + cnt * step;
+                    hi = min(hi, nlo + step);
+                    lo = nlo;
                 }
-                const uint32_t v0 = *s.p0, v1 = *s.p1;
-                s.p0 += s.st0; s.p1 += s.st1;
-                const int kind = v0 == '-' ? (v1 == '-' ? 3 : 1) : (v1 == '-' ? 2 : 0);
-                if (warm) { warm = false; prev = kind; continue; }
-                cnt_m += (kind == 0 && v0 == v1); cnt_x += (kind == 0 && v0 != v1);
-                const bool gap = kind == 1 || kind == 2;
-                cnt_e += (gap && prev == kind); cnt_o += (gap && prev != kind);
-                prev = kind;
-                const int sh = (k & 7) * 8;
-                if (k < 8) { w0l |= (unsigned long long)v0 << sh; w1l |= (unsigned long long)v1 << sh; }
-                else { w0h |= (unsigned long long)v0 << sh; w1h |= (unsigned long long)v1 << sh; }
-                ++k;
+                if (lane == 0) s_ilo = lo;
             }
-            if (nb == 16) {
-                *reinterpret_cast<uint4 *>(aln0 + b0) = make_uint4((uint32_t)w0l, (uint32_t)(w0l >> 32), (uint32_t)w0h, (uint32_t)(w0h >> 32));
-                *reinterpret_cast<uint4 *>(aln1 + b0) = make_uint4((uint32_t)w1l, (uint32_t)(w1l >> 32), (uint32_t)w1h, (uint32_t)(w1h >> 32));
+        } else if (tid == 0) {
+            s_ilo = 0;
+        }
+        if (tid < 4) s_cnt[tid] = 0;
+        if (tid < 2 && c_lo == 0) sbuf[tid][16 + (int)(g_lo - base0) - 1] = 0;      // no column before the pair's first
+        __syncthreads();
+        // ---- phase 1: items -> shared memory, ASM_WIN items per window: their offsets and sources are
+        //      staged first (one round trip), then 8 lanes per item copy bytes, two items per group in flight
+        for (int i0 = s_ilo; i0 < n_items; i0 += ASM_WIN) {
+            const int nw = min(ASM_WIN, n_items - i0);
+            for (int u = tid; u <= nw; u += ASM_THREADS) {
+                s_io[u] = i0 + u < n_items ? __ldg(io + i0 + u) : aln_len;
+                if (u < nw) s_is[u] = __ldg(is + i0 + u);
+            }
+            __syncthreads();
+            const bool more = s_io[nw] < c_hi && i0 + nw < n_items;      // uniform: another window follows
+            const int grp = tid / ASM_G, gl = tid % ASM_G;
+            constexpr int NG = ASM_THREADS / ASM_G;
+            for (int u0 = 0; u0 < nw && s_io[u0] < c_hi; u0 += 2 * NG) {
+                const uint8_t *p0[2], *p1[2];
+                int st0[2], st1[2], cnt[2], qoff[2];
+                uint32_t r0[2][4], r1[2][4];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int u = u0 + grp + h * NG;
+                    cnt[h] = 0; p0[h] = p1[h] = g_dash; st0[h] = st1[h] = 0; qoff[h] = 0;
+                    if (u < nw) {
+                        const int start = s_io[u], end = s_io[u + 1];
+                        if (start < c_hi && end > c_lo1 && end > start) {
+                            const long long rec = s_is[u];
+                            const int kind = (int)(rec & 3);
+                            const long long src = rec >> 2;
+                            const int from = max(start, c_lo1), to = min(end, c_hi);
+                            const int d0 = from - start;
+                            cnt[h] = to - from;
+                            qoff[h] = 16 + (int)(tr.a_off + from - base0);
+                            if (kind == 3) { p0[h] = p1[h] = seqs + src + d0; st0[h] = st1[h] = 1; }
+                            else if (kind == 0) { p0[h] = strbuf + src - d0; p1[h] = p0[h] + tr.row_len; st0[h] = st1[h] = -1; }
+                            else if (kind == 1) { p0[h] = seqs + src + d0; st0[h] = 1; }
+                            else { p1[h] = seqs + src + d0; st1[h] = 1; }
+                        }
+                    }
+                }
+                // up to 32 columns of each of the two items: all loads first, then the stores
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int d = gl + ASM_G * v;
+                        if (d < cnt[h]) { r0[h][v] = p0[h][d * st0[h]]; r1[h][v] = p1[h][d * st1[h]]; }
+                    }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) {
+                        const int d = gl + ASM_G * v;
+                        if (d < cnt[h]) { sbuf[0][qoff[h] + d] = (uint8_t)r0[h][v]; sbuf[1][qoff[h] + d] = (uint8_t)r1[h][v]; }
+                    }
+                    for (int d = gl + 4 * ASM_G; d < cnt[h]; d += ASM_G) {         // longer items
+                        sbuf[0][qoff[h] + d] = p0[h][d * st0[h]]; sbuf[1][qoff[h] + d] = p1[h][d * st1[h]];
+                    }
+                }
+            }
+            if (!more) break;
+            __syncthreads();                                // s_io / s_is are reused by the next window
+        }
+        __syncthreads();
+        // ---- phase 2: shared memory -> both rows, 16 bytes per thread; column classification
+        int cnt_m = 0, cnt_x = 0, cnt_o = 0, cnt_e = 0;
+        const int nchunk = (int)((g_hi - base0 + 15) >> 4);
+        for (int j = tid; j < nchunk; j += ASM_THREADS) {
+            const int64_t cb = base0 + 16 * (int64_t)j;
+            const uint4 v0 = *reinterpret_cast<const uint4 *>(sbuf[0] + 16 + 16 * j);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(sbuf[1] + 16 + 16 * j);
+            const int b_lo = cb < g_lo ? (int)(g_lo - cb) : 0, b_hi = cb + 16 > g_hi ? (int)(g_hi - cb) : 16;
+            if (b_lo == 0 && b_hi == 16) {
+                *reinterpret_cast<uint4 *>(aln0 + cb) = v0;
+                *reinterpret_cast<uint4 *>(aln1 + cb) = v1;
             } else {
-                for (int q = 0; q < nb; ++q) {
-                    aln0[b0 + q] = (uint8_t)((q < 8 ? w0l >> (8 * q) : w0h >> (8 * (q - 8))) & 0xFF);
-                    aln1[b0 + q] = (uint8_t)((q < 8 ? w1l >> (8 * q) : w1h >> (8 * (q - 8))) & 0xFF);
+                for (int q = b_lo; q < b_hi; ++q) { aln0[cb + q] = sbuf[0][16 + 16 * j + q]; aln1[cb + q] = sbuf[1][16 + 16 * j + q]; }
+            }
+            if (want_sop) {
+                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+                // gap-only-in-row-1 / row-2 masks of the previous word (its last byte is the column before this chunk)
+                const uint32_t pw0 = *reinterpret_cast<const uint32_t *>(sbuf[0] + 12 + 16 * j), pw1 = *reinterpret_cast<const uint32_t *>(sbuf[1] + 12 + 16 * j);
+                uint32_t pe0 = __vcmpeq4(pw0, 0x2D2D2D2Du), pe1 = __vcmpeq4(pw1, 0x2D2D2D2Du);
+                uint32_t pg1 = pe0 & ~pe1, pg2 = pe1 & ~pe0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    // valid bytes of this word
+                    const int lo_b = b_lo - 4 * q, hi_b = b_hi - 4 * q;
+                    uint32_t vm = 0xFFFFFFFFu;
+                    if (lo_b > 0) vm &= lo_b >= 4 ? 0u : (0xFFFFFFFFu << (8 * lo_b));
+                    if (hi_b < 4) vm &= hi_b <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - hi_b)));
+                    const uint32_t e0 = __vcmpeq4(w0[q], 0x2D2D2D2Du), e1 = __vcmpeq4(w1[q], 0x2D2D2D2Du);
+                    const uint32_t eq = __vcmpeq4(w0[q], w1[q]);
+                    const uint32_t nuc = ~(e0 | e1) & vm;
+                    const uint32_t g1 = e0 & ~e1, g2 = e1 & ~e0;
+                    const uint32_t ext = ((g1 & ((g1 << 8) | (pg1 >> 24))) | (g2 & ((g2 << 8) | (pg2 >> 24)))) & vm;
+                    const uint32_t opn = (g1 | g2) & vm & ~ext;
+                    cnt_m += __popc(nuc & eq); cnt_x += __popc(nuc & ~eq);
+                    cnt_e += __popc(ext); cnt_o += __popc(opn);
+                    pg1 = g1; pg2 = g2;
                 }
             }
         }
-        if (out.sop && !compact) {
+        if (want_sop) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 cnt_m += __shfl_xor_sync(0xffffffffu, cnt_m, o); cnt_x += __shfl_xor_sync(0xffffffffu, cnt_x, o);
@@ -307,7 +407,7 @@ asm_copy_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
             }
             if (lane == 0) { atomicAdd(&s_cnt[0], cnt_m); atomicAdd(&s_cnt[1], cnt_x); atomicAdd(&s_cnt[2], cnt_o); atomicAdd(&s_cnt[3], cnt_e); }
             __syncthreads();
-            if (tid < 4 && s_cnt[tid]) atomicAdd(out.sop + 4 * pair + tid, s_cnt[tid]);
+            if (tid < 4 && s_cnt[tid]) atomicAdd(sop + 4 * tr.pair + tid, s_cnt[tid] >> 3);     // popc counts 8 bits per column
         }
     }
 }
@@ -342,14 +442,15 @@ cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStrea
 
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
                             const int32_t *runs, const Slot *slots, const uint8_t *strbuf, int32_t *item_off,
-                            AsmScanRec *scan, int64_t *tile_off, AsmOut out, uint8_t *aln0, uint8_t *aln1,
-                            int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags, int num_sms,
-                            cudaStream_t st, int *launches) {
+                            long long *item_src, AsmScanRec *scan, AsmTile *tiles, AsmOut out,
+                            uint8_t *aln0, uint8_t *aln1, int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags,
+                            int num_sms, cudaStream_t st, int *launches) {
     if (num_pairs <= 0) return cudaSuccess;
     const int64_t nblk = asm_scan_blocks(num_pairs);
-    asm_layout_kernel<<<(unsigned)nblk, LAY_THREADS, 0, st>>>(pout, num_pairs, slots, runs, item_off, scan, ctr, out, tile_off, flags);
-    asm_copy_kernel<<<num_sms * 16, ASM_THREADS, 0, st>>>(seqs, pairs, num_pairs, pout, runs, item_off, ctr, strbuf, out, tile_off,
-                                                          aln0, aln1, runs_out, seg_cols, flags);
+    asm_layout_kernel<<<(unsigned)nblk, LAY_THREADS, 0, st>>>(pout, pairs, num_pairs, slots, runs, item_off, item_src, scan, ctr, out,
+                                                              tiles, flags);
+    asm_copy_kernel<<<num_sms * 10, ASM_THREADS, 0, st>>>(seqs, runs, item_off, item_src, ctr, strbuf, out.sop, tiles, aln0, aln1,
+                                                          runs_out, seg_cols, flags);
     *launches += 2;
     return cudaGetLastError();
 }

@@ -92,11 +92,22 @@ struct AsmOut {
 // (aligned columns, reported runs, copy tiles) + flag (0 none, 1 aggregate, 2 prefix)
 struct AsmScanRec { unsigned long long agg[3]; unsigned long long pre[3]; unsigned int flag; unsigned int pad[3]; };
 inline int64_t asm_scan_blocks(int64_t num_pairs) { return (num_pairs + 63) / 64; }
+// everything the copy pass needs to know about one tile of ASM_TILE_COLS output columns of one pair
+struct AsmTile {
+    int64_t a_off;        // first output byte of the pair's rows
+    int64_t item_base;    // the pair's items start at item_off / item_src + item_base
+    int64_t run_base, run_off;   // the pair's runs in the pool / in the compacted output
+    int32_t aln_len, n_items, row_len, tp;   // tp: index of the tile inside the pair
+    int32_t pair, R, n_slots, ok;
+};
+static_assert(sizeof(AsmTile) == 64, "AsmTile is four 16-byte words");
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
                             const int32_t *runs, const Slot *slots, const uint8_t *strbuf, int32_t *item_off,
-                            AsmScanRec *scan, int64_t *tile_off, AsmOut out, uint8_t *aln0, uint8_t *aln1,
-                            int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags, int num_sms,
-                            cudaStream_t st, int *launches);
+                            long long *item_src, AsmScanRec *scan, AsmTile *tiles, AsmOut out,
+                            uint8_t *aln0, uint8_t *aln1, int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags,
+                            int num_sms, cudaStream_t st, int *launches);
+// copy tiles of ASM_TILE_COLS output columns: a batch of P pairs and B input bytes has at most B / ASM_TILE_COLS + P of them
+constexpr int ASM_TILE_COLS = 2048;
 
 cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStream_t st);
 cudaError_t launch_clear(Counters *ctr, int32_t *status, int64_t n, AsmScanRec *scan, int64_t nscan, cudaStream_t st);

@@ -123,6 +123,57 @@ kmer_stats_large_kernel(const uint8_t *__restrict__ seq, int64_t n, int k, unsig
         if (bad) atomicOr(&counts[3], 1u);
     }
 }
+// k >= 32: the k-mer does not fit the 64-bit key, so a slot names it by reference -- hash tag (high
+// 32 bits) | position of the claiming occurrence (bit 31: it is a seq2 position) -- and a probe with a
+// matching tag compares the k bases of the two occurrences (exact for every k; the reference's
+// predict_final_p scans k up to ceil(log2(shortest)) + 9, src/dbga/utils.py:395-413).
+__global__ void __launch_bounds__(256)
+kmer_stats_wide_kernel(const uint8_t *__restrict__ seq0, const uint8_t *__restrict__ seq1, int64_t n, int k, int phase,
+                       unsigned long long *__restrict__ keys, uint32_t *__restrict__ flag, uint64_t cap,
+                       unsigned int *__restrict__ counts) {
+    const uint8_t *seq = phase ? seq1 : seq0;
+    const int64_t N = n - k + 1;
+    int c_new = 0, c_sh = 0, bad = 0;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < N; p += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long hv = 0x9E3779B97F4A7C15ULL;
+        for (int j = 0; j < k; ++j) {
+            const uint8_t ch = seq[p + j];
+            bad |= !is_acgt(ch);
+            hv = (hv ^ (unsigned long long)base_code(ch)) * 0x100000001B3ULL;
+        }
+        hv ^= hv >> 33; hv *= 0xff51afd7ed558ccdULL; hv ^= hv >> 33;
+        const unsigned long long mine = (hv & 0xFFFFFFFF00000000ULL) | (phase ? 0x80000000ULL : 0ULL) | (unsigned long long)p;
+        uint64_t h = (hv & 0xFFFFFFFFULL) % cap;
+        for (;;) {
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&keys[h]);
+            if (cur == ~0ULL) {
+                cur = atomicCAS(&keys[h], ~0ULL, mine);
+                if (cur == ~0ULL) break;
+            }
+            if ((cur >> 32) == (hv >> 32)) {
+                const uint8_t *other = ((cur & 0x80000000ULL) ? seq1 : seq0) + (cur & 0x7FFFFFFFULL);
+                bool same = true;
+                for (int j = 0; j < k && same; ++j) same = other[j] == seq[p + j];
+                if (same) break;
+            }
+            h = h + 1 == cap ? 0 : h + 1;
+        }
+        const uint32_t old = atomicOr(&flag[h], phase == 0 ? 1u : 2u);
+        if (phase == 0) c_new += !(old & 1u);
+        else if (!(old & 2u)) { ++c_new; c_sh += (int)(old & 1u); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c_new += __shfl_xor_sync(0xffffffffu, c_new, o);
+        c_sh += __shfl_xor_sync(0xffffffffu, c_sh, o);
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c_new) atomicAdd(&counts[phase], (unsigned)c_new);
+        if (c_sh) atomicAdd(&counts[2], (unsigned)c_sh);
+        if (bad) atomicOr(&counts[3], 1u);
+    }
+}
 __global__ void kmer_stats_large_init(unsigned long long *keys, uint32_t *flag, uint64_t cap, unsigned int *counts) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
         keys[i] = ~0ULL; flag[i] = 0u;
@@ -135,6 +186,11 @@ cudaError_t launch_kmer_stats_large(const uint8_t *seq0, int64_t n0, const uint8
                                     int num_sms, cudaStream_t st) {
     const unsigned long long kmask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);
     kmer_stats_large_init<<<num_sms * 4, 256, 0, st>>>(keys, flag, cap, counts);
+    if (k >= 32) {
+        kmer_stats_wide_kernel<<<num_sms * 8, 256, 0, st>>>(seq0, seq1, n0, k, 0, keys, flag, cap, counts);
+        kmer_stats_wide_kernel<<<num_sms * 8, 256, 0, st>>>(seq0, seq1, n1, k, 1, keys, flag, cap, counts);
+        return cudaGetLastError();
+    }
     kmer_stats_large_kernel<<<num_sms * 8, 256, 0, st>>>(seq0, n0, k, kmask, 0, keys, flag, cap, counts);
     kmer_stats_large_kernel<<<num_sms * 8, 256, 0, st>>>(seq1, n1, k, kmask, 1, keys, flag, cap, counts);
     return cudaGetLastError();

@@ -119,8 +119,59 @@ __device__ __forceinline__ uint32_t g_find(const GSlot *tbl, uint32_t mask, uint
     }
 }
 
+// ---- k >= 32 ("wide" k-mers; the reference accepts any k <= len, utils.py:129-131, and its own
+// front-ends reach k = 33 and beyond on sequences of more than 2^21 bases, adaptive_debruijn.py:54-56).
+// A k-mer no longer fits the 64-bit key, so the slot names it by reference instead: key = hash tag
+// (high 32 bits) | position of the occurrence that claimed the slot (seq1 position p, or
+// 0x80000000 | q for a seq2 position).  A probe compares the tag and, on a tag match, the 2k bits
+// of the two occurrences word by word in the packed sequences -- exact for every k.
+struct WideCtx { const uint32_t *pk0, *pk1; int k; };
+__device__ __forceinline__ uint32_t wide_word(const uint32_t *pk, int p, int j) {      // bases p + 16 j .. p + 16 j + 15
+    const int w = (p >> 4) + j, sh = (p & 15) * 2;
+    return __funnelshift_r(pk[w], pk[w + 1], sh);
+}
+__device__ __forceinline__ uint64_t wide_hash(const uint32_t *pk, int p, int k) {
+    uint64_t h = 0x9E3779B97F4A7C15ULL;
+    const int full = k >> 4, rem = k & 15;
+    for (int j = 0; j < full; ++j) { h ^= wide_word(pk, p, j); h *= 0xff51afd7ed558ccdULL; h ^= h >> 29; }
+    if (rem) { h ^= wide_word(pk, p, full) & ((1u << (2 * rem)) - 1u); h *= 0xff51afd7ed558ccdULL; h ^= h >> 29; }
+    h *= 0xc4ceb9fe1a85ec53ULL; h ^= h >> 32;
+    return h;
+}
+__device__ __forceinline__ bool wide_same(const WideCtx &c, uint32_t ra, uint32_t rb) {
+    const uint32_t *pa = (ra & 0x80000000u) ? c.pk1 : c.pk0, *pb = (rb & 0x80000000u) ? c.pk1 : c.pk0;
+    const int a = (int)(ra & 0x7FFFFFFFu), b = (int)(rb & 0x7FFFFFFFu);
+    const int full = c.k >> 4, rem = c.k & 15;
+    for (int j = 0; j < full; ++j) if (wide_word(pa, a, j) != wide_word(pb, b, j)) return false;
+    if (rem) { const uint32_t m = (1u << (2 * rem)) - 1u; if ((wide_word(pa, a, full) ^ wide_word(pb, b, full)) & m) return false; }
+    return true;
+}
+// find-or-claim / find for the occurrence `me` (a position code) whose k-mer hashes to hv
+__device__ __forceinline__ uint32_t gw_insert(GSlot *tbl, uint32_t mask, const WideCtx &c, uint64_t hv, uint32_t me) {
+    uint32_t h = (uint32_t)hv & mask;
+    const uint64_t mine = (hv & 0xFFFFFFFF00000000ULL) | me;
+    for (;;) {
+        uint64_t cur = *reinterpret_cast<volatile uint64_t *>(&tbl[h].key);
+        if (cur == ~0ULL) {
+            cur = (uint64_t)atomicCAS(reinterpret_cast<unsigned long long *>(&tbl[h].key), ~0ULL, (unsigned long long)mine);
+            if (cur == ~0ULL) return h;
+        }
+        if ((cur >> 32) == (hv >> 32) && wide_same(c, (uint32_t)cur, me)) return h;
+        h = (h + 1) & mask;
+    }
+}
+__device__ __forceinline__ uint32_t gw_find(const GSlot *tbl, uint32_t mask, const WideCtx &c, uint64_t hv, uint32_t me) {
+    uint32_t h = (uint32_t)hv & mask;
+    for (;;) {
+        const uint64_t cur = tbl[h].key;
+        if (cur == ~0ULL) return 0xFFFFFFFFu;
+        if ((cur >> 32) == (hv >> 32) && wide_same(c, (uint32_t)cur, me)) return h;
+        h = (h + 1) & mask;
+    }
+}
+
 // phase: 0 = insert seq1; 1 = seq2 lookup/claim (memo into aof); 2 = finalize aof (+flags)
-template <int PHASE, bool FULL>
+template <int PHASE, bool FULL, bool WIDE>
 __global__ void __launch_bounds__(256)
 hash_large_kernel(const PairDesc *__restrict__ pairs, const LargeDesc *__restrict__ ld,
                   const int32_t *__restrict__ pair_list, int k, const uint32_t *__restrict__ packed,
@@ -135,19 +186,21 @@ hash_large_kernel(const PairDesc *__restrict__ pairs, const LargeDesc *__restric
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t kmask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
     GSlot *tbl = table + L.tbl;
+    const WideCtx wc{packed + L.pk0, packed + L.pk1, k};
     if (PHASE == 0) {
         if (i >= N0) return;
-        const uint32_t h = g_insert(tbl, L.mask, kmer_at<uint64_t>(packed + L.pk0, i, kmask));
+        const uint32_t h = WIDE ? gw_insert(tbl, L.mask, wc, wide_hash(wc.pk0, i, k), (uint32_t)i)
+                                : g_insert(tbl, L.mask, kmer_at<uint64_t>(packed + L.pk0, i, kmask));
         occ_mark(&tbl[h].v0, (uint32_t)i);
     } else if (PHASE == 1) {
         if (i >= N1) return;
-        const uint64_t key = kmer_at<uint64_t>(packed + L.pk1, i, kmask);
+        const uint64_t key = WIDE ? wide_hash(wc.pk1, i, k) : kmer_at<uint64_t>(packed + L.pk1, i, kmask);
         uint32_t h;
         if (FULL) {
-            h = g_insert(tbl, L.mask, key);
+            h = WIDE ? gw_insert(tbl, L.mask, wc, key, 0x80000000u | (uint32_t)i) : g_insert(tbl, L.mask, key);
             occ_mark(&tbl[h].v1, (uint32_t)i);
         } else {
-            h = g_find(tbl, L.mask, key);
+            h = WIDE ? gw_find(tbl, L.mask, wc, key, 0x80000000u | (uint32_t)i) : g_find(tbl, L.mask, key);
             if (h != 0xFFFFFFFFu) {
                 if (tbl[h].v0 < V_DUP) occ_mark(&tbl[h].v1, (uint32_t)i);
                 else h = 0xFFFFFFFFu;
@@ -166,7 +219,8 @@ hash_large_kernel(const PairDesc *__restrict__ pairs, const LargeDesc *__restric
             aof[pd.q_base + i] = a;
         }
         if (FULL && i < N0) {
-            const uint32_t h = g_find(tbl, L.mask, kmer_at<uint64_t>(packed + L.pk0, i, kmask));
+            const uint32_t h = WIDE ? gw_find(tbl, L.mask, wc, wide_hash(wc.pk0, i, k), (uint32_t)i)
+                                    : g_find(tbl, L.mask, kmer_at<uint64_t>(packed + L.pk0, i, kmask));
             nd0[pd.p_base + i] = !(tbl[h].v0 == V_DUP || tbl[h].v1 == V_DUP);
         }
     }
@@ -183,15 +237,13 @@ cudaError_t launch_stage1_large(const uint8_t *seqs, const PairDesc *pairs, cons
     dim3 gp((words + 255) / 256, 2 * count), gk((max_n + 255) / 256, count);
     pack_large_kernel<<<gp, 256, 0, st>>>(seqs, pairs, ld, list, k, packed, status);
     GSlot *tbl = reinterpret_cast<GSlot *>(table);
-    if (full) {
-        hash_large_kernel<0, true><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1);
-        hash_large_kernel<1, true><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1);
-        hash_large_kernel<2, true><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1);
-    } else {
-        hash_large_kernel<0, false><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1);
-        hash_large_kernel<1, false><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1);
-        hash_large_kernel<2, false><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1);
-    }
+#define DBGA_HL(PH, F, W) hash_large_kernel<PH, F, W><<<gk, 256, 0, st>>>(pairs, ld, list, k, packed, tbl, status, aof, nd0, nd1)
+    const bool wide = k >= 32;
+    if (full && wide) { DBGA_HL(0, true, true); DBGA_HL(1, true, true); DBGA_HL(2, true, true); }
+    else if (full) { DBGA_HL(0, true, false); DBGA_HL(1, true, false); DBGA_HL(2, true, false); }
+    else if (wide) { DBGA_HL(0, false, true); DBGA_HL(1, false, true); DBGA_HL(2, false, true); }
+    else { DBGA_HL(0, false, false); DBGA_HL(1, false, false); DBGA_HL(2, false, false); }
+#undef DBGA_HL
     *launches += 4;
     return cudaGetLastError();
 }

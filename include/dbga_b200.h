@@ -42,7 +42,8 @@ extern "C" {
 /* Tie-order encoding shared with oracle/: index into XMY, XYM, MXY, MYX, YXM, YMX
  * (first state wins ties; X consumes a seq1 character, Y a seq2 character). */
 typedef struct dbga_params {
-    int32_t k;            /* k-mer size, 1..31 (larger: DBGA_ERR_ARG)                   */
+    int32_t k;            /* k-mer size >= 1 (k > a sequence's length: DBGA_K_INVALID); k >= 32 runs on
+                             by-reference keys in a global-memory table (any k, slower per pair)    */
     int32_t score[16];    /* substitution scores, row-major over ACGT x ACGT            */
     int32_t gap_open;     /* d  (debruijn_pairwise.py:423)                              */
     int32_t gap_extend;   /* e  (:424)                                                  */

@@ -144,9 +144,10 @@ int32_t oracle_gotoh(const uint8_t *x, int64_t m, const uint8_t *y, int64_t n,
 
 /* ------------------------------------------------------------------- stages 1 and 2 */
 typedef struct {
-    uint64_t key;     /* 2-bit packed k-mer; slot empty when c0 == 0 && c1 == 0 */
+    uint64_t key;     /* 2-bit packed k-mer (k <= 32) or a hash of it (k > 32); slot empty when c0 == 0 && c1 == 0 */
     int32_t c0, c1;   /* occurrence counts (saturate at 2) */
     int32_t p0, p1;   /* first position in s0 / s1 */
+    const uint8_t *rep; /* k > 32: codes of the occurrence that claimed the slot (compared base by base) */
 } slot_t;
 
 static inline uint64_t mix64(uint64_t z) {
@@ -154,13 +155,20 @@ static inline uint64_t mix64(uint64_t z) {
     z *= 0xc4ceb9fe1a85ec53ULL; z ^= z >> 33; return z;
 }
 
-static slot_t *tbl_find(slot_t *t, uint64_t mask, uint64_t key) {
+/* cur != NULL (k > 32): key is a hash; equal hashes are confirmed on the k codes themselves */
+static slot_t *tbl_find(slot_t *t, uint64_t mask, uint64_t key, const uint8_t *cur, int32_t k) {
     uint64_t h = mix64(key) & mask;
     for (;;) {
         slot_t *s = &t[h];
-        if ((s->c0 | s->c1) == 0 || s->key == key) return s;
+        if ((s->c0 | s->c1) == 0) { s->rep = cur; return s; }
+        if (s->key == key && (!cur || memcmp(s->rep, cur, (size_t)k) == 0)) return s;
         h = (h + 1) & mask;
     }
+}
+static uint64_t hash_codes(const uint8_t *c, int32_t k) {
+    uint64_t h = 1469598103934665603ULL;
+    for (int32_t i = 0; i < k; ++i) { h ^= c[i]; h *= 1099511628211ULL; }
+    return h;
 }
 
 /* Result of one pair.  Arrays are malloc'd here and released with oracle_free_pair. */
@@ -211,7 +219,8 @@ int32_t oracle_align_pair(const uint8_t *s0, int64_t n0, const uint8_t *s1, int6
                           int32_t want_graph, int32_t stages, oracle_pair *r) {
     static const char L[4] = {'A', 'C', 'G', 'T'};
     memset(r, 0, sizeof(*r));
-    if (k < 1 || k > 32 || k > n0 || k > n1) { r->status = ST_K_INVALID; return r->status; }
+    if (k < 1 || k > n0 || k > n1) { r->status = ST_K_INVALID; return r->status; }   /* utils.py:129-131 */
+    const int wide = k > 32;
     uint8_t *c0 = malloc((size_t)n0), *c1 = malloc((size_t)n1);
     int bad = 0;
     for (int64_t i = 0; i < n0; ++i) { int c = code_of(s0[i]); if (c < 0) bad = 1; c0[i] = (uint8_t)c; }
@@ -221,13 +230,15 @@ int32_t oracle_align_pair(const uint8_t *s0, int64_t n0, const uint8_t *s1, int6
     uint64_t cap = 16;
     while (cap < (uint64_t)(2 * (N0 + N1))) cap <<= 1;
     slot_t *tbl = calloc(cap, sizeof(slot_t));
-    const uint64_t kmask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const uint64_t kmask = (k >= 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
     slot_t **sl0 = malloc(sizeof(slot_t *) * (size_t)N0), **sl1 = malloc(sizeof(slot_t *) * (size_t)N1);
     uint64_t key = 0;
     for (int64_t i = 0; i < n0; ++i) {
         key = ((key << 2) | c0[i]) & kmask;
         if (i >= k - 1) {
-            slot_t *s = tbl_find(tbl, cap - 1, key);
+            const uint8_t *cur = wide ? c0 + (i - k + 1) : NULL;
+            if (wide) key = hash_codes(cur, k);
+            slot_t *s = tbl_find(tbl, cap - 1, key, cur, k);
             if (s->c0 == 0) s->p0 = (int32_t)(i - k + 1);
             s->key = key; if (s->c0 < 2) s->c0++;
             sl0[i - k + 1] = s;
@@ -237,7 +248,9 @@ int32_t oracle_align_pair(const uint8_t *s0, int64_t n0, const uint8_t *s1, int6
     for (int64_t i = 0; i < n1; ++i) {
         key = ((key << 2) | c1[i]) & kmask;
         if (i >= k - 1) {
-            slot_t *s = tbl_find(tbl, cap - 1, key);
+            const uint8_t *cur = wide ? c1 + (i - k + 1) : NULL;
+            if (wide) key = hash_codes(cur, k);
+            slot_t *s = tbl_find(tbl, cap - 1, key, cur, k);
             if (s->c1 == 0) s->p1 = (int32_t)(i - k + 1);
             s->key = key; if (s->c1 < 2) s->c1++;
             sl1[i - k + 1] = s;

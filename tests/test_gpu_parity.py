@@ -453,3 +453,34 @@ def test_very_long_pairs_take_the_cluster_stage2(aligner):
              O.synth_pair(70000, 0.01, 0.002, 413)]
     for k in (15, 11):
         check_batch(aligner, pairs, k)
+
+
+@pytest.mark.parametrize("k", [32, 33, 40, 64, 101])
+def test_wide_kmers_vs_oracle(aligner, k):
+    """k >= 32 (the reference accepts any k <= len, utils.py:129-131; adpt_dbg_alignment starts at
+    k = 33 beyond 2^21 bases): by-reference keys in the global-memory table, against the oracle."""
+    rng = random.Random(4000 + k)
+    pairs = []
+    for t in range(40):
+        n = rng.choice([k, k + 1, 150, 600, 1500, 4000])
+        n = max(n, k)
+        s0 = rand_seq(rng, n, rng.choice(["ACGT", "ACGT", "AC"]))
+        if rng.random() < 0.3 and n > 300:
+            s0 = s0[:200] + s0[100:300] + s0[200:]                  # repeated k-mers
+        s1 = mutate(rng, s0, rng.choice([0, 0.005, 0.02]), rng.choice([0, 0.002]))
+        if len(s1) < k:
+            s1 = s0
+        pairs.append((s0, s1))
+    pairs.append(("A" * (k + 30), "A" * (k + 10)))                # every k-mer duplicate
+    pairs.append((pairs[0][0], pairs[0][0][: k - 1] if k > 1 else "A"))   # K_INVALID
+    assert check_batch(aligner, pairs, k) >= 10
+    res = aligner.align_pairs(pairs[:6], k, want_graph=True, stages=2)
+    for i in range(6):
+        ref = CO.align_pair(*pairs[i], k, want_graph=True, stages=2)
+        if ref.status in (O.OK, O.CYCLE):
+            nd0, nd1 = res.graph_flags(i)
+            assert np.array_equal(nd0, ref.nondup0) and np.array_equal(nd1, ref.nondup1)
+    st, d0, d1, sh = aligner.kmer_stats(pairs[:20], k)
+    for i in range(20):
+        if st[i] == O.OK:
+            assert (d0[i], d1[i], sh[i]) == O.kmer_stats(*pairs[i], k), i
