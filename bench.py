@@ -328,6 +328,7 @@ def run_ours(args):
     if not args.no_variants:
         vsteps = max(3, args.steps // 2)
         variants["rows+anchor_runs (flags=0, the round-1 form)"], _, _ = time_e2e(0, steps=vsteps)
+        variants["rows + per-pair quality counts (flags=NO_RUNS|SOP)"], _, _ = time_e2e(_lib.FLAG_NO_RUNS | _lib.FLAG_SOP, steps=vsteps)
         variants["compact_rows (segment columns + runs; flags=COMPACT_ROWS)"], _, _ = time_e2e(_lib.FLAG_COMPACT_ROWS, steps=vsteps)
         variants["compact_rows + dbga_expand_rows on the host (full rows in host memory)"], _, rows = \
             time_e2e(_lib.FLAG_COMPACT_ROWS, expand=True, steps=vsteps)

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdbga_b200.so")
 
 OK, CYCLE, K_INVALID, BAD_CHAR, TOO_LARGE = 0, 1, 2, 3, 4
-FLAG_NO_RUNS, FLAG_COMPACT_ROWS = 1, 2
+FLAG_NO_RUNS, FLAG_COMPACT_ROWS, FLAG_SOP = 1, 2, 4
 ORDERS = ("XMY", "XYM", "MXY", "MYX", "YXM", "YMX")
 
 # every symbol include/dbga_b200.h declares
@@ -26,6 +26,7 @@ EXPORTS = (
     "dbga_kmer_stats", "dbga_version",
     "dbga_align_batch_packed", "dbga_packed_words", "dbga_pack_ascii", "dbga_expand_rows",
     "dbga_multi_create", "dbga_multi_destroy", "dbga_multi_last_error", "dbga_align_batch_multi",
+    "dbga_fasta_read", "dbga_fasta_free", "dbga_fasta_write",
 )
 MAX_SHARDS = 16
 
@@ -56,6 +57,12 @@ class Result(C.Structure):
 class MultiResult(C.Structure):
     _fields_ = [("num_shards", C.c_int32), ("pad", C.c_int32), ("pair_lo", C.c_int64 * (MAX_SHARDS + 1)),
                 ("shard", Result * MAX_SHARDS), ("ms_total", C.c_float)]
+
+
+class Fasta(C.Structure):
+    _fields_ = [("num_records", C.c_int64), ("offsets", C.POINTER(C.c_int64)), ("seqs", C.POINTER(C.c_uint8)),
+                ("packed", C.POINTER(C.c_uint32)), ("packed_words", C.c_int64), ("name_off", C.POINTER(C.c_int64)),
+                ("names", C.POINTER(C.c_char)), ("bad_records", C.c_int64)]
 
 
 _lib = None
@@ -115,6 +122,12 @@ def load():
     lib.dbga_pack_ascii.restype = C.c_int64
     lib.dbga_expand_rows.argtypes = [vp, i64p, C.POINTER(Result), vp, vp, C.c_int64, i64p, C.c_int]
     lib.dbga_expand_rows.restype = C.c_int
+    lib.dbga_fasta_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(Fasta))]
+    lib.dbga_fasta_read.restype = C.c_int
+    lib.dbga_fasta_free.argtypes = [C.POINTER(Fasta)]
+    lib.dbga_fasta_free.restype = None
+    lib.dbga_fasta_write.argtypes = [C.c_char_p, C.POINTER(Fasta), C.POINTER(Result), C.c_int64, C.c_int, C.c_int, C.c_int]
+    lib.dbga_fasta_write.restype = C.c_int64
     lib.dbga_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     lib.dbga_multi_create.restype = C.c_int
     lib.dbga_multi_destroy.argtypes = [vp]

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdbga_b200.so")
-SOURCES = ["stage12_small.cu", "stage1_kmer.cu", "stage2_anchor.cu", "stage3_dp.cu", "stage3_dp16.cu", "assemble.cu", "pack.cu", "kmer_stats.cu", "intpeak.cu", "api.cu"]
+SOURCES = ["stage12_small.cu", "stage1_kmer.cu", "stage2_anchor.cu", "stage3_dp.cu", "stage3_dp16.cu", "assemble.cu", "pack.cu", "fasta_io.cu", "kmer_stats.cu", "intpeak.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

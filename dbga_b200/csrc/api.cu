@@ -52,6 +52,7 @@ struct dbga_ctx {
     // ---- plan
     bool planned = false, ran = false;
     int64_t P = 0, total_bytes = 0, sumN0 = 0, sumN1 = 0;
+    int64_t seq_extent = 0;       // bytes of the device sequence buffer the plan's offsets reach (relative to its base)
     int max_n0 = 0, max_n1 = 0;
     dbga_params prm{};
     bool no_anchors = false;
@@ -283,6 +284,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     ctx->P = P;
     ctx->h_pairs.resize((size_t)P);
     ctx->total_bytes = P > 0 ? offsets[2 * P] - off_base : 0;
+    ctx->seq_extent = P > 0 ? offsets[2 * P] - off_base : 0;
     int64_t qb = 0, pb = 0;
     int mx0 = 0, mx1 = 0;
     for (int64_t i = 0; i < P; ++i) {
@@ -480,7 +482,7 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     if (!any_non_tiny) ctx->grid_warp = 0;
     if (!any_cta) ctx->grid_cta = ctx->grid_cluster = 0;
     if (params->stages == 3) {
-        RESERVE(d_str, 2 * std::max<int64_t>(ctx->total_bytes, 1));
+        RESERVE(d_str, 2 * std::max<int64_t>(ctx->total_bytes, 1) + 16);      // + slack: the assembler reads whole words
         if (ctx->grid_warp) RESERVE(d_bnd_w, (size_t)ctx->grid_warp * 2 * ctx->bnd_stride_warp * 16);
         if (ctx->grid_cta) RESERVE(d_bnd_c, (size_t)ctx->grid_cta * 2 * ctx->bnd_stride_cta * 16);
         RESERVE(d_aln0, std::max<int64_t>(ctx->total_bytes, 1));
@@ -651,7 +653,7 @@ int run_pipeline(dbga_ctx *ctx) {
                                     (uint8_t *)ctx->d_str.p, (int32_t *)ctx->d_item_off.p, (long long *)ctx->d_item_src.p,
                                     (AsmScanRec *)ctx->d_scan.p, (AsmTile *)ctx->d_tile_pair.p, ao,
                                     (uint8_t *)ctx->d_aln0.p, (uint8_t *)ctx->d_aln1.p,
-                                    (int32_t *)ctx->d_runs_out.p, (int32_t *)ctx->d_segcols.p, ctr, ctx->prm.flags,
+                                    (int32_t *)ctx->d_runs_out.p, (int32_t *)ctx->d_segcols.p, ctr, ctx->seq_extent, ctx->prm.flags,
                                     ctx->num_sms, st, &ctx->launches));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[5], st));
     return DBGA_SUCCESS;
@@ -712,7 +714,8 @@ int fetch_enqueue(dbga_ctx *ctx, const HostDst &d, int64_t total_aln, int64_t to
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.nanch, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln_off, ctx->d_aln_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
     DBGA_CUDA_CHECK(cudaMemcpyAsync(d.run_off, ctx->d_run_off.p, 8 * (P + 1), cudaMemcpyDeviceToHost, st));
-    if (ctx->prm.stages == 3) DBGA_CUDA_CHECK(cudaMemcpyAsync(d.sop, ctx->d_sop.p, 16 * P, cudaMemcpyDeviceToHost, st));
+    if (ctx->prm.stages == 3 && (ctx->prm.flags & DBGA_FLAG_SOP))
+        DBGA_CUDA_CHECK(cudaMemcpyAsync(d.sop, ctx->d_sop.p, 16 * P, cudaMemcpyDeviceToHost, st));
     }
     if (total_aln) {
         DBGA_CUDA_CHECK(cudaMemcpyAsync(d.aln0, ctx->d_aln0.p, total_aln, cudaMemcpyDeviceToHost, st));
@@ -771,7 +774,7 @@ int do_fetch(dbga_ctx *ctx, dbga_result *out) {
     out->status = d.status; out->score = d.score; out->dp_cells = d.cells; out->dp_segments = d.nseg;
     out->n_anchors = d.nanch; out->run_off = d.run_off; out->runs = d.runs; out->aln_off = d.aln_off;
     out->aln0 = d.aln0; out->aln1 = d.aln1;
-    out->sop = seg ? d.sop : nullptr; out->seg_cols = compact ? d.segcols : nullptr;
+    out->sop = (seg && (ctx->prm.flags & DBGA_FLAG_SOP)) ? d.sop : nullptr; out->seg_cols = compact ? d.segcols : nullptr;
     out->ms_plan = ctx->ms_plan;
     if (!seg && P) { for (int64_t i = 0; i <= P; ++i) d.aln_off[i] = 0; }
     if (full) {
@@ -1086,7 +1089,8 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_cells.p, ctx->d_cells.p, 8 * P, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nseg.p, ctx->d_nseg.p, 4 * P, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_nanch.p, ctx->d_nanch.p, 8 * P, cudaMemcpyDeviceToHost, st));
-        if (seg) DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_sop.p, ctx->d_sop.p, 16 * P, cudaMemcpyDeviceToHost, st));
+        if (seg && (params->flags & DBGA_FLAG_SOP))
+            DBGA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_sop.p, ctx->d_sop.p, 16 * P, cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(aln_off, ctx->d_aln_off.p, 8 * (P + nchunks), cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(cudaMemcpyAsync(run_off, ctx->d_run_off.p, 8 * (P + nchunks), cudaMemcpyDeviceToHost, st));
         DBGA_CUDA_CHECK(wait_stream(ctx, st));
@@ -1115,7 +1119,8 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
     out->dp_cells = (int64_t *)ctx->h_cells.p; out->dp_segments = (int32_t *)ctx->h_nseg.p;
     out->n_anchors = (int64_t *)ctx->h_nanch.p; out->run_off = run_off; out->runs = (int32_t *)ctx->h_runs.p;
     out->aln_off = aln_off; out->aln0 = (uint8_t *)ctx->h_aln0.p; out->aln1 = (uint8_t *)ctx->h_aln1.p;
-    out->sop = seg ? (int32_t *)ctx->h_sop.p : nullptr; out->seg_cols = compact ? (int32_t *)ctx->h_segcols.p : nullptr;
+    out->sop = (seg && (params->flags & DBGA_FLAG_SOP)) ? (int32_t *)ctx->h_sop.p : nullptr;
+    out->seg_cols = compact ? (int32_t *)ctx->h_segcols.p : nullptr;
     out->ms_plan = plan_ms_total;
     if (no_runs) out->runs = nullptr;
     out->ms_stage1 = ms[0]; out->ms_stage2 = ms[1]; out->ms_stage3 = ms[2]; out->ms_assemble = ms[3];

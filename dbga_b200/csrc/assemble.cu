@@ -20,7 +20,7 @@ namespace dbga {
 // totals; the block totals of (aligned columns, reported runs, copy tiles) are then scanned across
 // CTAs with a decoupled look-back, so aln_off / run_off / tile_off come out of the same launch.
 constexpr int ASM_TILE = 2048;        // output columns per copy tile
-constexpr int ASM_THREADS = 128;
+constexpr int ASM_THREADS = 64;
 constexpr int LAY_PAIRS = 64;
 constexpr int LAY_THREADS = 256;
 
@@ -37,9 +37,10 @@ __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
     return v;
 }
 
-__global__ void __launch_bounds__(LAY_THREADS, 5)
+__global__ void __launch_bounds__(LAY_THREADS, 4)
 asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__ pairs, int64_t num_pairs,
-                  const Slot *__restrict__ slots, const int32_t *__restrict__ runs, int32_t *__restrict__ item_off,
+                  const Slot *__restrict__ slots, const int32_t *__restrict__ runs, const uint8_t *__restrict__ strbuf,
+                  int32_t *__restrict__ item_off,
                   long long *__restrict__ item_src, AsmScanRec *__restrict__ scan, Counters *__restrict__ ctr, AsmOut out,
                   AsmTile *__restrict__ tiles, int flags) {
     __shared__ long long s_v[3][LAY_PAIRS];
@@ -48,6 +49,7 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
     __shared__ unsigned int s_ticket;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const bool compact = (flags & DBGA_FLAG_COMPACT_ROWS) != 0, no_runs = (flags & DBGA_FLAG_NO_RUNS) != 0 && !compact;
+    const bool want_sop = (flags & DBGA_FLAG_SOP) != 0 && out.sop != nullptr;
     if (tid == 0) s_ticket = atomicAdd(&ctr->scan_ticket, 1u);
     __syncthreads();
     const int64_t blk = s_ticket, pair0 = blk * LAY_PAIRS;
@@ -71,7 +73,8 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
         const int w = wid + (LAY_THREADS / 32) * j;
         const int64_t pair = pair0 + w;
         long long sc = 0, ce = 0, nrep = 0;
-        unsigned int carry = 0;
+        int c_m = 0, c_x = 0, c_o = 0, c_e = 0;            // match, mismatch, gap_open, gap_extend
+        unsigned int carry = 0, carry_run = 1;
         int ns = 0, ntile = 0;
         int st = s_meta[w].status;
         if (pair < num_pairs) {
@@ -85,11 +88,16 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
                 int32_t *io = item_off + 2 * slot_base;
                 long long *is = item_src + 2 * slot_base;
                 bool big = false;
+                int carry_kind = 0;                 // kind of the last column emitted so far (0: both bases)
                 // lane handles slot t and the run that follows it (items 2t, 2t + 1)
                 for (int tb = 0; tb < n_slots; tb += 32) {
                     const int t = tb + lane;
-                    unsigned int len_s = 0, len_r = 0;
+                    unsigned int len_s = 0, len_r = 0, run_emit = 0;
                     long long src_s = 0, src_r = 0;
+                    // alignment-quality counts of the slot's emitted columns (pairwise_alignment_score,
+                    // reference src/dbga/utils.py:440-504), its first / last column kind, and what to classify
+                    int first_kind = 0, last_kind = 0, q_len = 0, q_skip = 0;
+                    long long q_rows = -1;          // scratch offset of the reversed row 1 of a DP slot
                     if (t < n_slots) {
                         const Slot *sp = slots + slot_base + t;
                         const int4 xy = *reinterpret_cast<const int4 *>(sp);             // (x0, m, y0, n)
@@ -102,15 +110,86 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
                         if (xy.y > 0 && xy.w > 0) {
                             sc += sl.x; ce += (long long)xy.y * xy.w; ++ns;
                             src_s = ((2 * off0 + xy.x + xy.z + (sl.y - 1 - skip)) << 2) | 0;      // reversed rows in the scratch
+                            q_rows = 2 * off0 + xy.x + xy.z; q_len = sl.y; q_skip = skip;
                         } else if (xy.y > 0) {
                             src_s = ((off0 + xy.x + skip) << 2) | 1;                     // utils.py:187-188
+                            if (len_s) { c_o += 1; c_e += len_s - 1; first_kind = last_kind = 2; }
                         } else {
                             src_s = ((off1 + xy.z + skip) << 2) | 2;                     // utils.py:189-190
+                            if (len_s) { c_o += 1; c_e += len_s - 1; first_kind = last_kind = 1; }
                         }
                         if (t < R) {
-                            if (!compact) len_r = (unsigned int)(rn.z - (t == R - 1 ? 1 : 0));      // last merge node is left to the tail
+                            run_emit = (unsigned int)(rn.z - (t == R - 1 ? 1 : 0));     // last merge node is left to the tail
+                            if (!compact) len_r = run_emit;
                             src_r = ((off0 + rn.x) << 2) | 3;
+                            c_m += run_emit;                                             // inside a run every column is a match
                         }
+                    }
+                    // ---- classify the columns of the DP slots: a lane walks its own short slot; long slots
+                    //      are taken one at a time by the whole warp (32 columns per step)
+                    const int row_len = s_meta[w].row_len;
+                    if (!want_sop) q_rows = -1;
+                    if (q_rows >= 0 && q_len - q_skip <= 64) {
+                        const uint8_t *rx = strbuf + q_rows, *ry = rx + row_len;
+                        int prev = 0;
+                        for (int c = q_skip; c < q_len; ++c) {
+                            const uint32_t b0 = rx[q_len - 1 - c], b1 = ry[q_len - 1 - c];
+                            const int kind = b0 == '-' ? (b1 == '-' ? 3 : 1) : (b1 == '-' ? 2 : 0);
+                            c_m += (kind == 0 && b0 == b1); c_x += (kind == 0 && b0 != b1);
+                            const bool gap = kind == 1 || kind == 2;
+                            c_e += (gap && prev == kind); c_o += (gap && prev != kind);
+                            if (c == q_skip) first_kind = kind;
+                            prev = kind;
+                        }
+                        last_kind = prev;
+                    }
+                    for (unsigned int todo = __ballot_sync(0xffffffffu, q_rows >= 0 && q_len - q_skip > 64); todo; todo &= todo - 1) {
+                        const int L = __ffs(todo) - 1;
+                        const long long rows = __shfl_sync(0xffffffffu, q_rows, L);
+                        const int ln = __shfl_sync(0xffffffffu, q_len, L), sk = __shfl_sync(0xffffffffu, q_skip, L);
+                        const uint8_t *rx = strbuf + rows, *ry = rx + row_len;
+                        int am = 0, ax = 0, ao2 = 0, ae = 0;
+                        unsigned int p1 = 0, p2 = 0;            // bit 0: the previous column was a gap in row 1 / row 2 only
+                        int fk = 0, lk = 0;
+                        for (int c0 = sk; c0 < ln; c0 += 32) {
+                            const int c = c0 + lane;
+                            uint32_t b0 = 'A', b1 = 'C';
+                            const bool have = c < ln;
+                            if (have) { b0 = rx[ln - 1 - c]; b1 = ry[ln - 1 - c]; }
+                            const unsigned int vm = __ballot_sync(0xffffffffu, have);
+                            const unsigned int g0 = __ballot_sync(0xffffffffu, have && b0 == '-'), g1b = __ballot_sync(0xffffffffu, have && b1 == '-');
+                            const unsigned int eq = __ballot_sync(0xffffffffu, have && b0 == b1);
+                            const unsigned int nuc = vm & ~(g0 | g1b), k1 = g0 & ~g1b, k2 = g1b & ~g0;
+                            const unsigned int ext = (k1 & ((k1 << 1) | p1)) | (k2 & ((k2 << 1) | p2));
+                            am += __popc(nuc & eq); ax += __popc(nuc & ~eq); ae += __popc(ext); ao2 += __popc((k1 | k2) & ~ext);
+                            const int top = 31 - __clz((int)vm);
+                            p1 = (k1 >> top) & 1u; p2 = (k2 >> top) & 1u;
+                            lk = p1 ? 1 : (p2 ? 2 : (((g0 & g1b) >> top) & 1u ? 3 : 0));
+                            if (c0 == sk) fk = (k1 & 1u) ? 1 : ((k2 & 1u) ? 2 : ((g0 & g1b & 1u) ? 3 : 0));
+                        }
+                        if (lane == L) { c_m += am; c_x += ax; c_o += ao2; c_e += ae; first_kind = fk; last_kind = lk; }
+                    }
+                    // ---- a slot's first column follows the previous run's last column (both bases) -- or, when
+                    //      that run emitted nothing (the last run of a pair may), the previous slot's last column
+                    if (want_sop) {
+                        int prev_last = __shfl_up_sync(0xffffffffu, last_kind, 1);
+                        const unsigned int prev_run = __shfl_up_sync(0xffffffffu, run_emit, 1);
+                        const unsigned int prev_len = __shfl_up_sync(0xffffffffu, len_s, 1);
+                        if (lane == 0) prev_last = carry_kind;
+                        const bool joined = t > 0 && t < n_slots && len_s > 0 && (lane == 0 ? carry_run == 0 : prev_run == 0) &&
+                                            (lane == 0 ? true : prev_len > 0);
+                        if (joined && (first_kind == 1 || first_kind == 2) && first_kind == prev_last) { c_o -= 1; c_e += 1; }
+                        // what the next block of 32 slots follows
+                        const int my_last = run_emit > 0 ? 0 : (len_s > 0 ? last_kind : -1);      // -1: nothing emitted here
+                        int lastk = carry_kind;
+                        unsigned int lastrun = carry_run;
+#pragma unroll 1
+                        for (int l2 = 0; l2 < 32; ++l2) {
+                            const int k2 = __shfl_sync(0xffffffffu, my_last, l2);
+                            const unsigned int r2 = __shfl_sync(0xffffffffu, run_emit, l2);
+                            if (tb + l2 < n_slots && k2 >= 0) { lastk = k2; lastrun = r2; }
+                        }
+                        carry_kind = lastk; carry_run = lastrun;
                     }
                     const unsigned int len = len_s + len_r;
                     unsigned int inc = len;
@@ -141,7 +220,12 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
                 ce += __shfl_xor_sync(0xffffffffu, ce, o);
                 ns += __shfl_xor_sync(0xffffffffu, ns, o);
             }
-            if (!ok) { carry = 0; sc = 0; ce = 0; ns = 0; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                c_m += __shfl_xor_sync(0xffffffffu, c_m, o); c_x += __shfl_xor_sync(0xffffffffu, c_x, o);
+                c_o += __shfl_xor_sync(0xffffffffu, c_o, o); c_e += __shfl_xor_sync(0xffffffffu, c_e, o);
+            }
+            if (!ok) { carry = 0; sc = 0; ce = 0; ns = 0; c_m = c_x = c_o = c_e = 0; }
             nrep = (report && !no_runs && st != DBGA_TOO_LARGE) ? R : 0;     // cycle pairs still report the anchors that cycle
             ntile = (int)((carry + ASM_TILE - 1) / ASM_TILE);
             if (ntile == 0 && (nrep > 0 || (compact && ok && n_slots > 0))) ntile = 1;   // runs / segment widths are copied by the pair's first tile
@@ -149,7 +233,7 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
                 out.score[pair] = sc; out.cells[pair] = ce; out.nseg[pair] = ns;
                 out.nanch[pair] = (ok || st == DBGA_CYCLE) ? n_anchors : 0;
                 out.status[pair] = st;
-                if (out.sop) *reinterpret_cast<int4 *>(out.sop + 4 * pair) = make_int4(0, 0, 0, 0);
+                if (want_sop) *reinterpret_cast<int4 *>(out.sop + 4 * pair) = make_int4(c_m, c_x, c_o, c_e);
             }
         }
         if (lane == 0) { s_v[0][w] = carry; s_v[1][w] = nrep; s_v[2][w] = ntile; s_meta[w].status = st; }
@@ -226,33 +310,41 @@ asm_layout_kernel(const PairOut *__restrict__ pout, const PairDesc *__restrict__
 // emitted column, step -1.  kind 1 / 2: one side empty (utils.py:187-190): sequence bytes of seq1 /
 // seq2 against '-'.  kind 3: a run of anchors, both rows are the same seq1 bytes.
 //
-// asm_copy_kernel: a CTA takes one tile of ASM_TILE output columns of one pair (tile_pair[] names
-// the pair).  Phase 1 is item-centric (8 lanes per item, no divergence inside a group) and stages
-// the two rows in shared memory at the alignment of their final addresses; phase 2 is
-// output-centric: a thread owns a 16-byte aligned chunk of both rows (128-bit stores) and
-// classifies its 16 columns for pairwise_alignment_score (reference src/dbga/utils.py:440-504:
-// match / mismatch / gap_open / gap_extend; a gap column extends iff the previous column is a gap
-// in the same row only) with byte-SIMD compares -- the column before the tile is staged too.
-__device__ const uint8_t g_dash[16] = {'-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-', '-'};
-constexpr int ASM_G = 8;                      // lanes per item in phase 1
-constexpr int ASM_SBUF = ASM_TILE + 48;       // 16 bytes of slack before (previous column at 15) + tile + alignment slack
+// asm_copy_kernel: a CTA takes one tile of ASM_TILE output columns of one pair (one AsmTile record
+// written by the layout pass says everything about it).  Phase 1 is item-centric and stages the two
+// rows in shared memory at the alignment of their final addresses; phase 2 is output-centric: a
+// thread owns a 16-byte aligned chunk of both rows (128-bit stores).
+constexpr int ASM_G = 4;                      // lanes per item in phase 1
+constexpr int ASM_SBUF = ASM_TILE + 32;       // tile + alignment slack (multiple of 16)
 constexpr int ASM_WIN = 256;                  // items whose offsets / sources are staged at a time
 
-__global__ void __launch_bounds__(ASM_THREADS, 10)
+// four bytes at any address: two aligned words and a funnel shift.  At least one of the four bytes
+// belongs to the caller's data; the others may lie up to three bytes before / after it (the caller
+// masks them off).  The first aligned word is read only if it starts inside the buffer; the second
+// shares its word with a wanted byte or lies in the 8 bytes of slack every buffer of the library
+// has behind its last byte (include/dbga_b200.h: device sequences must be readable up to there).
+__device__ __forceinline__ uint32_t ld_u32_any(const uint8_t *p, const uint32_t *lo_w) {
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(p) & 3) * 8;
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(p - (sh >> 3));
+    const uint32_t lo = q >= lo_w ? __ldg(q) : 0u;
+    const uint32_t hi = sh ? __ldg(q + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__global__ void __launch_bounds__(ASM_THREADS, 16)
 asm_copy_kernel(const uint8_t *__restrict__ seqs, const int32_t *__restrict__ runs, const int32_t *__restrict__ item_off,
                 const long long *__restrict__ item_src, const Counters *__restrict__ ctr,
-                const uint8_t *__restrict__ strbuf, int32_t *__restrict__ sop, const AsmTile *__restrict__ tiles,
+                const uint8_t *__restrict__ strbuf, const AsmTile *__restrict__ tiles,
                 uint8_t *__restrict__ aln0, uint8_t *__restrict__ aln1, int32_t *__restrict__ runs_out,
-                int32_t *__restrict__ seg_cols, int flags) {
+                int32_t *__restrict__ seg_cols, int64_t seq_bytes, int flags) {
     __shared__ __align__(16) uint8_t sbuf[2][ASM_SBUF];
     __shared__ int s_io[ASM_WIN + 1];
     __shared__ long long s_is[ASM_WIN];
-    __shared__ int s_cnt[4];
     __shared__ int s_ilo;
     const int tid = threadIdx.x, lane = tid & 31;
     const bool compact = (flags & DBGA_FLAG_COMPACT_ROWS) != 0, no_runs = (flags & DBGA_FLAG_NO_RUNS) != 0 && !compact;
-    const bool want_sop = sop != nullptr && !compact;
     const long long total_tiles = (long long)ctr->total_tiles;
+    const uint32_t *seq_lo = reinterpret_cast<const uint32_t *>(seqs), *str_lo = reinterpret_cast<const uint32_t *>(strbuf);
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         AsmTile tr;
         {
@@ -274,18 +366,17 @@ asm_copy_kernel(const uint8_t *__restrict__ seqs, const int32_t *__restrict__ ru
         }
         const int c_lo = tr.tp * ASM_TILE, c_hi = min(c_lo + ASM_TILE, aln_len);
         if (c_hi <= c_lo) continue;
-        const int c_lo1 = c_lo > 0 ? c_lo - 1 : 0;          // one column early: the previous column's kind
         const int64_t g_lo = tr.a_off + c_lo, g_hi = tr.a_off + c_hi;
-        const int64_t base0 = g_lo & ~(int64_t)15;
+        const int64_t base0 = g_lo & ~(int64_t)15;          // sbuf[r][x] is output byte base0 + x of row r
         __syncthreads();                                    // the previous tile's phase 2 is done with sbuf
         if (aln_len > ASM_TILE) {
-            // first item of the tile: last item whose start is <= c_lo1 (warp 0, 32 probes per round)
+            // first item of the tile: last item whose start is <= c_lo (warp 0, 32 probes per round)
             if (tid < 32) {
-                int lo = 0, hi = n_items;                   // start[lo] <= c_lo1 < start[hi]
+                int lo = 0, hi = n_items;                   // start[lo] <= c_lo < start[hi]
                 while (hi - lo > 1) {
                     const int step = (hi - lo + 31) >> 5;
                     const int idx = lo + (lane + 1) * step;
-                    const bool le = idx < hi && __ldg(io + idx) <= c_lo1;
+                    const bool le = idx < hi && __ldg(io + idx) <= c_lo;
                     const int cnt = __popc(__ballot_sync(0xffffffffu, le));
                     const int nlo = lo + cnt * step;
                     hi = min(hi, nlo + step);
@@ -296,11 +387,12 @@ asm_copy_kernel(const uint8_t *__restrict__ seqs, const int32_t *__restrict__ ru
         } else if (tid == 0) {
             s_ilo = 0;
         }
-        if (tid < 4) s_cnt[tid] = 0;
-        if (tid < 2 && c_lo == 0) sbuf[tid][16 + (int)(g_lo - base0) - 1] = 0;      // no column before the pair's first
+        for (int z = tid; z < 2 * ASM_SBUF / 16; z += ASM_THREADS) reinterpret_cast<uint4 *>(&sbuf[0][0])[z] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
         // ---- phase 1: items -> shared memory, ASM_WIN items per window: their offsets and sources are
-        //      staged first (one round trip), then 8 lanes per item copy bytes, two items per group in flight
+        //      staged first (one round trip); then 4 lanes per item move whole 32-bit words of the staged
+        //      rows (a run feeds both rows from one fetch; the scratch rows of a DP segment are read
+        //      backwards), bytes only in an item's first and last word; two items per group in flight
         for (int i0 = s_ilo; i0 < n_items; i0 += ASM_WIN) {
             const int nw = min(ASM_WIN, n_items - i0);
             for (int u = tid; u <= nw; u += ASM_THREADS) {
@@ -311,48 +403,57 @@ asm_copy_kernel(const uint8_t *__restrict__ seqs, const int32_t *__restrict__ ru
             const bool more = s_io[nw] < c_hi && i0 + nw < n_items;      // uniform: another window follows
             const int grp = tid / ASM_G, gl = tid % ASM_G;
             constexpr int NG = ASM_THREADS / ASM_G;
-            for (int u0 = 0; u0 < nw && s_io[u0] < c_hi; u0 += 2 * NG) {
-                const uint8_t *p0[2], *p1[2];
-                int st0[2], st1[2], cnt[2], qoff[2];
-                uint32_t r0[2][4], r1[2][4];
+            // Runs (odd items) and segments (even items) alternate; a warp that took them as they come
+            // would run both code paths on every step with a quarter of its lanes each.  So: first all
+            // runs of the window, then all segments, each pass with one straight-line word loop.
+            // The bytes of a word that lie outside the item are masked off and the word is OR-ed into the
+            // (zeroed) buffer: an item's first and last word take the same path as the others, and two
+            // items may share a word.
+            const int par_run = (R > 0) ? 1 - (i0 & 1) : nw;              // window index of the first run (none when R == 0)
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                const int first = pass == 0 ? par_run : (R > 0 ? (i0 & 1) : 0);
+                for (int u0 = first; u0 < nw && s_io[u0] < c_hi; u0 += 4 * NG) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int u = u0 + grp + h * NG;
-                    cnt[h] = 0; p0[h] = p1[h] = g_dash; st0[h] = st1[h] = 0; qoff[h] = 0;
-                    if (u < nw) {
+                    for (int h = 0; h < 2; ++h) {
+                        const int u = u0 + 2 * (grp + h * NG);
+                        if (u >= nw) continue;
                         const int start = s_io[u], end = s_io[u + 1];
-                        if (start < c_hi && end > c_lo1 && end > start) {
-                            const long long rec = s_is[u];
+                        if (start >= c_hi || end <= c_lo || end == start) continue;
+                        const long long rec = s_is[u];
+                        const int from = max(start, c_lo), to = min(end, c_hi);
+                        const int q = (int)(tr.a_off + from - base0), n = to - from;      // bytes [q, q + n) of sbuf
+                        if (pass == 0) {
+                            const uint8_t *p = seqs + (rec >> 2) + (from - start);
+                            for (int wq = (q >> 2) + gl; 4 * wq < q + n; wq += ASM_G) {
+                                const int d = 4 * wq - q;                                  // item column of the word's byte 0
+                                uint32_t mk = 0xFFFFFFFFu;
+                                if (d < 0) mk <<= 8 * (-d);
+                                if (d + 4 > n) mk &= 0xFFFFFFFFu >> (8 * (d + 4 - n));
+                                const uint32_t v = ld_u32_any(p + d, seq_lo) & mk;       // inside a run both rows are the same bytes
+                                atomicOr(reinterpret_cast<uint32_t *>(sbuf[0] + 4 * wq), v);
+                                atomicOr(reinterpret_cast<uint32_t *>(sbuf[1] + 4 * wq), v);
+                            }
+                        } else {
                             const int kind = (int)(rec & 3);
-                            const long long src = rec >> 2;
-                            const int from = max(start, c_lo1), to = min(end, c_hi);
-                            const int d0 = from - start;
-                            cnt[h] = to - from;
-                            qoff[h] = 16 + (int)(tr.a_off + from - base0);
-                            if (kind == 3) { p0[h] = p1[h] = seqs + src + d0; st0[h] = st1[h] = 1; }
-                            else if (kind == 0) { p0[h] = strbuf + src - d0; p1[h] = p0[h] + tr.row_len; st0[h] = st1[h] = -1; }
-                            else if (kind == 1) { p0[h] = seqs + src + d0; st0[h] = 1; }
-                            else { p1[h] = seqs + src + d0; st1[h] = 1; }
+                            // rows of a DP segment sit reversed in the scratch (column c at p - c), a one-sided
+                            // segment is sequence bytes against '-'
+                            const uint8_t *p = (kind == 0 ? strbuf - (from - start) : seqs + (from - start)) + (rec >> 2);
+                            for (int wq = (q >> 2) + gl; 4 * wq < q + n; wq += ASM_G) {
+                                const int d = 4 * wq - q;
+                                uint32_t mk = 0xFFFFFFFFu;
+                                if (d < 0) mk <<= 8 * (-d);
+                                if (d + 4 > n) mk &= 0xFFFFFFFFu >> (8 * (d + 4 - n));
+                                uint32_t v0, v1;
+                                if (kind == 0) {
+                                    v0 = __byte_perm(ld_u32_any(p - d - 3, str_lo), 0u, 0x0123);
+                                    v1 = __byte_perm(ld_u32_any(p + tr.row_len - d - 3, str_lo), 0u, 0x0123);
+                                } else if (kind == 1) { v0 = ld_u32_any(p + d, seq_lo); v1 = 0x2D2D2D2Du; }
+                                else { v0 = 0x2D2D2D2Du; v1 = ld_u32_any(p + d, seq_lo); }
+                                atomicOr(reinterpret_cast<uint32_t *>(sbuf[0] + 4 * wq), v0 & mk);
+                                atomicOr(reinterpret_cast<uint32_t *>(sbuf[1] + 4 * wq), v1 & mk);
+                            }
                         }
-                    }
-                }
-                // up to 32 columns of each of the two items: all loads first, then the stores
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int d = gl + ASM_G * v;
-                        if (d < cnt[h]) { r0[h][v] = p0[h][d * st0[h]]; r1[h][v] = p1[h][d * st1[h]]; }
-                    }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int d = gl + ASM_G * v;
-                        if (d < cnt[h]) { sbuf[0][qoff[h] + d] = (uint8_t)r0[h][v]; sbuf[1][qoff[h] + d] = (uint8_t)r1[h][v]; }
-                    }
-                    for (int d = gl + 4 * ASM_G; d < cnt[h]; d += ASM_G) {         // longer items
-                        sbuf[0][qoff[h] + d] = p0[h][d * st0[h]]; sbuf[1][qoff[h] + d] = p1[h][d * st1[h]];
                     }
                 }
             }
@@ -360,54 +461,19 @@ asm_copy_kernel(const uint8_t *__restrict__ seqs, const int32_t *__restrict__ ru
             __syncthreads();                                // s_io / s_is are reused by the next window
         }
         __syncthreads();
-        // ---- phase 2: shared memory -> both rows, 16 bytes per thread; column classification
-        int cnt_m = 0, cnt_x = 0, cnt_o = 0, cnt_e = 0;
-        const int nchunk = (int)((g_hi - base0 + 15) >> 4);
-        for (int j = tid; j < nchunk; j += ASM_THREADS) {
-            const int64_t cb = base0 + 16 * (int64_t)j;
-            const uint4 v0 = *reinterpret_cast<const uint4 *>(sbuf[0] + 16 + 16 * j);
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(sbuf[1] + 16 + 16 * j);
-            const int b_lo = cb < g_lo ? (int)(g_lo - cb) : 0, b_hi = cb + 16 > g_hi ? (int)(g_hi - cb) : 16;
-            if (b_lo == 0 && b_hi == 16) {
-                *reinterpret_cast<uint4 *>(aln0 + cb) = v0;
-                *reinterpret_cast<uint4 *>(aln1 + cb) = v1;
-            } else {
-                for (int q = b_lo; q < b_hi; ++q) { aln0[cb + q] = sbuf[0][16 + 16 * j + q]; aln1[cb + q] = sbuf[1][16 + 16 * j + q]; }
-            }
-            if (want_sop) {
-                const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
-                // gap-only-in-row-1 / row-2 masks of the previous word (its last byte is the column before this chunk)
-                const uint32_t pw0 = *reinterpret_cast<const uint32_t *>(sbuf[0] + 12 + 16 * j), pw1 = *reinterpret_cast<const uint32_t *>(sbuf[1] + 12 + 16 * j);
-                uint32_t pe0 = __vcmpeq4(pw0, 0x2D2D2D2Du), pe1 = __vcmpeq4(pw1, 0x2D2D2D2Du);
-                uint32_t pg1 = pe0 & ~pe1, pg2 = pe1 & ~pe0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    // valid bytes of this word
-                    const int lo_b = b_lo - 4 * q, hi_b = b_hi - 4 * q;
-                    uint32_t vm = 0xFFFFFFFFu;
-                    if (lo_b > 0) vm &= lo_b >= 4 ? 0u : (0xFFFFFFFFu << (8 * lo_b));
-                    if (hi_b < 4) vm &= hi_b <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - hi_b)));
-                    const uint32_t e0 = __vcmpeq4(w0[q], 0x2D2D2D2Du), e1 = __vcmpeq4(w1[q], 0x2D2D2D2Du);
-                    const uint32_t eq = __vcmpeq4(w0[q], w1[q]);
-                    const uint32_t nuc = ~(e0 | e1) & vm;
-                    const uint32_t g1 = e0 & ~e1, g2 = e1 & ~e0;
-                    const uint32_t ext = ((g1 & ((g1 << 8) | (pg1 >> 24))) | (g2 & ((g2 << 8) | (pg2 >> 24)))) & vm;
-                    const uint32_t opn = (g1 | g2) & vm & ~ext;
-                    cnt_m += __popc(nuc & eq); cnt_x += __popc(nuc & ~eq);
-                    cnt_e += __popc(ext); cnt_o += __popc(opn);
-                    pg1 = g1; pg2 = g2;
-                }
-            }
+        // ---- phase 2: shared memory -> both rows, 16 bytes per thread; the bytes of the pair's first and
+        //      last chunk that belong to it go out one per thread
+        const int64_t f_lo = (g_lo + 15) & ~(int64_t)15, f_hi = g_hi & ~(int64_t)15;     // whole chunks: [f_lo, f_hi)
+        for (int64_t cb = f_lo + 16 * (int64_t)tid; cb < f_hi; cb += 16 * ASM_THREADS) {
+            *reinterpret_cast<uint4 *>(aln0 + cb) = *reinterpret_cast<const uint4 *>(sbuf[0] + (cb - base0));
+            *reinterpret_cast<uint4 *>(aln1 + cb) = *reinterpret_cast<const uint4 *>(sbuf[1] + (cb - base0));
         }
-        if (want_sop) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                cnt_m += __shfl_xor_sync(0xffffffffu, cnt_m, o); cnt_x += __shfl_xor_sync(0xffffffffu, cnt_x, o);
-                cnt_o += __shfl_xor_sync(0xffffffffu, cnt_o, o); cnt_e += __shfl_xor_sync(0xffffffffu, cnt_e, o);
-            }
-            if (lane == 0) { atomicAdd(&s_cnt[0], cnt_m); atomicAdd(&s_cnt[1], cnt_x); atomicAdd(&s_cnt[2], cnt_o); atomicAdd(&s_cnt[3], cnt_e); }
-            __syncthreads();
-            if (tid < 4 && s_cnt[tid]) atomicAdd(sop + 4 * tr.pair + tid, s_cnt[tid] >> 3);     // popc counts 8 bits per column
+        {
+            const int64_t h_hi = f_lo < g_hi ? f_lo : g_hi;                              // head bytes [g_lo, h_hi)
+            const int64_t t_lo = f_hi > h_hi ? f_hi : h_hi;                              // tail bytes [t_lo, g_hi)
+            const int64_t hb = g_lo + (tid & 15), tb2 = t_lo + (tid & 15);
+            if (tid < 16 && hb < h_hi) { aln0[hb] = sbuf[0][hb - base0]; aln1[hb] = sbuf[1][hb - base0]; }
+            if (tid >= 16 && tid < 32 && tb2 < g_hi) { aln0[tb2] = sbuf[0][tb2 - base0]; aln1[tb2] = sbuf[1][tb2 - base0]; }
         }
     }
 }
@@ -443,14 +509,14 @@ cudaError_t launch_publish(const void *src, void *dst_host, int bytes, cudaStrea
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
                             const int32_t *runs, const Slot *slots, const uint8_t *strbuf, int32_t *item_off,
                             long long *item_src, AsmScanRec *scan, AsmTile *tiles, AsmOut out,
-                            uint8_t *aln0, uint8_t *aln1, int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags,
-                            int num_sms, cudaStream_t st, int *launches) {
+                            uint8_t *aln0, uint8_t *aln1, int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int64_t seq_bytes,
+                            int flags, int num_sms, cudaStream_t st, int *launches) {
     if (num_pairs <= 0) return cudaSuccess;
     const int64_t nblk = asm_scan_blocks(num_pairs);
-    asm_layout_kernel<<<(unsigned)nblk, LAY_THREADS, 0, st>>>(pout, pairs, num_pairs, slots, runs, item_off, item_src, scan, ctr, out,
-                                                              tiles, flags);
-    asm_copy_kernel<<<num_sms * 10, ASM_THREADS, 0, st>>>(seqs, runs, item_off, item_src, ctr, strbuf, out.sop, tiles, aln0, aln1,
-                                                          runs_out, seg_cols, flags);
+    asm_layout_kernel<<<(unsigned)nblk, LAY_THREADS, 0, st>>>(pout, pairs, num_pairs, slots, runs, strbuf, item_off, item_src, scan, ctr,
+                                                              out, tiles, flags);
+    asm_copy_kernel<<<num_sms * 16, ASM_THREADS, 0, st>>>(seqs, runs, item_off, item_src, ctr, strbuf, tiles, aln0, aln1,
+                                                          runs_out, seg_cols, seq_bytes, flags);
     *launches += 2;
     return cudaGetLastError();
 }

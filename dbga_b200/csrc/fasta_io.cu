@@ -1,0 +1,275 @@
+// FASTA on the wire: the reference loads one pair per file through cogent3
+// (src/dbga/utils.py:95-96 load_unaligned_seqs) and writes aln.to_fasta() (src/dbga/cli.py:135-136,
+// 60-column blocks).  A batch run wants many pairs per file: the reader parses straight into the
+// C ABI's layout -- one pinned ASCII buffer + offsets, and optionally the 2-bit packed form that
+// dbga_align_batch_packed uploads -- and the writer produces the wrapped records of every aligned
+// pair from a result, expanding a COMPACT_ROWS result on the fly (the columns inside a run of
+// anchors are the input's own bytes).  Host code only; all passes are split over host threads.
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include "common.cuh"
+
+namespace {
+
+template <class Fn> void par_for(int64_t n, int threads, int64_t grain, Fn fn) {
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    threads = (int)std::min<int64_t>(threads, std::max<int64_t>(1, n / std::max<int64_t>(grain, 1)));
+    if (threads <= 1) { fn((int64_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back([=]() { fn(n * t / threads, n * (t + 1) / threads); });
+    for (auto &x : th) x.join();
+}
+
+struct FastaImpl {
+    dbga_fasta pub{};
+    std::vector<int64_t> offsets, name_off;
+    std::vector<char> names;
+    uint8_t *seqs = nullptr;       // pinned (plain memory when no CUDA device is present: parsing needs none)
+    uint32_t *packed = nullptr;
+    bool pinned = true;
+};
+
+void *host_buf(size_t bytes, bool &pinned) {
+    void *p = nullptr;
+    if (pinned && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p;
+    cudaGetLastError();
+    pinned = false;
+    return malloc(bytes);
+}
+void host_release(void *p, bool pinned) {
+    if (!p) return;
+    if (pinned) cudaFreeHost(p); else free(p);
+}
+
+inline bool is_space(uint8_t c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }
+
+}  // namespace
+
+extern "C" {
+
+int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta **out) {
+    if (!path || !out) return DBGA_ERR_ARG;
+    *out = nullptr;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return DBGA_ERR_ARG;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return DBGA_ERR_ARG; }
+    const int64_t size = (int64_t)sb.st_size;
+    const uint8_t *data = nullptr;
+    if (size > 0) {
+        data = (const uint8_t *)mmap(nullptr, (size_t)size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (data == MAP_FAILED) { close(fd); return DBGA_ERR_NOMEM; }
+        madvise((void *)data, (size_t)size, MADV_SEQUENTIAL);
+    }
+    close(fd);
+    FastaImpl *f = new FastaImpl();
+    // ---- pass 1: record starts ('>' at the start of a line), found in parallel slices
+    std::vector<std::vector<int64_t>> found;
+    {
+        int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+        T = (int)std::max<int64_t>(1, std::min<int64_t>(T, size / (1 << 20)));
+        found.resize((size_t)T);
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t)
+            th.emplace_back([&, t]() {
+                const int64_t lo = size * t / T, hi = size * (t + 1) / T;
+                const uint8_t *p = data + lo, *end = data + hi;
+                while (p < end) {
+                    const uint8_t *q = (const uint8_t *)memchr(p, '>', (size_t)(end - p));
+                    if (!q) break;
+                    if (q == data || q[-1] == '\n') found[(size_t)t].push_back(q - data);
+                    p = q + 1;
+                }
+            });
+        for (auto &x : th) x.join();
+    }
+    std::vector<int64_t> starts;
+    for (auto &v : found) starts.insert(starts.end(), v.begin(), v.end());
+    const int64_t R = (int64_t)starts.size();
+    starts.push_back(size);
+    // ---- pass 2: per record, where the header ends and how many sequence bytes follow
+    std::vector<int64_t> body((size_t)R), nlen((size_t)R + 1, 0), nstart((size_t)R, 0);
+    f->offsets.assign((size_t)R + 1, 0);
+    par_for(R, threads, 64, [&](int64_t lo, int64_t hi) {
+        for (int64_t r = lo; r < hi; ++r) {
+            const uint8_t *p = data + starts[(size_t)r] + 1, *end = data + starts[(size_t)r + 1];
+            const uint8_t *eol = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+            if (!eol) eol = end;
+            // label = first word of the header line
+            const uint8_t *a = p;
+            while (a < eol && (*a == ' ' || *a == '\t')) ++a;
+            const uint8_t *b = a;
+            while (b < eol && !is_space(*b)) ++b;
+            nlen[(size_t)r + 1] = b - a;
+            nstart[(size_t)r] = a - data;
+            body[(size_t)r] = (eol < end ? eol + 1 : end) - data;
+            int64_t n = 0;
+            for (const uint8_t *q = data + body[(size_t)r]; q < end; ++q) n += !is_space(*q);
+            f->offsets[(size_t)r + 1] = n;
+        }
+    });
+    for (int64_t r = 0; r < R; ++r) { f->offsets[(size_t)r + 1] += f->offsets[(size_t)r]; nlen[(size_t)r + 1] += nlen[(size_t)r]; }
+    const int64_t total = f->offsets[(size_t)R];
+    f->name_off = nlen;
+    f->names.resize((size_t)nlen[(size_t)R] + 1);
+    f->seqs = (uint8_t *)host_buf((size_t)std::max<int64_t>(total + 64, 64), f->pinned);
+    int64_t words = 0;
+    if (want_packed) {
+        words = (total >> 4) + R + 1;
+        f->packed = (uint32_t *)(f->pinned ? host_buf((size_t)(4 * words + 64), f->pinned) : malloc((size_t)(4 * words + 64)));
+    }
+    if (!f->seqs || (want_packed && !f->packed)) {
+        host_release(f->seqs, f->pinned); host_release(f->packed, f->pinned);
+        if (size > 0) munmap((void *)data, (size_t)size);
+        delete f;
+        return DBGA_ERR_NOMEM;
+    }
+    // ---- pass 3: labels, upper-cased bases, and (optionally) the canonical 2-bit words
+    std::atomic<int64_t> bad{0};
+    par_for(R, threads, 64, [&](int64_t lo, int64_t hi) {
+        int64_t nbad = 0;
+        for (int64_t r = lo; r < hi; ++r) {
+            const uint8_t *end = data + starts[(size_t)r + 1];
+            memcpy(f->names.data() + nlen[(size_t)r], data + nstart[(size_t)r], (size_t)(nlen[(size_t)r + 1] - nlen[(size_t)r]));
+            uint8_t *dst = f->seqs + f->offsets[(size_t)r];
+            const int64_t len = f->offsets[(size_t)r + 1] - f->offsets[(size_t)r];
+            int64_t n = 0;
+            for (const uint8_t *q = data + body[(size_t)r]; q < end; ++q) {
+                uint8_t c = *q;
+                if (is_space(c)) continue;
+                if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
+                dst[n++] = c;
+            }
+            if (f->packed) {
+                uint32_t *pw = f->packed + (f->offsets[(size_t)r] >> 4) + r;
+                bool b = false;
+                for (int64_t w = 0; w * 16 < len; ++w) {
+                    const int64_t nv = std::min<int64_t>(16, len - 16 * w);
+                    uint32_t word = 0;
+                    for (int64_t i = 0; i < nv; ++i) {
+                        const uint8_t c = dst[16 * w + i];
+                        const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
+                        b |= "ACGT"[code] != (char)c;
+                        word |= code << (2 * i);
+                    }
+                    pw[w] = word;
+                }
+                nbad += b;
+            }
+        }
+        bad += nbad;
+    });
+    if (size > 0) munmap((void *)data, (size_t)size);
+    f->pub.num_records = R;
+    f->pub.offsets = f->offsets.data();
+    f->pub.seqs = f->seqs;
+    f->pub.packed = f->packed;
+    f->pub.packed_words = words;
+    f->pub.name_off = f->name_off.data();
+    f->pub.names = f->names.data();
+    f->pub.bad_records = bad.load();
+    *out = &f->pub;
+    return DBGA_SUCCESS;
+}
+
+void dbga_fasta_free(dbga_fasta *pub) {
+    if (!pub) return;
+    FastaImpl *f = reinterpret_cast<FastaImpl *>(pub);       // pub is the first member
+    host_release(f->seqs, f->pinned);
+    host_release(f->packed, f->pinned);
+    delete f;
+}
+
+int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_result *res, int64_t first_record,
+                         int width, int append, int threads) {
+    if (!path || !in || !res || width < 1) return -1;
+    const int64_t P = res->num_pairs;
+    if (first_record < 0 || first_record + 2 * P > in->num_records) return -1;
+    const bool compact = res->seg_cols != nullptr;
+    if (P > 0 && (!res->status || !res->aln_off || !res->aln0 || !res->aln1)) return -1;
+    if (compact && P > 0 && (!res->runs || !res->run_off)) return -1;
+    // ---- bytes of every pair's two records
+    std::vector<int64_t> pos((size_t)P + 1, 0), full((size_t)P, 0);
+    par_for(P, threads, 256, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            if (res->status[i] != DBGA_OK) continue;
+            int64_t len = res->aln_off[i + 1] - res->aln_off[i];
+            if (compact) {
+                const int64_t r0 = res->run_off[i], Rn = res->run_off[i + 1] - r0;
+                for (int64_t r = 0; r < Rn; ++r) len += res->runs[3 * (r0 + r) + 2];
+                if (Rn > 0) len -= 1;
+            }
+            full[(size_t)i] = len;
+            const int64_t rec = first_record + 2 * i;
+            const int64_t lines = (len + width - 1) / width;
+            const int64_t n0 = in->name_off[rec + 1] - in->name_off[rec], n1 = in->name_off[rec + 2] - in->name_off[rec + 1];
+            // ">label\n", then the row in blocks of `width` columns, every block followed by "\n"
+            pos[(size_t)i + 1] = (2 + n0 + len + lines) + (2 + n1 + len + lines);
+        }
+    });
+    int64_t written = 0;
+    for (int64_t i = 0; i < P; ++i) { written += res->status[i] == DBGA_OK; pos[(size_t)i + 1] += pos[(size_t)i]; }
+    const int64_t total = pos[(size_t)P];
+    const int fd = open(path, O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC), 0644);
+    if (fd < 0) return -1;
+    std::vector<uint8_t> buf((size_t)total);
+    par_for(P, threads, 256, [&](int64_t lo, int64_t hi) {
+        std::vector<uint8_t> row;
+        for (int64_t i = lo; i < hi; ++i) {
+            if (res->status[i] != DBGA_OK) continue;
+            const int64_t len = full[(size_t)i];
+            uint8_t *o = buf.data() + pos[(size_t)i];
+            for (int s = 0; s < 2; ++s) {
+                const int64_t rec = first_record + 2 * i + s;
+                const int64_t nn = in->name_off[rec + 1] - in->name_off[rec];
+                *o++ = '>';
+                memcpy(o, in->names + in->name_off[rec], (size_t)nn); o += nn;
+                *o++ = '\n';
+                const uint8_t *src = (s ? res->aln1 : res->aln0) + res->aln_off[i];
+                if (compact) {
+                    // rebuild the row: segment columns from the result, run bodies from the input (seq1's bytes
+                    // on both rows: inside a run the two sequences are identical, debruijn_pairwise.py:384-388)
+                    row.resize((size_t)len);
+                    const int64_t r0 = res->run_off[i], Rn = res->run_off[i + 1] - r0;
+                    const int32_t *sc = res->seg_cols + r0 + i;
+                    const uint8_t *s0 = in->seqs + in->offsets[first_record + 2 * i];
+                    uint8_t *w = row.data();
+                    for (int64_t t = 0; t <= Rn; ++t) {
+                        memcpy(w, src, (size_t)sc[t]); w += sc[t]; src += sc[t];
+                        if (t < Rn) {
+                            const int32_t a = res->runs[3 * (r0 + t)], l = res->runs[3 * (r0 + t) + 2] - (t == Rn - 1 ? 1 : 0);
+                            memcpy(w, s0 + a, (size_t)l); w += l;
+                        }
+                    }
+                    src = row.data();
+                }
+                for (int64_t c = 0; c < len; c += width) {
+                    const int64_t n = std::min<int64_t>(width, len - c);
+                    memcpy(o, src + c, (size_t)n); o += n;
+                    *o++ = '\n';
+                }
+            }
+        }
+    });
+    int64_t off = 0;
+    while (off < total) {
+        const ssize_t w = write(fd, buf.data() + off, (size_t)std::min<int64_t>(total - off, 1LL << 30));
+        if (w <= 0) { close(fd); return -1; }
+        off += w;
+    }
+    close(fd);
+    return written;
+}
+
+}  // extern "C"

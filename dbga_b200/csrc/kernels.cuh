@@ -104,8 +104,8 @@ static_assert(sizeof(AsmTile) == 64, "AsmTile is four 16-byte words");
 cudaError_t launch_assemble(const uint8_t *seqs, const PairDesc *pairs, int64_t num_pairs, const PairOut *pout,
                             const int32_t *runs, const Slot *slots, const uint8_t *strbuf, int32_t *item_off,
                             long long *item_src, AsmScanRec *scan, AsmTile *tiles, AsmOut out,
-                            uint8_t *aln0, uint8_t *aln1, int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int flags,
-                            int num_sms, cudaStream_t st, int *launches);
+                            uint8_t *aln0, uint8_t *aln1, int32_t *runs_out, int32_t *seg_cols, Counters *ctr, int64_t seq_bytes,
+                            int flags, int num_sms, cudaStream_t st, int *launches);
 // copy tiles of ASM_TILE_COLS output columns: a batch of P pairs and B input bytes has at most B / ASM_TILE_COLS + P of them
 constexpr int ASM_TILE_COLS = 2048;
 

@@ -62,9 +62,10 @@ typedef struct dbga_params {
  * COMPACT_ROWS  aln0 / aln1 carry only the columns the DP (or an empty-side segment) produced; the
  *               columns inside a run of anchors are the caller's own input bytes and are not sent.
  *               seg_cols tells how many columns each segment has; dbga_expand_rows rebuilds the
- *               full gapped rows on the host.  Implies runs; sop is not computed. */
+ *               full gapped rows on the host.  Implies runs. */
 #define DBGA_FLAG_NO_RUNS 1
 #define DBGA_FLAG_COMPACT_ROWS 2
+#define DBGA_FLAG_SOP 4          /* also count match / mismatch / gap_open / gap_extend per pair (dbga_result.sop) */
 
 typedef struct dbga_ctx dbga_ctx;
 
@@ -97,7 +98,7 @@ typedef struct dbga_result {
     int64_t kernel_launches;    /* kernels of this library launched for the batch         */
     /* [4P] match, mismatch, gap_open, gap_extend of every aligned pair: the reference's
        pairwise_alignment_score (src/dbga/utils.py:440-504), counted on the device while the rows
-       are written (zero for pairs that are not DBGA_OK; not computed with COMPACT_ROWS)          */
+       are laid out (DBGA_FLAG_SOP only, NULL otherwise; zero for pairs that are not DBGA_OK)       */
     const int32_t *sop;
     /* COMPACT_ROWS only: [run_off[P] + P] columns of segment t of pair i at seg_cols[run_off[i] + i + t],
        t = 0 .. (number of runs of pair i)                                                        */
@@ -156,6 +157,29 @@ void dbga_multi_destroy(dbga_multi *m);
 const char *dbga_multi_last_error(dbga_multi *m);
 int dbga_align_batch_multi(dbga_multi *m, const uint8_t *seqs, const uint32_t *packed, const int64_t *offsets,
                            int64_t num_pairs, const dbga_params *params, dbga_multi_result *out);
+
+/* FASTA on the wire (reference: load_sequences -> cogent3.load_unaligned_seqs, src/dbga/utils.py:95-96;
+ * output aln.to_fasta(), src/dbga/cli.py:135-136, rows in blocks of 60 columns).  dbga_fasta_read parses a
+ * file of R records straight into the batch layout: upper-cased bases without line breaks in one pinned
+ * buffer + offsets[R+1] (records 2i and 2i+1 are pair i), the labels (first word of each header line), and,
+ * with want_packed, the canonical 2-bit words of the same records (bad_records counts those that hold a
+ * character outside ACGT: use the ASCII buffer then).  dbga_fasta_write writes the two wrapped records of every
+ * DBGA_OK pair of a result whose pair 0 is records first_record, first_record + 1 of `in`; a COMPACT_ROWS result
+ * is expanded on the fly.  Returns the number of pairs written, -1 on error.  threads <= 0: all host cores. */
+typedef struct dbga_fasta {
+    int64_t num_records;
+    const int64_t *offsets;     /* [R+1] into seqs                                  */
+    const uint8_t *seqs;        /* pinned host memory                               */
+    const uint32_t *packed;     /* pinned; NULL unless want_packed                  */
+    int64_t packed_words;
+    const int64_t *name_off;    /* [R+1] into names                                 */
+    const char *names;
+    int64_t bad_records;
+} dbga_fasta;
+int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta **out);
+void dbga_fasta_free(dbga_fasta *f);
+int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_result *res, int64_t first_record,
+                         int width, int append, int threads);
 
 /* Host-side expansion of a COMPACT_ROWS result into the full gapped rows (what the call returns
  * without the flag): row0 / row1 receive aln_off_full[P] bytes each, aln_off_full [P+1] the offsets.

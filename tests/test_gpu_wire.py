@@ -43,8 +43,10 @@ def test_sop_counts_reference_goldens(aligner, ref_fixtures):
     tests/test_host_api.py."""
     from dbga_b200 import quality
     pairs = [O.synth_pair(400, 0.05, 0.03, 100 + s) for s in range(300)] + [tuple(fx["seqs"]) for fx in ref_fixtures["e2e"]]
+    from dbga_b200 import _lib
+    assert aligner.align_pairs(pairs[:4], 3).sop is None            # only on request
     for k in (3, 7):
-        res = aligner.align_pairs(pairs, k)
+        res = aligner.align_pairs(pairs, k, flags=_lib.FLAG_SOP)
         assert res.sop is not None and res.sop.shape == (len(pairs), 4)
         n = 0
         for i in range(len(pairs)):
@@ -59,9 +61,9 @@ def test_sop_counts_reference_goldens(aligner, ref_fixtures):
 
 
 def test_sop_counts_in_a_pipelined_batch(aligner, batch):
-    from dbga_b200 import quality
+    from dbga_b200 import _lib, quality
     pairs, buf, offs = batch
-    res = aligner.align_buffers(buf, offs, aligner.params(9))
+    res = aligner.align_buffers(buf, offs, aligner.params(9, flags=_lib.FLAG_SOP))
     assert res.timing["launches"] > 40                            # several chunks
     for i in list(range(0, len(pairs), 211)) + [17, 18, 4000]:
         if res.status[i] != O.OK:
@@ -72,6 +74,46 @@ def test_sop_counts_in_a_pipelined_batch(aligner, batch):
     # whole-batch identity: every column is exactly one of the four kinds
     ok = res.status == O.OK
     assert np.array_equal(res.sop[ok].sum(axis=1), np.diff(res.aln_off)[ok])
+    # the same counts come with the compact result form
+    comp = aligner.align_buffers(buf, offs, aligner.params(9, flags=_lib.FLAG_SOP | _lib.FLAG_COMPACT_ROWS))
+    assert np.array_equal(comp.sop, res.sop)
+
+
+def test_sop_long_segments_and_conventions(aligner):
+    """Slots of more than 64 columns are classified by the whole warp; gap-rich alignments under a
+    second convention; a 200 kb pair with multi-kb bubbles."""
+    from dbga_b200 import _lib, quality
+    from dbga_b200.synth import synth_long_pair
+    import random
+    rng = random.Random(77)
+    pairs = []
+    for _ in range(40):
+        n = rng.choice([300, 900, 2500])
+        x = "".join(rng.choice("ACGT") for _ in range(n))
+        y = list(x)
+        for _ in range(rng.randint(1, 4)):                                    # long indels and diverged windows
+            p = rng.randrange(20, n - 120)
+            if rng.random() < 0.5:
+                del y[p:p + rng.randint(5, 90)]
+            else:
+                y[p:p] = [rng.choice("ACGT") for _ in range(rng.randint(5, 90))]
+        pairs.append((x, "".join(y)))
+    for kw in ({}, dict(gap_len_mode=1, xy_allowed=True, pred_order="MXY", end_order="XYM")):
+        res = aligner.align_pairs(pairs, 11, flags=_lib.FLAG_SOP, **kw)
+        n = 0
+        for i in range(len(pairs)):
+            if res.status[i] != O.OK:
+                continue
+            lo, hi = int(res.aln_off[i]), int(res.aln_off[i + 1])
+            assert res.sop[i].tolist() == list(quality.score_rows(res.aln0[lo:hi], res.aln1[lo:hi]).values()), (i, kw)
+            n += 1
+        assert n > 10
+    for seed in range(1, 30):
+        buf, offs = synth_long_pair(n=200_000, n_bubbles=4, seed=seed)
+        res = aligner.align_buffers(buf, offs, aligner.params(15, flags=_lib.FLAG_SOP))
+        if res.status[0] == O.OK:
+            assert res.sop[0].tolist() == list(quality.score_rows(res.aln0, res.aln1).values())
+            break
 
 
 def test_no_runs_flag(aligner, batch):
