@@ -837,7 +837,7 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
     {
         // sizes in bytes: 8, 16, 32, ... up to chunk_bytes, and back down to 8 MB at the end -- the last
         // chunk's kernels and download are the tail nothing can overlap with
-        int64_t first_mb = 8;
+        int64_t first_mb = packed ? 32 : 8;
         if (const char *e = getenv("DBGA_FIRST_MB")) first_mb = std::max(1, atoi(e));
         chunk_bytes = std::min<int64_t>(chunk_bytes, std::max<int64_t>(4LL << 20, total_bytes / 4));      // small batches still pipeline
         const int64_t small = std::min<int64_t>(std::min<int64_t>(first_mb << 20, chunk_bytes), std::max<int64_t>(2LL << 20, total_bytes / 8));
@@ -878,7 +878,8 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
     RESERVE(d_aln_off, 8 * (P + 2 + nchunks)); RESERVE(d_run_off, 8 * (P + 2 + nchunks));
     int64_t *aln_off = (int64_t *)ctx->h_aln_off.p, *run_off = (int64_t *)ctx->h_run_off.p;
     std::vector<int64_t> aln_base((size_t)nchunks + 1, 0), run_base((size_t)nchunks + 1, 0);
-    float ms[4] = {0, 0, 0, 0}, plan_ms_total = 0.f;
+    float ms[4] = {0, 0, 0, 0};
+    std::vector<float> plan_ms((size_t)nchunks, 0.f);
     int64_t cells = 0, nsegs = 0, launches = 0;
     auto fail_lane = [&](dbga_ctx *l, int rc) { snprintf(ctx->err, sizeof(ctx->err), "%s", l->err); return rc; };
 
@@ -901,7 +902,7 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
         if (cudaSetDevice(ctx->device) != cudaSuccess) return DBGA_ERR_CUDA;
         int rc = do_plan(l, offsets + 2 * a, b - a, params, no_anchors, base);
         if (rc != DBGA_SUCCESS) return rc;
-        plan_ms_total += l->ms_plan;
+        plan_ms[(size_t)c] = l->ms_plan;
         // chunk c's offsets land at [a + c, a + c + n + 1) (one extra slot per chunk), fixed up at the end
         l->use_ext = true;
         l->ext.status = (int32_t *)ctx->d_status_out.p + a; l->ext.score = (int64_t *)ctx->d_score.p + a;
@@ -1036,7 +1037,15 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
     // The producer runs on its own host thread so that planning the next chunk never delays the
     // download of a finished one.  It may run at most NL - 1 chunks ahead of the consumer (a lane
     // is reused only after its previous chunk has been committed).
-    std::atomic<int> issued{0}, committed{0}, prod_rc{DBGA_SUCCESS};
+    // Two producer threads take alternate chunks (lanes are independent contexts; the shared upload
+    // stream takes copies from both): planning + ~20 launches cost ~0.4 ms of host time per chunk,
+    // which one thread cannot hide behind a 0.15 - 0.7 ms upload.
+    int n_prod = 2;
+    if (const char *e = getenv("DBGA_PRODUCERS")) n_prod = std::max(1, std::min(2, atoi(e)));
+    if (!spin) n_prod = 1;                       // few host cores per GPU: do not add threads
+    std::vector<std::atomic<int>> issued((size_t)nchunks);
+    for (auto &f : issued) f.store(0);
+    std::atomic<int> committed{0}, prod_rc{DBGA_SUCCESS};
     std::atomic<bool> stop{false};
     std::mutex mu;
     std::condition_variable cv;
@@ -1051,30 +1060,32 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
         { std::lock_guard<std::mutex> lk(mu); var.store(v, std::memory_order_release); }
         cv.notify_all();
     };
-    std::thread producer([&]() {
-        for (int c = 0; c < nchunks && !stop.load(); ++c) {
+    auto produce = [&](int first) {
+        for (int c = first; c < nchunks && !stop.load(); c += n_prod) {
             wait_until([&]() { return c - committed.load(std::memory_order_acquire) < NL || stop.load(); });
             if (stop.load()) break;
             const int rc = issue(c);
             if (rc != DBGA_SUCCESS) {
-                snprintf(ctx->err, sizeof(ctx->err), "pipeline producer: %.400s", ctx->lanes[c % NL]->err);
+                { std::lock_guard<std::mutex> lk(mu); snprintf(ctx->err, sizeof(ctx->err), "pipeline producer: %.400s", ctx->lanes[c % NL]->err); }
                 publish(prod_rc, rc);
                 break;
             }
-            publish(issued, c + 1);
+            publish(issued[(size_t)c], 1);
         }
-    });
+    };
+    std::vector<std::thread> producers;
+    for (int t = 0; t < n_prod; ++t) producers.emplace_back(produce, t);
     int main_rc = DBGA_SUCCESS;
     for (int c = 0; c < nchunks; ++c) {
-        wait_until([&]() { return issued.load(std::memory_order_acquire) > c || prod_rc.load() != DBGA_SUCCESS; });
-        if (issued.load(std::memory_order_acquire) <= c) { main_rc = prod_rc.load(); break; }
+        wait_until([&]() { return issued[(size_t)c].load(std::memory_order_acquire) != 0 || prod_rc.load() != DBGA_SUCCESS; });
+        if (issued[(size_t)c].load(std::memory_order_acquire) == 0) { main_rc = prod_rc.load(); break; }
         main_rc = commit(c);
         if (main_rc != DBGA_SUCCESS) break;
         publish(committed, c + 1);
     }
     if (spin) stop.store(true);
     else { { std::lock_guard<std::mutex> lk(mu); stop.store(true); } cv.notify_all(); }
-    producer.join();
+    for (auto &t : producers) t.join();
     if (main_rc != DBGA_SUCCESS) {
         for (int i = 0; i < NL; ++i) cudaStreamSynchronize(ctx->lanes[i]->stream);
         cudaStreamSynchronize(ctx->copy_stream);
@@ -1121,7 +1132,8 @@ int align_pipelined(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, 
     out->aln_off = aln_off; out->aln0 = (uint8_t *)ctx->h_aln0.p; out->aln1 = (uint8_t *)ctx->h_aln1.p;
     out->sop = (seg && (params->flags & DBGA_FLAG_SOP)) ? (int32_t *)ctx->h_sop.p : nullptr;
     out->seg_cols = compact ? (int32_t *)ctx->h_segcols.p : nullptr;
-    out->ms_plan = plan_ms_total;
+    out->ms_plan = 0.f;
+    for (float v : plan_ms) out->ms_plan += v;
     if (no_runs) out->runs = nullptr;
     out->ms_stage1 = ms[0]; out->ms_stage2 = ms[1]; out->ms_stage3 = ms[2]; out->ms_assemble = ms[3];
     out->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
@@ -1138,7 +1150,9 @@ int align_common(dbga_ctx *ctx, const uint8_t *seqs, const uint32_t *packed, con
     if (P >= 64 && !params->want_graph && ctx->own_stream) {
         const int64_t total = offsets[2 * P] - offsets[0];
         if (total >= (16LL << 20)) {
-            int64_t chunk_mb = 32;
+            // chunk sizes are in input bases; 2-bit input puts a quarter of the bytes on the wire, so its chunks
+            // hold four times the bases (every chunk costs ~0.4 ms of host time and ~20 launches)
+            int64_t chunk_mb = packed ? 128 : 32;
             if (const char *e = getenv("DBGA_CHUNK_MB")) chunk_mb = std::max(1, atoi(e));
             return align_pipelined(ctx, seqs, packed, seq0, offsets, P, params, out, no_anchors, std::max<int64_t>(chunk_mb << 20, total / 200));
         }
