@@ -246,6 +246,7 @@ def run_ours(args):
 
     # ---------------- device-resident leg (`value`): plan once, K x kernels only
     al.plan(offs, prm)
+    al.plan(offs, prm)                  # the second plan shows the steady-state host cost (buffers exist)
     for _ in range(max(3, args.warmup)):
         al.run(d_seqs.data_ptr())
         res = al.fetch(unpack=False)      # also sizes the pools (re-runs stage 2.. on overflow)

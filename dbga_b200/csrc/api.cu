@@ -135,7 +135,7 @@ bool decide_spin(int peers) {
     int local = 1;
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) local = std::max(1, atoi(e));
     const int cores = (int)std::max(1u, std::thread::hardware_concurrency());
-    return cores / std::max(peers, local) >= 4;
+    return cores / std::max(peers, local) >= 6;
 }
 
 // waits for everything queued on st so far

@@ -145,6 +145,20 @@ __host__ __device__ inline int64_t tb_bytes_wavefront(int64_t m, int64_t n, int 
     return ((m + rows_per_warp - 1) / rows_per_warp) * (n + WF16_TB_PAD) * rows_per_warp;
 }
 
+// Opt-in limit for dynamic shared memory, raised to the device maximum (less the kernel's static
+// shared memory) at every launch site: the value a kernel is allowed never depends on the launch,
+// so host threads that launch the same kernel with different sizes (pipeline producers, one thread
+// per GPU) cannot undercut each other.
+template <class Kernel> inline cudaError_t allow_max_dyn_smem(Kernel kern) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    int dev = 0, optin = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 // ------------------------------------------------------------------ small device utils
 __device__ __forceinline__ int base_code(uint8_t c) {
     // A=0 C=1 G=2 T=3 for upper-case ACGT; callers validate separately

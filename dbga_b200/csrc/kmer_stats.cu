@@ -210,14 +210,14 @@ cudaError_t launch_kmer_stats(const uint8_t *seqs, const int64_t *offsets, int64
     cudaError_t e;
     if (k <= 15) {
         auto kern = kmer_stats_kernel<uint32_t>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = allow_max_dyn_smem(kern)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem)) != cudaSuccess) return e;
         const int64_t grid = std::min<int64_t>(count, (int64_t)num_sms * std::max(occ, 1));
         const uint32_t kmask = (2 * k >= 32) ? ~0u : ((1u << (2 * k)) - 1u);
         kern<<<(int)grid, 256, smem, st>>>(seqs, offsets, off_base, count, k, kmask, cap, cap / 4u, words, max_keys, max_n, status, out);
     } else {
         auto kern = kmer_stats_kernel<uint64_t>;
-        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = allow_max_dyn_smem(kern)) != cudaSuccess) return e;
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem)) != cudaSuccess) return e;
         const int64_t grid = std::min<int64_t>(count, (int64_t)num_sms * std::max(occ, 1));
         const uint64_t kmask = (2 * k >= 64) ? ~0ULL : ((1ULL << (2 * k)) - 1ULL);

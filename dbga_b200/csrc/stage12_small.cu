@@ -363,7 +363,7 @@ static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const in
                             int32_t *aof, int num_sms, cudaStream_t st) {
     const size_t smem = stage12_small_smem(sizeof(KeyT), cap, words, maxq, TPB > 256);
     auto kern = stage12_small_kernel<KeyT, FULL, TPB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = allow_max_dyn_smem(kern);
     if (e != cudaSuccess) return e;
     int occ = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TPB, smem);

@@ -360,10 +360,10 @@ static void launch_dp_thread_reg_t(const uint8_t *seqs, const PairDesc *pairs, S
                                    const unsigned int *count_dev, DpParams prm, uint8_t *strbuf, int grid, cudaStream_t st) {
     const size_t smem = (size_t)(4 * NG) * NG * 4 * TINY_THREADS;
     if (prm.xy) {
-        cudaFuncSetAttribute(dp_thread_reg_kernel<NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        allow_max_dyn_smem(dp_thread_reg_kernel<NG, true>);
         dp_thread_reg_kernel<NG, true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
     } else {
-        cudaFuncSetAttribute(dp_thread_reg_kernel<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        allow_max_dyn_smem(dp_thread_reg_kernel<NG, false>);
         dp_thread_reg_kernel<NG, false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
     }
 }
@@ -394,10 +394,10 @@ cudaError_t launch_dp_thread(const uint8_t *seqs, const PairDesc *pairs, Slot *s
     const size_t smem = dp_thread_smem(tb.b[c1 - 1], tbs);
     const int grid = dp_thread_grid(num_sms);
     if (prm.xy) {
-        cudaFuncSetAttribute(dp_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        allow_max_dyn_smem(dp_thread_kernel<true>);
         dp_thread_kernel<true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch, tbs ? 1 : 0);
     } else {
-        cudaFuncSetAttribute(dp_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        allow_max_dyn_smem(dp_thread_kernel<false>);
         dp_thread_kernel<false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, c0, c1, tb, prm, strbuf, tb_scratch, tbs ? 1 : 0);
     }
     return cudaGetLastError();

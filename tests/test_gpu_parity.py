@@ -280,7 +280,9 @@ def test_extreme_scores_and_limits(aligner):
     with pytest.raises(RuntimeError, match="substitution score"):
         aligner.align_pairs(pairs, 4, match=501)
     with pytest.raises(RuntimeError, match="k must be"):
-        aligner.align_pairs(pairs, 32)
+        aligner.align_pairs(pairs, 0)
+    res = aligner.align_pairs(pairs, 32)                 # wide k-mers are a supported path (test_wide_kmers_vs_oracle)
+    assert set(res.status.tolist()) <= {O.OK, O.CYCLE, O.K_INVALID}
 
 
 def test_scratch_limit_is_an_explicit_status():
