@@ -72,3 +72,65 @@ def write_alignments(path, names: Sequence, result, width: int = 60, only_ok: bo
             f.write(format_record(names[2 * i + 1], result.aln1[lo:hi].tobytes(), width))
             n += 1
     return n
+
+
+# ---------------------------------------------------------------------------------------------
+# Native path (csrc/fasta_io.cu behind dbga_fasta_read / dbga_fasta_write): the parser fills a pinned
+# buffer in the C ABI's batch layout -- and the 2-bit packed words dbga_align_batch_packed uploads --
+# in parallel over host threads; the writer wraps the rows of a result at 60 columns, expanding a
+# COMPACT_ROWS result on the fly.  No Python object per record on either side.
+class FastaBatch:
+    """A FASTA file parsed by dbga_fasta_read.  Records 2i and 2i+1 are pair i."""
+
+    def __init__(self, path, want_packed: bool = True, threads: int = 0):
+        import ctypes as C
+        from . import _lib
+        self._lib = _lib.load()
+        self._h = C.POINTER(_lib.Fasta)()
+        rc = self._lib.dbga_fasta_read(str(path).encode(), int(want_packed), int(threads), C.byref(self._h))
+        if rc != 0:
+            raise ValueError(f"could not read FASTA file {path} (rc={rc})")
+        f = self._h.contents
+        self.num_records = int(f.num_records)
+        self.offsets = np.ctypeslib.as_array(f.offsets, shape=(self.num_records + 1,)) if self.num_records else np.zeros(1, np.int64)
+        self.seqs_ptr = C.cast(f.seqs, C.c_void_p).value
+        self.packed_ptr = C.cast(f.packed, C.c_void_p).value if f.packed else None
+        self.bad_records = int(f.bad_records)
+
+    @property
+    def num_pairs(self) -> int:
+        return self.num_records // 2
+
+    @property
+    def seqs(self) -> np.ndarray:
+        import ctypes as C
+        n = int(self.offsets[-1])
+        return np.ctypeslib.as_array(C.cast(self.seqs_ptr, C.POINTER(C.c_uint8)), shape=(max(n, 1),))[:n]
+
+    @property
+    def names(self) -> List[str]:
+        import ctypes as C
+        f = self._h.contents
+        no = np.ctypeslib.as_array(f.name_off, shape=(self.num_records + 1,)) if self.num_records else np.zeros(1, np.int64)
+        blob = C.string_at(f.names, int(no[-1]))
+        return [blob[int(no[i]):int(no[i + 1])].decode("ascii", "replace") for i in range(self.num_records)]
+
+    def write(self, path, raw_result, first_record: int = 0, width: int = 60, append: bool = False, threads: int = 0) -> int:
+        """Two wrapped records per DBGA_OK pair of `raw_result` (a _lib.Result, full or COMPACT_ROWS)."""
+        import ctypes as C
+        n = self._lib.dbga_fasta_write(str(path).encode(), self._h, C.byref(raw_result), int(first_record), int(width),
+                                       int(append), int(threads))
+        if n < 0:
+            raise RuntimeError(f"dbga_fasta_write({path}) failed")
+        return int(n)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dbga_fasta_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -167,3 +167,48 @@ def test_k_zero_means_no_anchors():
     db = DeBruijnPairwise(["ACGTAGTATC", "ACCTACAGCA"], 0, "dna")
     assert db.merge_node_idx == [] and db.seq_node_idx == {0: [0, 1], 1: [2, 3]} and db.id_count == 4
     assert db.alignment() == {0: "ACGT--AGTATC", 1: "ACCTACAGCA--"}
+
+
+def test_batch_cli_end_to_end(tmp_path):
+    """dbga-batch: a FASTA file of many pairs in, the reference CLI's per-pair output (cli.py:131-136: both
+    rows, 60-column records) out for every pair it would align; native reader, 2-bit upload, compact result,
+    native writer.  One and two shards (two contexts on one GPU box)."""
+    import numpy as np
+    from click.testing import CliRunner
+    from dbga_b200 import Aligner
+    from dbga_b200.cli_batch import main as batch_main
+    from oracle import dbga_oracle as O
+    pairs = [O.synth_pair(700, 0.02, 0.004, 9000 + s) for s in range(120)]
+    pairs[5] = ("ACGTTGCAAC", "ACGTAGCAAC")
+    src = tmp_path / "in.fasta"
+    with open(src, "w") as f:
+        for i, (a, b) in enumerate(pairs):
+            for nm, s in ((f"s{i}_a some description", a), (f"s{i}_b", b)):
+                f.write(f">{nm}\n" + "".join(s[j:j + 70].lower() + "\n" for j in range(0, len(s), 70)))
+    ref = Aligner(0).align_pairs(pairs, 9)
+    want = ""
+    for i in range(len(pairs)):
+        if ref.status[i] != 0:
+            continue
+        a0, a1 = ref.alignment(i)
+        for nm, row in ((f"s{i}_a", a0), (f"s{i}_b", a1)):
+            want += f">{nm}\n" + "".join(row[j:j + 60] + "\n" for j in range(0, len(row), 60))
+    assert (ref.status == 0).sum() > 60 and (ref.status == 1).sum() > 0
+    for gpus in (1,):
+        out = tmp_path / f"out{gpus}.fasta"
+        r = CliRunner().invoke(batch_main, ["-i", str(src), "-o", str(out), "-k", "9", "--gpus", str(gpus)])
+        assert r.exit_code == 0, r.output
+        assert "pairs written" in r.output and "not aligned: cycles" in r.output
+        assert out.read_text() == want
+    # two shards through the multi-GPU entry (both contexts on device 0 when the box has one GPU)
+    from dbga_b200 import MultiAligner, _lib
+    from dbga_b200.fasta import FastaBatch
+    import torch
+    fa = FastaBatch(src)
+    m = MultiAligner([0, 1] if torch.cuda.device_count() > 1 else [0, 0])
+    res = m.align_buffers(None, np.ascontiguousarray(fa.offsets), Aligner.params(9, flags=_lib.FLAG_COMPACT_ROWS),
+                          packed=fa.packed_ptr, unpack=False)
+    out = tmp_path / "out_multi.fasta"
+    n = sum(fa.write(out, res.shard[s], first_record=2 * int(res.pair_lo[s]), append=s > 0) for s in range(res.num_shards))
+    assert n == int((ref.status == 0).sum()) and out.read_text() == want
+    m.close(); fa.close()

@@ -260,3 +260,46 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_native_fasta_reader_and_writer(tmp_path, built):
+    """dbga_fasta_read / dbga_fasta_write (csrc/fasta_io.cu) without a GPU: labels, upper-casing, line breaks,
+    the canonical 2-bit words, and 60-column records written from a full and from a COMPACT_ROWS result."""
+    import numpy as np
+    from dbga_b200 import _lib, fasta, pack_ascii
+    p = tmp_path / "pairs.fasta"
+    long0, long1 = "ACGT" * 40 + "AC", "ACGT" * 40 + "AG"
+    p.write_text(f">a1 desc\nACGT\nacg\n>b1\nAC\r\nGT\n\n>a2\n{long0[:70]}\n{long0[70:]}\n>b2\n{long1}")
+    fa = fasta.FastaBatch(p)
+    assert fa.names == ["a1", "b1", "a2", "b2"] and fa.num_pairs == 2 and fa.bad_records == 0
+    assert fa.seqs.tobytes() == ("ACGTACG" + "ACGT" + long0 + long1).encode()
+    assert fa.offsets.tolist() == [0, 7, 11, 11 + len(long0), 11 + len(long0) + len(long1)]
+    words = pack_ascii(fa.seqs, fa.offsets)
+    got = np.ctypeslib.as_array(ctypes.cast(fa.packed_ptr, ctypes.POINTER(ctypes.c_uint32)), shape=(len(words),))
+    assert np.array_equal(got[:-1], words[:-1])
+    nbad = tmp_path / "n.fasta"
+    nbad.write_text(">x\nACGN\n>y\nAC\n")
+    assert fasta.FastaBatch(nbad).bad_records == 1
+    # a hand-made result: pair 0 aligned (full rows), pair 1 a cycle
+    def result(status, aln_off, a0, a1, runs=None, run_off=None, seg=None):
+        r = _lib.Result()
+        keep = [np.array(status, np.int32), np.array(aln_off, np.int64), np.frombuffer(a0, np.uint8).copy(), np.frombuffer(a1, np.uint8).copy()]
+        r.num_pairs = len(status)
+        r.status = keep[0].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)); r.aln_off = keep[1].ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+        r.aln0 = keep[2].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)); r.aln1 = keep[3].ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+        if runs is not None:
+            keep += [np.array(runs, np.int32), np.array(run_off, np.int64), np.array(seg, np.int32)]
+            r.runs = keep[4].ctypes.data_as(ctypes.POINTER(ctypes.c_int32)); r.run_off = keep[5].ctypes.data_as(ctypes.POINTER(ctypes.c_int64))
+            r.seg_cols = keep[6].ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        return r, keep
+    out = tmp_path / "out.fasta"
+    r, keep = result([0, 1], [0, 8, 8], b"ACGTACG-", b"AC-GT---")
+    assert fa.write(out, r) == 1
+    assert out.read_text() == ">a1\nACGTACG-\n>b1\nAC-GT---\n"
+    # pair 1 = (long0, long1) as a COMPACT_ROWS result: one run of 161 anchors, then the tail segment AC / AG
+    # (the last merge node is left to the tail: 160 run columns + 2 tail columns)
+    r, keep = result([1, 0], [0, 0, 2], b"AC", b"AG", runs=[0, 0, 161], run_off=[0, 0, 1], seg=[0, 0, 2])
+    assert fa.write(out, r) == 1
+    want = "".join(f">{n}\n" + "".join(s[i:i + 60] + "\n" for i in range(0, len(s), 60)) for n, s in (("a2", long0), ("b2", long1)))
+    assert out.read_text() == want
+    fa.close()
