@@ -42,41 +42,96 @@ def _merge_node_text(dbg: DeBruijnPairwise, node_id: int, seq_idx: int) -> str:
     return text
 
 
+class _Task:
+    """One (sub)alignment of the descent: its rows are the concatenation of `parts`, each either a finished
+    (row0, row1) pair of strings or a child task."""
+    __slots__ = ("seqs", "k_index", "parts", "leaf")
+
+    def __init__(self, seqs, k_index):
+        self.seqs, self.k_index, self.parts, self.leaf = tuple(seqs), k_index, None, None
+
+    def rows(self) -> Tuple[str, str]:
+        if self.leaf is not None:
+            return self.leaf
+        done = [p.rows() if isinstance(p, _Task) else p for p in self.parts]
+        return "".join(x[0] for x in done), "".join(x[1] for x in done)
+
+
+def adpt_dbg_alignment_batch(pairs: Sequence[Sequence[str]], k_index: int, k_choice: Tuple[int, ...], s: dict,
+                             d: int, e: int, device: int = 0) -> List[Tuple[str, str]]:
+    """The reference's recursion (adaptive_debruijn.py:91-224) run level by level: every bubble of every
+    task that reaches k = k_choice[i] goes into ONE batched stage 1-2 call, the graphs come back
+    together, and the bubbles they leave form the next level; everything that cannot be split any
+    further is aligned by one batched dna_global_aln call at the end.  Same results as the recursion
+    (a cycle at any level raises the reference's ValueError), a C-ABI call per level instead of one
+    per bubble per level."""
+    from .batch import default_aligner
+    from .utils import CYCLE_MESSAGE, _raise_for_status
+    al = default_aligner(device)
+    roots = [_Task(p, k_index) for p in pairs]
+    level, leaves = list(roots), []
+    while level:
+        todo, nxt = [], []
+        for t in level:
+            if not 0 <= t.k_index < len(k_choice) or k_choice[t.k_index] <= 0 or k_choice[t.k_index] > min(map(len, t.seqs)):
+                leaves.append(t)
+            else:
+                todo.append(t)
+        by_k: dict = {}
+        for t in todo:
+            by_k.setdefault(k_choice[t.k_index], []).append(t)
+        for k, tasks in by_k.items():
+            res = al.align_pairs([t.seqs for t in tasks], k, stages=2, want_graph=True)
+            for i, t in enumerate(tasks):
+                st = int(res.status[i])
+                if st == 1:
+                    raise ValueError(CYCLE_MESSAGE)                  # debruijn_pairwise.py:73-76
+                if st != 0:
+                    _raise_for_status(st)
+                nd0, nd1 = res.graph_flags(i)
+                dbg = DeBruijnPairwise._from_graph(t.seqs, k, nd0, nd1, res.anchors(i), device)
+                if len(dbg.merge_node_idx) < 2:
+                    child = _Task(t.seqs, t.k_index + 1)            # nothing to anchor on at this k
+                    t.parts = [child]
+                    nxt.append(child)
+                    continue
+                exp1 = [list(x) if isinstance(x, list) else x for x in dbg.expansion[0]]
+                exp2 = [list(x) if isinstance(x, list) else x for x in dbg.expansion[1]]
+                t.parts = []
+                for j in range(len(exp1) - 2):
+                    part1, part2 = exp1[j], exp2[j]
+                    if isinstance(part1, list):
+                        # a bubble is always followed by its closing merge node
+                        child = _Task((dbg.extract_bubble_seq(part1 + [exp1[j + 1]], 0),
+                                       dbg.extract_bubble_seq(part2 + [exp2[j + 1]], 1)), t.k_index + 1)
+                        t.parts.append(child)
+                        nxt.append(child)
+                    else:
+                        t.parts.append((_merge_node_text(dbg, part1, 0), _merge_node_text(dbg, part2, 1)))
+                # last merge node + last bubble (the last merge node may be the end of a sequence)
+                child = _Task((dbg.extract_bubble_seq([exp1[-2]] + exp1[-1], 0),
+                               dbg.extract_bubble_seq([exp2[-2]] + exp2[-1], 1)), t.k_index + 1)
+                t.parts.append(child)
+                nxt.append(child)
+        level = nxt
+    # ---- leaves: dna_global_aln (utils.py:157-192), one batched call for those with two non-empty sides
+    both = [t for t in leaves if t.seqs[0] and t.seqs[1]]
+    if both:
+        res = al.global_align_pairs([t.seqs for t in both], d=d, e=e, s=s)
+        for i, t in enumerate(both):
+            _raise_for_status(int(res.status[i]))
+            t.leaf = res.alignment(i)
+    for t in leaves:
+        if t.leaf is None:                                           # an empty side: utils.py:187-192
+            x, y = t.seqs
+            t.leaf = (x, "-" * len(x)) if x else (("-" * len(y), y) if y else ("", ""))
+    return [t.rows() for t in roots]
+
+
 def adpt_dbg_alignment_recursive(seqs: Sequence[str], k_index: int, k_choice: Tuple[int, ...], s: dict,
                                  d: int, e: int) -> Tuple[str, ...]:
     """Align two strings, descending through `k_choice` (adaptive_debruijn.py:91-224)."""
-    def leaf():
-        return dna_global_aln(*seqs, s, d, e)
-
-    if not 0 <= k_index < len(k_choice):
-        return leaf()
-    k = k_choice[k_index]
-    if k <= 0 or k > min(map(len, seqs)):
-        return leaf()
-    dbg = DeBruijnPairwise(tuple(seqs), k, moltype="dna")
-    if len(dbg.merge_node_idx) < 2:
-        # no (or a single) merge node: nothing to anchor on at this k
-        return adpt_dbg_alignment_recursive(seqs, k_index + 1, k_choice, s, d, e)
-
-    exp1, exp2 = [list(x) if isinstance(x, list) else x for x in dbg.expansion[0]], \
-                 [list(x) if isinstance(x, list) else x for x in dbg.expansion[1]]
-    rows: Tuple[List[str], List[str]] = ([], [])
-    for i in range(len(exp1) - 2):
-        part1, part2 = exp1[i], exp2[i]
-        if isinstance(part1, list):
-            # a bubble is always followed by its closing merge node
-            sub = (dbg.extract_bubble_seq(part1 + [exp1[i + 1]], 0),
-                   dbg.extract_bubble_seq(part2 + [exp2[i + 1]], 1))
-            aligned = adpt_dbg_alignment_recursive(sub, k_index + 1, k_choice, s, d, e)
-            rows[0].append(aligned[0]); rows[1].append(aligned[1])
-        else:
-            rows[0].append(_merge_node_text(dbg, part1, 0))
-            rows[1].append(_merge_node_text(dbg, part2, 1))
-    # last merge node + last bubble (the last merge node may be the end of a sequence)
-    tail = (dbg.extract_bubble_seq([exp1[-2]] + exp1[-1], 0), dbg.extract_bubble_seq([exp2[-2]] + exp2[-1], 1))
-    aligned = adpt_dbg_alignment_recursive(tail, k_index + 1, k_choice, s, d, e)
-    rows[0].append(aligned[0]); rows[1].append(aligned[1])
-    return "".join(rows[0]), "".join(rows[1])
+    return adpt_dbg_alignment_batch([tuple(seqs)], k_index, k_choice, s, d, e)[0]
 
 
 def adpt_dbg_alignment(data: Any, moltype: str, match: int = 10, transition: int = -1, transversion: int = -8,

@@ -24,6 +24,9 @@ from .utils import (CYCLE_MESSAGE, Edge, Node, NodeType, _raise_for_status,  # n
                     load_sequences, read_nucleotide_from_kmers)
 
 
+_DEFAULT_KEY = (10, -1, -8, 10, 2, ())      # alignment()'s default arguments (debruijn_pairwise.py:420-424)
+
+
 class DeBruijnPairwise:
     """Pairwise de Bruijn graph aligner.
 
@@ -42,6 +45,7 @@ class DeBruijnPairwise:
         self.avg_len = sum(map(len, self.sequences)) / self.num_seq
         self._device = device
         self._views: Dict[str, Any] = {}
+        self._cached = None
         assert self.num_seq == len(self.sequences) == 2          # debruijn_pairwise.py:216
         for seq in self.sequences:                               # utils.py:129-130
             if k < 0 or k > len(seq):
@@ -53,7 +57,10 @@ class DeBruijnPairwise:
             self._nd1 = np.zeros(len(s1) + 1, np.uint8)
             self._anchors = np.zeros((0, 2), np.int32)
             return
-        res = default_aligner(device).align_pairs([(s0, s1)], k, stages=2, want_graph=True)
+        # One GPU call for the whole path with the reference's default scoring: the constructor needs stages 1-2
+        # (graph flags, merge nodes, cycle check, debruijn_pairwise.py:70-76) and alignment() with its default
+        # arguments then returns the rows computed here instead of running stages 1-2 a second time.
+        res = default_aligner(device).align_pairs([(s0, s1)], k, stages=3, want_graph=True)
         status = int(res.status[0])
         if status not in (0, 1):
             _raise_for_status(status)
@@ -61,6 +68,23 @@ class DeBruijnPairwise:
         self._anchors = res.anchors(0)
         if status == 1:
             raise ValueError(CYCLE_MESSAGE)                      # debruijn_pairwise.py:73-76
+        self._cached = (_DEFAULT_KEY, res.alignment(0))
+
+    @classmethod
+    def _from_graph(cls, sequences: Tuple[str, str], k: int, nd0: np.ndarray, nd1: np.ndarray, anchors: np.ndarray,
+                    device: int = 0) -> "DeBruijnPairwise":
+        """An instance over stage 1-2 results that a batched call already produced (adaptive descent: one call
+        per level for all bubbles); same attributes and views as the constructor's."""
+        self = object.__new__(cls)
+        self.sc = load_sequences(data=tuple(sequences), moltype="dna")
+        self.k, self.moltype = k, "dna"
+        self.names = tuple(self.sc.names)
+        self.sequences = tuple(str(x) for x in sequences)
+        self.num_seq = 2
+        self.avg_len = sum(map(len, self.sequences)) / 2
+        self._device, self._views, self._cached = device, {}, None
+        self._nd0, self._nd1, self._anchors = nd0, nd1, anchors
+        return self
 
     # ------------------------------------------------------------------ graph views
     def _ids(self):
@@ -263,7 +287,11 @@ class DeBruijnPairwise:
             _raise_for_status(int(res.status[0]))
             a0, a1 = res.alignment(0)
             return {self.names[0]: a0, self.names[1]: a1}            # plain dict (:453-457)
-        res = al.align_pairs([(s0, s1)], self.k, d=d, e=e, s=s, **conv)
-        _raise_for_status(int(res.status[0]))
-        a0, a1 = res.alignment(0)
+        key = (match, transition, transversion, d, e, tuple(sorted(conv.items())))
+        if self._cached is not None and self._cached[0] == key:
+            a0, a1 = self._cached[1]                                  # computed by the constructor's call
+        else:
+            res = al.align_pairs([(s0, s1)], self.k, d=d, e=e, s=s, **conv)
+            _raise_for_status(int(res.status[0]))
+            a0, a1 = res.alignment(0)
         return seqcoll.make_aligned_seqs({self.names[0]: a0, self.names[1]: a1}, moltype=self.moltype)

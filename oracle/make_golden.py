@@ -161,6 +161,19 @@ def main():
             fixtures["adaptive_fuzz"].append({"seqs": [s0, s1], "k_choice": list(kc), "error": type(ex).__name__})
             continue
         fixtures["adaptive_fuzz"].append({"seqs": [s0, s1], "k_choice": list(kc), "aln": list(got)})
+    # the top-level adaptive front-end (adaptive_debruijn.py:17-88) on pairs long enough to pass its entropy and
+    # similarity gates (k runs from about log2(len) + 10 down to 13); FASTA text with 60-column rows
+    from dbga.adaptive_debruijn import adpt_dbg_alignment
+    trng = random.Random(99)
+    fixtures["adaptive_top"] = []
+    for n, ps, pi in ((3000, 0.01, 0.003), (5000, 0.02, 0.004), (4000, 0.005, 0.001), (2500, 0.3, 0.05)):
+        s0 = "".join(trng.choice("ACGT") for _ in range(n))
+        s1 = mutate(trng, s0, ps, pi)
+        try:
+            text = adpt_dbg_alignment([s0, s1], "dna")
+            fixtures["adaptive_top"].append({"seqs": [s0, s1], "fasta": text})
+        except Exception as ex:
+            fixtures["adaptive_top"].append({"seqs": [s0, s1], "error": type(ex).__name__})
     json.dump(fixtures, open(os.path.join(ROOT, "tests", "golden", "ref_fixtures.json"), "w"), indent=1)
 
     rng = random.Random(20261019)

@@ -212,3 +212,49 @@ def test_batch_cli_end_to_end(tmp_path):
     n = sum(fa.write(out, res.shard[s], first_record=2 * int(res.pair_lo[s]), append=s > 0) for s in range(res.num_shards))
     assert n == int((ref.status == 0).sum()) and out.read_text() == want
     m.close(); fa.close()
+
+
+def test_adaptive_top_level_goldens_and_call_count(ref_fixtures):
+    """adpt_dbg_alignment (reference adaptive_debruijn.py:17-88) on pairs long enough to pass its similarity and
+    entropy gates, against FASTA text recorded from the reference's own function (oracle/make_golden.py; rows in
+    60-column blocks) -- and the level-synchronous descent makes a C-ABI call per level, not per bubble."""
+    from dbga_b200 import adaptive_debruijn as AD, batch
+    al = batch.default_aligner(0)
+    calls = {"n": 0}
+    real = al.align_buffers
+
+    def counting(*a, **kw):
+        calls["n"] += 1
+        return real(*a, **kw)
+    al.align_buffers = counting
+    try:
+        for fx in ref_fixtures["adaptive_top"]:
+            calls["n"] = 0
+            if "error" in fx:
+                with pytest.raises(Exception):
+                    AD.adpt_dbg_alignment(list(fx["seqs"]), "dna")
+                continue
+            got = AD.adpt_dbg_alignment(list(fx["seqs"]), "dna")
+            assert got == fx["fasta"]
+            assert max(len(l) for l in got.splitlines()) <= 60
+            # k runs over at most ~6 odd values; kmer statistics + one call per level + one for the leaves
+            assert calls["n"] <= 16, calls["n"]
+    finally:
+        al.align_buffers = real
+
+
+def test_adaptive_batch_of_pairs_equals_one_by_one():
+    from dbga_b200 import make_dna_scoring_dict
+    from dbga_b200.adaptive_debruijn import adpt_dbg_alignment_batch, adpt_dbg_alignment_recursive
+    from oracle import dbga_oracle as O
+    s = make_dna_scoring_dict(10, -1, -8)
+    pairs = [O.synth_pair(600, 0.03, 0.01, 500 + i) for i in range(24)]
+    kc = (13, 9, 5)
+    one, ok = [], []
+    for p in pairs:
+        try:
+            one.append(adpt_dbg_alignment_recursive(p, 0, kc, s, 10, 2)); ok.append(p)
+        except ValueError:
+            pass
+    assert len(ok) >= 8
+    assert adpt_dbg_alignment_batch(ok, 0, kc, s, 10, 2) == one
