@@ -54,6 +54,26 @@ void host_release(void *p, bool pinned) {
 
 inline bool is_space(uint8_t c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }
 
+// Bases of a record's body [p, end): whole lines at a time (memchr / memcpy); a line that holds blanks or a
+// carriage return goes byte by byte.  dst == nullptr: only count.  Returns the number of bases.
+inline int64_t copy_body(const uint8_t *p, const uint8_t *end, uint8_t *dst) {
+    int64_t n = 0;
+    while (p < end) {
+        const uint8_t *eol = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const size_t ll = (size_t)(eol - p);
+        if (ll && !memchr(p, ' ', ll) && !memchr(p, '\r', ll) && !memchr(p, '\t', ll)) {
+            if (dst) memcpy(dst + n, p, ll);
+            n += (int64_t)ll;
+        } else {
+            for (const uint8_t *q = p; q < eol; ++q)
+                if (!is_space(*q)) { if (dst) dst[n] = *q; ++n; }
+        }
+        p = eol + 1;
+    }
+    return n;
+}
+
 }  // namespace
 
 extern "C" {
@@ -114,9 +134,7 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
             nlen[(size_t)r + 1] = b - a;
             nstart[(size_t)r] = a - data;
             body[(size_t)r] = (eol < end ? eol + 1 : end) - data;
-            int64_t n = 0;
-            for (const uint8_t *q = data + body[(size_t)r]; q < end; ++q) n += !is_space(*q);
-            f->offsets[(size_t)r + 1] = n;
+            f->offsets[(size_t)r + 1] = copy_body(data + body[(size_t)r], end, nullptr);
         }
     });
     for (int64_t r = 0; r < R; ++r) { f->offsets[(size_t)r + 1] += f->offsets[(size_t)r]; nlen[(size_t)r + 1] += nlen[(size_t)r]; }
@@ -144,28 +162,37 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
             memcpy(f->names.data() + nlen[(size_t)r], data + nstart[(size_t)r], (size_t)(nlen[(size_t)r + 1] - nlen[(size_t)r]));
             uint8_t *dst = f->seqs + f->offsets[(size_t)r];
             const int64_t len = f->offsets[(size_t)r + 1] - f->offsets[(size_t)r];
-            int64_t n = 0;
-            for (const uint8_t *q = data + body[(size_t)r]; q < end; ++q) {
-                uint8_t c = *q;
-                if (is_space(c)) continue;
-                if (c >= 'a' && c <= 'z') c = (uint8_t)(c - 32);
-                dst[n++] = c;
-            }
+            copy_body(data + body[(size_t)r], end, dst);
+            for (int64_t i = 0; i < len; ++i) dst[i] = (uint8_t)(dst[i] - (((uint8_t)(dst[i] - 'a') < 26u) << 5));   // upper-case (vectorised)
             if (f->packed) {
                 uint32_t *pw = f->packed + (f->offsets[(size_t)r] >> 4) + r;
-                bool b = false;
-                for (int64_t w = 0; w * 16 < len; ++w) {
-                    const int64_t nv = std::min<int64_t>(16, len - 16 * w);
+                uint32_t diff = 0;
+                int64_t w = 0;
+                for (; 16 * (w + 1) <= len; ++w) {          // 16 bases -> one word, four bytes at a time
                     uint32_t word = 0;
-                    for (int64_t i = 0; i < nv; ++i) {
-                        const uint8_t c = dst[16 * w + i];
-                        const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
-                        b |= "ACGT"[code] != (char)c;
-                        word |= code << (2 * i);
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t x;
+                        memcpy(&x, dst + 16 * w + 4 * j, 4);
+                        const uint32_t codes = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
+                        // the base each code stands for, rebuilt with byte arithmetic: A C G T = 65 67 71 84
+                        const uint32_t lo = codes & 0x01010101u, hi = (codes >> 1) & 0x01010101u;
+                        const uint32_t expect = 0x41414141u + 2u * lo + 6u * hi + 11u * (lo & hi);
+                        diff |= expect ^ x;
+                        word |= ((codes * 0x01041040u) >> 24) << (8 * j);
                     }
                     pw[w] = word;
                 }
-                nbad += b;
+                if (16 * w < len) {
+                    uint32_t word = 0;
+                    for (int64_t i = 16 * w; i < len; ++i) {
+                        const uint8_t c = dst[i];
+                        const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
+                        diff |= (uint32_t)("ACGT"[code] != (char)c);
+                        word |= code << (2 * (i - 16 * w));
+                    }
+                    pw[w] = word;
+                }
+                nbad += diff != 0;
             }
         }
         bad += nbad;
@@ -221,15 +248,24 @@ int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_resu
     int64_t written = 0;
     for (int64_t i = 0; i < P; ++i) { written += res->status[i] == DBGA_OK; pos[(size_t)i + 1] += pos[(size_t)i]; }
     const int64_t total = pos[(size_t)P];
-    const int fd = open(path, O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC), 0644);
+    // the records are laid out in place in a mapping of the output file (no staging copy, no write())
+    const int fd = open(path, O_RDWR | O_CREAT | (append ? 0 : O_TRUNC), 0644);
     if (fd < 0) return -1;
-    std::vector<uint8_t> buf((size_t)total);
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); return -1; }
+    const int64_t at = append ? (int64_t)sb.st_size : 0;
+    if (total == 0) { close(fd); return written; }
+    if (ftruncate(fd, (off_t)(at + total)) != 0) { close(fd); return -1; }
+    const int64_t page = sysconf(_SC_PAGESIZE), map_lo = at / page * page;
+    uint8_t *map = (uint8_t *)mmap(nullptr, (size_t)(at + total - map_lo), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_lo);
+    if (map == MAP_FAILED) { close(fd); return -1; }
+    uint8_t *out_base = map + (at - map_lo);
     par_for(P, threads, 256, [&](int64_t lo, int64_t hi) {
         std::vector<uint8_t> row;
         for (int64_t i = lo; i < hi; ++i) {
             if (res->status[i] != DBGA_OK) continue;
             const int64_t len = full[(size_t)i];
-            uint8_t *o = buf.data() + pos[(size_t)i];
+            uint8_t *o = out_base + pos[(size_t)i];
             for (int s = 0; s < 2; ++s) {
                 const int64_t rec = first_record + 2 * i + s;
                 const int64_t nn = in->name_off[rec + 1] - in->name_off[rec];
@@ -262,12 +298,7 @@ int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_resu
             }
         }
     });
-    int64_t off = 0;
-    while (off < total) {
-        const ssize_t w = write(fd, buf.data() + off, (size_t)std::min<int64_t>(total - off, 1LL << 30));
-        if (w <= 0) { close(fd); return -1; }
-        off += w;
-    }
+    munmap(map, (size_t)(at + total - map_lo));
     close(fd);
     return written;
 }

@@ -68,16 +68,16 @@ __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, in
             }
             s.cls = cls;
         }
-        // warp-aggregated work-list append per DP class
-        for (int c = 0; c < NUM_CLS; ++c) {
-            const unsigned bal = __ballot_sync(0xffffffffu, cls == c);
-            if (bal) {
-                unsigned int pos = 0;
-                const int leader = __ffs(bal) - 1;
-                if (lane == leader) pos = atomicAdd(&ctr->n_cls[c], (unsigned)__popc(bal));
-                pos = __shfl_sync(0xffffffffu, pos, leader);
-                if (cls == c) pools.lists[(int64_t)c * pools.list_cap + pos + __popc(bal & ((1u << lane) - 1u))] = (int32_t)(slot_base + t);
-            }
+        // warp-aggregated work-list append per DP class: the lanes of one class find each other with
+        // one MATCH, the first of them reserves room for all
+        {
+            const unsigned peers = __match_any_sync(0xffffffffu, cls);
+            const int leader = __ffs(peers) - 1;
+            unsigned int pos = 0;
+            if (cls != CLS_NONE && lane == leader) pos = atomicAdd(&ctr->n_cls[cls], (unsigned)__popc(peers));
+            pos = __shfl_sync(0xffffffffu, pos, leader);
+            if (cls != CLS_NONE)
+                pools.lists[(int64_t)cls * pools.list_cap + pos + __popc(peers & ((1u << lane) - 1u))] = (int32_t)(slot_base + t);
         }
         if (t < n_slots) pools.slots[slot_base + t] = s;
     }

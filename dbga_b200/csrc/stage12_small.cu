@@ -25,7 +25,8 @@ namespace dbga {
 constexpr uint32_t MDUP0 = 0x80000000u;  // medium pairs' merged word: repeated in seq1
 constexpr uint32_t DUP0 = 0x10000u;      // cnt[]: the k-mer occurs more than once in seq1 (seq-2 counts stay below 2^16)
 struct S12Shared {
-    int nS, nE, nA, big;
+    unsigned int nSE;      // run starts appended (low 16 bits) | run ends appended (high 16 bits); both < 65 000
+    int nA, big;
     long long bcast[2];
     long long red[32];
 };
@@ -80,7 +81,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             continue;
         }
         __syncthreads();            // previous pair's shared state is no longer in use
-        if (tid == 0) { sh.nS = 0; sh.nE = 0; sh.nA = 0; sh.big = 0; }
+        if (tid == 0) { sh.nSE = 0u; sh.nA = 0; sh.big = 0; }
         // ---- pack + table init
         bool bad = false;
         {
@@ -93,7 +94,8 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         }
         auto init_table = [&]() {       // keys + pos0 = all ones, cnt = 0
             uint4 *t4 = reinterpret_cast<uint4 *>(keys);
-            const int n_ff = (int)((cap * (sizeof(KeyT) + (MEDIUM ? 0 : 2))) / 16), n_00 = (int)(cap * 4 / 16);
+            // (the 16-bit positions need no initial value unless seq-2-only k-mers can own a slot: graph mode)
+            const int n_ff = (int)((cap * (sizeof(KeyT) + ((MEDIUM || !FULL) ? 0 : 2))) / 16), n_00 = (int)(cap * 4 / 16);
             for (int i = tid; i < n_ff; i += T) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
             uint4 *z4 = reinterpret_cast<uint4 *>(cnt);
             for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -202,34 +204,51 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             continue;
         }
         __syncthreads();                              // table dead from here on
-        // ---- stage 2: run starts / ends (rare) appended unordered
+        // ---- stage 2: run starts / ends (rare) appended unordered.  Every lane flags what its two
+        //      positions start / end; the warp's counts are scanned with shuffles and ONE shared-memory
+        //      add per warp step reserves room for all of them (starts in the low half of the counter
+        //      word, ends in the high half), instead of an atomic per start / end.
         int cA = 0;
         {
             const uint32_t *memo2 = reinterpret_cast<const uint32_t *>(memo);
             auto is_next = [](uint32_t x, uint32_t y) { return x != NONE16 && y != NONE16 && y == x + 1u; };   // y continues x's run
-            for (int q = 2 * tid; q < N1; q += 2 * T) {
-                const uint32_t w = memo2[q >> 1];             // the odd half past N1 was left NONE16 by B2
-                if (w == 0xFFFFFFFFu) continue;
-                const uint32_t a0 = w & 0xFFFFu, a1 = w >> 16;
-                const uint32_t pv = q > 0 ? memo[q - 1] : NONE16;
-                const uint32_t nx = q + 2 < N1 ? memo[q + 2] : NONE16;
-                if (a0 != NONE16) {
-                    ++cA;
-                    if (!is_next(pv, a0)) ska[atomicAdd(&sh.nS, 1)] = ((uint32_t)q << 16) | a0;
-                    if (!is_next(a0, a1)) ske[atomicAdd(&sh.nE, 1)] = (uint16_t)q;
+            for (int q0 = 0; q0 < N1; q0 += 2 * T) {
+                const int q = q0 + 2 * tid;
+                uint32_t a0 = NONE16, a1 = NONE16, pv = NONE16, nx = NONE16;
+                if (q < N1) {
+                    const uint32_t w = memo2[q >> 1];             // the odd half past N1 was left NONE16 by B2
+                    a0 = w & 0xFFFFu; a1 = w >> 16;
+                    if (w != 0xFFFFFFFFu) {
+                        pv = q > 0 ? memo[q - 1] : NONE16;
+                        nx = q + 2 < N1 ? memo[q + 2] : NONE16;
+                    }
                 }
-                if (a1 != NONE16) {
-                    ++cA;
-                    if (!is_next(a0, a1)) ska[atomicAdd(&sh.nS, 1)] = ((uint32_t)(q + 1) << 16) | a1;
-                    if (!is_next(a1, nx)) ske[atomicAdd(&sh.nE, 1)] = (uint16_t)(q + 1);
+                const bool h0 = a0 != NONE16, h1 = a1 != NONE16, link = is_next(a0, a1);
+                const bool s0 = h0 && !is_next(pv, a0), e0 = h0 && !link, s1 = h1 && !link, e1 = h1 && !is_next(a1, nx);
+                cA += (int)h0 + (int)h1;
+                const uint32_t mine = (uint32_t)s0 + (uint32_t)s1 + (((uint32_t)e0 + (uint32_t)e1) << 16);
+                if (__ballot_sync(0xffffffffu, mine != 0u) == 0u) continue;      // nothing starts or ends here (warp-uniform)
+                uint32_t inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
                 }
+                uint32_t base = 0;
+                if (lane == 31) base = atomicAdd(&sh.nSE, inc);
+                base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+                uint32_t ps = base & 0xFFFFu, pe = base >> 16;
+                if (s0) ska[ps++] = ((uint32_t)q << 16) | a0;
+                if (s1) ska[ps] = ((uint32_t)(q + 1) << 16) | a1;
+                if (e0) ske[pe++] = (uint16_t)q;
+                if (e1) ske[pe] = (uint16_t)(q + 1);
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cA += __shfl_xor_sync(0xffffffffu, cA, o);
         if (lane == 0 && cA) atomicAdd(&sh.nA, cA);
         __syncthreads();
-        const int R = sh.nS;
+        const int R = (int)(sh.nSE & 0xFFFFu);
         const uint32_t *S = srt_s;
         const uint16_t *E = srt_e;
         if (R <= RANK_SORT_MAX) {
