@@ -253,6 +253,10 @@ int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
             h.lut[a] = w;
         }
         h.mul[0] = 0xFFFFFFFFu; h.mul[1] = 4; h.mul[2] = 16; h.mul[3] = 256;
+        {   // compact traceback fields: [X came from M] = ((u & 3) - pX) / (pM - pX), times 4; same for Y, times 8
+            const int pM = ORDER_PRIO[p.pred_order][0], pX = ORDER_PRIO[p.pred_order][1], pY = ORDER_PRIO[p.pred_order][2];
+            h.nmul[0] = (uint32_t)(4 / (pM - pX)); h.nmul[1] = (uint32_t)(8 / (pM - pY));
+        }
         h.tbk = 4 * ORDER_PRIO[p.pred_order][1] + 16 * ORDER_PRIO[p.pred_order][2];
         h.q0 = 4 * (0 - h.off);
         h.qneg = -30968;

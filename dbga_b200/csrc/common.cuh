@@ -89,6 +89,7 @@ struct Dp16 {
     uint32_t tagM, tagX, tagY; // priority (0..2) in both halves
     uint32_t lut[4];          // per seq1 base: int8 4 * (S + 2 ge) + priority(M) for seq2 base A, C, G, T
     uint32_t mul[4];          // -1, 4, 16, 256: IMAD multipliers kept in registers
+    uint32_t nmul[2];         // compact traceback (4 bits per cell): 4 / (pM - pX), 8 / (pM - pY) as 32-bit integers
     uint32_t tbk;             // 4 * priority(X) + 16 * priority(Y): bias of a raw traceback byte
     int32_t q0, qneg, qy0;    // 16-bit encodings (no tag) of M[0][0], "minus infinity", Y^[0][c]
     int32_t off;              // V offset: stored = 4 * (V - off) + priority

@@ -54,9 +54,15 @@ __device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_per
 // four bytes stored as one word less bias4 (exact 32-bit arithmetic, see stage3_dp16.cu);
 // pr_sh < 0: bytes in matrix-row order, no bias.  The 32-bit kernels pass constants, which
 // fold away after inlining.
+// nib_sh >= 2: the compact table of the packed kernel (X <-> Y off, R = 1 << nib_sh >= 4 rows per half-lane):
+// FOUR bits per cell -- bits 0-1 the predecessor tag of M, bit 2 "X came from M", bit 3 "Y came from M" --
+// two matrix rows per byte; a lane's R bytes of a step row hold, per group of four rows r..r+3 of its two
+// half-lanes, [low (r, r+1), low (r+2, r+3), high (r, r+1), high (r+2, r+3)].  A step row is then half as
+// many bytes as it covers matrix rows.
 struct WalkGeom {
     int roww_sh, rdiv_sh, pr_sh;
     uint32_t bias4;
+    int nib_sh = -1;
 };
 
 __device__ __forceinline__ int wf_col(int c, int pr_sh) {
@@ -64,6 +70,12 @@ __device__ __forceinline__ int wf_col(int c, int pr_sh) {
     const int pr = 1 << pr_sh;
     const int q = c & (2 * pr - 1), hh = q >> pr_sh, r = q & (pr - 1);
     return c - q + 4 * (r >> 1) + 2 * hh + (r & 1);
+}
+// byte column of matrix row c (within its block) in the compact table; the cell is nibble (c & 1) of it
+__device__ __forceinline__ int wf_col_nib(int c, int nib_sh) {
+    const int R = 1 << nib_sh;
+    const int q = c & (2 * R - 1), hh = q >> nib_sh, r = q & (R - 1);
+    return ((c - q) >> 1) + 4 * (r >> 2) + 2 * hh + ((r >> 1) & 1);
 }
 
 // One warp walks; every lane runs the same walk (uniform control flow).  win: 32 x 64 bytes of
@@ -76,6 +88,8 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
                                             const WalkGeom g) {
     constexpr int WIN_W = 64;                        // traceback window width in bytes (every row is >= 64 bytes)
     const int roww_mask = (1 << g.roww_sh) - 1;
+    const bool nib = g.nib_sh >= 0;
+    const int rowb_sh = nib ? g.roww_sh - 1 : g.roww_sh;         // log2 of the bytes per step row
     int i = m, j = n, len = 0;
     // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
     // runs the same walk (uniform control flow).  Only the kind of each step is kept, as
@@ -123,20 +137,33 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
         if (g.pr_sh < 0) return win[r][c];
         return ((*reinterpret_cast<const uint32_t *>(&win[r][c & ~3]) + g.bias4) >> (8 * (c & 3))) & 0xFFu;
     };
+    // table column (byte) of matrix row cb of a block
+    auto col_of = [&](int cb) -> int { return nib ? wf_col_nib(cb, g.nib_sh) : wf_col(cb, g.pr_sh); };
+    // the cell's fields in the byte form (bits 0-1 pred of M, 2-3 of X, 4-5 of Y): the compact form is
+    // expanded through pmap's inverse -- only "came from M" or "stayed" exist for X and Y there
+    const uint32_t tagM_ = (((pmap >> 0) & 3u) == 0u) ? 0u : ((((pmap >> 2) & 3u) == 0u) ? 1u : 2u);
+    const uint32_t tagX_ = (((pmap >> 0) & 3u) == 1u) ? 0u : ((((pmap >> 2) & 3u) == 1u) ? 1u : 2u);
+    const uint32_t tagY_ = (((pmap >> 0) & 3u) == 2u) ? 0u : ((((pmap >> 2) & 3u) == 2u) ? 1u : 2u);
+    auto cell = [&](int r, int c, int cb) -> uint32_t {
+        if (!nib) return tb_byte(r, c);
+        const uint32_t v = ((uint32_t)win[r][c] >> (4 * (cb & 1))) & 15u;
+        return (v & 3u) | (((v & 4u) ? tagM_ : tagX_) << 2) | (((v & 8u) ? tagM_ : tagY_) << 4);
+    };
     while (i > 0 || j > 0) {
         if (i == 0) { emit(2, j); break; }           // first row / column: one long gap
         if (j == 0) { emit(1, i); break; }
         const int i0 = i - 1;
         const int blk = i0 >> g.roww_sh, cb = i0 & roww_mask;      // (pass * GW + warp), l * R + r
         const int row = j + (cb >> g.rdiv_sh);
-        if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(cb - win_col_lo) >= (unsigned)WIN_W) {
+        const int ccol = nib ? wf_col_nib(cb, g.nib_sh) : cb;       // window position of the cell's byte (byte form: by matrix row)
+        if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(ccol - win_col_lo) >= (unsigned)WIN_W) {
             __syncwarp();
             win_blk = blk; win_row_hi = row;
-            win_col_lo = max(0, (cb & ~31) - 32);
+            win_col_lo = max(0, (ccol & ~31) - 32);
             const int rr = row - lane;
             uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
             if (rr >= 1) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(tb + (((int64_t)blk * tb_rows + rr) << g.roww_sh) + win_col_lo);
+                const uint4 *p = reinterpret_cast<const uint4 *>(tb + (((int64_t)blk * tb_rows + rr) << rowb_sh) + win_col_lo);
                 a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
             }
             uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
@@ -148,15 +175,16 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
             bool ok = false;
             if (il >= 0 && jl >= 1) {
                 const int bl = il >> g.roww_sh, cl = il & roww_mask;
-                const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh))), dc = (unsigned)(cl - win_col_lo);
+                const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh)));
+                const unsigned dc = (unsigned)((nib ? wf_col_nib(cl, g.nib_sh) : cl) - win_col_lo);
                 if (bl == win_blk && dr < 32u && dc < (unsigned)WIN_W)
-                    ok = ((pmap >> (2 * (tb_byte(dr, wf_col(cl, g.pr_sh) - win_col_lo) & 3u))) & 3u) == 0u;
+                    ok = ((pmap >> (2 * (cell(dr, col_of(cl) - win_col_lo, cl) & 3u))) & 3u) == 0u;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, ok);
             const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
             if (c > 0) { emit(0, c); i -= c; j -= c; continue; }
         }
-        const uint32_t d = tb_byte(win_row_hi - row, wf_col(cb, g.pr_sh) - win_col_lo);
+        const uint32_t d = cell(win_row_hi - row, col_of(cb) - win_col_lo, cb);
         emit(st, 1);
         const uint32_t tag = (d >> (2 * st)) & 3u;
         i -= (st != 2); j -= (st != 1);

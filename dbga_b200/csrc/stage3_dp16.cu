@@ -89,10 +89,16 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
     if (lane < 4) s_lut[lane] = h.lut[lane];
     __syncwarp();
     constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t c256 = h.mul[3];
-    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], h.mul[1], h.mul[2]};
+    // Compact traceback (no X <-> Y, R >= 4): FOUR bits per cell.  X can only come from M or X and Y from M
+    // or Y, so (u & 3) - pX is 0 or pM - pX and the field "X came from M" is that difference times
+    // 4 / (pM - pX) -- an integer multiplier (+-4 or +-2) in the same IMAD that the byte form runs with 4;
+    // likewise 8 / (pM - pY) for Y.  A cell is then (t & 3) + 4 [X from M] + 8 [Y from M], no bias, two
+    // matrix rows per byte, half the bytes per step (dp_walk.cuh: WalkGeom::nib_sh).
+    constexpr bool NIB = !XY && R >= 4;
+    const uint32_t c256 = h.mul[3], c16 = h.mul[2];
+    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], NIB ? h.nmul[0] : h.mul[1], NIB ? h.nmul[1] : h.mul[2]};
     const uint32_t K1 = h.tbk * 0x00010001u;
-    constexpr int ROWW = 64 * R;
+    constexpr int ROWW = NIB ? 32 * R : 64 * R;               // bytes per step row
     const uint32_t tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
     const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
     // row 0 as seen by lane 0's low half (arrives where the shuffle would put it: high half)
@@ -128,7 +134,7 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
         // offset by 16 so that negative steps have somewhere to write.
         const int nch = (te + 16) >> 4, t_start = te + 1 - 16 * nch;
         uint32_t yprev = 0, sel_cur = 0x8888u, sel_prev = 0x8888u;
-        uint8_t *tbw = tb + 16 * ROWW + lane * 2 * R;
+        uint8_t *tbw = tb + 16 * ROWW + lane * (NIB ? R : 2 * R);
         // code of column t = bits 2 (t - t0) of the chunk's word; t0 <= 0 only in the first chunk,
         // whose word is built from ys[0..15] so that nothing before ys is read
         uint32_t wy_next = (uint32_t)((unsigned long long)load_codes16(ys, n) << (2 * (1 - t_start)));
@@ -156,7 +162,21 @@ dp_wf16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                 wf16_rows<R, XY>(Mr, Xr, Yr, D, lutA, lutB, sel_cur, dgM, dgX, dgY, uM, uX, uY, cc);
                 // traceback bytes of the lane, per pair of rows (r, r+1): [low r, low r+1, high r, high r+1]
                 uint8_t *tbp = tbw + (int64_t)t * ROWW;
-                if constexpr (R == 1) {
+                if constexpr (NIB) {
+                    // two rows per byte (r, r+1), then the bytes of rows (r, r+1) and (r+2, r+3) of both half-lanes in
+                    // one word: [low (r, r+1), low (r+2, r+3), high (r, r+1), high (r+2, r+3)]
+                    uint32_t F[R / 4];
+#pragma unroll
+                    for (int g = 0; g < R / 4; ++g)
+                        F[g] = imad(imad(D[4 * g + 3], c16, D[4 * g + 2]), c256, imad(D[4 * g + 1], c16, D[4 * g]));
+                    if constexpr (R == 4) {
+                        *reinterpret_cast<uint32_t *>(tbp) = F[0];
+                    } else if constexpr (R == 8) {
+                        *reinterpret_cast<uint2 *>(tbp) = make_uint2(F[0], F[1]);
+                    } else {
+                        *reinterpret_cast<uint4 *>(tbp) = make_uint4(F[0], F[1], F[2], F[3]);
+                    }
+                } else if constexpr (R == 1) {
                     *reinterpret_cast<uint16_t *>(tbp) = (uint16_t)prmt(D[0] + K1, 0u, 0x4420u);
                 } else {
                     uint32_t E[R / 2];
@@ -366,8 +386,10 @@ dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
             const int rsh = 31 - __clz(R);
             // paired kernel: the 32-bit kernels' table (32 R bytes per row, matrix-row order, true bytes);
             // half-lane kernel: 64 R bytes per row, row pairs interleaved, biased words
-            const WalkGeom g = paired ? WalkGeom{5 + rsh, rsh, -1, 0u}
-                                      : WalkGeom{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u};
+            // (compact form, four bits per cell: R >= 4 rows per half-lane and no X <-> Y, as in dp_wf16_kernel)
+            const bool nibf = !paired && R >= 4 && !prm.xy;
+            const WalkGeom g = paired ? WalkGeom{5 + rsh, rsh, -1, 0u, -1}
+                                      : WalkGeom{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u, nibf ? rsh : -1};
             int st = s.len;                                  // half-lane kernel: the terminal state travels in slot.len
             if (paired) {                                    // paired kernel: last-column states at the head of the table
                 const uint16_t *eb = reinterpret_cast<const uint16_t *>(tb_pool + s.tb_off);
@@ -379,7 +401,7 @@ dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
                 if (cy > best) { best = cy; st = 2; }
                 if (lane == 0) slots[sid].score = (best >> 2) + prm.h.off - prm.ge_raw * (m + n);
             }
-            const int len = wf_traceback(win[w], tb_pool + s.tb_off + (16 << g.roww_sh), (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap,
+            const int len = wf_traceback(win[w], tb_pool + s.tb_off + (16 << (nibf ? g.roww_sh - 1 : g.roww_sh)), (int64_t)n + WF16_TB_PAD, xs, ys, m, n, st, pmap,
                                          ox, oy, lane, g);
             if (lane == 0) slots[sid].len = len;
             __syncwarp();
