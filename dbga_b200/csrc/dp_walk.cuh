@@ -54,6 +54,7 @@ __device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_per
 // four bytes stored as one word less bias4 (exact 32-bit arithmetic, see stage3_dp16.cu);
 // pr_sh < 0: bytes in matrix-row order, no bias.  The 32-bit kernels pass constants, which
 // fold away after inlining.
+// nib_sh == 0: the compact table of the two-segments-per-warp kernel (four bits per cell, byte = matrix row / 2).
 // nib_sh >= 2: the compact table of the packed kernel (X <-> Y off, R = 1 << nib_sh >= 4 rows per half-lane):
 // FOUR bits per cell -- bits 0-1 the predecessor tag of M, bit 2 "X came from M", bit 3 "Y came from M" --
 // two matrix rows per byte; a lane's R bytes of a step row hold, per group of four rows r..r+3 of its two
@@ -73,6 +74,7 @@ __device__ __forceinline__ int wf_col(int c, int pr_sh) {
 }
 // byte column of matrix row c (within its block) in the compact table; the cell is nibble (c & 1) of it
 __device__ __forceinline__ int wf_col_nib(int c, int nib_sh) {
+    if (nib_sh == 0) return c >> 1;                  // two-segments-per-warp kernel: bytes in matrix-row order
     const int R = 1 << nib_sh;
     const int q = c & (2 * R - 1), hh = q >> nib_sh, r = q & (R - 1);
     return ((c - q) >> 1) + 4 * (r >> 2) + 2 * hh + ((r >> 1) & 1);

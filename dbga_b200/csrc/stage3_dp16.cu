@@ -236,9 +236,11 @@ dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
     if (lane < 4) s_lut[lane] = h.lut[lane];
     __syncwarp();
     constexpr uint32_t FULL = 0xffffffffu;
-    constexpr int ROWW = 32 * R;
-    const uint32_t c256 = h.mul[3], K4 = h.tbk * 0x01010101u;
-    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], h.mul[1], h.mul[2]};
+    constexpr bool NIB = !XY;                                 // compact traceback: four bits per cell, two matrix rows per byte
+    constexpr int ROWW = NIB ? 16 * R : 32 * R;               // bytes per step row of a segment's table
+    constexpr int LB = NIB ? R / 2 : R;                       // bytes per lane per step
+    const uint32_t c256 = h.mul[3], c16 = h.mul[2], K4 = h.tbk * 0x01010101u;
+    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], NIB ? h.nmul[0] : h.mul[1], NIB ? h.nmul[1] : h.mul[2]};
     const uint32_t tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
     const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
     const uint32_t r0M0 = dup16(h.q0) | tagM, r0Y = dup16(h.qy0) | tagY;
@@ -261,7 +263,7 @@ dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
                     const PairDesc pd = pairs[s.pair];
                     have[e] = true; m[e] = s.m; n[e] = s.n;
                     xs[e] = seqs + pd.off0 + s.x0; ys[e] = seqs + pd.off1 + s.y0;
-                    tb[e] = tb_pool + s.tb_off + 16 * ROWW + lane * R;
+                    tb[e] = tb_pool + s.tb_off + 16 * ROWW + lane * LB;
                 }
             }
         }
@@ -308,8 +310,23 @@ dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
                 uint8_t *pa = tb[0] + (int64_t)min(t, te[0] + 1) * ROWW, *pb = tb[1] + (int64_t)min(t, te[1] + 1) * ROWW;
                 uint32_t E[R / 2];
 #pragma unroll
-                for (int q = 0; q < R / 2; ++q) E[q] = imad(D[2 * q + 1], c256, D[2 * q]) + K4;
-                if constexpr (R == 2) {
+                for (int q = 0; q < R / 2; ++q) E[q] = NIB ? imad(D[2 * q + 1], c16, D[2 * q]) : imad(D[2 * q + 1], c256, D[2 * q]) + K4;
+                if constexpr (NIB) {
+                    // E[q]: byte 0 = A's rows (2q, 2q+1), byte 2 = B's rows (2q, 2q+1)
+                    if constexpr (R == 2) {
+                        if (have[0]) *pa = (uint8_t)E[0];
+                        if (have[1]) *pb = (uint8_t)(E[0] >> 16);
+                    } else if constexpr (R == 4) {
+                        const uint32_t w2 = prmt(E[0], E[1], 0x6240u);            // [A01, A23, B01, B23]
+                        if (have[0]) *reinterpret_cast<uint16_t *>(pa) = (uint16_t)w2;
+                        if (have[1]) *reinterpret_cast<uint16_t *>(pb) = (uint16_t)(w2 >> 16);
+                    } else {
+                        static_assert(R == 8, "the paired kernel runs 2, 4 or 8 rows per lane");
+                        const uint32_t w01 = prmt(E[0], E[1], 0x6240u), w23 = prmt(E[2], E[3], 0x6240u);
+                        if (have[0]) *reinterpret_cast<uint32_t *>(pa) = prmt(w01, w23, 0x5410u);
+                        if (have[1]) *reinterpret_cast<uint32_t *>(pb) = prmt(w01, w23, 0x7632u);
+                    }
+                } else if constexpr (R == 2) {
                     if (have[0]) *reinterpret_cast<uint16_t *>(pa) = (uint16_t)E[0];
                     if (have[1]) *reinterpret_cast<uint16_t *>(pb) = (uint16_t)(E[0] >> 16);
                 } else {
@@ -336,17 +353,17 @@ dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
                 // traceback kernel picks the terminal cell out of them
                 const int jcol = t - lane;
                 if (jcol == n[0] && have[0]) {
-                    uint16_t *eb = reinterpret_cast<uint16_t *>(tb[0] - (int64_t)16 * ROWW - lane * R) + lane * R;
+                    uint16_t *eb = reinterpret_cast<uint16_t *>(tb[0] - (int64_t)16 * ROWW - lane * LB) + lane * R;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        eb[r] = (uint16_t)Mr[r]; eb[ROWW + r] = (uint16_t)Xr[r]; eb[2 * ROWW + r] = (uint16_t)Yr[r];
+                        eb[r] = (uint16_t)Mr[r]; eb[32 * R + r] = (uint16_t)Xr[r]; eb[64 * R + r] = (uint16_t)Yr[r];
                     }
                 }
                 if (jcol == n[1] && have[1]) {
-                    uint16_t *eb = reinterpret_cast<uint16_t *>(tb[1] - (int64_t)16 * ROWW - lane * R) + lane * R;
+                    uint16_t *eb = reinterpret_cast<uint16_t *>(tb[1] - (int64_t)16 * ROWW - lane * LB) + lane * R;
 #pragma unroll
                     for (int r = 0; r < R; ++r) {
-                        eb[r] = (uint16_t)(Mr[r] >> 16); eb[ROWW + r] = (uint16_t)(Xr[r] >> 16); eb[2 * ROWW + r] = (uint16_t)(Yr[r] >> 16);
+                        eb[r] = (uint16_t)(Mr[r] >> 16); eb[32 * R + r] = (uint16_t)(Xr[r] >> 16); eb[64 * R + r] = (uint16_t)(Yr[r] >> 16);
                     }
                 }
             }
@@ -387,8 +404,8 @@ dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pa
             // paired kernel: the 32-bit kernels' table (32 R bytes per row, matrix-row order, true bytes);
             // half-lane kernel: 64 R bytes per row, row pairs interleaved, biased words
             // (compact form, four bits per cell: R >= 4 rows per half-lane and no X <-> Y, as in dp_wf16_kernel)
-            const bool nibf = !paired && R >= 4 && !prm.xy;
-            const WalkGeom g = paired ? WalkGeom{5 + rsh, rsh, -1, 0u, -1}
+            const bool nibf = !prm.xy && (paired || R >= 4);
+            const WalkGeom g = paired ? WalkGeom{5 + rsh, rsh, -1, 0u, nibf ? 0 : -1}
                                       : WalkGeom{6 + rsh, rsh, R >= 2 ? rsh : -1, R >= 2 ? prm.h.tbk * 0x01010101u : 0u, nibf ? rsh : -1};
             int st = s.len;                                  // half-lane kernel: the terminal state travels in slot.len
             if (paired) {                                    // paired kernel: last-column states at the head of the table
