@@ -6,23 +6,13 @@ import torch
 from dbga_b200 import Aligner
 from dbga_b200.synth import synth_batch
 
-def cfg5_pair(n=1_000_000, n_bubbles=10, seed=1):
-    rng = np.random.default_rng(seed)
-    a = rng.integers(0, 4, n, dtype=np.uint8)
-    b = a.copy()
-    # very low background divergence
-    m = rng.random(n) < 0.0005
-    b[m] = (b[m] + rng.integers(1, 4, int(m.sum()), dtype=np.uint8)) & 3
-    pos = np.sort(rng.choice(np.arange(50_000, n - 50_000, 60_000), n_bubbles, replace=False))
-    for p in pos:
-        L = int(rng.integers(2000, 5000))
-        mm = rng.random(L) < 0.35
-        seg = b[p:p + L].copy()
-        seg[mm] = (seg[mm] + rng.integers(1, 4, int(mm.sum()), dtype=np.uint8)) & 3
-        b[p:p + L] = seg
-    lut = np.frombuffer(b"ACGT", np.uint8)
-    buf = np.concatenate([lut[a], lut[b]])
-    return buf, np.array([0, n, 2 * n], np.int64)
+from dbga_b200.synth import synth_long_pair
+
+
+def cfg5_pair(seed=3):
+    """BASELINE config [4]: 1 Mb pair, ten planted 2-5 kb bubbles with 30 % substitutions and 4 % indel
+    events (dbga_b200.synth.synth_long_pair; the pair tests/test_gpu_configs.py diffs against the oracle)."""
+    return synth_long_pair(seed=seed)
 
 def run(al, buf, offs, k, label, reps=3):
     d = torch.from_numpy(np.concatenate([buf, np.zeros(64, np.uint8)])).cuda()
@@ -56,12 +46,11 @@ if __name__ == "__main__":
         buf, offs = synth_batch(P, 30000, 0.004, 0.001, seed=4)
         run(al, buf, offs, 11, f"cfg4 sample: {P} x 30 kb pairs, k=11")
     if "cfg5" in which:
-        for seed in range(1, 6):
+        for seed in (3, 8, 9):                     # seeds the oracle accepts (1, 2, 4-7 are cycles: the reference raises)
             buf, offs = cfg5_pair(seed=seed)
-            full = run(al, buf, offs, 15, f"cfg5: 1 Mb pair, 10 planted 2-5 kb bubbles, k=15, seed {seed}", reps=2)
+            full = run(al, buf, offs, 15, f"cfg5: 1 Mb pair, 10 planted indel-rich 2-5 kb bubbles, k=15, seed {seed}", reps=3)
             if full.status[0] == 0:
                 a0, a1 = full.alignment(0)
-                n = 1_000_000
+                n = int(offs[1])
                 ok = (a0.replace("-", "").encode() == buf[:n].tobytes()) and (a1.replace("-", "").encode() == buf[n:].tobytes())
-                print("cfg5 degap check:", ok, "aligned length", len(a0))
-                break
+                print(json.dumps({"cfg5_seed": seed, "degap_check": bool(ok), "aligned_length": len(a0)}))
