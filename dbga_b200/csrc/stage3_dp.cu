@@ -241,7 +241,12 @@ dp_thread_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ 
 // previous row (T, U) and the per-column score selectors live in registers -- the column
 // loop is fully unrolled, so all indexing is static -- and only the traceback words go to
 // shared memory.  Saves the five shared-memory accesses per cell of the generic kernel.
-template <int NG, bool XY>
+// ENDT: the terminal cell is chosen with the same state priorities as the predecessors (end_order ==
+// pred_order, the default convention): its winner and score are then max(M, X, Y)[m][n] itself, which
+// the sweep keeps anyway (T[n]).  The row of T is parked in shared memory when a lane passes its own
+// last row (stores on the idle LSU pipe) instead of picking M, X, Y out of every cell with a compare
+// and three selects on the ALU pipe -- a quarter of the sweep's ALU instructions.
+template <int NG, bool XY, bool ENDT>
 __global__ void __launch_bounds__(TINY_THREADS)
 dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                      const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, DpParams prm,
@@ -258,6 +263,7 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     }
     __syncthreads();
     uint32_t *tbw = reinterpret_cast<uint32_t *>(smem_i) + tid;       // [row][word][thread]
+    int *trow = smem_i + NB * NG * TH + tid;                          // ENDT: [column][thread], T of the lane's last row
     const unsigned int count = *count_dev;
     for (unsigned int base = blockIdx.x * TH; base < count; base += gridDim.x * TH) {
         const unsigned int item = base + tid;
@@ -323,16 +329,26 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                     if (XY) un = max(un, Yn + gmo);
                     T[j] = __vimax3_s32(Mn, Xn, Yn);
                     U[j] = un;
-                    if (ncap == j) { eM = Mn; eX = Xn; eY = Yn; }
+                    if (!ENDT) { if (ncap == j) { eM = Mn; eX = Xn; eY = Yn; } }
                     diag = Tj; Ml = Mn; Yl = Yn; Xl = Xn;
                 }
                 tbrow[g * TH] = word;
             }
             tbrow += NG * TH;
+            if (ENDT && i == m) {
+#pragma unroll
+                for (int j = 1; j <= NB; ++j) trow[(j - 1) * TH] = T[j];
+            }
         }
         if (have) {
             int st, score;
-            pick_end(eM, eX, eY, prm, st, score);
+            if (ENDT) {
+                const int tn = trow[(n - 1) * TH];               // max(M, X, Y)[m][n], the winner's priority in its low bits
+                st = prio_to_state(tn & 3, prm);
+                score = strip(tn) >> 6;
+            } else {
+                pick_end(eM, eX, eY, prm, st, score);
+            }
             const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
                                   ((uint32_t)prio_to_state(2, prm) << 4);
             int i = m, j = n, len = 0;
@@ -358,14 +374,16 @@ dp_thread_reg_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
 template <int NG>
 static void launch_dp_thread_reg_t(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                    const unsigned int *count_dev, DpParams prm, uint8_t *strbuf, int grid, cudaStream_t st) {
-    const size_t smem = (size_t)(4 * NG) * NG * 4 * TINY_THREADS;
-    if (prm.xy) {
-        allow_max_dyn_smem(dp_thread_reg_kernel<NG, true>);
-        dp_thread_reg_kernel<NG, true><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
-    } else {
-        allow_max_dyn_smem(dp_thread_reg_kernel<NG, false>);
-        dp_thread_reg_kernel<NG, false><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf);
-    }
+    const size_t smem = (size_t)(4 * NG) * (NG + 1) * 4 * TINY_THREADS;      // traceback words + one row of T per thread
+    const bool endt = prm.endM * TAGMUL == prm.tagM && prm.endX * TAGMUL == prm.tagX && prm.endY * TAGMUL == prm.tagY;
+#define DBGA_REG_LAUNCH(XYF, EF)                                                                                   \
+    do {                                                                                                           \
+        allow_max_dyn_smem(dp_thread_reg_kernel<NG, XYF, EF>);                                                     \
+        dp_thread_reg_kernel<NG, XYF, EF><<<grid, TINY_THREADS, smem, st>>>(seqs, pairs, slots, list, count_dev, prm, strbuf); \
+    } while (0)
+    if (prm.xy) { if (endt) DBGA_REG_LAUNCH(true, true); else DBGA_REG_LAUNCH(true, false); }
+    else { if (endt) DBGA_REG_LAUNCH(false, true); else DBGA_REG_LAUNCH(false, false); }
+#undef DBGA_REG_LAUNCH
 }
 
 static size_t dp_thread_smem(int bound, bool tb_in_smem) {
