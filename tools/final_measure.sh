@@ -5,6 +5,7 @@ set -x
 T=${1:-final}
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -3 > gpurun_out/${T}_tests.log
+python __graft_entry__.py --smoke > gpurun_out/${T}_smoke.log 2>&1
 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
 python tools/dp_bench.py 8 16 32 64 128 256 512 1024 2048 4096 8192 > gpurun_out/${T}_dp_bench.jsonl 2>&1
