@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdbga_b200.so")
-SOURCES = ["stage12_small.cu", "stage1_kmer.cu", "stage2_anchor.cu", "stage3_dp.cu", "stage3_dp16.cu", "assemble.cu", "pack.cu", "fasta_io.cu", "kmer_stats.cu", "intpeak.cu", "api.cu"]
+SOURCES = ["hostpack.cpp", "stage12_small.cu", "stage1_kmer.cu", "stage2_anchor.cu", "stage3_dp.cu", "stage3_dp16.cu", "assemble.cu", "pack.cu", "fasta_io.cu", "kmer_stats.cu", "intpeak.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -36,7 +36,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(CSRC, src.replace(".cu", ".o"))
+        o = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
             jobs.append([nvcc] + NVCC_FLAGS + ["-c", s, "-o", o])

@@ -15,6 +15,8 @@
 
 using namespace dbga;
 
+namespace dbga { bool host_pack_seq(const uint8_t *src, int64_t len, uint32_t *dst); }   // hostpack.cpp
+
 namespace {
 
 struct DevBuf {
@@ -340,7 +342,9 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                 // medium: split the keys over 2..8 table partitions that take turns in shared memory
                 int parts = 0;
                 uint32_t pcap = 0;
-                if (k <= 31 && N0 < 65000 && N1 < 65000) {
+                // (N1 < 32768: the medium kernel's packed word counts seq-2 occurrences in bits 16-30 under the
+                //  "repeated in seq1" flag in bit 31; a k-mer with more occurrences than that must not carry into it)
+                if (k <= 31 && N0 < 65000 && N1 < 32768) {
                     for (int g = 2; g <= 8 && !parts; ++g) {
                         uint64_t w = keys * 170 / 100 / g + 64;       // 1.7 x the expected keys per partition
                         uint32_t gr = 256;
@@ -1441,18 +1445,7 @@ int64_t dbga_pack_ascii(const uint8_t *seqs, const int64_t *offsets, int64_t num
             const uint8_t *src = seqs + offsets[j];
             const int64_t len = offsets[j + 1] - offsets[j];
             uint32_t *dst = packed + (offsets[j] >> 4) + j;
-            bool b = false;
-            for (int64_t w = 0; w * 16 < len; ++w) {
-                const int64_t nv = std::min<int64_t>(16, len - 16 * w);
-                uint32_t word = 0;
-                for (int64_t i = 0; i < nv; ++i) {
-                    const uint8_t c = src[16 * w + i];
-                    const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
-                    b |= "ACGT"[code] != (char)c;
-                    word |= code << (2 * i);
-                }
-                dst[w] = word;
-            }
+            const bool b = host_pack_seq(src, len, dst);
             nbad += b;
         }
         bad += nbad;

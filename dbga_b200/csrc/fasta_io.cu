@@ -20,6 +20,8 @@
 
 #include "common.cuh"
 
+namespace dbga { bool host_pack_seq(const uint8_t *src, int64_t len, uint32_t *dst); }   // hostpack.cpp
+
 namespace {
 
 template <class Fn> void par_for(int64_t n, int threads, int64_t grain, Fn fn) {
@@ -166,33 +168,7 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
             for (int64_t i = 0; i < len; ++i) dst[i] = (uint8_t)(dst[i] - (((uint8_t)(dst[i] - 'a') < 26u) << 5));   // upper-case (vectorised)
             if (f->packed) {
                 uint32_t *pw = f->packed + (f->offsets[(size_t)r] >> 4) + r;
-                uint32_t diff = 0;
-                int64_t w = 0;
-                for (; 16 * (w + 1) <= len; ++w) {          // 16 bases -> one word, four bytes at a time
-                    uint32_t word = 0;
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t x;
-                        memcpy(&x, dst + 16 * w + 4 * j, 4);
-                        const uint32_t codes = ((x >> 1) ^ (x >> 2)) & 0x03030303u;
-                        // the base each code stands for, rebuilt with byte arithmetic: A C G T = 65 67 71 84
-                        const uint32_t lo = codes & 0x01010101u, hi = (codes >> 1) & 0x01010101u;
-                        const uint32_t expect = 0x41414141u + 2u * lo + 6u * hi + 11u * (lo & hi);
-                        diff |= expect ^ x;
-                        word |= ((codes * 0x01041040u) >> 24) << (8 * j);
-                    }
-                    pw[w] = word;
-                }
-                if (16 * w < len) {
-                    uint32_t word = 0;
-                    for (int64_t i = 16 * w; i < len; ++i) {
-                        const uint8_t c = dst[i];
-                        const uint32_t code = ((c >> 1) ^ (c >> 2)) & 3u;
-                        diff |= (uint32_t)("ACGT"[code] != (char)c);
-                        word |= code << (2 * (i - 16 * w));
-                    }
-                    pw[w] = word;
-                }
-                nbad += diff != 0;
+                nbad += dbga::host_pack_seq(dst, len, pw);          // hostpack.cpp: 32 bases per AVX2 step
             }
         }
         bad += nbad;

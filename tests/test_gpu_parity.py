@@ -486,3 +486,21 @@ def test_wide_kmers_vs_oracle(aligner, k):
     for i in range(20):
         if st[i] == O.OK:
             assert (d0[i], d1[i], sh[i]) == O.kmer_stats(*pairs[i], k), i
+
+
+def test_long_homopolymer_does_not_wrap_the_medium_counter(aligner):
+    """A k-mer repeated in seq1 and occurring more than 32 768 times in seq2 (a 33 kb homopolymer stretch):
+    the medium-pair kernel's packed counter would carry into its "repeated in seq1" flag, so such pairs
+    (seq2 longer than 32 767 k-mers) take the global-table path.  Stages 1-2 against the oracle."""
+    rng = random.Random(91)
+    r1, r2 = rand_seq(rng, 4000), rand_seq(rng, 4000)
+    s0 = r1 + "A" * 33000 + r2
+    s1 = mutate(rng, r1, 0.01, 0.002) + "A" * 33200 + mutate(rng, r2, 0.01, 0.002)
+    for k in (11, 15):
+        res = aligner.align_pairs([(s0, s1), (s1, s0)], k, stages=2, want_graph=True)
+        for i, (a, b) in enumerate(((s0, s1), (s1, s0))):
+            ref = CO.align_pair(a, b, k, stages=2, want_graph=True)
+            assert res.status[i] == ref.status
+            assert np.array_equal(res.anchors(i), ref.anchors)
+            nd0, nd1 = res.graph_flags(i)
+            assert np.array_equal(nd0, ref.nondup0) and np.array_equal(nd1, ref.nondup1)
