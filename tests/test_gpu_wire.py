@@ -184,3 +184,50 @@ def test_multi_entry_two_contexts(aligner, batch):
             assert r1.alignment(5) == full.alignment(lo1 + 5)
     finally:
         m.close()
+
+
+def test_wire_forms_edge_cases(aligner):
+    """Empty and one-pair batches, sequences shorter than a packed word, pairs without anchors, cycles,
+    k larger than a sequence and non-ACGT input in every result form; packed input that does not start
+    at offset 0; more shards than pairs."""
+    from dbga_b200 import MultiAligner, _lib, pack_ascii
+    from dbga_b200.batch import pack_pairs
+    rnd = O.synth_pair(300, 0.03, 0.01, 77)
+    pairs = [("ACGTTGCAAC", "ACGTAGCAAC"), ("ACG", "ACG"), ("AAAAAAAAAAAA", "AAAAAAAAAAAAAA"), rnd,
+             ("ACGTACGTAGCTAGCTAGCATCGATCGATCAGCTACGAT", "TTTTTGGGGGCCCCCAAAAATTTTTGGGGGCCCCCAAAAA"),
+             ("AC", "ACGTACGT"), ("ACGTNACGTACGT", "ACGTAACGTACGT"), O.synth_pair(900, 0.02, 0.004, 3)]
+    for k in (3, 5):
+        buf, offs = pack_pairs(pairs)
+        full = aligner.align_buffers(buf, offs, aligner.params(k))
+        assert set(full.status.tolist()) >= {O.OK, O.K_INVALID, O.BAD_CHAR}
+        lean = aligner.align_buffers(buf, offs, aligner.params(k, flags=_lib.FLAG_NO_RUNS | _lib.FLAG_SOP))
+        _same_rows(full, lean)
+        raw = aligner.align_buffers(buf, offs, aligner.params(k, flags=_lib.FLAG_COMPACT_ROWS), unpack=False)
+        off, r0, r1 = aligner.expand_rows(buf, offs, raw)
+        assert np.array_equal(off, full.aln_off) and np.array_equal(r0, full.aln0) and np.array_equal(r1, full.aln1)
+        # one pair at a time, every form
+        for i, p in enumerate(pairs):
+            b1, o1 = pack_pairs([p])
+            one = aligner.align_buffers(b1, o1, aligner.params(k))
+            assert one.status[0] == full.status[i] and one.alignment(0) == full.alignment(i)
+            raw1 = aligner.align_buffers(b1, o1, aligner.params(k, flags=_lib.FLAG_COMPACT_ROWS), unpack=False)
+            _, x0, x1 = aligner.expand_rows(b1, o1, raw1)
+            assert (x0.tobytes().decode(), x1.tobytes().decode()) == full.alignment(i)
+    # packed input: the pairs that can be packed, as a window of a larger batch (offsets[0] != 0)
+    good = [p for p in pairs if "N" not in p[0]]
+    buf, offs = pack_pairs(good)
+    words = pack_ascii(buf, offs)
+    ref = aligner.align_buffers(buf, offs, aligner.params(3))
+    win = aligner.align_buffers(buf, offs[4:], aligner.params(3))                   # pairs 2.. as their own batch (ASCII)
+    assert np.array_equal(win.status, ref.status[2:]) and win.alignment(1) == ref.alignment(3)
+    m = MultiAligner([0] * 12)                                                     # more shards than pairs
+    try:
+        for packed in (None, words):
+            shards = m.align_buffers(buf if packed is None else None, offs, aligner.params(3), packed=packed)
+            assert np.array_equal(np.concatenate([r.status for _, r in shards]), ref.status)
+            assert np.array_equal(np.concatenate([r.aln0 for _, r in shards]), ref.aln0)
+            assert np.array_equal(np.concatenate([r.aln1 for _, r in shards]), ref.aln1)
+    finally:
+        m.close()
+    empty = aligner.align_buffers(np.zeros(0, np.uint8), np.zeros(1, np.int64), aligner.params(3, flags=_lib.FLAG_COMPACT_ROWS | _lib.FLAG_SOP))
+    assert len(empty) == 0
