@@ -123,6 +123,10 @@ struct dbga_ctx {
     // sleep instead (cudaEventBlockingSync events, condition variable between producer and consumer).
     bool spin = true;
     cudaEvent_t ev_block = nullptr;
+    // long-segment DP (strip kernel + its traceback) runs beside the other DP classes: a few warps with a long
+    // dependent chain on one stream, the throughput kernels on the other
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -265,6 +269,10 @@ int make_dp_params(dbga_ctx *ctx, const dbga_params &p) {
         h.qy0 = 4 * (d.ge_raw - d.go_raw - h.off);
         h.per_step = std::max(0, smax) + 2 * d.ge_raw;
         h.ulimit = 8191 + h.off - 41;
+        // row strips in re-anchored frames (dp_wf16s_kernel): a frame must hold per_step * max(strip rows, block
+        // columns) above its anchor, and a frame-to-frame step must fit 16 bits
+        h.strip = !d.xy && (long long)h.per_step * (std::max(S16_ROWS, S16_CB) + 80) + S16_F0 + 300 <= h.ulimit &&
+                  4LL * h.per_step * S16_CB + 4000 <= 32767 && getenv("DBGA_NO_STRIPS") == nullptr ? 8 : 0;
     }
     return DBGA_SUCCESS;
 }
@@ -284,6 +292,12 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     ctx->no_anchors = no_anchors;
     int rc = make_dp_params(ctx, *params);
     if (rc != DBGA_SUCCESS) return rc;
+    // strip height of the long-segment kernel: with few pairs a long segment is latency-bound (a lone warp per SM
+    // sub-partition), so halve the step; with many the taller strip amortises the per-step overhead
+    if (ctx->dp.h.strip) {
+        ctx->dp.h.strip = P >= MANY_PAIRS ? 8 : 4;
+        if (const char *e = getenv("DBGA_STRIP_R")) { const int r = atoi(e); if (r == 4 || r == 8) ctx->dp.h.strip = r; }
+    }
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
     const int k = no_anchors ? 1 : params->k;
     const bool full = params->want_graph != 0 && !no_anchors;
@@ -486,13 +500,14 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         ctx->grid_cluster = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->num_sms / WF_CLUSTER, g));
     }
     const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
-    const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells;
+    // (with the strip kernel the long class also takes what the one-pass packed kernel cannot hold)
+    const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells || (ctx->dp.h.strip && any_non_tiny && mx0 > 256);
     if (!any_non_tiny) ctx->grid_warp = 0;
     if (!any_cta) ctx->grid_cta = ctx->grid_cluster = 0;
     if (params->stages == 3) {
         RESERVE(d_str, 2 * std::max<int64_t>(ctx->total_bytes, 1) + 16);      // + slack: the assembler reads whole words
         if (ctx->grid_warp) RESERVE(d_bnd_w, (size_t)ctx->grid_warp * 2 * ctx->bnd_stride_warp * 16);
-        if (ctx->grid_cta) RESERVE(d_bnd_c, (size_t)ctx->grid_cta * 2 * ctx->bnd_stride_cta * 16);
+        if (ctx->grid_cta && !ctx->dp.h.strip) RESERVE(d_bnd_c, (size_t)ctx->grid_cta * 2 * ctx->bnd_stride_cta * 16);
         RESERVE(d_aln0, std::max<int64_t>(ctx->total_bytes, 1));
         RESERVE(d_aln1, std::max<int64_t>(ctx->total_bytes, 1));
     }
@@ -543,6 +558,7 @@ int run_pipeline(dbga_ctx *ctx) {
     for (int c = 0; c < NUM_TINY; ++c) pools.tiny_bound[c] = ctx->tiny_bound[c];
     pools.list_cap = ctx->slots_cap;
     pools.warp_max_cells = ctx->warp_max_cells;
+    pools.strip_ok = ctx->dp.h.strip; pools.strip_per_step = ctx->dp.h.per_step; pools.strip_ulimit = ctx->dp.h.ulimit;
     Counters *ctr = (Counters *)ctx->d_ctr.p;
     PairDesc *pairs = (PairDesc *)ctx->d_pairs.p;
     PairOut *pout = (PairOut *)ctx->d_pout.p;
@@ -595,6 +611,26 @@ int run_pipeline(dbga_ctx *ctx) {
         }
     }
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[3], st));
+    const bool strips = seg && ctx->grid_cta && ctx->dp.h.strip;
+    if (strips) {
+        // long segments as packed row strips, one warp per strip; any grid is correct (device-wide ticket).  Forked
+        // onto the side stream: joined again before the assembler.
+        static std::atomic<uint32_t> run_nonce{(uint32_t)std::chrono::steady_clock::now().time_since_epoch().count() | 1u};
+        uint32_t nonce = run_nonce.fetch_add(1u);
+        if (nonce == 0u) nonce = run_nonce.fetch_add(1u);
+        cudaStream_t ss = ctx->side_stream;
+        const bool seen = ctx->seen_work[CLS_CTA];
+        DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, st));
+        DBGA_CUDA_CHECK(cudaStreamWaitEvent(ss, ctx->ev_fork, 0));
+        DBGA_CUDA_CHECK(launch_dp_strips16(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
+                                           &ctr->n_cls[CLS_CTA], ctr, seen ? ctx->num_sms * 16 : ctx->num_sms,
+                                           ctx->dp, (uint8_t *)ctx->d_tb.p, nonce, ss));
+        DBGA_CUDA_CHECK(launch_dp_traceback16(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, CLS_CTA, CLS_CTA,
+                                              seen ? ctx->num_sms * 4 : 8, ctx->dp, (uint8_t *)ctx->d_str.p,
+                                              (const uint8_t *)ctx->d_tb.p, ss));
+        DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev_join, ss));
+        ctx->launches += 2;
+    }
     if (seg) {
         {   // tiny classes: one launch per class that fits the register-resident kernel (bound <= 16),
             // one shared-memory launch for the rest
@@ -634,12 +670,12 @@ int run_pipeline(dbga_ctx *ctx) {
         if (ctx->grid_warp && ctx->dp.h.ok) {
             bool seen = false;
             for (int cls = CLS_WARP2; cls <= CLS_WARP16; ++cls) seen = seen || ctx->seen_work[cls];
-            DBGA_CUDA_CHECK(launch_dp_traceback16(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls,
+            DBGA_CUDA_CHECK(launch_dp_traceback16(seqs, pairs, pools.slots, pools.lists, pools.list_cap, ctr->n_cls, CLS_WARP2, CLS_WARP16,
                                                   seen ? ctx->num_sms * 16 : ctx->num_sms, ctx->dp, (uint8_t *)ctx->d_str.p,
                                                   (const uint8_t *)ctx->d_tb.p, st));
             ctx->launches += 1;
         }
-        if (ctx->grid_cta) {
+        if (ctx->grid_cta && !ctx->dp.h.strip) {
             const bool seen = ctx->seen_work[CLS_CTA];
             DBGA_CUDA_CHECK(launch_dp_long(seqs, pairs, pools.slots, pools.lists + (int64_t)CLS_CTA * pools.list_cap,
                                            &ctr->n_cls[CLS_CTA], seen ? ctx->grid_cluster : std::min(ctx->grid_cluster, 2),
@@ -649,6 +685,7 @@ int run_pipeline(dbga_ctx *ctx) {
             ctx->launches += 2;
         }
     }
+    if (strips) DBGA_CUDA_CHECK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     DBGA_CUDA_CHECK(cudaEventRecord(ctx->ev[4], st));
     dbga_ctx::MetaPtrs mp = ctx->ext;
     if (!ctx->use_ext) {
@@ -1217,6 +1254,9 @@ int create_ctx(int device, dbga_ctx **out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
     if (cudaEventCreateWithFlags(&ctx->ev_block, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return DBGA_ERR_CUDA; }
     *out = ctx;
     return DBGA_SUCCESS;
 }
@@ -1252,6 +1292,9 @@ void dbga_destroy(dbga_ctx *ctx) {
     for (HostBuf *b : hbs) if (b->p) cudaFreeHost(b->p);
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

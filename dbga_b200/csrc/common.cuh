@@ -97,6 +97,7 @@ struct Dp16 {
     int32_t ulimit;           // largest H^ the encoding can hold
     int32_t ok;
     int32_t pair;             // two segments per warp (dp_wf16p_kernel) for segments of up to 512 rows
+    int32_t strip;            // long segments as row strips in per-strip, per-column-block frames (dp_wf16s_kernel): rows per half-lane (8 or 4), 0 = off
 };
 
 struct DpParams {
@@ -126,8 +127,16 @@ __host__ __device__ inline bool wf16_ok(const Dp16 &h, int m, int n, int R16) {
 // all of whose cells -- padding rows and the partner's extra columns included -- stay below
 // the ceiling).  The open-ended class splits at 512 rows.
 constexpr int WF16_PAIR = 64;
+// Long segments (CLS_CTA) in the packed form: row strips of S16_ROWS rows, one warp per strip, strips of a
+// segment pipelined through boundary rows in HBM/L2.  Values are kept relative to a frame base that is
+// re-anchored per strip every S16_CB columns (on the strip's top boundary row), so the int16 range only has
+// to hold per_step * max(S16_ROWS, S16_CB) whatever the segment's size.  S16_F0: where a frame puts its anchor.
+constexpr int S16_ROWS = 512;                // the larger of the two strip heights (64 half-lanes x 8 or 4 rows)
+constexpr int S16_CB = 256;
+constexpr int S16_F0 = 300;
 __host__ __device__ inline int wf16_pick(const Dp16 &h, int cls, int m, int n) {
     if (!h.ok) return 0;
+    if (cls == CLS_CTA) return h.strip;              // rows per half-lane of the strip kernel (0: 32-bit kernels)
     if (h.pair) {
         const int R = wf_rows_per_lane(cls);
         // (not in the open-ended class: 16 rows per lane for two segments cost more registers than they save)

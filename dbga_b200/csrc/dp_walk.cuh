@@ -60,6 +60,7 @@ __device__ __forceinline__ uint32_t code_char(uint32_t code) { return __byte_per
 // two matrix rows per byte; a lane's R bytes of a step row hold, per group of four rows r..r+3 of its two
 // half-lanes, [low (r, r+1), low (r+2, r+3), high (r, r+1), high (r+2, r+3)].  A step row is then half as
 // many bytes as it covers matrix rows.
+constexpr int WALK_WIN_ROWS = 64;
 struct WalkGeom {
     int roww_sh, rdiv_sh, pr_sh;
     uint32_t bias4;
@@ -80,7 +81,7 @@ __device__ __forceinline__ int wf_col_nib(int c, int nib_sh) {
     return ((c - q) >> 1) + 4 * (r >> 2) + 2 * hh + ((r >> 1) & 1);
 }
 
-// One warp walks; every lane runs the same walk (uniform control flow).  win: 32 x 64 bytes of
+// One warp walks; every lane runs the same walk (uniform control flow).  win: WALK_WIN_ROWS x 64 bytes of
 // shared memory owned by the warp.  st: state chosen at the terminal cell.  pmap: packed table
 // tag -> state (0 = M, 1 = X, 2 = Y).  Rows are written reversed at ox / oy; returns the
 // number of alignment columns.
@@ -89,19 +90,20 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
                                             int st, uint32_t pmap, uint8_t *__restrict__ ox, uint8_t *__restrict__ oy, int lane,
                                             const WalkGeom g) {
     constexpr int WIN_W = 64;                        // traceback window width in bytes (every row is >= 64 bytes)
+    constexpr int WIN_ROWS = WALK_WIN_ROWS;          // step rows per window
     const int roww_mask = (1 << g.roww_sh) - 1;
     const bool nib = g.nib_sh >= 0;
     const int rowb_sh = nib ? g.roww_sh - 1 : g.roww_sh;         // log2 of the bytes per step row
     int i = m, j = n, len = 0;
-    // window: 32 consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
+    // window: WIN_ROWS consecutive step rows x 64 bytes of one (pass, warp) block.  Every lane
     // runs the same walk (uniform control flow).  Only the kind of each step is kept, as
     // two bit masks per group of 32 steps (bit t of mY: step t consumes a seq-1 base, of
     // mX: a seq-2 base); a full group is turned into the two rows' characters by all 32
     // lanes at once, so the sequence loads stay off the walk's dependency chain: a group's
     // characters are loaded when it is full and stored when the next one is (or at the end).
-    // In state M the 32 lanes probe the next 32 cells of the diagonal together and the
-    // walk jumps over the whole run of M -> M steps (most of the path between similar
-    // sequences); everything else goes one cell at a time.
+    // The 32 lanes probe the next 32 cells in the current state's direction together and the walk
+    // jumps over the whole run of steps that stay in the state (M -> M along the diagonal: most of
+    // the path between similar sequences; a gap up a column or along a row) plus the step that leaves it.
     int win_blk = -1, win_row_hi = 0, win_col_lo = 0;
     uint32_t mY = 0, mX = 0;
     int pos = 0, gbase = 0;
@@ -158,39 +160,44 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
         const int blk = i0 >> g.roww_sh, cb = i0 & roww_mask;      // (pass * GW + warp), l * R + r
         const int row = j + (cb >> g.rdiv_sh);
         const int ccol = nib ? wf_col_nib(cb, g.nib_sh) : cb;       // window position of the cell's byte (byte form: by matrix row)
-        if (blk != win_blk || (unsigned)(win_row_hi - row) >= 32u || (unsigned)(ccol - win_col_lo) >= (unsigned)WIN_W) {
+        if (blk != win_blk || (unsigned)(win_row_hi - row) >= (unsigned)WIN_ROWS || (unsigned)(ccol - win_col_lo) >= (unsigned)WIN_W) {
             __syncwarp();
             win_blk = blk; win_row_hi = row;
             win_col_lo = max(0, (ccol & ~31) - 32);
-            const int rr = row - lane;
-            uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
-            if (rr >= 1) {
-                const uint4 *p = reinterpret_cast<const uint4 *>(tb + (((int64_t)blk * tb_rows + rr) << rowb_sh) + win_col_lo);
-                a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
+#pragma unroll
+            for (int hrow = 0; hrow < WIN_ROWS; hrow += 32) {
+                const int rr = row - hrow - lane;
+                uint4 a = make_uint4(0, 0, 0, 0), b = a, c4 = a, d4 = a;
+                if (rr >= 1) {
+                    const uint4 *p = reinterpret_cast<const uint4 *>(tb + (((int64_t)blk * tb_rows + rr) << rowb_sh) + win_col_lo);
+                    a = p[0]; b = p[1]; c4 = p[2]; d4 = p[3];
+                }
+                uint4 *dst = reinterpret_cast<uint4 *>(&win[hrow + lane][0]);
+                dst[0] = a; dst[1] = b; dst[2] = c4; dst[3] = d4;
             }
-            uint4 *dst = reinterpret_cast<uint4 *>(&win[lane][0]);
-            dst[0] = a; dst[1] = b; dst[2] = c4; dst[3] = d4;
             __syncwarp();
         }
-        if (st == 0) {
-            const int il = i0 - lane, jl = j - lane;
-            bool ok = false;
-            if (il >= 0 && jl >= 1) {
-                const int bl = il >> g.roww_sh, cl = il & roww_mask;
-                const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh)));
-                const unsigned dc = (unsigned)((nib ? wf_col_nib(cl, g.nib_sh) : cl) - win_col_lo);
-                if (bl == win_blk && dr < 32u && dc < (unsigned)WIN_W)
-                    ok = ((pmap >> (2 * (cell(dr, col_of(cl) - win_col_lo, cl) & 3u))) & 3u) == 0u;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-            const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
-            if (c > 0) { emit(0, c); i -= c; j -= c; continue; }
+        // Lane l looks at the cell l steps further along the current state's direction (M: the diagonal, X: up the
+        // column, Y: along the row): does the path stay in this state there?  The walk takes the whole run of
+        // cells that do, plus the cell that ends it (still consumed in this state; its tag names the next one).
+        const int di = st != 2, dj = st != 1;
+        const int il = i0 - lane * di, jl = j - lane * dj;
+        uint32_t nxt = 3u;                           // 3: outside the matrix or the window
+        if (il >= 0 && jl >= 1) {
+            const int bl = il >> g.roww_sh, cl = il & roww_mask;
+            const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh)));
+            const int wc = col_of(cl);
+            const unsigned dc = (unsigned)((nib ? wc : cl) - win_col_lo);
+            if (bl == win_blk && dr < (unsigned)WIN_ROWS && dc < (unsigned)WIN_W)
+                nxt = (pmap >> (2 * ((cell(dr, wc - win_col_lo, cl) >> (2 * st)) & 3u))) & 3u;
         }
-        const uint32_t d = cell(win_row_hi - row, col_of(cb) - win_col_lo, cb);
-        emit(st, 1);
-        const uint32_t tag = (d >> (2 * st)) & 3u;
-        i -= (st != 2); j -= (st != 1);
-        st = (int)((pmap >> (2 * tag)) & 3u);
+        const uint32_t bal = __ballot_sync(0xffffffffu, nxt == (uint32_t)st);
+        const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
+        const uint32_t nx = __shfl_sync(0xffffffffu, nxt, c & 31);
+        const int take = c + ((c < 32 && nx != 3u) ? 1 : 0);       // lane 0's cell is inside the window: take >= 1
+        emit(st, take);
+        i -= take * di; j -= take * dj;
+        if (c < 32 && nx != 3u) st = (int)nx;
     }
     if (pos) flush(pos);
     drain();

@@ -25,7 +25,8 @@ struct Counters {
     unsigned long long total_aln;
     unsigned long long total_tiles;    // copy tiles of the assembler
     unsigned int scan_ticket;          // assembler's layout pass: next block of pairs
-    unsigned int pad;
+    unsigned int long_max_m;           // most rows of any long (CLS_CTA) segment
+    unsigned long long long_ticket;    // strip kernel: next (strip, segment) work item
 };
 
 struct Pools {
@@ -36,6 +37,8 @@ struct Pools {
     int64_t list_cap;
     int32_t tiny_bound[NUM_TINY];          // class c holds segments with max(m, n) <= tiny_bound[c]
     int64_t warp_max_cells;                // larger segments get a whole CTA
+    int32_t strip_ok, strip_per_step, strip_ulimit;   // packed strip kernel available: what the one-pass packed kernel
+                                           // cannot hold joins the long class instead of the 32-bit warp kernel
 };
 
 // ---- stages 1+2 fused (pairs whose table fits in shared memory)
@@ -75,10 +78,14 @@ cudaError_t launch_dp_wavefront(const uint8_t *seqs, const PairDesc *pairs, Slot
 cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                                   const unsigned int *count_dev, int grid, int cls, DpParams prm, uint8_t *strbuf,
                                   uint8_t *tb, cudaStream_t st, int *launches);
-// traceback of everything the packed kernels processed, all four warp classes in one launch
+// traceback of everything the packed kernels processed in classes cls_lo..cls_hi, one launch
 cudaError_t launch_dp_traceback16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
-                                  int64_t list_cap, const unsigned int *counts_dev, int grid, DpParams prm,
+                                  int64_t list_cap, const unsigned int *counts_dev, int cls_lo, int cls_hi, int grid, DpParams prm,
                                   uint8_t *strbuf, const uint8_t *tb, cudaStream_t st);
+// packed row-strip kernel over the long class (prm.h.strip); traceback by launch_dp_traceback16
+cudaError_t launch_dp_strips16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                               const unsigned int *count_dev, Counters *ctr, int grid, DpParams prm, uint8_t *tb,
+                               uint32_t nonce, cudaStream_t st);
 cudaError_t launch_dp_long(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
                            const unsigned int *count_dev, int grid_clusters, int grid_ctas, unsigned int few, DpParams prm,
                            uint8_t *strbuf, uint8_t *tb, int4 *bnd, int64_t bnd_stride, cudaStream_t st);

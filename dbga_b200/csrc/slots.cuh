@@ -58,6 +58,15 @@ __device__ __forceinline__ void build_slots(int64_t pair, const PairDesc &pd, in
                     // one warp per segment, rows per lane chosen so that short segments still use
                     // all 32 lanes; huge segments (few pairs in the batch) get a whole CTA
                     cls = cells > pools.warp_max_cells ? CLS_CTA : (s.m <= 64 ? CLS_WARP2 : (s.m <= 128 ? CLS_WARP4 : (s.m <= 256 ? CLS_WARP8 : CLS_WARP16)));
+                    if (cls == CLS_WARP16 && pools.strip_ok) {
+                        // what the one-pass packed kernel cannot hold (wf16_ok: more than 1024 rows, or past the
+                        // int16 ceiling) runs as packed row strips with the long class, not on the 32-bit warp kernel
+                        const int r16 = s.m <= 512 ? 8 : 16;
+                        const int mp = ((s.m + 2 * r16 - 1) / (2 * r16)) * (2 * r16);
+                        const long long lim = mp < s.n + 1 ? mp : s.n + 1;
+                        if (mp > 64 * r16 || (long long)pools.strip_per_step * lim + 64 > (long long)pools.strip_ulimit) cls = CLS_CTA;
+                    }
+                    if (cls == CLS_CTA) atomicMax(&ctr->long_max_m, (unsigned int)s.m);
                     const long long need = (tb_bytes_wavefront(s.m, s.n, wf_rows_per_lane(cls)) + 255) & ~255LL;
                     const long long off = (long long)atomicAdd(&ctr->tb_used, (unsigned long long)need);
                     if (off + need > pools.tb_cap) { *flag_big = 1; cls = CLS_NONE; }

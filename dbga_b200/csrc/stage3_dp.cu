@@ -437,7 +437,7 @@ dp_wf_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pair
     constexpr int ROWS_PASS = GW * 32 * R;
     __shared__ int4 ring[W + 1][RING];
     __shared__ WfShared sh;
-    __shared__ __align__(16) uint8_t win[32][64];      // traceback window
+    __shared__ __align__(16) uint8_t win[WALK_WIN_ROWS][64];      // traceback window
     __shared__ uint32_t s_lut[8];
     if (threadIdx.x == 0) {
 #pragma unroll

@@ -371,6 +371,219 @@ dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
     }
 }
 
+// ---------------------------------------------------------------------- long segments: row strips
+// Segments the one-pass kernels cannot hold (more than 64 R rows, or scores past the int16 ceiling): the
+// matrix is cut into strips of 64 R rows, one warp sweeps a strip over all columns exactly like
+// dp_wf16_kernel, and the strips of a segment run pipelined on different warps (anywhere on the chip).
+// Work items (strip, segment) are handed out through one device-wide ticket in strip-major order, so a
+// strip's producer always holds an earlier ticket (no deadlock whatever is resident), many segments fill
+// the chip with no waiting at all, and a lone multi-kb segment spreads over as many SMs as it has strips.
+//
+// Boundary rows.  Half-lane 63 of strip s stores, per column, one 16-byte entry {M | X << 16, nonce,
+// Y | delta << 16, nonce} with a plain volatile store; lanes 0-15 of strip s + 1 fetch 16 entries per chunk
+// of 16 steps and poll until both nonces (unique per run, process-wide) are there: every 8-byte half
+// validates itself, so there is no fence, no flag and no cleared memory.
+//
+// Frames.  A half-lane keeps 4 (V - base - off) + priority with a base per (strip, block of S16_CB
+// columns): block 0 uses base 0 (H^ <= per_step * min(i, j) is small there), block c >= 1 of strip s > 0
+// puts max(M, X, Y) of its top boundary row at column c * S16_CB at S16_F0.  Every cell of the strip in that
+// block then lies within [-(|smin| + 3 go), per_step * max(64 R, S16_CB) + 2 go] of the anchor (gap extension
+// is free in H^, so a detour costs two gap opens), which fits the int16 range for any segment size.  When a
+// half-lane crosses a block boundary it subtracts delta = 4 (base_c - base_{c-1}) from its live registers
+// (its row at the previous column and the diagonal inputs); lane 0 derives delta and the producer-to-consumer
+// offset from the boundary entry at the block start and the producer's own delta carried in that entry.
+__device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u4(uint4 *p, uint4 v) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+template <int R>
+__global__ void __launch_bounds__(32, 16)
+dp_wf16s_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
+                const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, Counters *ctr,
+                DpParams prm, uint8_t *__restrict__ tb_pool, uint32_t nonce) {
+    constexpr int ROWS = 64 * R, CB = S16_CB, ROWW = 32 * R;      // four traceback bits per cell: 32 R bytes per step row
+    static_assert(R == 4 || R == 8, "strip kernels: 4 or 8 rows per half-lane (prm.h.strip; dp_tb16_kernel reads the same value)");
+    __shared__ uint32_t s_lut[4];
+    __shared__ __align__(16) uint4 s_in[2][16];                   // lane 0's inputs of one chunk: row above (M, X, Y) and the selector
+    const int lane = threadIdx.x;
+    const Dp16 &h = prm.h;
+    if (lane < 4) s_lut[lane] = h.lut[lane];
+    __syncwarp();
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t c256 = h.mul[3], c16 = h.mul[2];
+    const Wf16Consts cc{h.G, h.tagX, h.tagY, h.mul[0], h.nmul[0], h.nmul[1]};
+    const uint32_t tagM = h.tagM, tagX = h.tagX, tagY = h.tagY;
+    const uint32_t negM = dup16(h.qneg) | tagM, negX = dup16(h.qneg) | tagX, negY = dup16(h.qneg) | tagY;
+    const uint32_t r0M0 = (dup16(h.q0) | tagM) << 16, r0Mn = negM << 16, r0X = negX << 16,
+                   r0Y = (dup16(h.qy0) | tagY) << 16, r0Yn = negY << 16;
+    const int AF = 4 * (S16_F0 - h.off);                          // encoded value of a frame's anchor
+    const unsigned int count = *count_dev;
+    if (count == 0) return;
+    const unsigned long long total = (unsigned long long)((ctr->long_max_m + ROWS - 1) / ROWS) * count;
+
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&ctr->long_ticket, 1ULL);
+        ticket = __shfl_sync(FULL, ticket, 0);
+        if (ticket >= total) break;
+        const int s = (int)(ticket / count);                      // strip-major: every segment's strip s before any strip s + 1
+        const int sid = list[ticket % count];
+        const Slot sl = slots[sid];
+        const int m = sl.m, n = sl.n;
+        const int S = (m + ROWS - 1) / ROWS;
+        if (s >= S) continue;
+        const PairDesc pd = pairs[sl.pair];
+        const uint8_t *xs = seqs + pd.off0 + sl.x0, *ys = seqs + pd.off1 + sl.y0;
+        const int i0 = s * ROWS;
+        const bool last = s == S - 1, producer = !last && lane == 31;
+        const int64_t tb_rows = (int64_t)n + WF16_TB_PAD;
+        uint8_t *tbseg = tb_pool + sl.tb_off;
+        uint8_t *tbw = tbseg + ((int64_t)s * tb_rows + 16) * ROWW + lane * R;
+        // boundary rows live behind the segment's S traceback blocks (the allocation is sized for a byte per cell)
+        uint4 *bnd = reinterpret_cast<uint4 *>(tbseg + (int64_t)S * tb_rows * ROWW);
+        const int64_t bstride = (int64_t)n + 1;
+        const uint4 *bin = bnd + (int64_t)(s - 1) * bstride;      // s > 0
+        uint4 *bout = bnd + (int64_t)s * bstride;                 // s < S - 1
+        uint32_t lutA[R], lutB[R], Mr[R], Xr[R], Yr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int iA = i0 + lane * 2 * R + r, iB = iA + R;    // 0-based matrix rows
+            lutA[r] = s_lut[iA < m ? base_code(xs[iA]) : 0];
+            lutB[r] = s_lut[iB < m ? base_code(xs[iB]) : 0];
+            Mr[r] = negM; Xr[r] = negX; Yr[r] = negY;
+        }
+        uint32_t dgM = negM, dgX = negX, dgY = negY;
+        // a strip that feeds another one runs all 64 half-lanes to column n; the last one stops at the terminal cell
+        const int ms = min(ROWS, m - i0);
+        const int ve = last ? (ms - 1) / R : 63, re = (ms - 1) % R, te = n + ve, le = ve >> 1;
+        uint32_t sel_cur = 0x8888u, sel_prev = 0x8888u;
+        int cross = CB;                                           // first column of the next block this lane's low half enters
+        uint32_t dlt = 0, dhi = 0;                                // delta of the block being entered (both halves); of the high half's block
+        int bsum = 0, rel = 0, a_prev = AF;                       // 4 * base of the newest block; producer -> consumer offset; last anchor
+        uint4 E = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t yy = 0;
+        auto fetch = [&](int t0) {                                // lanes 0-15: boundary entry and selector of column t0 + lane
+            const int c = t0 + lane;
+            E = make_uint4(0u, 0u, 0u, 0u); yy = 0;
+            if (lane < 16) {
+                if (s > 0 && c <= n) E = ld_volatile_u4(bin + c);
+                const uint32_t yc = (c >= 1 && c <= n) ? (uint32_t)base_code(ys[c - 1]) : 0u;
+                const uint32_t yp = (c >= 2 && c <= n + 1) ? (uint32_t)base_code(ys[c - 2]) : 0u;
+                yy = 0xC480u + 0x11u * yc + 0x1100u * yp;         // columns (c, c - 1) for lane 0's (low, high) half
+            }
+        };
+        fetch(0);
+        int buf = 0;
+        for (int t0 = 0; t0 <= te; t0 += 16, buf ^= 1) {
+            const int c = t0 + lane;
+            if (s > 0) {
+                const bool need = lane < 16 && c <= n;
+                for (;;) {
+                    const bool ok = !need || (E.y == nonce && E.w == nonce);
+                    if (__all_sync(FULL, ok)) break;
+                    if (!ok) { __nanosleep(32); E = ld_volatile_u4(bin + c); }
+                }
+                if ((t0 & (CB - 1)) == 0) {                       // lane 0 enters a block: its frame
+                    int dnew = 0;
+                    if (t0 > 0 && t0 <= n) {
+                        const int eM = (int)(int16_t)(E.x & 0xFFFFu), eX = (int)(int16_t)(E.x >> 16), eY = (int)(int16_t)(E.z & 0xFFFFu);
+                        int a = max(eM, max(eX, eY)) & ~3;
+                        int dP = (int)(int16_t)(E.z >> 16);
+                        a = __shfl_sync(FULL, a, 0); dP = __shfl_sync(FULL, dP, 0);
+                        dnew = dP + a - a_prev; a_prev = a; rel = AF - a; bsum += dnew;
+                    }
+                    dlt = dup16(dnew);
+                }
+            }
+            if (lane < 16) {
+                uint4 o;
+                if (s == 0) {
+                    o.x = c == 0 ? r0M0 : r0Mn; o.y = r0X; o.z = c >= 1 ? r0Y : r0Yn;
+                } else {
+                    const uint32_t rr = (uint32_t)rel;
+                    o.x = (E.x + rr) << 16; o.y = ((E.x >> 16) + rr) << 16; o.z = (E.z + rr) << 16;
+                }
+                o.w = yy;
+                s_in[buf][lane] = o;
+            }
+            __syncwarp();
+            if (t0 + 16 <= te) fetch(t0 + 16);
+            const int ns = min(16, te + 1 - t0);
+            // some half-lane of the warp enters a block during this chunk (lane l at steps c CB + 2 l, + 1)
+            const bool xing = s > 0 && t0 >= CB && (t0 & (CB - 1)) < 64;
+#pragma unroll 2
+            for (int sidx = 0; sidx < ns; ++sidx) {
+                const int t = t0 + sidx;
+                const uint4 in = s_in[buf][sidx];
+                const uint32_t sel_in = __shfl_up_sync(FULL, sel_prev, 1);
+                sel_prev = sel_cur;
+                sel_cur = lane == 0 ? in.w : sel_in;
+                uint32_t sM = __shfl_up_sync(FULL, Mr[R - 1], 1);
+                uint32_t sX = __shfl_up_sync(FULL, Xr[R - 1], 1);
+                uint32_t sY = __shfl_up_sync(FULL, Yr[R - 1], 1);
+                if (lane == 0) { sM = in.x; sX = in.y; sY = in.z; }
+                const uint32_t uM = prmt(sM, Mr[R - 1], 0x5432u), uX = prmt(sX, Xr[R - 1], 0x5432u),
+                               uY = prmt(sY, Yr[R - 1], 0x5432u);
+                // block boundary: the low half enters at d == 0, the high half one step later
+                if (xing) {
+                    const int d = t - 2 * lane - cross;
+                    if ((unsigned)d < 2u) {
+                        const uint32_t dd = d == 0 ? (dlt & 0xFFFFu) : (dlt & 0xFFFF0000u);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) { Mr[r] = __vsub2(Mr[r], dd); Xr[r] = __vsub2(Xr[r], dd); Yr[r] = __vsub2(Yr[r], dd); }
+                        dgM = __vsub2(dgM, dd); dgX = __vsub2(dgX, dd); dgY = __vsub2(dgY, dd);
+                        if (d == 1) { cross += CB; dhi = dlt & 0xFFFF0000u; }
+                    }
+                }
+                uint32_t D[R];
+                wf16_rows<R, false>(Mr, Xr, Yr, D, lutA, lutB, sel_cur, dgM, dgX, dgY, uM, uX, uY, cc);
+                uint8_t *tbp = tbw + (int64_t)t * ROWW;
+                uint32_t F[R / 4];
+#pragma unroll
+                for (int g = 0; g < R / 4; ++g)
+                    F[g] = imad(imad(D[4 * g + 3], c16, D[4 * g + 2]), c256, imad(D[4 * g + 1], c16, D[4 * g]));
+                if constexpr (R == 4) *reinterpret_cast<uint32_t *>(tbp) = F[0];
+                else *reinterpret_cast<uint2 *>(tbp) = make_uint2(F[0], F[1]);
+                dgM = uM; dgX = uX; dgY = uY;
+                // the strip's bottom row at column t - 63 (one predicated store: no divergent branch in the step)
+                const uint4 ent = make_uint4((Mr[R - 1] >> 16) | (Xr[R - 1] & 0xFFFF0000u), nonce, (Yr[R - 1] >> 16) | dhi, nonce);
+                if (producer && t >= 63) st_volatile_u4(bout + (t - 63), ent);
+            }
+        }
+        if (last) {
+            uint32_t eM = 0, eX = 0, eY = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (r == re) { eM = Mr[r]; eX = Xr[r]; eY = Yr[r]; }
+            eM = __shfl_sync(FULL, eM, le); eX = __shfl_sync(FULL, eX, le); eY = __shfl_sync(FULL, eY, le);
+            const int sh = (ve & 1) ? 16 : 0;
+            const int vM = (int)(int16_t)(eM >> sh), vX = (int)(int16_t)(eX >> sh), vY = (int)(int16_t)(eY >> sh);
+            const int cm = (vM & ~3) + prm.endM, cx = (vX & ~3) + prm.endX, cy = (vY & ~3) + prm.endY;
+            int best = cm, st = 0;
+            if (cx > best) { best = cx; st = 1; }
+            if (cy > best) { best = cy; st = 2; }
+            const int score = (best >> 2) + h.off + (bsum >> 2) - prm.ge_raw * (m + n);
+            if (lane == 0) { slots[sid].score = score; slots[sid].len = st; }    // dp_tb16_kernel walks from state st
+        }
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_dp_strips16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *list,
+                               const unsigned int *count_dev, Counters *ctr, int grid, DpParams prm, uint8_t *tb,
+                               uint32_t nonce, cudaStream_t st) {
+    if (grid <= 0 || !prm.h.strip) return cudaSuccess;
+    // few segments: 256-row strips (a lone warp's step is half as long, twice as many warps per segment)
+    if (prm.h.strip == 4) dp_wf16s_kernel<4><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
+    else dp_wf16s_kernel<8><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
+    return cudaGetLastError();
+}
+
 // Traceback of every segment the packed forward kernels processed: one warp per segment over
 // the four warp-class lists.  Kept out of the forward kernels because the walk is a chain of
 // memory latencies (window loads, character loads): inside them it held a third of the warps
@@ -379,13 +592,13 @@ constexpr int TB16_WARPS = 4;
 __global__ void __launch_bounds__(TB16_WARPS * 32)
 dp_tb16_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                const int32_t *__restrict__ lists, int64_t list_cap, const unsigned int *__restrict__ counts_dev,
-               DpParams prm, uint8_t *__restrict__ strbuf, const uint8_t *tb_pool) {
-    __shared__ __align__(16) uint8_t win[TB16_WARPS][32][64];
+               int cls_lo, int cls_hi, DpParams prm, uint8_t *__restrict__ strbuf, const uint8_t *tb_pool) {
+    __shared__ __align__(16) uint8_t win[TB16_WARPS][WALK_WIN_ROWS][64];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned int gw = blockIdx.x * TB16_WARPS + w, nw = gridDim.x * TB16_WARPS;
     const uint32_t pmap = ((uint32_t)prio_to_state(0, prm)) | ((uint32_t)prio_to_state(1, prm) << 2) |
                           ((uint32_t)prio_to_state(2, prm) << 4);
-    for (int cls = CLS_WARP2; cls <= CLS_WARP16; ++cls) {
+    for (int cls = cls_lo; cls <= cls_hi; ++cls) {             // warp classes; the long class: what dp_wf16s_kernel ran (wf16_pick)
         const unsigned int count = counts_dev[cls];
         const int32_t *list = lists + (int64_t)cls * list_cap;
         for (unsigned int item = gw; item < count; item += nw) {
@@ -471,10 +684,10 @@ cudaError_t launch_dp_wavefront16(const uint8_t *seqs, const PairDesc *pairs, Sl
 }
 
 cudaError_t launch_dp_traceback16(const uint8_t *seqs, const PairDesc *pairs, Slot *slots, const int32_t *lists,
-                                  int64_t list_cap, const unsigned int *counts_dev, int grid, DpParams prm,
+                                  int64_t list_cap, const unsigned int *counts_dev, int cls_lo, int cls_hi, int grid, DpParams prm,
                                   uint8_t *strbuf, const uint8_t *tb, cudaStream_t st) {
     if (grid <= 0 || !prm.h.ok) return cudaSuccess;
-    dp_tb16_kernel<<<grid, TB16_WARPS * 32, 0, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, prm, strbuf, tb);
+    dp_tb16_kernel<<<grid, TB16_WARPS * 32, 0, st>>>(seqs, pairs, slots, lists, list_cap, counts_dev, cls_lo, cls_hi, prm, strbuf, tb);
     return cudaGetLastError();
 }
 

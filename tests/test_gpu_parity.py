@@ -365,6 +365,60 @@ def test_packed16_wavefront(aligner):
     run(match=-50, transition=-60, transversion=-70, d=40, e=40)
 
 
+def test_packed16_row_strips(aligner):
+    """Long segments as packed row strips (dp_wf16s_kernel: 512-row strips pipelined through boundary rows,
+    frames re-anchored every 256 columns): one to many strips, partial last strips, segments whose scores
+    grow far past the int16 range (similar sequences), fall far below zero (random ones) or do both
+    (shifted copies: a long terminal gap, then matches), few and many segments per batch (strip-major ticket
+    order), every predecessor / terminal tie order, and scoring where the strip form is off (32-bit kernels)."""
+    rng = random.Random(4242)
+    shapes = [(513, 513), (1024, 1024), (1025, 1030), (1100, 1100), (1536, 700), (700, 1536), (2048, 2048), (2049, 255),
+              (3000, 5000), (5000, 3000), (4097, 300), (600, 9000), (9000, 600), (1500, 1500), (2600, 2500), (6500, 6400)]
+    pairs = []
+    for q, (m, n) in enumerate(shapes):
+        x = rand_seq(rng, m)
+        kind = q % 4
+        if kind == 0:
+            y = (mutate(rng, x, 0.05, 0.01) + rand_seq(rng, n))[:n]
+        elif kind == 1:
+            y = (mutate(rng, x, 0.3, 0.04) + rand_seq(rng, n))[:n]       # cfg5's bubbles
+        elif kind == 2:
+            y = rand_seq(rng, n)
+        else:
+            y = (rand_seq(rng, n // 3) + x)[:n]
+        pairs.append((x, y))
+
+    def run(sub, conv=O.DEFAULT, **score):
+        res = aligner.global_align_pairs(sub, gap_len_mode=conv.gap_len_mode, xy_allowed=conv.xy_allowed,
+                                         pred_order=conv.pred_order, end_order=conv.end_order, **score)
+        for i, (x, y) in enumerate(sub):
+            if len(x) < 100:
+                continue
+            sc, ax, ay = CO.gotoh(x, y, conv=conv, **score)
+            assert res.status[i] == O.OK
+            assert res.score[i] == sc, (i, len(x), len(y), conv, score)
+            assert res.alignment(i) == (ax, ay), (i, len(x), len(y), conv, score)
+
+    run(pairs)                                                           # few pairs: everything above 2^18 cells is long
+    filler = [(rand_seq(rng, 40), rand_seq(rng, 45)) for _ in range(600)]
+    run(pairs[:12] + filler)                                             # many pairs: only what the one-pass kernel cannot hold
+    for po, eo in (("MXY", "YMX"), ("YXM", "XMY"), ("MYX", "MYX")):
+        run(pairs[:9], O.Convention(1, False, po, eo))
+    run(pairs[:9], match=17, transition=-3, transversion=-20, d=30, e=3)   # per_step 23: the steepest the strip form takes
+    run(pairs[:6], match=22, transition=-4, transversion=-8, d=40, e=4)    # per_step 30: 32-bit kernels
+    run(pairs[:6], match=1, transition=0, transversion=-1, d=0, e=0)
+    # many long segments of one size: tickets of several strips per segment interleave over the whole grid
+    many = []
+    for _ in range(700):
+        x = rand_seq(rng, rng.randint(1030, 1700))
+        many.append((x, mutate(rng, x, 0.05, 0.01)))
+    res = aligner.global_align_pairs(many)
+    assert (res.status == O.OK).all()
+    for i in range(0, len(many), 7):
+        sc, ax, ay = CO.gotoh(*many[i])
+        assert (res.score[i],) + res.alignment(i) == (sc, ax, ay), (i, len(many[i][0]), len(many[i][1]))
+
+
 def test_packed16_full_size_properties(aligner):
     """The DP microbenchmark's shapes at size (thousands of segments per packed kernel, lists long
     enough that every warp pairs many different neighbours): degapped rows == inputs, the affine
