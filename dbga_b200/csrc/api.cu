@@ -295,7 +295,8 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     // strip height of the long-segment kernel: with few pairs a long segment is latency-bound (a lone warp per SM
     // sub-partition), so halve the step; with many the taller strip amortises the per-step overhead
     if (ctx->dp.h.strip) {
-        ctx->dp.h.strip = P >= MANY_PAIRS ? 8 : 4;
+        // (decided below, once the lengths are known: P * ceil(longest / 512) estimates the strips in flight)
+        ctx->dp.h.strip = 8;
         if (const char *e = getenv("DBGA_STRIP_R")) { const int r = atoi(e); if (r == 4 || r == 8) ctx->dp.h.strip = r; }
     }
     DBGA_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -500,6 +501,8 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         ctx->grid_cluster = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->num_sms / WF_CLUSTER, g));
     }
     const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
+    if (ctx->dp.h.strip && !getenv("DBGA_STRIP_R"))
+        ctx->dp.h.strip = P * (((int64_t)mx0 + S16_ROWS - 1) / S16_ROWS) >= (int64_t)ctx->num_sms * 8 ? 8 : 4;
     // (with the strip kernel the long class also takes what the one-pass packed kernel cannot hold)
     const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells || (ctx->dp.h.strip && any_non_tiny && mx0 > 256);
     if (!any_non_tiny) ctx->grid_warp = 0;

@@ -22,6 +22,8 @@
 // registers, which yields exactly X^[i][0] = ge - go and minus infinity for M and Y, so a
 // half-lane needs no start-up masking.  One pass only (m <= 64 R); traceback bytes use the
 // 32-bit kernels' step-major layout (row = step, 64 R bytes per row) and the shared walker.
+#include <cstdlib>
+
 #include "dp_walk.cuh"
 #include "kernels.cuh"
 
@@ -397,12 +399,14 @@ __device__ __forceinline__ uint4 ld_volatile_u4(const uint4 *p) {
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ void st_volatile_u4(uint4 *p, uint4 v) {
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+// predicated in the instruction itself: the one storing lane does not split the warp
+__device__ __forceinline__ void st_volatile_u4_if(uint4 *p, uint4 v, bool on) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n\t}"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((uint32_t)on));
 }
 
-template <int R>
-__global__ void __launch_bounds__(32, 16)
+template <int R, int OCC>
+__global__ void __launch_bounds__(32, OCC)
 dp_wf16s_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs, Slot *__restrict__ slots,
                 const int32_t *__restrict__ list, const unsigned int *__restrict__ count_dev, Counters *ctr,
                 DpParams prm, uint8_t *__restrict__ tb_pool, uint32_t nonce) {
@@ -479,14 +483,20 @@ dp_wf16s_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
         };
         fetch(0);
         int buf = 0;
+        uint8_t *tbp = tbw;                                       // step t writes row t of the strip's block
+        uint4 *boutp = bout - 63;
         for (int t0 = 0; t0 <= te; t0 += 16, buf ^= 1) {
             const int c = t0 + lane;
             if (s > 0) {
                 const bool need = lane < 16 && c <= n;
-                for (;;) {
+                // (a consumer that has caught up with its producer backs off: its polls take issue slots from the
+                // warps it shares the SM with -- possibly the producer itself)
+                for (unsigned int nap = 32;;) {
                     const bool ok = !need || (E.y == nonce && E.w == nonce);
                     if (__all_sync(FULL, ok)) break;
-                    if (!ok) { __nanosleep(32); E = ld_volatile_u4(bin + c); }
+                    __nanosleep(nap);
+                    if (OCC > 8 && nap < 2048u) nap *= 2u;        // (the few-segments form runs a warp per SM: nothing to yield to)
+                    if (!ok) E = ld_volatile_u4(bin + c);
                 }
                 if ((t0 & (CB - 1)) == 0) {                       // lane 0 enters a block: its frame
                     int dnew = 0;
@@ -542,17 +552,18 @@ dp_wf16s_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
                 }
                 uint32_t D[R];
                 wf16_rows<R, false>(Mr, Xr, Yr, D, lutA, lutB, sel_cur, dgM, dgX, dgY, uM, uX, uY, cc);
-                uint8_t *tbp = tbw + (int64_t)t * ROWW;
                 uint32_t F[R / 4];
 #pragma unroll
                 for (int g = 0; g < R / 4; ++g)
                     F[g] = imad(imad(D[4 * g + 3], c16, D[4 * g + 2]), c256, imad(D[4 * g + 1], c16, D[4 * g]));
                 if constexpr (R == 4) *reinterpret_cast<uint32_t *>(tbp) = F[0];
                 else *reinterpret_cast<uint2 *>(tbp) = make_uint2(F[0], F[1]);
+                tbp += ROWW;
                 dgM = uM; dgX = uX; dgY = uY;
-                // the strip's bottom row at column t - 63 (one predicated store: no divergent branch in the step)
+                // the strip's bottom row at column t - 63
                 const uint4 ent = make_uint4((Mr[R - 1] >> 16) | (Xr[R - 1] & 0xFFFF0000u), nonce, (Yr[R - 1] >> 16) | dhi, nonce);
-                if (producer && t >= 63) st_volatile_u4(bout + (t - 63), ent);
+                st_volatile_u4_if(boutp, ent, producer && t >= 63);
+                ++boutp;
             }
         }
         if (last) {
@@ -579,8 +590,9 @@ cudaError_t launch_dp_strips16(const uint8_t *seqs, const PairDesc *pairs, Slot 
                                uint32_t nonce, cudaStream_t st) {
     if (grid <= 0 || !prm.h.strip) return cudaSuccess;
     // few segments: 256-row strips (a lone warp's step is half as long, twice as many warps per segment)
-    if (prm.h.strip == 4) dp_wf16s_kernel<4><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
-    else dp_wf16s_kernel<8><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
+    // (few segments: every register the step wants, eight warps per SM at most)
+    if (prm.h.strip == 4) dp_wf16s_kernel<4, 8><<<grid / 2, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
+    else dp_wf16s_kernel<8, 16><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
     return cudaGetLastError();
 }
 
