@@ -30,7 +30,8 @@ struct HostBuf {
 
 struct SmallClass {
     uint32_t cap;
-    int parts;          // 1: fused stages 1+2; > 1: partitioned table, stage 1 only ("medium" pairs)
+    int parts;          // table partitions that take turns in shared memory (medium pairs; small pairs: 1)
+    bool medium;        // stage 1 only, by-reference slots; false: fused stages 1+2 ("small" pairs)
     int words, maxq;
     int begin, count;   // range in the small pair list
 };
@@ -354,23 +355,22 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
             if (fits) {
                 by_cap[{1, cap}].push_back((int32_t)i);
             } else {
-                // medium: split the keys over 2..8 table partitions that take turns in shared memory
+                // medium: 4-byte by-reference slots, the whole table in shared memory if it fits, else the keys
+                // split over 2..8 partitions that take turns in it
                 int parts = 0;
                 uint32_t pcap = 0;
-                // (N1 < 32768: the medium kernel's packed word counts seq-2 occurrences in bits 16-30 under the
-                //  "repeated in seq1" flag in bit 31; a k-mer with more occurrences than that must not carry into it)
-                if (k <= 31 && N0 < 65000 && N1 < 32768) {
-                    for (int g = 2; g <= 8 && !parts; ++g) {
+                // (16-bit positions + 1 in the slot, 16-bit slot numbers in memo[]; occurrences are flags, not counters)
+                if (k <= 31 && N0 < 65000 && N1 < 65000) {
+                    for (int g = 1; g <= 8 && !parts; ++g) {
                         uint64_t w = keys * 170 / 100 / g + 64;       // 1.7 x the expected keys per partition
                         uint32_t gr = 256;
                         while ((uint64_t)gr * 64 < w) gr <<= 1;        // fine granule: every slot counts against the partition count
                         const uint32_t c = (uint32_t)((w + gr - 1) / gr * gr);
-                        // (medium pairs keep memo[] in global memory and fold position and counters into one word:
-                        //  shared memory holds the packed sequences and 8- or 12-byte slots, nothing else)
-                        if (c <= 32768 && stage12_small_smem(key_bytes, c, words0, 0, true) <= 224 * 1024) { parts = g; pcap = c; }
+                        // (medium pairs keep memo[] in global memory: shared memory holds the packed sequences and the slots)
+                        if (c <= 65520 && stage12_small_smem(key_bytes, c, words0, 0, true) <= 224 * 1024) { parts = g; pcap = c; }
                     }
                 }
-                if (parts) by_cap[{parts, pcap}].push_back((int32_t)i);
+                if (parts) by_cap[{100 + parts, pcap}].push_back((int32_t)i);       // (after every small class: the list's tail goes to the generic stage 2)
                 else large.push_back((int32_t)i);
             }
         }
@@ -378,7 +378,8 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         for (auto &kv : by_cap) {
             const std::vector<int32_t> &members = kv.second;
             SmallClass c;
-            c.parts = kv.first.first; c.cap = kv.first.second; c.begin = (int)ctx->h_list.size(); c.count = (int)members.size();
+            c.medium = kv.first.first >= 100; c.parts = c.medium ? kv.first.first - 100 : 1;
+            c.cap = kv.first.second; c.begin = (int)ctx->h_list.size(); c.count = (int)members.size();
             int nmax = 0, qmax = 0;
             for (int32_t i : members) {
                 const PairDesc &pd = ctx->h_pairs[(size_t)i];
@@ -387,14 +388,14 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
                 ctx->h_list.push_back(i);
             }
             c.words = (((nmax + 15) / 16 + 3) + 1) & ~1;
-            c.maxq = c.parts > 1 ? 0 : qmax;
-            if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq, c.parts > 1) > SMEM_LIMIT) {
+            c.maxq = c.medium ? 0 : qmax;
+            if (stage12_small_smem(key_bytes, c.cap, c.words, c.maxq, c.medium) > SMEM_LIMIT) {
                 // mixed extremes inside one class: fall back to the large path for this class
                 ctx->h_list.resize((size_t)c.begin);
                 for (int32_t i : members) large.push_back(i);
                 continue;
             }
-            if (c.parts > 1 && stage2_first < 0) stage2_first = c.begin;
+            if (c.medium && stage2_first < 0) stage2_first = c.begin;
             ctx->classes.push_back(c);
         }
         ctx->large_begin = (int)ctx->h_list.size();
@@ -464,7 +465,8 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
     // ---- workspaces
     RESERVE(d_status, 4 * std::max<int64_t>(P, 1));
     RESERVE(d_status_out, 4 * std::max<int64_t>(P, 1));
-    RESERVE(d_aof, 4 * std::max<int64_t>(ctx->sumN1, 1));
+    // (+ the medium pairs' 16-bit memo[] scratch behind the int32 entries: sumN1 + two slack entries per pair)
+    RESERVE(d_aof, 4 * std::max<int64_t>(ctx->sumN1, 1) + 2 * (ctx->sumN1 + 2 * P + 2) + 16);
     if (full) { RESERVE(d_nd0, std::max<int64_t>(ctx->sumN0, 1)); RESERVE(d_nd1, std::max<int64_t>(ctx->sumN1, 1)); }
     RESERVE(d_pout, sizeof(PairOut) * std::max<int64_t>(P, 1));
     RESERVE(d_ctr, sizeof(Counters));
@@ -581,9 +583,10 @@ int run_pipeline(dbga_ctx *ctx) {
                 }
                 if (hi <= lo) continue;
                 DBGA_CUDA_CHECK(launch_stage12_small(seqs, pairs, (int32_t *)ctx->d_list.p + c.begin + lo, hi - lo, ctx->prm.k,
-                                                     c.cap, c.parts, c.words, c.maxq, full, seg, pout, pools, ctr,
+                                                     c.cap, c.medium, c.parts, c.words, c.maxq, full, seg, pout, pools, ctr,
                                                      ctx->max_abs_score, ctx->dp.go_raw, ctx->dp.ge_raw, (uint8_t *)ctx->d_nd0.p,
                                                      (uint8_t *)ctx->d_nd1.p, (int32_t *)ctx->d_status.p, (int32_t *)ctx->d_aof.p,
+                                                     (uint16_t *)((int32_t *)ctx->d_aof.p + std::max<int64_t>(ctx->sumN1, 1)),
                                                      ctx->num_sms, st));
                 ctx->launches += 1;
             }

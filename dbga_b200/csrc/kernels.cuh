@@ -44,9 +44,9 @@ struct Pools {
 // ---- stages 1+2 fused (pairs whose table fits in shared memory)
 size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq, bool medium);
 cudaError_t launch_stage12_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
-                                 uint32_t cap, int parts, int words, int maxq, bool full, bool want_segments,
+                                 uint32_t cap, bool medium, int parts, int words, int maxq, bool full, bool want_segments,
                                  PairOut *pout, Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,
-                                 uint8_t *nd0, uint8_t *nd1, int32_t *status, int32_t *aof, int num_sms,
+                                 uint8_t *nd0, uint8_t *nd1, int32_t *status, int32_t *aof, uint16_t *memo_g, int num_sms,
                                  cudaStream_t st);
 // ---- stage 1, global-memory table (large pairs)
 cudaError_t launch_stage1_large(const uint8_t *seqs, const PairDesc *pairs, const LargeDesc *ld,

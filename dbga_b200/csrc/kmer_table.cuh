@@ -160,4 +160,71 @@ __device__ __forceinline__ uint32_t bkt_find(const KeyT *keys, uint32_t nb, KeyT
     }
 }
 
+// ---- medium pairs: 4-byte slots that name their k-mer BY REFERENCE (half the bytes of a 32-bit key + word,
+// a third of a 64-bit one: a 30 kb pair's table fits shared memory in one piece).  A slot holds the position
+// (+ 1; 0 = empty) of the occurrence that claimed it, 11 bits of the hash (in a 12-bit tag that is never 0) and the occurrence flags; a probe
+// whose tag matches compares the k-mer at that position of the packed sequence with its own.  The position
+// never changes once claimed and the flags are only ever OR-ed in, so claimers and finders commute.
+constexpr uint32_t MR_SRC1 = 1u << 28;    // the reference points into seq2 (graph mode: k-mers private to seq2)
+constexpr uint32_t MR_SEEN1 = 1u << 29;   // occurs in seq2
+constexpr uint32_t MR_SEEN2 = 1u << 30;   // ... more than once
+constexpr uint32_t MR_DUP0 = 1u << 31;    // repeated in seq1
+__device__ __forceinline__ uint32_t mr_tag(uint32_t hv) { return (((hv >> 8) & 0xFFFu) << 16) | 0x10000u; }   // never 0: an empty slot matches no tag
+constexpr uint32_t MR_TAGM = 0x0FFF0000u;
+template <typename KeyT>
+__device__ __forceinline__ bool mr_same(uint32_t w, KeyT key, const uint32_t *pk0, const uint32_t *pk1, KeyT kmask) {
+    return Bucket<KeyT>::kmer((w & MR_SRC1) ? pk1 : pk0, (int)(w & 0xFFFFu) - 1, kmask) == key;
+}
+// The slot of `key` among the filled slots of a bucket as read (kk), or -1.  Branch-free up to the one k-mer
+// comparison almost every probe needs: the first slot whose tag matches is picked with selects; further tag
+// matches (a 2^-11 event per slot) are looked at only when that comparison fails.
+template <typename KeyT>
+__device__ __forceinline__ int mr_match(const uint4 kk, uint32_t tag, KeyT key, const uint32_t *pk0, const uint32_t *pk1, KeyT kmask) {
+    const bool t0 = (kk.x & MR_TAGM) == tag, t1 = (kk.y & MR_TAGM) == tag, t2 = (kk.z & MR_TAGM) == tag, t3 = (kk.w & MR_TAGM) == tag;
+    if (!(t0 || t1 || t2 || t3)) return -1;
+    const int ci = t0 ? 0 : (t1 ? 1 : (t2 ? 2 : 3));
+    const uint32_t c = t0 ? kk.x : (t1 ? kk.y : (t2 ? kk.z : kk.w));
+    if (mr_same<KeyT>(c, key, pk0, pk1, kmask)) return ci;
+    if (ci < 1 && t1 && mr_same<KeyT>(kk.y, key, pk0, pk1, kmask)) return 1;
+    if (ci < 2 && t2 && mr_same<KeyT>(kk.z, key, pk0, pk1, kmask)) return 2;
+    if (ci < 3 && t3 && mr_same<KeyT>(kk.w, key, pk0, pk1, kmask)) return 3;
+    return -1;
+}
+// find-or-claim (neww: the word a claimer leaves); slots of a bucket fill in order
+template <typename KeyT>
+__device__ __forceinline__ uint32_t mr_insert(uint32_t *tab, uint32_t nb, KeyT key, uint32_t hv, uint32_t neww,
+                                              const uint32_t *pk0, const uint32_t *pk1, KeyT kmask, bool &claimed) {
+    const uint32_t tag = mr_tag(hv);
+    uint32_t b = __umulhi(hv, nb);
+    for (;;) {
+        uint32_t *base = tab + 4 * b;
+        const uint4 kk = lds_v4(base);
+        const int hit = mr_match<KeyT>(kk, tag, key, pk0, pk1, kmask);
+        if (hit >= 0) { claimed = false; return 4 * b + hit; }
+        if (kk.w == 0u) {
+            // slots emp .. 3 were empty when the bucket was read; a lost race shows who took the slot
+            const int emp = kk.x == 0u ? 0 : (kk.y == 0u ? 1 : (kk.z == 0u ? 2 : 3));
+            for (int e = emp; e < 4; ++e) {
+                const uint32_t cur = atomicCAS(base + e, 0u, neww);
+                if (cur == 0u) { claimed = true; return 4 * b + e; }
+                if ((cur & MR_TAGM) == tag && mr_same<KeyT>(cur, key, pk0, pk1, kmask)) { claimed = false; return 4 * b + e; }
+            }
+        }
+        b = b + 1 == nb ? 0 : b + 1;
+    }
+}
+template <typename KeyT>
+__device__ __forceinline__ uint32_t mr_find(const uint32_t *tab, uint32_t nb, KeyT key, uint32_t hv, const uint32_t *pk0,
+                                            const uint32_t *pk1, KeyT kmask) {
+    const uint32_t tag = mr_tag(hv);
+    uint32_t b = __umulhi(hv, nb);
+    for (;;) {
+        const uint4 kk = lds_v4(tab + 4 * b);
+        const int hit = mr_match<KeyT>(kk, tag, key, pk0, pk1, kmask);
+        if (hit >= 0) return 4 * b + hit;
+        if (kk.w == 0u) return 0xFFFFFFFFu;          // the bucket never filled up: the key is not in the table
+        b = b + 1 == nb ? 0 : b + 1;
+    }
+}
+
 }  // namespace dbga

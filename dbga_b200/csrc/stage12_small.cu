@@ -22,7 +22,6 @@
 
 namespace dbga {
 
-constexpr uint32_t MDUP0 = 0x80000000u;  // medium pairs' merged word: repeated in seq1
 constexpr uint32_t DUP0 = 0x10000u;      // cnt[]: the k-mer occurs more than once in seq1 (seq-2 counts stay below 2^16)
 struct S12Shared {
     unsigned int nSE;      // run starts appended (low 16 bits) | run ends appended (high 16 bits); both < 65 000
@@ -31,18 +30,19 @@ struct S12Shared {
     long long red[32];
 };
 
-// parts > 1 ("medium" pairs): the key space is split by hash into `parts` partitions that take
-// turns in one shared-memory table of `cap` slots -- every round re-scans the packed
-// sequences (cheap) but inserts / looks up only its own partition's k-mers (the expensive
-// part stays constant).  Such pairs stop after stage 1: aof[] goes to HBM and the generic
-// stage-2 kernel takes over (their run count is not bounded by the table size).
+// TPB = 1024 ("medium" pairs, one CTA per SM): 4-byte slots that name their k-mer by reference
+// (kmer_table.cuh: mr_insert / mr_find), so that a 30 kb pair's table fits shared memory whole.  Longer
+// pairs split the key space by hash into `parts` partitions that take turns in the table -- every round
+// re-scans the packed sequences but inserts / looks up only its own partition's k-mers.  Medium pairs
+// stop after stage 1: aof[] goes to HBM and the generic stage-2 kernel takes over (their run count is
+// not bounded by the table size).
 template <typename KeyT, bool FULL, int TPB>
 __global__ void __launch_bounds__(TPB, TPB == 256 ? 5 : 1)      // five CTAs per SM for the small-pair case
 stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ pairs,
                      const int32_t *__restrict__ pair_list, int count, int k, KeyT kmask, uint32_t cap, uint32_t nb, int parts,
                      int words, int maxq, int want_segments, PairOut *__restrict__ pout, Pools pools,
                      Counters *__restrict__ ctr, SlotCfg cfg, uint8_t *__restrict__ nd0, uint8_t *__restrict__ nd1,
-                     int32_t *__restrict__ status, int32_t *__restrict__ aof) {
+                     int32_t *__restrict__ status, int32_t *__restrict__ aof, uint16_t *__restrict__ memo_g) {
     extern __shared__ __align__(16) uint8_t smem[];
     using B = Bucket<KeyT>;
     constexpr bool MEDIUM = TPB > 256;          // the small-pair instantiation compiles without any partition logic
@@ -51,12 +51,9 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     uint32_t *pk1 = pk0 + words;
     KeyT *keys = reinterpret_cast<KeyT *>(pk1 + words);
     // small pairs: a 16-bit seq-1 position and one 32-bit word per slot (occurrences in seq2 | DUP0 if
-    // repeated in seq1).  Medium pairs fold both into the word (8 bytes per slot with 32-bit keys,
-    // fewer table partitions): bits 0-15 seq-1 position + 1 (0: none), bits 16-31 occurrences in seq2
-    // with MDUP0 = bit 31 for "repeated in seq1"; every update is an atomic OR / ADD, so the claimer's
-    // position and a later finder's flag commute.
+    // repeated in seq1).  Medium pairs: the 4-byte by-reference slots and nothing else (cnt[] is the table).
     uint16_t *pos0 = reinterpret_cast<uint16_t *>(keys + cap);
-    uint32_t *cnt = MEDIUM ? reinterpret_cast<uint32_t *>(keys + cap) : reinterpret_cast<uint32_t *>(pos0 + cap);
+    uint32_t *cnt = MEDIUM ? reinterpret_cast<uint32_t *>(pk1 + words) : reinterpret_cast<uint32_t *>(pos0 + cap);
     uint16_t *memo = reinterpret_cast<uint16_t *>(cnt + cap);       // later: aof in shared memory
     // aliases valid once the table is dead (after phase B2)
     uint32_t *ska = reinterpret_cast<uint32_t *>(keys);             // unordered run starts (b<<16 | a), cap entries
@@ -92,10 +89,10 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 pk1[w] = r1 > 0 ? pack16_fast(s1 + 16 * w, r1, bad) : 0u;
             }
         }
-        auto init_table = [&]() {       // keys + pos0 = all ones, cnt = 0
+        auto init_table = [&]() {       // keys + pos0 = all ones, cnt = 0 (medium pairs: the table is cnt[], empty = 0)
             uint4 *t4 = reinterpret_cast<uint4 *>(keys);
             // (the 16-bit positions need no initial value unless seq-2-only k-mers can own a slot: graph mode)
-            const int n_ff = (int)((cap * (sizeof(KeyT) + ((MEDIUM || !FULL) ? 0 : 2))) / 16), n_00 = (int)(cap * 4 / 16);
+            const int n_ff = MEDIUM ? 0 : (int)((cap * (sizeof(KeyT) + (!FULL ? 0 : 2))) / 16), n_00 = (int)(cap * 4 / 16);
             for (int i = tid; i < n_ff; i += T) t4[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
             uint4 *z4 = reinterpret_cast<uint4 *>(cnt);
             for (int i = tid; i < n_00; i += T) z4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -107,16 +104,14 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
         }
         const int N0 = pd.n0 - k + 1, N1 = pd.n1 - k + 1;
         if (MEDIUM) {
-            // medium pairs keep memo[] in global memory (L2), in the tail of the pair's own aof[] region:
-            // the last 2 * N1e bytes of its 4 * N1 (N1e = N1 rounded up to even; 4-byte aligned either
-            // way).  That leaves the whole shared memory to the table: fewer partitions, fewer re-scans.
-            const int N1e = (N1 + 1) & ~1;
-            memo = reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(aof + pd.q_base) + 4 * (int64_t)N1 - 2 * (int64_t)N1e);
+            // medium pairs keep memo[] (the slot each seq-2 position found) in a global scratch (L2): the whole
+            // shared memory goes to the table.  Even start, two slack entries per pair: 32-bit accesses, disjoint regions.
+            memo = memo_g + ((pd.q_base + 2 * (int64_t)pair + 1) & ~(int64_t)1);
         }
         for (int g = 0; g < parts; ++g) {
             if (g > 0) { __syncthreads(); init_table(); __syncthreads(); }
             // partition of a k-mer: low 16 bits of its hash (the bucket uses the high bits)
-            auto in_part = [&](uint32_t hv) { return !MEDIUM || (int)(((hv & 0xFFFFu) * (uint32_t)parts) >> 16) == g; };
+            auto in_part = [&](uint32_t hv) { return !MEDIUM || parts == 1 || (int)(((hv & 0xFFFFu) * (uint32_t)parts) >> 16) == g; };
             // Every thread takes two adjacent positions per round: one pair of packed words
             // yields both k-mers and the two probes are independent (latency overlap).
             // ---- A: seq1 k-mers
@@ -124,9 +119,13 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 const uint32_t hv = B::mix(key);
                 if (!in_part(hv)) return;
                 bool claimed;
+                if (MEDIUM) {
+                    const uint32_t h = mr_insert<KeyT>(cnt, nb, key, hv, ((uint32_t)p + 1u) | mr_tag(hv), pk0, pk1, kmask, claimed);
+                    if (!claimed) atomicOr(&cnt[h], MR_DUP0);
+                    return;
+                }
                 const uint32_t h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
-                if (MEDIUM) atomicOr(&cnt[h], claimed ? (uint32_t)p + 1u : MDUP0);
-                else if (claimed) pos0[h] = (uint16_t)p;
+                if (claimed) pos0[h] = (uint16_t)p;
                 else cnt[h] = DUP0;
             };
             for (int p = 2 * tid; p < N0; p += 2 * T) {
@@ -137,72 +136,88 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             }
             __syncthreads();
             // ---- B1: seq2 k-mers; memo[q] = slot (or, medium pairs, what an earlier partition left)
-            auto phase_b1 = [&](KeyT key, uint32_t keep) -> uint32_t {
+            auto phase_b1 = [&](KeyT key, uint32_t keep, int q) -> uint32_t {
                 const uint32_t hv = B::mix(key);
                 if (!in_part(hv)) return keep;
                 uint32_t h;
+                if (MEDIUM) {
+                    bool claimed = false;
+                    if (FULL) h = mr_insert<KeyT>(cnt, nb, key, hv, ((uint32_t)q + 1u) | mr_tag(hv) | MR_SRC1 | MR_SEEN1, pk0, pk1, kmask, claimed);
+                    else h = mr_find<KeyT>(cnt, nb, key, hv, pk0, pk1, kmask);
+                    if (h != 0xFFFFFFFFu && !claimed) {
+                        const uint32_t old = atomicOr(&cnt[h], MR_SEEN1);
+                        if ((old & (MR_SEEN1 | MR_SEEN2)) == MR_SEEN1) atomicOr(&cnt[h], MR_SEEN2);
+                    }
+                    return h != 0xFFFFFFFFu ? h : (uint32_t)NONE16;
+                }
                 if (FULL) {
                     bool claimed;
                     h = bkt_insert<KeyT>(keys, nb, key, hv, claimed);
                 } else {
                     h = bkt_find<KeyT>(keys, nb, key, hv);
                 }
-                if (h != 0xFFFFFFFFu) atomicAdd(&cnt[h], MEDIUM ? 0x10000u : 1u);      // result unused: a fire-and-forget shared-memory add
+                if (h != 0xFFFFFFFFu) atomicAdd(&cnt[h], 1u);      // result unused: a fire-and-forget shared-memory add
                 return h != 0xFFFFFFFFu ? h : (uint32_t)NONE16;
             };
             uint32_t *memo2 = reinterpret_cast<uint32_t *>(memo);   // two positions per word
             for (int q = 2 * tid; q < N1; q += 2 * T) {
                 KeyT k0, k1;
                 B::kmer2(pk1, q, kmask, k0, k1);
-                const uint32_t old = MEDIUM ? memo2[q >> 1] : 0u;
-                const uint32_t m0 = phase_b1(k0, old & 0xFFFFu);
-                const uint32_t m1 = q + 1 < N1 ? phase_b1(k1, old >> 16) : (uint32_t)NONE16;
+                // (medium pairs: a position outside this partition gets NONE16 here and is skipped by this round's B2)
+                const uint32_t m0 = phase_b1(k0, NONE16, q);
+                const uint32_t m1 = q + 1 < N1 ? phase_b1(k1, NONE16, q + 1) : (uint32_t)NONE16;
                 memo2[q >> 1] = m0 | (m1 << 16);
             }
             __syncthreads();
             // ---- B2: anchors; memo[q] becomes aof[q] (position in seq1 or NONE16)
-            auto phase_b2 = [&](KeyT key, uint32_t h, int q) -> uint32_t {
-                if (MEDIUM && !in_part(B::mix(key))) return h;
+            auto phase_b2 = [&](uint32_t h, int q) -> uint32_t {
                 uint32_t a = NONE16;
                 if (h != NONE16) {
                     const uint32_t w = cnt[h];
-                    const bool d = MEDIUM ? (w >> 16) != 1u : w != 1u;     // repeated in seq1 (DUP0) or seen more than once in seq2
-                    if (!d) a = MEDIUM ? ((w & 0xFFFFu) - 1u) & 0xFFFFu : pos0[h];   // NONE16 when the k-mer is private to seq2 (graph mode)
+                    const bool d = MEDIUM ? (w & (MR_DUP0 | MR_SEEN2)) != 0u : w != 1u;     // repeated in seq1 (DUP0) or seen more than once in seq2
+                    if (!d) a = MEDIUM ? ((w & MR_SRC1) ? (uint32_t)NONE16 : (w & 0xFFFFu) - 1u) : pos0[h];   // NONE16 when the k-mer is private to seq2 (graph mode)
                     if (FULL) nd1[pd.q_base + q] = !d;
                 }
                 return a;
             };
-            for (int q = 2 * tid; q < N1; q += 2 * T) {
-                KeyT k0 = 0, k1 = 0;
-                if (MEDIUM) B::kmer2(pk1, q, kmask, k0, k1);
-                const uint32_t hh = memo2[q >> 1];
-                const uint32_t a0 = phase_b2(k0, hh & 0xFFFFu, q);
-                const uint32_t a1 = q + 1 < N1 ? phase_b2(k1, hh >> 16, q + 1) : (uint32_t)NONE16;
-                memo2[q >> 1] = a0 | (a1 << 16);
+            if (MEDIUM) {
+                // this partition's positions get their final aof[] entry (position in seq1 or -1) straight in HBM
+                int32_t *ga = aof + pd.q_base;
+                for (int q = 2 * tid; q < N1; q += 2 * T) {
+                    bool p0 = true, p1 = q + 1 < N1;
+                    if (parts > 1) {
+                        KeyT k0, k1;
+                        B::kmer2(pk1, q, kmask, k0, k1);
+                        p0 = in_part(B::mix(k0)); p1 = p1 && in_part(B::mix(k1));
+                    }
+                    const uint32_t hh = memo2[q >> 1];
+                    if (p0) { const uint32_t a = phase_b2(hh & 0xFFFFu, q); ga[q] = a == NONE16 ? -1 : (int32_t)a; }
+                    if (p1) { const uint32_t a = phase_b2(hh >> 16, q + 1); ga[q + 1] = a == NONE16 ? -1 : (int32_t)a; }
+                }
+            } else {
+                for (int q = 2 * tid; q < N1; q += 2 * T) {
+                    const uint32_t hh = memo2[q >> 1];
+                    const uint32_t a0 = phase_b2(hh & 0xFFFFu, q);
+                    const uint32_t a1 = q + 1 < N1 ? phase_b2(hh >> 16, q + 1) : (uint32_t)NONE16;
+                    memo2[q >> 1] = a0 | (a1 << 16);
+                }
             }
             if (FULL) {
                 for (int p = tid; p < N0; p += T) {
                     const KeyT key = B::kmer(pk0, p, kmask);
                     const uint32_t hv = B::mix(key);
                     if (!in_part(hv)) continue;
+                    if (MEDIUM) {
+                        const uint32_t h = mr_find<KeyT>(cnt, nb, key, hv, pk0, pk1, kmask);
+                        nd0[pd.p_base + p] = (cnt[h] & (MR_DUP0 | MR_SEEN2)) == 0u;
+                        continue;
+                    }
                     const uint32_t h = bkt_find<KeyT>(keys, nb, key, hv);
-                    nd0[pd.p_base + p] = (MEDIUM ? cnt[h] >> 16 : cnt[h]) <= 1u;      // not repeated in seq1, at most once in seq2
+                    nd0[pd.p_base + p] = cnt[h] <= 1u;      // not repeated in seq1, at most once in seq2
                 }
             }
         }
-        if (MEDIUM) {                                 // medium pair: hand aof[] to the generic stage 2
-            __syncthreads();
-            // expand in place, lowest positions first: the int32 written at q lands on the 16-bit entries
-            // 2q - N1 (+2) <= q, all read in this or an earlier round (read, barrier, write)
-            int32_t *ga = aof + pd.q_base;
-            for (int q0 = 0; q0 < N1; q0 += T) {
-                const int q = q0 + tid;
-                const uint16_t a = q < N1 ? memo[q] : NONE16;
-                __syncthreads();
-                if (q < N1) ga[q] = a == NONE16 ? -1 : (int32_t)a;
-            }
-            continue;
-        }
+        if (MEDIUM) continue;                         // medium pair: aof[] is complete, the generic stage 2 takes over
         __syncthreads();                              // table dead from here on
         // ---- stage 2: run starts / ends (rare) appended unordered.  Every lane flags what its two
         //      positions start / end; the warp's counts are scanned with shuffles and ONE shared-memory
@@ -372,14 +387,15 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
 
 // medium: the partitioned-table instantiation (no 16-bit position array, no shared-memory memo[])
 size_t stage12_small_smem(int key_bytes, uint32_t cap, int words, int maxq, bool medium) {
-    return (size_t)words * 8 + (size_t)cap * (key_bytes + (medium ? 4 : 6)) + (size_t)((maxq + 7) / 8 * 8) * 2 + 16;
+    if (medium) return (size_t)words * 8 + (size_t)cap * 4 + 16;       // packed sequences + by-reference slots
+    return (size_t)words * 8 + (size_t)cap * (key_bytes + 6) + (size_t)((maxq + 7) / 8 * 8) * 2 + 16;
 }
 
 template <typename KeyT, bool FULL, int TPB>
 static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
                             uint32_t cap, int parts, int words, int maxq, bool want_segments, PairOut *pout,
                             Pools pools, Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int32_t *status,
-                            int32_t *aof, int num_sms, cudaStream_t st) {
+                            int32_t *aof, uint16_t *memo_g, int num_sms, cudaStream_t st) {
     const size_t smem = stage12_small_smem(sizeof(KeyT), cap, words, maxq, TPB > 256);
     auto kern = stage12_small_kernel<KeyT, FULL, TPB>;
     cudaError_t e = allow_max_dyn_smem(kern);
@@ -391,36 +407,36 @@ static cudaError_t launch_t(const uint8_t *seqs, const PairDesc *pairs, const in
     int grid = num_sms * occ;
     if (grid > count) grid = count;
     const KeyT kmask = (2 * k >= (int)(8 * sizeof(KeyT))) ? ~(KeyT)0 : (((KeyT)1 << (2 * k)) - 1);
-    kern<<<grid, TPB, smem, st>>>(seqs, pairs, list, count, k, kmask, cap, cap / (uint32_t)Bucket<KeyT>::W, parts, words, maxq,
-                                  want_segments ? 1 : 0, pout, pools, ctr, cfg, nd0, nd1, status, aof);
+    kern<<<grid, TPB, smem, st>>>(seqs, pairs, list, count, k, kmask, cap, cap / (uint32_t)(TPB > 256 ? 4 : Bucket<KeyT>::W), parts, words, maxq,
+                                  want_segments ? 1 : 0, pout, pools, ctr, cfg, nd0, nd1, status, aof, memo_g);
     return cudaGetLastError();
 }
 
 template <typename KeyT>
-static cudaError_t launch_k(bool full, int parts, const uint8_t *seqs, const PairDesc *pairs, const int32_t *list,
+static cudaError_t launch_k(bool full, bool medium, int parts, const uint8_t *seqs, const PairDesc *pairs, const int32_t *list,
                             int count, int k, uint32_t cap, int words, int maxq, bool want_segments, PairOut *pout,
                             Pools pools, Counters *ctr, SlotCfg cfg, uint8_t *nd0, uint8_t *nd1, int32_t *status,
-                            int32_t *aof, int num_sms, cudaStream_t st) {
-#define DBGA_S12_ARGS seqs, pairs, list, count, k, cap, parts, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, status, aof, num_sms, st
-    if (parts > 1) return full ? launch_t<KeyT, true, 1024>(DBGA_S12_ARGS) : launch_t<KeyT, false, 1024>(DBGA_S12_ARGS);
+                            int32_t *aof, uint16_t *memo_g, int num_sms, cudaStream_t st) {
+#define DBGA_S12_ARGS seqs, pairs, list, count, k, cap, parts, words, maxq, want_segments, pout, pools, ctr, cfg, nd0, nd1, status, aof, memo_g, num_sms, st
+    if (medium) return full ? launch_t<KeyT, true, 1024>(DBGA_S12_ARGS) : launch_t<KeyT, false, 1024>(DBGA_S12_ARGS);
     return full ? launch_t<KeyT, true, 256>(DBGA_S12_ARGS) : launch_t<KeyT, false, 256>(DBGA_S12_ARGS);
 #undef DBGA_S12_ARGS
 }
 
-// parts == 1: stages 1+2 fused (small pairs).  parts > 1: stage 1 only with a partitioned table
-// (medium pairs); status[] / aof[] feed the generic stage-2 kernel.
+// !medium: stages 1+2 fused (small pairs).  medium: stage 1 only with by-reference slots, `parts` table
+// partitions; status[] / aof[] feed the generic stage-2 kernel.
 cudaError_t launch_stage12_small(const uint8_t *seqs, const PairDesc *pairs, const int32_t *list, int count, int k,
-                                 uint32_t cap, int parts, int words, int maxq, bool full, bool want_segments,
+                                 uint32_t cap, bool medium, int parts, int words, int maxq, bool full, bool want_segments,
                                  PairOut *pout, Pools pools, Counters *ctr, int max_abs_score, int go_raw, int ge_raw,
-                                 uint8_t *nd0, uint8_t *nd1, int32_t *status, int32_t *aof, int num_sms,
+                                 uint8_t *nd0, uint8_t *nd1, int32_t *status, int32_t *aof, uint16_t *memo_g, int num_sms,
                                  cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     const SlotCfg cfg{max_abs_score, go_raw, ge_raw};
     if (k <= 15)
-        return launch_k<uint32_t>(full, parts, seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr,
-                                  cfg, nd0, nd1, status, aof, num_sms, st);
-    return launch_k<uint64_t>(full, parts, seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg,
-                              nd0, nd1, status, aof, num_sms, st);
+        return launch_k<uint32_t>(full, medium, parts, seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr,
+                                  cfg, nd0, nd1, status, aof, memo_g, num_sms, st);
+    return launch_k<uint64_t>(full, medium, parts, seqs, pairs, list, count, k, cap, words, maxq, want_segments, pout, pools, ctr, cfg,
+                              nd0, nd1, status, aof, memo_g, num_sms, st);
 }
 
 }  // namespace dbga
