@@ -191,8 +191,18 @@ __device__ __forceinline__ int mr_match(const uint4 kk, uint32_t tag, KeyT key, 
     return -1;
 }
 // find-or-claim (neww: the word a claimer leaves); slots of a bucket fill in order
+// Probe sequence: double hashing over buckets -- the step (1, 3, 5 or 7 by two hash bits; `steps` holds the four
+// choices, a step that divides the bucket count replaced by 1) keeps overflowing keys from piling up behind full
+// buckets, and in a warp the longest probe sequence of 32 lanes is what every lane waits for.
+__host__ __device__ inline uint32_t mr_steps(uint32_t nb) {
+    return 1u | ((nb % 3u ? 3u : 1u) << 8) | ((nb % 5u ? 5u : 1u) << 16) | ((nb % 7u ? 7u : 1u) << 24);
+}
+__device__ __forceinline__ uint32_t mr_next(uint32_t b, uint32_t hv, uint32_t nb, uint32_t steps) {
+    b += (steps >> (8u * ((hv >> 4) & 3u))) & 0xFFu;
+    return b >= nb ? b - nb : b;
+}
 template <typename KeyT>
-__device__ __forceinline__ uint32_t mr_insert(uint32_t *tab, uint32_t nb, KeyT key, uint32_t hv, uint32_t neww,
+__device__ __forceinline__ uint32_t mr_insert(uint32_t *tab, uint32_t nb, uint32_t steps, KeyT key, uint32_t hv, uint32_t neww,
                                               const uint32_t *pk0, const uint32_t *pk1, KeyT kmask, bool &claimed) {
     const uint32_t tag = mr_tag(hv);
     uint32_t b = __umulhi(hv, nb);
@@ -210,11 +220,11 @@ __device__ __forceinline__ uint32_t mr_insert(uint32_t *tab, uint32_t nb, KeyT k
                 if ((cur & MR_TAGM) == tag && mr_same<KeyT>(cur, key, pk0, pk1, kmask)) { claimed = false; return 4 * b + e; }
             }
         }
-        b = b + 1 == nb ? 0 : b + 1;
+        b = mr_next(b, hv, nb, steps);
     }
 }
 template <typename KeyT>
-__device__ __forceinline__ uint32_t mr_find(const uint32_t *tab, uint32_t nb, KeyT key, uint32_t hv, const uint32_t *pk0,
+__device__ __forceinline__ uint32_t mr_find(const uint32_t *tab, uint32_t nb, uint32_t steps, KeyT key, uint32_t hv, const uint32_t *pk0,
                                             const uint32_t *pk1, KeyT kmask) {
     const uint32_t tag = mr_tag(hv);
     uint32_t b = __umulhi(hv, nb);
@@ -223,7 +233,7 @@ __device__ __forceinline__ uint32_t mr_find(const uint32_t *tab, uint32_t nb, Ke
         const int hit = mr_match<KeyT>(kk, tag, key, pk0, pk1, kmask);
         if (hit >= 0) return 4 * b + hit;
         if (kk.w == 0u) return 0xFFFFFFFFu;          // the bucket never filled up: the key is not in the table
-        b = b + 1 == nb ? 0 : b + 1;
+        b = mr_next(b, hv, nb, steps);
     }
 }
 

@@ -63,6 +63,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
     __shared__ S12Shared sh;
 
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t steps = mr_steps(nb);        // medium pairs: probe steps (kmer_table.cuh)
     // nb = cap / B::W buckets (cap is a multiple of 16, not necessarily a power of two) and
     // kmask = 4^k - 1 come in as parameters: constant-bank operands instead of registers
     unsigned long long my_cells = 0, my_nseg = 0;
@@ -120,7 +121,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 if (!in_part(hv)) return;
                 bool claimed;
                 if (MEDIUM) {
-                    const uint32_t h = mr_insert<KeyT>(cnt, nb, key, hv, ((uint32_t)p + 1u) | mr_tag(hv), pk0, pk1, kmask, claimed);
+                    const uint32_t h = mr_insert<KeyT>(cnt, nb, steps, key, hv, ((uint32_t)p + 1u) | mr_tag(hv), pk0, pk1, kmask, claimed);
                     if (!claimed) atomicOr(&cnt[h], MR_DUP0);
                     return;
                 }
@@ -142,8 +143,8 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 uint32_t h;
                 if (MEDIUM) {
                     bool claimed = false;
-                    if (FULL) h = mr_insert<KeyT>(cnt, nb, key, hv, ((uint32_t)q + 1u) | mr_tag(hv) | MR_SRC1 | MR_SEEN1, pk0, pk1, kmask, claimed);
-                    else h = mr_find<KeyT>(cnt, nb, key, hv, pk0, pk1, kmask);
+                    if (FULL) h = mr_insert<KeyT>(cnt, nb, steps, key, hv, ((uint32_t)q + 1u) | mr_tag(hv) | MR_SRC1 | MR_SEEN1, pk0, pk1, kmask, claimed);
+                    else h = mr_find<KeyT>(cnt, nb, steps, key, hv, pk0, pk1, kmask);
                     if (h != 0xFFFFFFFFu && !claimed) {
                         const uint32_t old = atomicOr(&cnt[h], MR_SEEN1);
                         if ((old & (MR_SEEN1 | MR_SEEN2)) == MR_SEEN1) atomicOr(&cnt[h], MR_SEEN2);
@@ -208,7 +209,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                     const uint32_t hv = B::mix(key);
                     if (!in_part(hv)) continue;
                     if (MEDIUM) {
-                        const uint32_t h = mr_find<KeyT>(cnt, nb, key, hv, pk0, pk1, kmask);
+                        const uint32_t h = mr_find<KeyT>(cnt, nb, steps, key, hv, pk0, pk1, kmask);
                         nd0[pd.p_base + p] = (cnt[h] & (MR_DUP0 | MR_SEEN2)) == 0u;
                         continue;
                     }
