@@ -503,8 +503,12 @@ int do_plan(dbga_ctx *ctx, const int64_t *offsets, int64_t P, const dbga_params 
         ctx->grid_cluster = (int)std::max<int64_t>(1, std::min<int64_t>(2 * ctx->num_sms / WF_CLUSTER, g));
     }
     const bool any_non_tiny = (mx0 > TINY_MAX) || (mx1 > TINY_MAX);
-    if (ctx->dp.h.strip && !getenv("DBGA_STRIP_R"))
-        ctx->dp.h.strip = P * (((int64_t)mx0 + S16_ROWS - 1) / S16_ROWS) >= (int64_t)ctx->num_sms * 8 ? 8 : 4;
+    if (ctx->dp.h.strip && !getenv("DBGA_STRIP_R")) {
+        // strips expected in flight: whole sequences are the segments without anchoring; between anchors long
+        // segments are the exception (a few bubbles per pair at most), so count one per pair
+        const int64_t est = no_anchors ? P * (((int64_t)mx0 + S16_ROWS - 1) / S16_ROWS) : P;
+        ctx->dp.h.strip = est >= (int64_t)ctx->num_sms * 8 ? 8 : 4;
+    }
     // (with the strip kernel the long class also takes what the one-pass packed kernel cannot hold)
     const bool any_cta = (int64_t)mx0 * mx1 > ctx->warp_max_cells || (ctx->dp.h.strip && any_non_tiny && mx0 > 256);
     if (!any_non_tiny) ctx->grid_warp = 0;

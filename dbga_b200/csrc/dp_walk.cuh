@@ -143,24 +143,39 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
     };
     // table column (byte) of matrix row cb of a block
     auto col_of = [&](int cb) -> int { return nib ? wf_col_nib(cb, g.nib_sh) : wf_col(cb, g.pr_sh); };
-    // the cell's fields in the byte form (bits 0-1 pred of M, 2-3 of X, 4-5 of Y): the compact form is
-    // expanded through pmap's inverse -- only "came from M" or "stayed" exist for X and Y there
-    const uint32_t tagM_ = (((pmap >> 0) & 3u) == 0u) ? 0u : ((((pmap >> 2) & 3u) == 0u) ? 1u : 2u);
-    const uint32_t tagX_ = (((pmap >> 0) & 3u) == 1u) ? 0u : ((((pmap >> 2) & 3u) == 1u) ? 1u : 2u);
-    const uint32_t tagY_ = (((pmap >> 0) & 3u) == 2u) ? 0u : ((((pmap >> 2) & 3u) == 2u) ? 1u : 2u);
-    auto cell = [&](int r, int c, int cb) -> uint32_t {
-        if (!nib) return tb_byte(r, c);
-        const uint32_t v = ((uint32_t)win[r][c] >> (4 * (cb & 1))) & 15u;
-        return (v & 3u) | (((v & 4u) ? tagM_ : tagX_) << 2) | (((v & 8u) ? tagM_ : tagY_) << 4);
-    };
     while (i > 0 || j > 0) {
         if (i == 0) { emit(2, j); break; }           // first row / column: one long gap
         if (j == 0) { emit(1, i); break; }
         const int i0 = i - 1;
-        const int blk = i0 >> g.roww_sh, cb = i0 & roww_mask;      // (pass * GW + warp), l * R + r
-        const int row = j + (cb >> g.rdiv_sh);
-        const int ccol = nib ? wf_col_nib(cb, g.nib_sh) : cb;       // window position of the cell's byte (byte form: by matrix row)
-        if (blk != win_blk || (unsigned)(win_row_hi - row) >= (unsigned)WIN_ROWS || (unsigned)(ccol - win_col_lo) >= (unsigned)WIN_W) {
+        // Lane l looks at the cell l steps further along the current state's direction (M: the diagonal, X: up the
+        // column, Y: along the row): does the path stay in this state there?  The walk takes the whole run of
+        // cells that do, plus the cell that ends it (still consumed in this state; its tag names the next one).
+        const int di = st != 2, dj = st != 1;
+        const int il = i0 - lane * di, jl = j - lane * dj;
+        uint32_t nxt = 3u;                           // 3: outside the matrix or the window
+        if (il >= 0 && jl >= 1) {
+            const int bl = il >> g.roww_sh, cl = il & roww_mask;
+            const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh)));
+            const int wc = col_of(cl);
+            const unsigned dc = (unsigned)((nib ? wc : cl) - win_col_lo);
+            if (bl == win_blk && dr < (unsigned)WIN_ROWS && dc < (unsigned)WIN_W) {
+                if (nib) {
+                    // compact cell: bits 0-1 the predecessor tag of M, bit 2 "X came from M", bit 3 "Y came from M"
+                    const uint32_t v = (uint32_t)win[dr][wc - win_col_lo] >> (4 * (cl & 1));
+                    nxt = st == 0 ? (pmap >> (2 * (v & 3u))) & 3u : ((v & (st == 1 ? 4u : 8u)) ? 0u : (uint32_t)st);
+                } else {
+                    nxt = (pmap >> (2 * ((tb_byte(dr, wc - win_col_lo) >> (2 * st)) & 3u))) & 3u;
+                }
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, nxt == (uint32_t)st);
+        const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
+        const uint32_t nx = __shfl_sync(0xffffffffu, nxt, c & 31);
+        if (c == 0 && nx == 3u) {
+            // the walk's own cell is outside the window (lane 0 is inside the matrix here): centre a new one on it
+            const int blk = i0 >> g.roww_sh, cb = i0 & roww_mask;      // (pass * GW + warp), l * R + r
+            const int row = j + (cb >> g.rdiv_sh);
+            const int ccol = nib ? wf_col_nib(cb, g.nib_sh) : cb;       // window position of the cell's byte (byte form: by matrix row)
             __syncwarp();
             win_blk = blk; win_row_hi = row;
             win_col_lo = max(0, (ccol & ~31) - 32);
@@ -176,25 +191,9 @@ __device__ __forceinline__ int wf_traceback(uint8_t (*win)[64], const uint8_t *_
                 dst[0] = a; dst[1] = b; dst[2] = c4; dst[3] = d4;
             }
             __syncwarp();
+            continue;
         }
-        // Lane l looks at the cell l steps further along the current state's direction (M: the diagonal, X: up the
-        // column, Y: along the row): does the path stay in this state there?  The walk takes the whole run of
-        // cells that do, plus the cell that ends it (still consumed in this state; its tag names the next one).
-        const int di = st != 2, dj = st != 1;
-        const int il = i0 - lane * di, jl = j - lane * dj;
-        uint32_t nxt = 3u;                           // 3: outside the matrix or the window
-        if (il >= 0 && jl >= 1) {
-            const int bl = il >> g.roww_sh, cl = il & roww_mask;
-            const unsigned dr = (unsigned)(win_row_hi - (jl + (cl >> g.rdiv_sh)));
-            const int wc = col_of(cl);
-            const unsigned dc = (unsigned)((nib ? wc : cl) - win_col_lo);
-            if (bl == win_blk && dr < (unsigned)WIN_ROWS && dc < (unsigned)WIN_W)
-                nxt = (pmap >> (2 * ((cell(dr, wc - win_col_lo, cl) >> (2 * st)) & 3u))) & 3u;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, nxt == (uint32_t)st);
-        const int c = bal == 0xffffffffu ? 32 : __ffs((int)~bal) - 1;
-        const uint32_t nx = __shfl_sync(0xffffffffu, nxt, c & 31);
-        const int take = c + ((c < 32 && nx != 3u) ? 1 : 0);       // lane 0's cell is inside the window: take >= 1
+        const int take = c + ((c < 32 && nx != 3u) ? 1 : 0);
         emit(st, take);
         i -= take * di; j -= take * dj;
         if (c < 32 && nx != 3u) st = (int)nx;

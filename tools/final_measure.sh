@@ -29,4 +29,19 @@ DP_PAIRS=3814 ncu --set full --clock-control none --import-source on -k regex:'d
 python tools/ncu_dp_summary.py ${T}_dp1024 gpurun_out/${T}_dp1024.ncu-rep "DP_PAIRS=3814 python tools/dp_bench.py 1024 (-k regex:'dp_wf16|dp_tb16' -s 12 -c 6)" > /dev/null 2>&1
 cp profiles/${T}_dp1024_ncu_full_summary.csv gpurun_out/ 2>/dev/null
 rm -f gpurun_out/${T}_dp1024.ncu-rep
+# long-segment strip kernel (dp_wf16s_kernel) + its traceback at L = 2048, and the 1 Mb pair's launch list
+DP_PAIRS=953 ncu --set full --clock-control none --import-source on -k regex:'dp_wf16s|dp_tb16' -s 3 -c 3 \
+    -o gpurun_out/${T}_dp2048 -f python tools/dp_bench.py 2048 > gpurun_out/${T}_ncu_dp2048.log 2>&1
+python tools/ncu_dp_summary.py ${T}_dp2048 gpurun_out/${T}_dp2048.ncu-rep "DP_PAIRS=953 python tools/dp_bench.py 2048 (-k regex:'dp_wf16s|dp_tb16' -s 3 -c 3)" > /dev/null 2>&1
+python tools/ncu_lines.py gpurun_out/${T}_dp2048.ncu-rep dp_wf16s 0.01 > gpurun_out/${T}_dp_wf16s_lines.txt 2>&1
+cp profiles/${T}_dp2048_ncu_full_summary.csv gpurun_out/ 2>/dev/null
+rm -f gpurun_out/${T}_dp2048.ncu-rep
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_cfg5_launches.csv \
+    python tools/cfg5_one.py > gpurun_out/${T}_ncu_cfg5.log 2>&1
+# medium-pair stage 1 (by-reference table) on a cfg4 sample
+CFG4_PAIRS=1480 ncu --set full --clock-control none --import-source on -k regex:'stage12_small' --launch-skip 2 -c 1 \
+    -o gpurun_out/${T}_cfg4 -f python tools/big_bench.py cfg4 > gpurun_out/${T}_ncu_cfg4.log 2>&1
+python tools/ncu_lines.py gpurun_out/${T}_cfg4.ncu-rep stage12_small 0.008 > gpurun_out/${T}_cfg4_stage1_lines.txt 2>&1
+ncu -i gpurun_out/${T}_cfg4.ncu-rep --page raw --csv > gpurun_out/${T}_cfg4_stage1_raw.csv 2>/dev/null
+rm -f gpurun_out/${T}_cfg4.ncu-rep
 tail -2 gpurun_out/${T}_tests.log; tail -c 900 gpurun_out/${T}_bench.json
