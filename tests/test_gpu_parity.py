@@ -543,9 +543,11 @@ def test_wide_kmers_vs_oracle(aligner, k):
 
 
 def test_long_homopolymer_does_not_wrap_the_medium_counter(aligner):
-    """A k-mer repeated in seq1 and occurring more than 32 768 times in seq2 (a 33 kb homopolymer stretch):
-    the medium-pair kernel's packed counter would carry into its "repeated in seq1" flag, so such pairs
-    (seq2 longer than 32 767 k-mers) take the global-table path.  Stages 1-2 against the oracle."""
+    """A k-mer repeated in seq1 and occurring more than 32 768 times in seq2 (a 33 kb homopolymer stretch).
+    Round 1's medium-pair kernel counted seq-2 occurrences in 15 bits under its "repeated in seq1" flag (a
+    count that large would have carried into it); the by-reference slots keep occurrences as flags
+    ("seen", "seen again") that only get OR-ed in, so such pairs (41 kb: two table partitions, in graph
+    mode four) stay on the shared-memory path.  Stages 1-2 against the oracle."""
     rng = random.Random(91)
     r1, r2 = rand_seq(rng, 4000), rand_seq(rng, 4000)
     s0 = r1 + "A" * 33000 + r2
