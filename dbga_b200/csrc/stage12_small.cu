@@ -26,6 +26,7 @@ constexpr uint32_t DUP0 = 0x10000u;      // cnt[]: the k-mer occurs more than on
 struct S12Shared {
     unsigned int nSE;      // run starts appended (low 16 bits) | run ends appended (high 16 bits); both < 65 000
     int nA, big;
+    int next[4];           // medium pairs: next block of positions of phase A / B1 / B2 (warps take 64 at a time)
     long long bcast[2];
     long long red[32];
 };
@@ -79,7 +80,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             continue;
         }
         __syncthreads();            // previous pair's shared state is no longer in use
-        if (tid == 0) { sh.nSE = 0u; sh.nA = 0; sh.big = 0; }
+        if (tid == 0) { sh.nSE = 0u; sh.nA = 0; sh.big = 0; sh.next[0] = sh.next[1] = sh.next[2] = 0; }
         // ---- pack + table init
         bool bad = false;
         {
@@ -110,7 +111,7 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
             memo = memo_g + ((pd.q_base + 2 * (int64_t)pair + 1) & ~(int64_t)1);
         }
         for (int g = 0; g < parts; ++g) {
-            if (g > 0) { __syncthreads(); init_table(); __syncthreads(); }
+            if (g > 0) { __syncthreads(); init_table(); if (tid == 0) { sh.next[0] = sh.next[1] = sh.next[2] = 0; } __syncthreads(); }
             // partition of a k-mer: low 16 bits of its hash (the bucket uses the high bits)
             auto in_part = [&](uint32_t hv) { return !MEDIUM || parts == 1 || (int)(((hv & 0xFFFFu) * (uint32_t)parts) >> 16) == g; };
             // Every thread takes two adjacent positions per round: one pair of packed words
@@ -129,11 +130,31 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 if (claimed) pos0[h] = (uint16_t)p;
                 else cnt[h] = DUP0;
             };
-            for (int p = 2 * tid; p < N0; p += 2 * T) {
-                KeyT k0, k1;
-                B::kmer2(pk0, p, kmask, k0, k1);
-                phase_a(k0, p);
-                if (p + 1 < N0) phase_a(k1, p + 1);
+            // Medium pairs: a warp takes the next 64 positions whenever it is done with its last ones (one shared-memory
+            // add per warp and block): the number of buckets a probe needs is long-tailed, and with a fixed share per
+            // warp the whole CTA waited at the phase's barrier for the unluckiest one.
+            auto next_block = [&](int which) -> int {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh.next[which], 64);
+                return __shfl_sync(0xffffffffu, base, 0);
+            };
+            if (MEDIUM) {
+                for (int base = next_block(0); base < N0; base = next_block(0)) {
+                    const int p = base + 2 * lane;
+                    if (p < N0) {
+                        KeyT k0, k1;
+                        B::kmer2(pk0, p, kmask, k0, k1);
+                        phase_a(k0, p);
+                        if (p + 1 < N0) phase_a(k1, p + 1);
+                    }
+                }
+            } else {
+                for (int p = 2 * tid; p < N0; p += 2 * T) {
+                    KeyT k0, k1;
+                    B::kmer2(pk0, p, kmask, k0, k1);
+                    phase_a(k0, p);
+                    if (p + 1 < N0) phase_a(k1, p + 1);
+                }
             }
             __syncthreads();
             // ---- B1: seq2 k-mers; memo[q] = slot (or, medium pairs, what an earlier partition left)
@@ -161,13 +182,21 @@ stage12_small_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restric
                 return h != 0xFFFFFFFFu ? h : (uint32_t)NONE16;
             };
             uint32_t *memo2 = reinterpret_cast<uint32_t *>(memo);   // two positions per word
-            for (int q = 2 * tid; q < N1; q += 2 * T) {
+            auto b1_pair = [&](int q) {
                 KeyT k0, k1;
                 B::kmer2(pk1, q, kmask, k0, k1);
                 // (medium pairs: a position outside this partition gets NONE16 here and is skipped by this round's B2)
                 const uint32_t m0 = phase_b1(k0, NONE16, q);
                 const uint32_t m1 = q + 1 < N1 ? phase_b1(k1, NONE16, q + 1) : (uint32_t)NONE16;
                 memo2[q >> 1] = m0 | (m1 << 16);
+            };
+            if (MEDIUM) {
+                for (int base = next_block(1); base < N1; base = next_block(1)) {
+                    const int q = base + 2 * lane;
+                    if (q < N1) b1_pair(q);
+                }
+            } else {
+                for (int q = 2 * tid; q < N1; q += 2 * T) b1_pair(q);
             }
             __syncthreads();
             // ---- B2: anchors; memo[q] becomes aof[q] (position in seq1 or NONE16)
