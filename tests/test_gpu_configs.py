@@ -98,3 +98,32 @@ def test_cfg5_shorter_pairs_other_conventions(aligner):
         if done == 3:
             break
     assert done == 3
+
+
+def test_long_segments_through_the_pipelined_batch(aligner):
+    """Long DP segments inside a batch large enough for the chunked pipeline of dbga_align_batch (>= 16 MB:
+    four lanes, each with its own pools, streams and side stream for the long class): 900 pairs of 12 kb
+    with one planted indel-rich 1.5-2.5 kb bubble each, k = 15.  Every bubble is more than one packed pass
+    holds, so it runs as row strips (dp_wf16s_kernel) -- in chunks of a few hundred pairs, i.e. with both
+    strip heights in one call.  Everything against the oracle, and the device-resident plan path must give
+    byte-identical rows."""
+    from dbga_b200.synth import synth_long_pair
+    bufs, offs, base = [], [0], 0
+    for s in range(900):
+        b, o = synth_long_pair(n=12_000, n_bubbles=1, seed=1000 + s, bubble_len=(1500, 2500))
+        bufs.append(b)
+        offs += [base + int(o[1]), base + int(o[2])]
+        base += int(o[2])
+    buf, offs = np.concatenate(bufs), np.asarray(offs, np.int64)
+    assert buf.nbytes >= 16 << 20
+    res, ref = diff_vs_oracle(aligner, buf, offs, 15)
+    ok = ref["status"] == O.OK
+    assert ok.sum() > 700 and (ref["dp_cells"][ok] > 1_000_000).sum() > 500
+    assert res.timing["launches"] > 40                                 # several chunks ran
+    import torch
+    d = torch.from_numpy(np.concatenate([buf, np.zeros(64, np.uint8)])).cuda()
+    aligner.plan(offs, aligner.params(15))
+    aligner.run(d.data_ptr())
+    direct = aligner.fetch()
+    assert np.array_equal(direct.status, res.status) and np.array_equal(direct.score, res.score)
+    assert np.array_equal(direct.aln_off, res.aln_off) and np.array_equal(direct.aln0, res.aln0) and np.array_equal(direct.aln1, res.aln1)
