@@ -174,6 +174,7 @@ def main():
             fixtures["adaptive_top"].append({"seqs": [s0, s1], "fasta": text})
         except Exception as ex:
             fixtures["adaptive_top"].append({"seqs": [s0, s1], "error": type(ex).__name__})
+    fixtures["sop_fuzz"] = sop_fuzz()
     json.dump(fixtures, open(os.path.join(ROOT, "tests", "golden", "ref_fixtures.json"), "w"), indent=1)
 
     rng = random.Random(20261019)
@@ -203,5 +204,46 @@ def main():
                 f.write(f">{nm}\n{sq}\n")
 
 
+class _TwoRows:
+    """What pairwise_alignment_score reads of a cogent3 ArrayAlignment (src/dbga/utils.py:440-504)."""
+    def __init__(self, r0, r1):
+        self.seqs = [r0, r1]
+        self.num_seqs = 2
+        self.seq_len = len(r0)
+
+
+def sop_fuzz():
+    """Outputs of the reference's own pairwise_alignment_score loop (src/dbga/utils.py:440-504) on seeded random
+    two-row alignments -- gap runs that switch rows, both-gap columns, runs of mismatches -- recorded as
+    ref_fixtures.json: sop_fuzz.  Pins dbga_b200/quality.py and the device counts (DBGA_FLAG_SOP)."""
+    from dbga.utils import pairwise_alignment_score
+    rng = random.Random(4404)
+    out = []
+    for _ in range(300):
+        n = rng.choice([1, 2, 5, 17, 64, 200])
+        pg = rng.choice([0.0, 0.05, 0.3, 0.7])
+        rows = []
+        for _r in range(2):
+            row, c = [], "A"
+            for _i in range(n):
+                if rng.random() < pg or (row and row[-1] == "-" and rng.random() < 0.5):
+                    c = "-"
+                else:
+                    c = rng.choice("ACGT")
+                row.append(c)
+            rows.append("".join(row))
+        if rng.random() < 0.5:          # mostly matching rows: copy row 0's bases where row 1 has a base
+            rows[1] = "".join(a if (b != "-" and a != "-" and rng.random() < 0.8) else b for a, b in zip(rows[0], rows[1]))
+        out.append({"rows": rows, "counts": pairwise_alignment_score(_TwoRows(rows[0], rows[1]))})
+    return out
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-sop" in sys.argv:
+        path = os.path.join(ROOT, "tests", "golden", "ref_fixtures.json")
+        fx = json.load(open(path))
+        fx["sop_fuzz"] = sop_fuzz()
+        json.dump(fx, open(path, "w"), indent=1)
+        print(f"wrote {len(fx['sop_fuzz'])} sop cases")
+    else:
+        main()

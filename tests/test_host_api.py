@@ -227,17 +227,20 @@ def test_sop_reference_goldens():
 
 
 def test_sop_matches_reference_loop():
-    """Property check against a direct transcription-free re-derivation: random alignments,
-    counts must satisfy columns = match + mismatch + gap_open + gap_extend + both-gap columns."""
+    """dbga_b200.quality against 300 outputs recorded from the reference's own pairwise_alignment_score loop
+    (src/dbga/utils.py:440-504, run unmodified by oracle/make_golden.py: sop_fuzz) on random two-row
+    alignments: gap runs that switch rows, both-gap columns, runs of mismatches.  Plus the column identity
+    match + mismatch + gap_open + gap_extend + both-gap columns == columns."""
+    import json
     from dbga_b200.quality import score_rows
-    rng = np.random.default_rng(3)
-    for _ in range(200):
-        n = int(rng.integers(1, 60))
-        r1 = rng.choice(np.frombuffer(b"ACGT-", np.uint8), n)
-        r2 = rng.choice(np.frombuffer(b"ACGT-", np.uint8), n)
+    cases = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fixtures.json")))["sop_fuzz"]
+    assert len(cases) == 300
+    for c in cases:
+        r1 = np.frombuffer(c["rows"][0].encode(), np.uint8)
+        r2 = np.frombuffer(c["rows"][1].encode(), np.uint8)
         s = score_rows(r1, r2)
-        both_gap = int(((r1 == 45) & (r2 == 45)).sum())
-        assert sum(s.values()) + both_gap == n
+        assert s == c["counts"], c["rows"]
+        assert sum(s.values()) + int(((r1 == 45) & (r2 == 45)).sum()) == len(r1)
 
 
 def test_bench_reference_arm_contract():

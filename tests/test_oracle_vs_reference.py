@@ -51,3 +51,34 @@ def test_live_reference_fuzz():
         sys.path[:] = saved
         for m in [m for m in sys.modules if m == "dbga" or m.startswith("dbga.") or m.startswith("cogent3") or m == "graphviz"]:
             del sys.modules[m]
+
+
+def test_live_reference_sop():
+    """dbga_b200.quality.score_rows against the reference's pairwise_alignment_score loop (src/dbga/utils.py:440-504),
+    run live on random two-row alignments (the recorded form: tests/golden/ref_fixtures.json sop_fuzz)."""
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    shim = os.path.join(os.path.dirname(here), "oracle", "cogent3_shim")
+    saved = list(sys.path)
+    sys.path[:0] = [shim, REF]
+    try:
+        from dbga.utils import pairwise_alignment_score
+        from dbga_b200.quality import score_rows
+
+        class TwoRows:
+            def __init__(self, r0, r1):
+                self.seqs, self.num_seqs, self.seq_len = [r0, r1], 2, len(r0)
+
+        rng = random.Random(5)
+        for _ in range(500):
+            n = rng.randint(1, 80)
+            pg = rng.choice([0.05, 0.3, 0.6])
+            r0 = "".join("-" if rng.random() < pg else rng.choice("ACGT") for _ in range(n))
+            r1 = "".join("-" if rng.random() < pg else (a if a != "-" and rng.random() < 0.6 else rng.choice("ACGT")) for a in r0)
+            want = pairwise_alignment_score(TwoRows(r0, r1))
+            got = score_rows(np.frombuffer(r0.encode(), np.uint8), np.frombuffer(r1.encode(), np.uint8))
+            assert got == want, (r0, r1)
+    finally:
+        sys.path[:] = saved
+        for m in [m for m in sys.modules if m == "dbga" or m.startswith("dbga.") or m.startswith("cogent3") or m == "graphviz"]:
+            del sys.modules[m]
