@@ -10,6 +10,8 @@ from dbga_b200.synth import synth_batch
 def main():
     Ls = [int(x) for x in sys.argv[1:]] or [16, 64, 256, 1024, 4096]
     al = Aligner(0)
+    if os.environ.get("DP_SCRATCH_GB"):            # more segments than 4 G cells' worth: the traceback pool is sized at a byte per cell
+        al.set_scratch_limit(int(os.environ["DP_SCRATCH_GB"]) << 30)
     peak = al.int_peak()
     roof = peak["mix_ops_per_s"] / 9 / 1e9
     out = []
