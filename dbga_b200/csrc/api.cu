@@ -739,6 +739,7 @@ int fetch_resolve(dbga_ctx *ctx, bool counters_already_copied) {
             DBGA_CUDA_CHECK(cudaMemcpyAsync(hc, ctx->d_ctr.p, sizeof(Counters), cudaMemcpyDeviceToHost, st));
             DBGA_CUDA_CHECK(cudaStreamSynchronize(st));
         }
+        if (hc->strip_timeout) return fail(ctx, DBGA_ERR_CUDA, "long-segment strip kernel: a boundary row never arrived (internal error)");
         bool grow = false;
         if ((int64_t)hc->runs_used > ctx->runs_cap) { ctx->runs_cap = (int64_t)hc->runs_used + 1024; grow = true; }
         if ((int64_t)hc->slots_used > ctx->slots_cap) { ctx->slots_cap = (int64_t)hc->slots_used + 1024; grow = true; }

@@ -27,6 +27,8 @@ struct Counters {
     unsigned int scan_ticket;          // assembler's layout pass: next block of pairs
     unsigned int long_max_m;           // most rows of any long (CLS_CTA) segment
     unsigned long long long_ticket;    // strip kernel: next (strip, segment) work item
+    unsigned int strip_timeout;        // strip kernel: a boundary entry never arrived (reported as an error, never a hang)
+    unsigned int pad2;
 };
 
 struct Pools {

@@ -491,9 +491,14 @@ dp_wf16s_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
                 const bool need = lane < 16 && c <= n;
                 // (a consumer that has caught up with its producer backs off: its polls take issue slots from the
                 // warps it shares the SM with -- possibly the producer itself)
+                long long t_wait = 0;
                 for (unsigned int nap = 32;;) {
                     const bool ok = !need || (E.y == nonce && E.w == nonce);
                     if (__all_sync(FULL, ok)) break;
+                    // a producer is never more than a chunk's work away; seconds of waiting mean a bug -- say so and go on
+                    // (the host turns the flag into an error) rather than hang the device
+                    if (t_wait == 0) t_wait = clock64();
+                    else if (__any_sync(FULL, clock64() - t_wait > 10000000000LL)) { if (lane == 0) atomicExch(&ctr->strip_timeout, 1u); break; }
                     __nanosleep(nap);
                     if (OCC > 8 && nap < 2048u) nap *= 2u;        // (the few-segments form runs a warp per SM: nothing to yield to)
                     if (!ok) E = ld_volatile_u4(bin + c);
