@@ -41,6 +41,8 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
                               PairOut *__restrict__ pout, Pools pools, Counters *__restrict__ ctr,
                               int max_abs_score, int go_raw, int ge_raw, int cluster_above) {
     __shared__ ScanSmem sm;
+    // one bit per seq-2 position: "a run starts here" / "a run ends here" (pass 1 -> pass 2)
+    __shared__ uint32_t maskS[S2_CLUSTER_ABOVE / 32 + 1], maskE[S2_CLUSTER_ABOVE / 32 + 1];
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = (T + 31) >> 5;
     unsigned long long my_cells = 0, my_nseg = 0;
 
@@ -89,16 +91,21 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
                 if (q >= q_hi) a[u] = -1;
             }
         };
+        // (the ballots are the warp's counts and, kept as one bit per position, all that pass 2 needs: run boundaries
+        // are rare -- a couple of hundred in 30 000 positions -- so pass 2 walks 32 positions per lane-word and
+        // touches aof[] again only where a run starts)
         int cS = 0, cE = 0;
         long long cA = 0;
         for (int base = q_lo; base < q_hi; base += 32 * U) {
             int a[U]; bool isS[U], isE[U];
             load_block(base, a, isS, isE);
 #pragma unroll
-            for (int u = 0; u < U; ++u) { cA += a[u] >= 0; cS += isS[u]; cE += isE[u]; }
+            for (int u = 0; u < U; ++u) {
+                const unsigned bS = __ballot_sync(0xffffffffu, isS[u]), bE = __ballot_sync(0xffffffffu, isE[u]);
+                cA += a[u] >= 0; cS += __popc(bS); cE += __popc(bE);
+                if (lane == 0 && base + 32 * u < q_hi) { maskS[(base >> 5) + u] = bS; maskE[(base >> 5) + u] = bE; }
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { cS += __shfl_xor_sync(0xffffffffu, cS, o); cE += __shfl_xor_sync(0xffffffffu, cE, o); }
         __syncthreads();
         if (lane == 0) { sm.warpS[wid] = cS; sm.warpE[wid] = cE; }
         __syncthreads();
@@ -126,23 +133,33 @@ __global__ void stage2_kernel(const PairDesc *__restrict__ pairs, const int32_t 
             continue;
         }
         int32_t *runs = pools.runs + 3 * run_base;
-        // ---- pass 2: ordered compaction of run starts (a, b) and run ends (b), per warp chunk
-        for (int base = q_lo; base < q_hi; base += 32 * U) {
-            int a[U]; bool isS[U], isE[U];
-            load_block(base, a, isS, isE);
-            const unsigned lt = (1u << lane) - 1u;
+        // ---- pass 2: ordered compaction of run starts (a, b) and run ends (b), per warp chunk, from the bit masks:
+        //      a lane takes one word of 32 positions, the warp scans the words' counts, every set bit is one store
+        for (int w0 = q_lo >> 5; q_lo < q_hi && 32 * w0 < q_hi; w0 += 32) {      // (an empty chunk starts at N1, not at a word)
+            const int w = w0 + lane;
+            const bool have = 32 * w < q_hi;
+            uint32_t mS = have ? maskS[w] : 0u, mE = have ? maskE[w] : 0u;
+            int nS = __popc(mS), nE = __popc(mE), iS = nS, iE = nE;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int q = base + 32 * u + lane;
-                const unsigned bS = __ballot_sync(0xffffffffu, isS[u]), bE = __ballot_sync(0xffffffffu, isE[u]);
-                if (isS[u]) {
-                    const int idx = offS + __popc(bS & lt);
-                    runs[3 * (int64_t)idx] = a[u];
-                    runs[3 * (int64_t)idx + 1] = q;
-                }
-                if (isE[u]) runs[3 * (int64_t)(offE + __popc(bE & lt)) + 2] = q;   // end b, turned into len below
-                offS += __popc(bS); offE += __popc(bE);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int vS = __shfl_up_sync(0xffffffffu, iS, o), vE = __shfl_up_sync(0xffffffffu, iE, o);
+                if (lane >= o) { iS += vS; iE += vE; }
             }
+            int idxS = offS + iS - nS, idxE = offE + iE - nE;
+            while (mS) {
+                const int q = 32 * w + __ffs((int)mS) - 1;
+                mS &= mS - 1;
+                runs[3 * (int64_t)idxS] = a_of[q];
+                runs[3 * (int64_t)idxS + 1] = q;
+                ++idxS;
+            }
+            while (mE) {
+                const int q = 32 * w + __ffs((int)mE) - 1;
+                mE &= mE - 1;
+                runs[3 * (int64_t)idxE + 2] = q;                   // end b, turned into len below
+                ++idxE;
+            }
+            offS += __shfl_sync(0xffffffffu, iS, 31); offE += __shfl_sync(0xffffffffu, iE, 31);
         }
         __syncthreads();
         // ---- run lengths, then the colinearity check (utils.py:266-291): seq-1 positions of
