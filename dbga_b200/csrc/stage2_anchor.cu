@@ -259,7 +259,7 @@ stage2_cluster_kernel(const PairDesc *__restrict__ pairs, const int32_t *__restr
         const int32_t *a_of = aof + pd.q_base;
         const int chunk = (((N1 + gnw - 1) / gnw) + 31) & ~31;
         const int q_lo = min(N1, gwid * chunk), q_hi = min(N1, q_lo + chunk);
-        constexpr int U = 4;
+        constexpr int U = 8;                             // (eight independent loads per lane: 128 warps sweep 1 M positions, latency-bound)
         auto load_block = [&](int base, int (&a)[U], bool (&isS)[U], bool (&isE)[U]) {      // as in stage2_kernel
             int edge_lo = -1, edge_hi = -1;
             if (lane == 0 && base > 0) edge_lo = a_of[base - 1];
