@@ -594,8 +594,8 @@ cudaError_t launch_dp_strips16(const uint8_t *seqs, const PairDesc *pairs, Slot 
                                const unsigned int *count_dev, Counters *ctr, int grid, DpParams prm, uint8_t *tb,
                                uint32_t nonce, cudaStream_t st) {
     if (grid <= 0 || !prm.h.strip) return cudaSuccess;
-    // few segments: 256-row strips (a lone warp's step is half as long, twice as many warps per segment)
-    // (few segments: every register the step wants, eight warps per SM at most)
+    // few strips in flight: 256-row strips (a lone warp's step is half as long, twice as many warps per segment), every
+    // register the step wants (eight warps per SM at most), no poll back-off; many: 512-row strips, sixteen warps per SM
     if (prm.h.strip == 4) dp_wf16s_kernel<4, 8><<<grid / 2, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
     else dp_wf16s_kernel<8, 16><<<grid, 32, 0, st>>>(seqs, pairs, slots, list, count_dev, ctr, prm, tb, nonce);
     return cudaGetLastError();
