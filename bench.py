@@ -425,11 +425,15 @@ def run_ours(args):
     # library's CUDA events on the launching stream (forward kernels + traceback kernel)
     if not args.no_dp_micro:
         micro = []
-        for L, Pm in ((1024, 3814), (4096, 238)):
+        # (4096 x 4096 twice: the microbenchmark's 4 G-cell budget -- 238 segments, fewer row strips than the chip
+        #  has warp slots -- and a batch that fills the chip; its traceback pool is sized at a byte per cell: 16 GB)
+        for L, Pm in ((1024, 3814), (4096, 238), (4096, 960)):
             mb, mo = synth_batch(Pm, L, 0.05, 0.01, seed=L)
             d_m = torch.from_numpy(np.concatenate([mb, np.zeros(64, np.uint8)])).to(dev)
             torch.cuda.synchronize()
             alm = Aligner(local)
+            if Pm * L * L > 6e9:
+                alm.set_scratch_limit(40 << 30)
             alm.plan(mo, alm.params(1), global_only=True)
             t3 = []
             for it in range(6):
@@ -445,6 +449,7 @@ def run_ours(args):
             del d_m
         dp["microbench"] = micro[0]
         dp["microbench_4096"] = micro[1]
+        dp["microbench_4096_chip_filling_batch"] = micro[2]
 
     # ---------------- CPU baseline on this box's host cores (rank 0, N=1 only)
     cpu = None
