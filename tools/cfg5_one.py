@@ -1,3 +1,5 @@
+"""One device-resident run of BASELINE config [4] (1 Mb pair, ten indel-rich bubbles, k = 15) -- the command the
+round's ncu launch list of the long-segment kernels is taken on (tools/final_measure.sh)."""
 import sys, os, json
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch

@@ -1,3 +1,4 @@
+"""Per-stage CUDA-event times of the cfg3 batch (stages 1+2, stage 3, assembly), device-resident: a quick A/B check."""
 import sys, os
 sys.path.insert(0, os.getcwd())
 import numpy as np, torch
