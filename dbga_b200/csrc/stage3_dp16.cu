@@ -384,7 +384,10 @@ dp_wf16p_kernel(const uint8_t *__restrict__ seqs, const PairDesc *__restrict__ p
 // Boundary rows.  Half-lane 63 of strip s stores, per column, one 16-byte entry {M | X << 16, nonce,
 // Y | delta << 16, nonce} with a plain volatile store; lanes 0-15 of strip s + 1 fetch 16 entries per chunk
 // of 16 steps and poll until both nonces (unique per run, process-wide) are there: every 8-byte half
-// validates itself, so there is no fence, no flag and no cleared memory.
+// validates itself, so there is no fence, no flag and no cleared memory.  (The one hardware assumption: an aligned
+// 8-byte half of a 16-byte store becomes visible whole -- the same assumption the low-latency protocols of
+// collective libraries make for their {data, flag} words.  Stale memory passes both 32-bit checks with probability
+// 2^-64 per entry; an entry of an earlier run carries an earlier nonce.)
 //
 // Frames.  A half-lane keeps 4 (V - base - off) + priority with a base per (strip, block of S16_CB
 // columns): block 0 uses base 0 (H^ <= per_step * min(i, j) is small there), block c >= 1 of strip s > 0
