@@ -10,8 +10,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
+#include <chrono>
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -20,7 +23,10 @@
 
 #include "common.cuh"
 
-namespace dbga { bool host_pack_seq(const uint8_t *src, int64_t len, uint32_t *dst); }   // hostpack.cpp
+namespace dbga {
+bool host_pack_seq(const uint8_t *src, int64_t len, uint32_t *dst);                                // hostpack.cpp
+int64_t host_fasta_body(const uint8_t *p, const uint8_t *end, uint8_t *dst, int64_t room);         // hostpack.cpp
+}
 
 namespace {
 
@@ -42,39 +48,60 @@ struct FastaImpl {
     bool pinned = true;
 };
 
+// Pinned buffers are kept for the next file when a batch is freed: page-locking costs ~0.4 ms per MB (150-190 ms
+// for the 375 MB of a 100 000-pair file, ten times the parsing itself), and a tool that streams files through the
+// aligner would pay it on every one.  A freed buffer is reused by a request of up to its size and at least half of
+// it; at most PIN_CACHE_BYTES stay parked (the rest is released).
+struct PinCache {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_list;
+    size_t parked = 0;
+    std::map<void *, size_t> size_of;          // live pinned buffers handed out by host_buf
+};
+constexpr size_t PIN_CACHE_BYTES = (size_t)4 << 30;
+PinCache &pin_cache() { static PinCache *c = new PinCache(); return *c; }     // (never destroyed: no CUDA calls at exit)
+
 void *host_buf(size_t bytes, bool &pinned) {
     void *p = nullptr;
-    if (pinned && cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) return p;
+    if (pinned) {
+        PinCache &c = pin_cache();
+        {
+            std::lock_guard<std::mutex> lk(c.mu);
+            size_t best = (size_t)-1, bi = 0;
+            for (size_t i = 0; i < c.free_list.size(); ++i)
+                if (c.free_list[i].second >= bytes && c.free_list[i].second / 2 <= bytes && c.free_list[i].second < best) { best = c.free_list[i].second; bi = i; }
+            if (best != (size_t)-1) {
+                p = c.free_list[bi].first;
+                c.parked -= best;
+                c.free_list.erase(c.free_list.begin() + (long)bi);
+                c.size_of[p] = best;
+                return p;
+            }
+        }
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(c.mu);
+            c.size_of[p] = bytes;
+            return p;
+        }
+    }
     cudaGetLastError();
     pinned = false;
     return malloc(bytes);
 }
-void host_release(void *p, bool pinned) {
+void host_release(void *p, bool) {
     if (!p) return;
-    if (pinned) cudaFreeHost(p); else free(p);
+    PinCache &c = pin_cache();
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(c.mu);
+        auto it = c.size_of.find(p);
+        if (it != c.size_of.end()) { bytes = it->second; c.size_of.erase(it); }
+        if (bytes && c.parked + bytes <= PIN_CACHE_BYTES) { c.free_list.emplace_back(p, bytes); c.parked += bytes; return; }
+    }
+    if (bytes) cudaFreeHost(p); else free(p);          // (a buffer host_buf did not pin came from malloc)
 }
 
 inline bool is_space(uint8_t c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }
-
-// Bases of a record's body [p, end): whole lines at a time (memchr / memcpy); a line that holds blanks or a
-// carriage return goes byte by byte.  dst == nullptr: only count.  Returns the number of bases.
-inline int64_t copy_body(const uint8_t *p, const uint8_t *end, uint8_t *dst) {
-    int64_t n = 0;
-    while (p < end) {
-        const uint8_t *eol = (const uint8_t *)memchr(p, '\n', (size_t)(end - p));
-        if (!eol) eol = end;
-        const size_t ll = (size_t)(eol - p);
-        if (ll && !memchr(p, ' ', ll) && !memchr(p, '\r', ll) && !memchr(p, '\t', ll)) {
-            if (dst) memcpy(dst + n, p, ll);
-            n += (int64_t)ll;
-        } else {
-            for (const uint8_t *q = p; q < eol; ++q)
-                if (!is_space(*q)) { if (dst) dst[n] = *q; ++n; }
-        }
-        p = eol + 1;
-    }
-    return n;
-}
 
 }  // namespace
 
@@ -95,6 +122,8 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
         madvise((void *)data, (size_t)size, MADV_SEQUENTIAL);
     }
     close(fd);
+    const auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *w) { if (getenv("DBGA_FASTA_TRACE")) fprintf(stderr, "[fasta] %s %.1f ms\n", w, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count()); };
     FastaImpl *f = new FastaImpl();
     // ---- pass 1: record starts ('>' at the start of a line), found in parallel slices
     std::vector<std::vector<int64_t>> found;
@@ -116,6 +145,7 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
             });
         for (auto &x : th) x.join();
     }
+    lap("pass1 find");
     std::vector<int64_t> starts;
     for (auto &v : found) starts.insert(starts.end(), v.begin(), v.end());
     const int64_t R = (int64_t)starts.size();
@@ -136,9 +166,10 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
             nlen[(size_t)r + 1] = b - a;
             nstart[(size_t)r] = a - data;
             body[(size_t)r] = (eol < end ? eol + 1 : end) - data;
-            f->offsets[(size_t)r + 1] = copy_body(data + body[(size_t)r], end, nullptr);
+            f->offsets[(size_t)r + 1] = dbga::host_fasta_body(data + body[(size_t)r], end, nullptr, 0);      // bases of the record
         }
     });
+    lap("pass2 count");
     for (int64_t r = 0; r < R; ++r) { f->offsets[(size_t)r + 1] += f->offsets[(size_t)r]; nlen[(size_t)r + 1] += nlen[(size_t)r]; }
     const int64_t total = f->offsets[(size_t)R];
     f->name_off = nlen;
@@ -155,6 +186,7 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
         delete f;
         return DBGA_ERR_NOMEM;
     }
+    lap("alloc");
     // ---- pass 3: labels, upper-cased bases, and (optionally) the canonical 2-bit words
     std::atomic<int64_t> bad{0};
     par_for(R, threads, 64, [&](int64_t lo, int64_t hi) {
@@ -164,8 +196,7 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
             memcpy(f->names.data() + nlen[(size_t)r], data + nstart[(size_t)r], (size_t)(nlen[(size_t)r + 1] - nlen[(size_t)r]));
             uint8_t *dst = f->seqs + f->offsets[(size_t)r];
             const int64_t len = f->offsets[(size_t)r + 1] - f->offsets[(size_t)r];
-            copy_body(data + body[(size_t)r], end, dst);
-            for (int64_t i = 0; i < len; ++i) dst[i] = (uint8_t)(dst[i] - (((uint8_t)(dst[i] - 'a') < 26u) << 5));   // upper-case (vectorised)
+            dbga::host_fasta_body(data + body[(size_t)r], end, dst, len);       // blanks dropped, upper-cased, 32 bytes per step
             if (f->packed) {
                 uint32_t *pw = f->packed + (f->offsets[(size_t)r] >> 4) + r;
                 nbad += dbga::host_pack_seq(dst, len, pw);          // hostpack.cpp: 32 bases per AVX2 step
@@ -173,7 +204,9 @@ int dbga_fasta_read(const char *path, int want_packed, int threads, dbga_fasta *
         }
         bad += nbad;
     });
+    lap("pass3 copy+pack");
     if (size > 0) munmap((void *)data, (size_t)size);
+    lap("munmap");
     f->pub.num_records = R;
     f->pub.offsets = f->offsets.data();
     f->pub.seqs = f->seqs;

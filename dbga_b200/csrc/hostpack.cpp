@@ -76,6 +76,52 @@ __attribute__((target("avx2"))) static bool pack_seq_avx2(const uint8_t *src, in
 static const bool g_have_avx2 = __builtin_cpu_supports("avx2");
 #endif
 
+// ---- FASTA record bodies (fasta_io.cu): the bases of [p, end) -- everything but '\n', '\r', ' ', '\t' --
+// counted, or copied upper-cased to dst (which holds exactly `room` bytes: never written past, the records of a
+// file are filled by different threads side by side).  32 bytes per step: a step without a blank is one load, four
+// compares and one store; a blank ends the step behind it.
+static inline bool is_blank(uint8_t c) { return c == '\n' || c == '\r' || c == ' ' || c == '\t'; }
+static int64_t body_scalar(const uint8_t *p, const uint8_t *end, uint8_t *dst) {
+    int64_t n = 0;
+    for (; p < end; ++p)
+        if (!is_blank(*p)) { if (dst) dst[n] = (uint8_t)(*p - (((uint8_t)(*p - 'a') < 26u) << 5)); ++n; }
+    return n;
+}
+#ifdef DBGA_X86
+__attribute__((target("avx2,bmi,popcnt"))) static int64_t body_avx2(const uint8_t *p, const uint8_t *end, uint8_t *dst, int64_t room) {
+    const __m256i nl = _mm256_set1_epi8('\n'), cr = _mm256_set1_epi8('\r'), sp = _mm256_set1_epi8(' '), tb = _mm256_set1_epi8('\t');
+    const __m256i a1 = _mm256_set1_epi8('a' - 1), z1 = _mm256_set1_epi8('z' + 1), c20 = _mm256_set1_epi8(0x20);
+    int64_t n = 0;
+    if (!dst) {
+        for (; p + 32 <= end; p += 32) {
+            const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+            const __m256i b = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, nl), _mm256_cmpeq_epi8(v, cr)),
+                                              _mm256_or_si256(_mm256_cmpeq_epi8(v, sp), _mm256_cmpeq_epi8(v, tb)));
+            n += 32 - __builtin_popcount((unsigned)_mm256_movemask_epi8(b));
+        }
+        return n + body_scalar(p, end, nullptr);
+    }
+    while (p + 32 <= end && n + 32 <= room) {
+        const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(p));
+        const __m256i b = _mm256_or_si256(_mm256_or_si256(_mm256_cmpeq_epi8(v, nl), _mm256_cmpeq_epi8(v, cr)),
+                                          _mm256_or_si256(_mm256_cmpeq_epi8(v, sp), _mm256_cmpeq_epi8(v, tb)));
+        const unsigned m = (unsigned)_mm256_movemask_epi8(b);
+        const __m256i low = _mm256_and_si256(_mm256_cmpgt_epi8(v, a1), _mm256_cmpgt_epi8(z1, v));
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(dst + n), _mm256_sub_epi8(v, _mm256_and_si256(low, c20)));
+        if (m == 0) { p += 32; n += 32; }
+        else { const int k = __builtin_ctz(m); p += k + 1; n += k; }        // the bytes behind the blank are rewritten by the next step
+    }
+    return n + body_scalar(p, end, dst + n);
+}
+#endif
+int64_t host_fasta_body(const uint8_t *p, const uint8_t *end, uint8_t *dst, int64_t room) {
+#ifdef DBGA_X86
+    if (g_have_avx2) return body_avx2(p, end, dst, room);
+#endif
+    (void)room;
+    return body_scalar(p, end, dst);
+}
+
 // one sequence; returns true when it holds a character outside ACGT (packed as A)
 bool host_pack_seq(const uint8_t *src, int64_t len, uint32_t *dst) {
 #ifdef DBGA_X86
