@@ -233,6 +233,8 @@ int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_resu
     const int64_t P = res->num_pairs;
     if (first_record < 0 || first_record + 2 * P > in->num_records) return -1;
     const bool compact = res->seg_cols != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *w) { if (getenv("DBGA_FASTA_TRACE")) fprintf(stderr, "[fasta write] %s %.1f ms\n", w, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count()); };
     if (P > 0 && (!res->status || !res->aln_off || !res->aln0 || !res->aln1)) return -1;
     if (compact && P > 0 && (!res->runs || !res->run_off)) return -1;
     // ---- bytes of every pair's two records
@@ -254,6 +256,7 @@ int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_resu
             pos[(size_t)i + 1] = (2 + n0 + len + lines) + (2 + n1 + len + lines);
         }
     });
+    lap("sizes");
     int64_t written = 0;
     for (int64_t i = 0; i < P; ++i) { written += res->status[i] == DBGA_OK; pos[(size_t)i + 1] += pos[(size_t)i]; }
     const int64_t total = pos[(size_t)P];
@@ -269,6 +272,7 @@ int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_resu
     uint8_t *map = (uint8_t *)mmap(nullptr, (size_t)(at + total - map_lo), PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)map_lo);
     if (map == MAP_FAILED) { close(fd); return -1; }
     uint8_t *out_base = map + (at - map_lo);
+    lap("open + truncate + map");
     par_for(P, threads, 256, [&](int64_t lo, int64_t hi) {
         std::vector<uint8_t> row;
         for (int64_t i = lo; i < hi; ++i) {
@@ -307,8 +311,10 @@ int64_t dbga_fasta_write(const char *path, const dbga_fasta *in, const dbga_resu
             }
         }
     });
+    lap("records");
     munmap(map, (size_t)(at + total - map_lo));
     close(fd);
+    lap("unmap + close");
     return written;
 }
 
