@@ -165,7 +165,9 @@ int dbga_align_batch_multi(dbga_multi *m, const uint8_t *seqs, const uint32_t *p
  * with want_packed, the canonical 2-bit words of the same records (bad_records counts those that hold a
  * character outside ACGT: use the ASCII buffer then).  dbga_fasta_write writes the two wrapped records of every
  * DBGA_OK pair of a result whose pair 0 is records first_record, first_record + 1 of `in`; a COMPACT_ROWS result
- * is expanded on the fly.  Returns the number of pairs written, -1 on error.  threads <= 0: all host cores. */
+ * is expanded on the fly.  Returns the number of pairs written, -1 on error.  threads <= 0: all host cores.
+ * dbga_fasta_free keeps the batch's pinned buffers (up to 4 GiB in all) for the next dbga_fasta_read of the process:
+ * page-locking costs about ten times the parsing, and a tool that streams files pays it once. */
 typedef struct dbga_fasta {
     int64_t num_records;
     const int64_t *offsets;     /* [R+1] into seqs                                  */
