@@ -183,6 +183,55 @@ def test_two_rank_sharding_gloo(tmp_path):
     assert "SHARD_OK" in outs[0][0]
 
 
+GATHER_SCRIPT = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from dbga_b200.batch import BatchResult
+from dbga_b200.sharding import shard_range, gather_batch_result
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+
+def shard(lo, hi):
+    # pair i: i % 5 aligned columns of byte 65 + i % 20 / 97 + i % 20, i % 3 runs (i, i + 1, 2 + r), sop row (i, 0, 1, 2)
+    lens = np.array([i % 5 for i in range(lo, hi)], np.int64)
+    nr = np.array([i % 3 for i in range(lo, hi)], np.int64)
+    off = lambda l: np.concatenate([[0], np.cumsum(l)]).astype(np.int64)
+    a0 = np.concatenate([np.full(i % 5, 65 + i % 20, np.uint8) for i in range(lo, hi)] + [np.zeros(0, np.uint8)])
+    a1 = np.concatenate([np.full(i % 5, 97 + i % 20, np.uint8) for i in range(lo, hi)] + [np.zeros(0, np.uint8)])
+    runs = np.array([[i, i + 1, 2 + r] for i in range(lo, hi) for r in range(i % 3)], np.int32).reshape(-1, 3)
+    ids = np.arange(lo, hi)
+    return BatchResult(status=(ids % 2).astype(np.int32), score=ids * 7, dp_cells=ids * 11, dp_segments=ids % 4, n_anchors=ids * 3,
+                       run_off=off(nr), runs=runs, aln_off=off(lens), aln0=a0, aln1=a1,
+                       sop=np.stack([ids, 0 * ids, 0 * ids + 1, 0 * ids + 2], 1).astype(np.int32))
+
+P = 23
+lo, hi = shard_range(P, rank, 2)
+got = gather_batch_result(shard(lo, hi))
+if rank == 0:
+    want = shard(0, P)
+    for f in ("status", "score", "dp_cells", "dp_segments", "n_anchors", "run_off", "runs", "aln_off", "aln0", "aln1", "sop"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    assert got.alignment(9) == want.alignment(9) and np.array_equal(got.anchors(8), want.anchors(8))
+    print("GATHER_OK")
+else:
+    assert got is None
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_array_gather_gloo(tmp_path):
+    """gather_batch_result: the shards' BatchResults joined on rank 0 as arrays (offsets rebased), world size 2 over gloo."""
+    script = tmp_path / "gather.py"
+    script.write_text(GATHER_SCRIPT.format(root=ROOT, port=29613))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0][0]
+
+
 def test_shard_range_partitions():
     from dbga_b200.sharding import shard_range
     for n in (0, 1, 7, 100_000):
