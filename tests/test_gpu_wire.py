@@ -231,3 +231,44 @@ def test_wire_forms_edge_cases(aligner):
         m.close()
     empty = aligner.align_buffers(np.zeros(0, np.uint8), np.zeros(1, np.int64), aligner.params(3, flags=_lib.FLAG_COMPACT_ROWS | _lib.FLAG_SOP))
     assert len(empty) == 0
+
+
+SHARDED_SCRIPT = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, {root!r})
+from dbga_b200 import Aligner
+from dbga_b200.sharding import align_buffers_sharded
+from dbga_b200.synth import synth_batch
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+al = Aligner(0)
+buf, offs = synth_batch(301, 600, 0.02, 0.004, seed=5)
+prm = al.params(9)
+got = align_buffers_sharded(al, buf, offs, prm)
+if dist.get_rank() == 0:
+    want = al.align_buffers(buf, offs, prm)
+    for f in ("status", "score", "dp_cells", "dp_segments", "n_anchors", "run_off", "runs", "aln_off", "aln0", "aln1"):
+        assert np.array_equal(getattr(got, f), getattr(want, f)), f
+    print("SHARDED_OK", int((want.status == 0).sum()))
+else:
+    assert got is None
+al.close()
+dist.destroy_process_group()
+"""
+
+
+def test_two_ranks_shard_one_batch_and_gather_arrays(tmp_path):
+    """One process per rank (both on cuda:0 here), pairs sharded by index, the shards' results gathered on rank 0 as
+    arrays (dbga_b200.sharding.align_buffers_sharded): identical to the single-process result."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "sharded.py"
+    script.write_text(SHARDED_SCRIPT.format(root=root, port=29617))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARDED_OK" in outs[0][0]
