@@ -10,6 +10,10 @@ python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>> gpurun_out/${T}_bench.err
 python tools/dp_bench.py 8 16 32 64 128 256 512 1024 2048 4096 8192 > gpurun_out/${T}_dp_bench.jsonl 2>&1
 python tools/big_bench.py > gpurun_out/${T}_big_bench.jsonl 2>&1
+# the long-segment kernel on batches that fill the chip (the traceback pool is sized at a byte per cell: raise the scratch limit)
+(DP_PAIRS=3840 DP_SCRATCH_GB=40 python tools/dp_bench.py 2048 | head -1; DP_PAIRS=960 DP_SCRATCH_GB=40 python tools/dp_bench.py 4096 | head -1
+ DP_PAIRS=480 DP_SCRATCH_GB=80 python tools/dp_bench.py 8192 | head -1; DP_PAIRS=120 DP_SCRATCH_GB=80 python tools/dp_bench.py 16384 | head -1) \
+    > gpurun_out/${T}_dp_bench_filled.jsonl 2>&1
 python bench.py --workload cfg4 --steps 5 --no-dp-micro --no-variants --cpu-seconds 5 > gpurun_out/${T}_bench_cfg4.json 2>> gpurun_out/${T}_bench.err
 python tools/fasta_e2e.py > gpurun_out/${T}_fasta_e2e.json 2>> gpurun_out/${T}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv \
