@@ -95,3 +95,36 @@ def test_strip_frames_hold_the_int16_range():
         for x, y in cases:
             for rows in (256, 512):
                 check_frames(x, y, score, d, e, rows)
+
+
+def test_frame_deltas_chain_to_the_anchor():
+    """The bookkeeping lane 0 of a strip does at every block start (stage3_dp16.cu): from the boundary entry's anchor
+    a_c (encoded in the PRODUCER's frame) and the producer's own delta carried in the entry it derives its frame step
+    delta^s_c = delta^(s-1)_c + a_c - a_(c-1), with a_0 = AF = 4 (S16_F0 - off).  Summed up, the steps must put the
+    strip's base exactly S16_F0 below its anchor, T(i0, c CB) - S16_F0, for every strip and block, and every step
+    must fit the 16 bits it travels in."""
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 4, 2300)
+    b = a.copy(); mut = rng.random(a.size) < 0.05; b[mut] = (b[mut] + 1) & 3
+    for x, y in ((a, b), (a, rng.integers(0, 4, 2100)), (a, np.concatenate([rng.integers(0, 4, 700), a])[:2300])):
+        M, X, Y = gotoh_hat(x, y, dna_score(10, -1, -8), 10, 2)
+        T = np.maximum(M, np.maximum(X, Y))
+        AF = 4 * (F0 - OFF)
+        for rows in (256, 512):
+            nblk = (len(y) + 1 + CB - 1) // CB
+            delta_prev_strip = np.zeros(nblk, np.int64)          # strip 0: base 0 everywhere
+            base_prev_strip = np.zeros(nblk, np.int64)
+            for i0 in range(rows, len(x), rows):
+                delta, base = np.zeros(nblk, np.int64), np.zeros(nblk, np.int64)
+                a_prev, bsum = AF, 0
+                for c in range(1, nblk):
+                    if c * CB > len(y):
+                        break
+                    a_c = 4 * (int(T[i0, c * CB]) - int(base_prev_strip[c]) - OFF)      # what the producer stored (tag stripped)
+                    d = int(delta_prev_strip[c]) + a_c - a_prev
+                    assert -32768 <= d <= 32767 and -32768 <= a_c <= 32767
+                    a_prev = a_c
+                    bsum += d
+                    delta[c], base[c] = d, bsum // 4
+                    assert bsum % 4 == 0 and base[c] == int(T[i0, c * CB]) - F0
+                delta_prev_strip, base_prev_strip = delta, base
